@@ -1,0 +1,711 @@
+// extern "C" shim: implements include/acf_b200.h on top of the sm_100a kernels.
+// No CPU fallback lives here: every compute entry point needs a CUDA device and says so when it fails.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/acf_b200.h"
+#include "common.cuh"
+
+namespace acfb200 {
+
+static thread_local char g_err[1024] = "";
+const char* last_error() { return g_err; }
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::recursive_mutex g_mu;
+static std::atomic<long long> g_launches{0};
+static int g_force_variant = -1;
+
+#define ACF_TRY(expr)            \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != 0) return _rc; \
+    } while (0)
+
+// Grow-only device buffer.
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, bool zero = false)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;  // a little slack so slowly growing sizes do not thrash
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            cudaGetLastError();
+            return e == cudaErrorMemoryAllocation ? ACFB200_ERR_NOMEM : ACFB200_ERR_CUDA;
+        }
+        cap = want;
+        if (zero) {
+            e = cudaMemset(p, 0, want);
+            if (e != cudaSuccess) {
+                set_error("cudaMemset failed: %s", cudaGetErrorString(e));
+                return ACFB200_ERR_CUDA;
+            }
+        }
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const
+    {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+struct Workspace {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    Buf series, y, vel, desc, partials, out, scratch, small, fftwork;
+    void release()
+    {
+        series.release();
+        y.release();
+        vel.release();
+        desc.release();
+        partials.release();
+        out.release();
+        scratch.release();
+        small.release();
+        fftwork.release();
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+        device = -1;
+    }
+};
+
+static std::vector<Workspace*> g_ws;  // one per device, created lazily
+
+static int get_ws(Workspace** out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("no usable CUDA device (cudaGetDevice: %s); libacf_b200 has no CPU path", cudaGetErrorString(e));
+        cudaGetLastError();
+        return ACFB200_ERR_CUDA;
+    }
+    if ((int)g_ws.size() <= dev) g_ws.resize(dev + 1, nullptr);
+    if (!g_ws[dev]) {
+        Workspace* w = new Workspace();
+        w->device = dev;
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) {
+            set_error("cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+            delete w;
+            return ACFB200_ERR_CUDA;
+        }
+        if (prop.major < 10) {
+            set_error("device %d is sm_%d%d; libacf_b200 is built for sm_100a (B200) only", dev, prop.major,
+                      prop.minor);
+            delete w;
+            return ACFB200_ERR_CUDA;
+        }
+        w->sm_count = prop.multiProcessorCount;
+        e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+            delete w;
+            return ACFB200_ERR_CUDA;
+        }
+        g_ws[dev] = w;
+    }
+    *out = g_ws[dev];
+    return 0;
+}
+
+static inline size_t even_up(long long n) { return (size_t)((n + 1) & ~1ll); }
+
+// Direct lag sums of `nseries` device-resident series described by host-side descs.
+static int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long long ncorr, double* d_out,
+                      int normalise, cudaStream_t st)
+{
+    const int ns = (int)descs.size();
+    long long max_i_end = 1;
+    for (const auto& d : descs) {
+        if (d.n < 0 || d.i_end < 0 || d.i_end > d.n) {
+            set_error("series with n=%lld i_end=%lld: need 0 <= i_end <= n", d.n, d.i_end);
+            return ACFB200_ERR_ARG;
+        }
+        if (d.i_end > max_i_end) max_i_end = d.i_end;
+    }
+    DirectPlan plan;
+    ACF_TRY(plan_direct(max_i_end, ncorr, ns, ws->sm_count, g_force_variant, &plan));
+    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)ns));
+    ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, ns) * sizeof(double)));
+    // pageable source: the runtime stages it before returning, so `descs` may die right after
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * (size_t)ns, cudaMemcpyHostToDevice, st));
+    ACF_TRY(launch_direct(plan, ws->desc.as<SeriesDesc>(), ns, ncorr, ws->partials.as<double>(), st));
+    ACF_TRY(launch_reduce_partials(plan, ws->desc.as<SeriesDesc>(), ns, ncorr, ws->partials.as<double>(), d_out,
+                                   normalise, st));
+    g_launches += 2;
+    return 0;
+}
+
+static int check_common(const void* p, long long n, long long ncorr, const char* what)
+{
+    if (!p) {
+        set_error("%s: null pointer", what);
+        return ACFB200_ERR_ARG;
+    }
+    if (n < 1) {
+        set_error("%s: need at least one sample (n=%lld)", what, n);
+        return ACFB200_ERR_ARG;
+    }
+    if (ncorr < 1) {
+        set_error("%s: ncorr must be >= 1 (got %lld)", what, ncorr);
+        return ACFB200_ERR_ARG;
+    }
+    return 0;
+}
+
+// The main() sequence on a device-resident series; d_acf/d_vacf device [ncorr].
+static int pipeline_device(Workspace* ws, const double* d_series, long long n, long long ncorr, double dt,
+                           double cutoff, double* d_acf, double* d_vacf, acfb200_result* res, cudaStream_t st)
+{
+    if (n < 3) {
+        set_error("acf_pipeline: need n >= 3 samples (velocity series has n-2), got %lld", n);
+        return ACFB200_ERR_ARG;
+    }
+    ACF_TRY(ws->y.ensure(even_up(n) * 8));
+    ACF_TRY(ws->vel.ensure(even_up(n) * 8));
+    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch), true));
+    ACF_TRY(ws->small.ensure(64));
+    ReduceScratch* sc = ws->scratch.as<ReduceScratch>();
+    double* d_y = ws->y.as<double>();
+    double* d_v = ws->vel.as<double>();
+    ACF_TRY(launch_sum(d_series, n, sc, st));
+    ACF_TRY(launch_center_velocity(d_series, n, sc, d_y, d_v, dt, st));
+    ACF_TRY(launch_subtract_mean(d_v, n - 2, &sc->vel_sum, &sc->vel_mean, st));
+    g_launches += 3;
+    const long long m = n - 2;  // ACFcalculator.cpp:718
+    std::vector<SeriesDesc> descs = {{d_y, m, m}, {d_v, m, m}};
+    ACF_TRY(ws->out.ensure((size_t)2 * ncorr * 8));
+    double* d_o = ws->out.as<double>();
+    ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
+    double* d_int = ws->small.as<double>();
+    long long* d_brk = reinterpret_cast<long long*>(d_int + 1);
+    ACF_TRY(launch_integrate_cutoff(d_o, ncorr, dt, cutoff, d_int, d_brk, nullptr, st));
+    g_launches += 1;
+    if (d_acf) ACF_CUDA_OK(cudaMemcpyAsync(d_acf, d_o, ncorr * 8, cudaMemcpyDeviceToDevice, st));
+    if (d_vacf) ACF_CUDA_OK(cudaMemcpyAsync(d_vacf, d_o + ncorr, ncorr * 8, cudaMemcpyDeviceToDevice, st));
+    if (res) {
+        double h_sc[4], h_int[2], h_a0 = 0, h_v0 = 0;
+        ACF_CUDA_OK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+        ACF_CUDA_OK(cudaMemcpyAsync(h_int, d_int, sizeof(h_int), cudaMemcpyDeviceToHost, st));
+        ACF_CUDA_OK(cudaMemcpyAsync(&h_a0, d_o, 8, cudaMemcpyDeviceToHost, st));
+        ACF_CUDA_OK(cudaMemcpyAsync(&h_v0, d_o + ncorr, 8, cudaMemcpyDeviceToHost, st));
+        ACF_CUDA_OK(cudaStreamSynchronize(st));
+        res->avg = h_sc[1];
+        res->vel_avg = h_sc[3];
+        res->var = h_a0;
+        res->var_vel = h_v0;
+        res->acf_int = h_int[0];
+        long long brk;
+        memcpy(&brk, &h_int[1], 8);
+        res->cutoff_index = brk;
+        res->n_used = m;
+        res->diffusivity = res->var * res->var / res->acf_int * 0.1;  // ACFcalculator.cpp:905
+    }
+    return 0;
+}
+
+}  // namespace acfb200
+
+using namespace acfb200;
+typedef std::lock_guard<std::recursive_mutex> Lock;
+
+extern "C" {
+
+const char* acfb200_version(void) { return "acf_b200 0.1 (sm_100a)"; }
+const char* acfb200_last_error(void) { return last_error(); }
+
+int acfb200_device_count(int* count)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        if (count) *count = 0;
+        return ACFB200_ERR_CUDA;
+    }
+    if (count) *count = c;
+    return 0;
+}
+
+int acfb200_set_device(int device)
+{
+    ACF_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+
+int64_t acfb200_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int acfb200_release(void)
+{
+    Lock lk(g_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (Workspace* w : g_ws)
+        if (w) {
+            cudaSetDevice(w->device);
+            w->release();
+            delete w;
+        }
+    g_ws.clear();
+    cudaSetDevice(cur);
+    return 0;
+}
+
+int acfb200_set_variant(int variant)
+{
+    if (variant >= direct_variant_count()) {
+        set_error("variant %d out of range (0..%d)", variant, direct_variant_count() - 1);
+        return ACFB200_ERR_ARG;
+    }
+    g_force_variant = variant < 0 ? -1 : variant;
+    return 0;
+}
+int acfb200_variant_count(void) { return direct_variant_count(); }
+const char* acfb200_variant_name(int v) { return direct_variant_name(v); }
+
+int acfb200_describe_plan(int64_t n, int64_t ncorr, int nseries, char* buf, int buflen)
+{
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaGetLastError();
+    DirectPlan p;
+    ACF_TRY(plan_direct(n, ncorr, nseries, sms, g_force_variant, &p));
+    if (buf && buflen > 0)
+        snprintf(buf, buflen,
+                 "variant=%s warps=%d ts=%d ti=%d bsz=%d lag_tiles=%d chunks=%d nseries=%d grid=%dx%dx%d block=%d "
+                 "smem=%zu mpad=%d useful_lag_frac=%.4f",
+                 direct_variant_name(p.variant), p.warps, p.ts, p.ti, p.bsz, p.lag_tiles, p.chunks, nseries,
+                 p.lag_tiles, p.chunks, nseries, p.warps * 32, p.smem_bytes, p.mpad, (double)ncorr / p.mpad);
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// -------------------------------------------------------------------------------------------------
+int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int nseries, int64_t ncorr,
+                                   double* corr)
+{
+    Lock lk(g_mu);
+    if (!y || !n || !corr || nseries < 1) {
+        set_error("calc_correlation_batch: null argument or nseries < 1");
+        return ACFB200_ERR_ARG;
+    }
+    for (int s = 0; s < nseries; ++s) ACF_TRY(check_common(y[s], n[s], ncorr, "calc_correlation"));
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    size_t total = 0;
+    for (int s = 0; s < nseries; ++s) total += even_up(n[s]);
+    ACF_TRY(ws->series.ensure(total * 8));
+    ACF_TRY(ws->out.ensure((size_t)nseries * ncorr * 8));
+    std::vector<SeriesDesc> descs(nseries);
+    size_t off = 0;
+    for (int s = 0; s < nseries; ++s) {
+        double* d = ws->series.as<double>() + off;
+        ACF_CUDA_OK(cudaMemcpyAsync(d, y[s], (size_t)n[s] * 8, cudaMemcpyHostToDevice, ws->stream));
+        descs[s] = {d, (long long)n[s], (long long)n[s]};
+        off += even_up(n[s]);
+    }
+    ACF_TRY(run_direct(ws, descs, ncorr, ws->out.as<double>(), 1, ws->stream));
+    ACF_CUDA_OK(cudaMemcpyAsync(corr, ws->out.p, (size_t)nseries * ncorr * 8, cudaMemcpyDeviceToHost, ws->stream));
+    ACF_CUDA_OK(cudaStreamSynchronize(ws->stream));
+    return 0;
+}
+
+int acfb200_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr)
+{
+    return acfb200_calc_correlation_batch(&y, &n, 1, ncorr, corr);
+}
+
+int acfb200_variance(const double* y, int64_t n, double* var)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_common(y, n, 1, "variance"));
+    if (!var) {
+        set_error("variance: null output");
+        return ACFB200_ERR_ARG;
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    ACF_TRY(ws->series.ensure(even_up(n) * 8));
+    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch), true));
+    ReduceScratch* sc = ws->scratch.as<ReduceScratch>();
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->series.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, ws->stream));
+    ACF_TRY(launch_sumsq(ws->series.as<double>(), n, sc, ws->stream));
+    g_launches += 1;
+    ACF_CUDA_OK(cudaMemcpyAsync(var, &sc->meansq, 8, cudaMemcpyDeviceToHost, ws->stream));
+    ACF_CUDA_OK(cudaStreamSynchronize(ws->stream));
+    return 0;
+}
+
+int acfb200_calc_subtract_average(double* y, int64_t n, double* avg)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_common(y, n, 1, "calc_subtract_average"));
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    ACF_TRY(ws->series.ensure(even_up(n) * 8));
+    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch), true));
+    ReduceScratch* sc = ws->scratch.as<ReduceScratch>();
+    double* d = ws->series.as<double>();
+    ACF_CUDA_OK(cudaMemcpyAsync(d, y, (size_t)n * 8, cudaMemcpyHostToDevice, ws->stream));
+    ACF_TRY(launch_sum(d, n, sc, ws->stream));
+    ACF_TRY(launch_subtract_mean(d, n, &sc->sum, &sc->mean, ws->stream));
+    g_launches += 2;
+    ACF_CUDA_OK(cudaMemcpyAsync(y, d, (size_t)n * 8, cudaMemcpyDeviceToHost, ws->stream));
+    double m = 0.0;
+    ACF_CUDA_OK(cudaMemcpyAsync(&m, &sc->mean, 8, cudaMemcpyDeviceToHost, ws->stream));
+    ACF_CUDA_OK(cudaStreamSynchronize(ws->stream));
+    if (avg) *avg = m;
+    return 0;
+}
+
+int acfb200_velocity_series(const double* y, int64_t n, double dt, double* vel)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_common(y, n, 1, "velocity_series"));
+    if (n < 3 || !vel) {
+        set_error("velocity_series: need n >= 3 and a non-null output (n=%lld)", (long long)n);
+        return ACFB200_ERR_ARG;
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    ACF_TRY(ws->series.ensure(even_up(n) * 8));
+    ACF_TRY(ws->y.ensure(even_up(n) * 8));
+    ACF_TRY(ws->vel.ensure(even_up(n) * 8));
+    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch), true));
+    ReduceScratch* sc = ws->scratch.as<ReduceScratch>();
+    double* d = ws->series.as<double>();
+    ACF_CUDA_OK(cudaMemcpyAsync(d, y, (size_t)n * 8, cudaMemcpyHostToDevice, ws->stream));
+    // the reference differentiates the series it is given (already centred by the caller): mean "0"
+    ACF_CUDA_OK(cudaMemsetAsync(&sc->sum, 0, 8, ws->stream));
+    ACF_TRY(launch_center_velocity(d, n, sc, ws->y.as<double>(), ws->vel.as<double>(), dt, ws->stream));
+    ACF_TRY(launch_subtract_mean(ws->vel.as<double>(), n - 2, &sc->vel_sum, &sc->vel_mean, ws->stream));
+    g_launches += 2;
+    ACF_CUDA_OK(cudaMemcpyAsync(vel, ws->vel.p, (size_t)(n - 2) * 8, cudaMemcpyDeviceToHost, ws->stream));
+    ACF_CUDA_OK(cudaStreamSynchronize(ws->stream));
+    return 0;
+}
+
+int acfb200_integrate_corr_cutoff(const double* acf, int64_t ncorr, double dt, double cutoff, double* integral,
+                                  int64_t* break_index)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_common(acf, 1, ncorr, "integrate_corr_cutoff"));
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    ACF_TRY(ws->out.ensure((size_t)ncorr * 8));
+    ACF_TRY(ws->small.ensure(64));
+    double* d_int = ws->small.as<double>();
+    long long* d_brk = reinterpret_cast<long long*>(d_int + 1);
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->out.p, acf, (size_t)ncorr * 8, cudaMemcpyHostToDevice, ws->stream));
+    ACF_TRY(launch_integrate_cutoff(ws->out.as<double>(), ncorr, dt, cutoff, d_int, d_brk, nullptr, ws->stream));
+    g_launches += 1;
+    double h[2];
+    ACF_CUDA_OK(cudaMemcpyAsync(h, d_int, 16, cudaMemcpyDeviceToHost, ws->stream));
+    ACF_CUDA_OK(cudaStreamSynchronize(ws->stream));
+    if (integral) *integral = h[0];
+    if (break_index) memcpy(break_index, &h[1], 8);
+    return 0;
+}
+
+int acfb200_integrate_corr(const double* acf, int64_t ncorr, double dt, double* integral)
+{
+    return acfb200_integrate_corr_cutoff(acf, ncorr, dt, 0.0, integral, nullptr);
+}
+
+int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, int nwindows, int64_t ncorr, double dt,
+                               double cutoff, double* acf, double* vacf, acfb200_result* result)
+{
+    Lock lk(g_mu);
+    if (!series || !n || nwindows < 1) {
+        set_error("acf_pipeline_batch: null argument or nwindows < 1");
+        return ACFB200_ERR_ARG;
+    }
+    for (int w = 0; w < nwindows; ++w) {
+        ACF_TRY(check_common(series[w], n[w], ncorr, "acf_pipeline"));
+        if (n[w] < 3) {
+            set_error("acf_pipeline: window %d has %lld samples, need >= 3", w, (long long)n[w]);
+            return ACFB200_ERR_ARG;
+        }
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    cudaStream_t st = ws->stream;
+    size_t total = 0, max_n = 0;
+    for (int w = 0; w < nwindows; ++w) {
+        total += even_up(n[w]);
+        if ((size_t)n[w] > max_n) max_n = (size_t)n[w];
+    }
+    ACF_TRY(ws->series.ensure(even_up((long long)max_n) * 8));
+    ACF_TRY(ws->y.ensure(total * 8));
+    ACF_TRY(ws->vel.ensure(total * 8));
+    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch) * (size_t)nwindows, true));
+    ACF_TRY(ws->out.ensure((size_t)2 * nwindows * ncorr * 8));
+    ACF_TRY(ws->small.ensure((size_t)16 * nwindows));
+    ReduceScratch* sc = ws->scratch.as<ReduceScratch>();
+    std::vector<SeriesDesc> descs(2 * (size_t)nwindows);
+    size_t off = 0;
+    for (int w = 0; w < nwindows; ++w) {
+        double* d_x = ws->series.as<double>();
+        double* d_y = ws->y.as<double>() + off;
+        double* d_v = ws->vel.as<double>() + off;
+        // the staging buffer is reused window to window: stream order keeps the copies behind the kernels
+        ACF_CUDA_OK(cudaMemcpyAsync(d_x, series[w], (size_t)n[w] * 8, cudaMemcpyHostToDevice, st));
+        ACF_TRY(launch_sum(d_x, n[w], sc + w, st));
+        ACF_TRY(launch_center_velocity(d_x, n[w], sc + w, d_y, d_v, dt, st));
+        ACF_TRY(launch_subtract_mean(d_v, n[w] - 2, &sc[w].vel_sum, &sc[w].vel_mean, st));
+        g_launches += 3;
+        const long long m = n[w] - 2;
+        descs[2 * w] = {d_y, m, m};
+        descs[2 * w + 1] = {d_v, m, m};
+        off += even_up(n[w]);
+    }
+    double* d_o = ws->out.as<double>();  // [window][acf|vacf][ncorr]
+    ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
+    double* d_small = ws->small.as<double>();
+    for (int w = 0; w < nwindows; ++w) {
+        ACF_TRY(launch_integrate_cutoff(d_o + (size_t)2 * w * ncorr, ncorr, dt, cutoff, d_small + 2 * w,
+                                        reinterpret_cast<long long*>(d_small + 2 * w + 1), nullptr, st));
+        g_launches += 1;
+    }
+    std::vector<double> h_o((size_t)2 * nwindows * ncorr), h_small(2 * (size_t)nwindows);
+    std::vector<ReduceScratch> h_sc;  // only the 4 leading doubles of each are needed
+    std::vector<double> h_means(4 * (size_t)nwindows);
+    ACF_CUDA_OK(cudaMemcpyAsync(h_o.data(), d_o, h_o.size() * 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(h_small.data(), d_small, h_small.size() * 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaMemcpy2DAsync(h_means.data(), 32, sc, sizeof(ReduceScratch), 32, nwindows, cudaMemcpyDeviceToHost,
+                                  st));
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
+    for (int w = 0; w < nwindows; ++w) {
+        const double* a = h_o.data() + (size_t)2 * w * ncorr;
+        if (acf) memcpy(acf + (size_t)w * ncorr, a, (size_t)ncorr * 8);
+        if (vacf) memcpy(vacf + (size_t)w * ncorr, a + ncorr, (size_t)ncorr * 8);
+        if (result) {
+            acfb200_result& r = result[w];
+            r.avg = h_means[4 * w + 1];
+            r.vel_avg = h_means[4 * w + 3];
+            r.var = a[0];
+            r.var_vel = a[ncorr];
+            r.acf_int = h_small[2 * w];
+            long long brk;
+            memcpy(&brk, &h_small[2 * w + 1], 8);
+            r.cutoff_index = brk;
+            r.n_used = n[w] - 2;
+            r.diffusivity = r.var * r.var / r.acf_int * 0.1;  // ACFcalculator.cpp:905
+        }
+    }
+    return 0;
+}
+
+int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double dt, double cutoff, double* acf,
+                         double* vacf, acfb200_result* result)
+{
+    return acfb200_acf_pipeline_batch(&series, &n, 1, ncorr, dt, cutoff, acf, vacf, result);
+}
+
+int acfb200_spring_rescale(double* acf, double* vacf, int64_t ncorr, double k_spring, double mass_amu,
+                           double temperature, double* var, double* var_vel)
+{
+    if (!acf || !vacf || ncorr < 1) {
+        set_error("spring_rescale: null argument or ncorr < 1");
+        return ACFB200_ERR_ARG;
+    }
+    // ACFcalculator.cpp:730-753, constants :37 (kB) and :42 (R); O(ncorr) host arithmetic in the
+    // same evaluation order, so the result is bit-identical to the reference's.
+    const double kB = 1.38064852E-23, R = 8.314;
+    const double mass = 1.66054e-27 * mass_amu;
+    const double k = k_spring * 4184.0;
+    const double v = R * temperature / k;
+    double factor = v / acf[0];
+    for (int64_t i = 0; i < ncorr; ++i) acf[i] *= factor;
+    const double vv = 1.0E-10 * kB * temperature / mass;
+    factor = vv / vacf[0];
+    for (int64_t i = 0; i < ncorr; ++i) vacf[i] *= factor;
+    if (var) *var = v;
+    if (var_vel) *var_vel = vv;
+    return 0;
+}
+
+int acfb200_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t ncorr, double dt, double box_length,
+                       double temperature, double* acf, double* integrals, double* eta)
+{
+    Lock lk(g_mu);
+    if (!comps || ncomp < 1) {
+        set_error("green_kubo: null argument or ncomp < 1");
+        return ACFB200_ERR_ARG;
+    }
+    for (int c = 0; c < ncomp; ++c) ACF_TRY(check_common(comps[c], n, ncorr, "green_kubo"));
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    cudaStream_t st = ws->stream;
+    const size_t pitch = even_up(n);
+    ACF_TRY(ws->series.ensure(pitch * ncomp * 8));
+    ACF_TRY(ws->out.ensure((size_t)ncomp * ncorr * 8));
+    ACF_TRY(ws->small.ensure((size_t)16 * ncomp));
+    std::vector<SeriesDesc> descs(ncomp);
+    for (int c = 0; c < ncomp; ++c) {
+        double* d = ws->series.as<double>() + pitch * c;
+        ACF_CUDA_OK(cudaMemcpyAsync(d, comps[c], (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        descs[c] = {d, (long long)n, (long long)n};
+    }
+    double* d_o = ws->out.as<double>();
+    ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
+    double* d_small = ws->small.as<double>();
+    for (int c = 0; c < ncomp; ++c) {
+        ACF_TRY(launch_integrate_cutoff(d_o + (size_t)c * ncorr, ncorr, dt, 0.0, d_small + 2 * c,
+                                        reinterpret_cast<long long*>(d_small + 2 * c + 1), nullptr, st));
+        g_launches += 1;
+    }
+    std::vector<double> h_small(2 * (size_t)ncomp);
+    if (acf) ACF_CUDA_OK(cudaMemcpyAsync(acf, d_o, (size_t)ncomp * ncorr * 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(h_small.data(), d_small, h_small.size() * 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
+    const double kB = 1.38064852E-23;
+    for (int c = 0; c < ncomp; ++c) {
+        const double I = h_small[2 * c];
+        if (integrals) integrals[c] = I;
+        // viscosity.cpp:206, same evaluation order
+        if (eta) eta[c] = box_length * box_length * box_length / (kB * temperature) * I * 1E-30 * 1E-15 * 1E10;
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// device-resident entry points
+// -------------------------------------------------------------------------------------------------
+int acfb200_calc_correlation_batch_device(const double* const* d_y, const int64_t* n, const int64_t* i_end,
+                                          int nseries, int64_t ncorr, double* d_out, int normalise, void* stream)
+{
+    Lock lk(g_mu);
+    if (!d_y || !n || !d_out || nseries < 1) {
+        set_error("calc_correlation_batch_device: null argument or nseries < 1");
+        return ACFB200_ERR_ARG;
+    }
+    std::vector<SeriesDesc> descs(nseries);
+    for (int s = 0; s < nseries; ++s) {
+        ACF_TRY(check_common(d_y[s], n[s], ncorr, "calc_correlation_device"));
+        descs[s] = {d_y[s], (long long)n[s], (long long)(i_end ? i_end[s] : n[s])};
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    return run_direct(ws, descs, ncorr, d_out, normalise, (cudaStream_t)stream);
+}
+
+int acfb200_lag_sums_device(const double* d_x, int64_t n, int64_t i_end, int64_t ncorr, double* d_sums, void* stream)
+{
+    return acfb200_calc_correlation_batch_device(&d_x, &n, &i_end, 1, ncorr, d_sums, 0, stream);
+}
+
+int acfb200_calc_correlation_device(const double* d_y, int64_t n, int64_t ncorr, double* d_corr, void* stream)
+{
+    return acfb200_calc_correlation_batch_device(&d_y, &n, nullptr, 1, ncorr, d_corr, 1, stream);
+}
+
+int acfb200_normalise_device(const double* d_sums, int64_t n_total, int64_t ncorr, double* d_corr, void* stream)
+{
+    if (!d_sums || !d_corr || ncorr < 1) {
+        set_error("normalise_device: null argument or ncorr < 1");
+        return ACFB200_ERR_ARG;
+    }
+    ACF_TRY(launch_normalise(d_sums, n_total, ncorr, d_corr, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+int acfb200_acf_pipeline_device(const double* d_series, int64_t n, int64_t ncorr, double dt, double cutoff,
+                                double* d_acf, double* d_vacf, acfb200_result* result, void* stream)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_common(d_series, n, ncorr, "acf_pipeline_device"));
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    return pipeline_device(ws, d_series, n, ncorr, dt, cutoff, d_acf, d_vacf, result, (cudaStream_t)stream);
+}
+
+int acfb200_calc_correlation_fft_device(const double* d_y, int64_t n, int64_t ncorr, double* d_corr, void* stream)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_common(d_y, n, ncorr, "calc_correlation_fft_device"));
+    if (!d_corr) {
+        set_error("calc_correlation_fft_device: null output");
+        return ACFB200_ERR_ARG;
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    size_t bytes = 0;
+    long long L = 0;
+    ACF_TRY(fft_acf_workspace_bytes(n, ncorr, &bytes, &L));
+    ACF_TRY(ws->fftwork.ensure(bytes));
+    int launches = launch_fft_acf(d_y, n, ncorr, d_corr, 1, ws->fftwork.p, ws->fftwork.cap, (cudaStream_t)stream);
+    if (launches < 0) return -launches;
+    g_launches += launches;
+    return 0;
+}
+
+int acfb200_calc_correlation_fft(const double* y, int64_t n, int64_t ncorr, double* corr)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_common(y, n, ncorr, "calc_correlation_fft"));
+    if (!corr) {
+        set_error("calc_correlation_fft: null output");
+        return ACFB200_ERR_ARG;
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    ACF_TRY(ws->series.ensure(even_up(n) * 8));
+    ACF_TRY(ws->out.ensure((size_t)ncorr * 8));
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->series.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, ws->stream));
+    ACF_TRY(acfb200_calc_correlation_fft_device(ws->series.as<double>(), n, ncorr, ws->out.as<double>(), ws->stream));
+    ACF_CUDA_OK(cudaMemcpyAsync(corr, ws->out.p, (size_t)ncorr * 8, cudaMemcpyDeviceToHost, ws->stream));
+    ACF_CUDA_OK(cudaStreamSynchronize(ws->stream));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// measurement
+// -------------------------------------------------------------------------------------------------
+int acfb200_measure_dfma_peak(double* tflops, double* effective_sm_mhz)
+{
+    Lock lk(g_mu);
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    return measure_dfma_peak(tflops, effective_sm_mhz, 3);
+}
+
+int acfb200_measure_hbm_copy(double* gb_per_s)
+{
+    Lock lk(g_mu);
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    return measure_hbm_copy(gb_per_s, (size_t)1 << 30, 5);
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// Shared declarations for the sm_100a ACF kernels (internal; the public surface is include/acf_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace acfb200 {
+
+// One series of a batch as the direct-lag kernel sees it.
+//   S[k] = sum_{i < i_end, i + k < n} x[i] * x[i + k]
+// i_end == n for a whole series; i_end < n for a time block that carries a halo.
+struct SeriesDesc {
+    const double* x;
+    long long n;
+    long long i_end;
+};
+
+// Launch geometry chosen on the host for one direct-lag launch (see plan_direct()).
+struct DirectPlan {
+    int variant;        // index into the kernel-variant table
+    int rk, lk, pf;     // lags per thread, lag lanes per warp, prefetch distance (pairs)
+    int warps;          // warps per CTA == lag blocks per CTA
+    int ts;             // i-steps per lane group per tile (multiple of the ring size)
+    int ti;             // i values per tile = (32/lk) * ts
+    int bsz;            // doubles staged for the shifted operand
+    int lag_tiles;      // gridDim.x
+    int chunks;         // gridDim.y  (time chunks per series)
+    int mpad;           // lag_tiles * warps * lk * rk  (row pitch of the partial-sum buffer)
+    size_t smem_bytes;
+};
+
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+// direct_lag.cu
+int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count, int force_variant,
+                DirectPlan* plan);
+size_t direct_partial_elems(const DirectPlan& p, int nseries);
+// Raw lag sums per (series, chunk) into `partials`; then reduce_partials folds the chunks in fixed order.
+int launch_direct(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
+                  double* d_partials, cudaStream_t st);
+// out[s*ncorr + k] = sum_c partials[s][c][k]  (normalise=0)  or that / (n_s - k)  (normalise=1)
+int launch_reduce_partials(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
+                           const double* d_partials, double* d_out, int normalise, cudaStream_t st);
+// out[k] = sums[k] / (n - k) with the reference's k >= n behaviour (NaN at k == n, -0 beyond).
+int launch_normalise(const double* d_sums, long long n, long long ncorr, double* d_out, cudaStream_t st);
+int direct_variant_count();
+const char* direct_variant_name(int v);
+
+// series_ops.cu
+constexpr int kReduceBlocks = 592;  // 4 per SM on a 148-SM part; partial sums are folded in fixed order
+// Device scratch of one series' reductions.  Must be zero-initialised once (the tickets reset themselves).
+struct ReduceScratch {
+    double sum;       // sum of the series            (launch_sum)
+    double mean;      // sum / n                      (launch_center_velocity)
+    double vel_sum;   // sum of the raw velocities    (launch_center_velocity)
+    double vel_mean;  // vel_sum / (n-2)              (launch_subtract_mean on the velocities)
+    double meansq;    // sum(x^2)/n                   (launch_sumsq)
+    double pad[3];
+    double partial[kReduceBlocks];
+    unsigned int ticket[4];
+};
+int launch_sum(const double* d_x, long long n, ReduceScratch* sc, cudaStream_t st);
+// y[i] = x[i] - sum/n, and (d_vel != null) vel_raw[i-1] = (y[i+1]-y[i-1])/(2.0*dt) with sc->vel_sum = sum(vel_raw)
+int launch_center_velocity(const double* d_x, long long n, ReduceScratch* sc, double* d_y,
+                           double* d_vel /*may be null*/, double dt, cudaStream_t st);
+// x[i] -= d_sum[0]/n ; d_mean_out (nullable) receives the mean
+int launch_subtract_mean(double* d_x, long long n, const double* d_sum, double* d_mean_out, cudaStream_t st);
+int launch_sumsq(const double* d_x, long long n, ReduceScratch* sc, cudaStream_t st);
+
+// integrate.cu
+// Trapezoid integral with the reference's cutoff rule; optional running integral (prefix scan).
+//   d_out[0] = integral, d_brk[0] = break index or -1; d_cum (nullable) = cumulative integral, ncorr entries
+int launch_integrate_cutoff(const double* d_acf, long long ncorr, double dt, double cutoff, double* d_out,
+                            long long* d_brk, double* d_cum, cudaStream_t st);
+// acf[i] *= target / acf[0]  (spring rescale, ACFcalculator.cpp:740-742 / :746-749)
+int launch_rescale(double* d_acf, long long ncorr, double target, cudaStream_t st);
+
+// peaks.cu
+int measure_dfma_peak(double* tflops, double* sm_mhz_effective, int iters);
+int measure_hbm_copy(double* gbs, size_t bytes, int iters);
+
+// fft_acf.cu
+int fft_acf_workspace_bytes(long long n, long long ncorr, size_t* bytes, long long* L);
+int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_out, int normalise,
+                   void* d_work, size_t work_bytes, cudaStream_t st);
+
+#define ACF_CUDA_OK(call)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ::acfb200::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,              \
+                                 cudaGetErrorString(_e));                                          \
+            return 2;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+}  // namespace acfb200

@@ -1,0 +1,165 @@
+/*
+ * acf_b200.h -- C ABI of libacf_b200.so: the B200 (sm_100a) implementation of ACFCalculator's
+ * autocorrelation hot path.
+ *
+ * The reference (RowleyGroup/ACFCalculator) has no plugin/FFI layer: its hot path is a handful of C++
+ * free functions called from main().  Each entry point below stands in for one
+ * of those functions -- same argument meaning, caller-allocated outputs, int64 lengths, and an int
+ * status instead of exceptions -- so a maintainer can swap the body of the reference function for one
+ * call (INTEGRATION.md shows the patch).  Paths cited are into the reference tree.
+ *
+ * Conventions
+ *   - All series are contiguous FP64.  "host" entry points take host pointers and do their own
+ *     H2D/D2H copies; "_device" entry points take device pointers and a cudaStream_t (as void*) and
+ *     never synchronise the host unless stated.
+ *   - Return value: ACFB200_OK (0) or an ACFB200_ERR_* code; acfb200_last_error() then returns a
+ *     message (thread-local).  Nothing throws across the ABI.  There is no CPU fallback: without a
+ *     usable GPU every compute entry point returns ACFB200_ERR_CUDA.
+ *   - Calls are serialised by an internal lock (the reference is not re-entrant either, it keeps its
+ *     state in file-scope globals, ACFcalculator.cpp:70-74).
+ */
+#ifndef ACF_B200_H
+#define ACF_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ACFB200_API __attribute__((visibility("default")))
+#else
+#define ACFB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACFB200_OK 0
+#define ACFB200_ERR_ARG 1   /* bad argument */
+#define ACFB200_ERR_CUDA 2  /* CUDA runtime / driver / launch failure, or no device */
+#define ACFB200_ERR_NOMEM 3 /* host or device allocation failed */
+
+/* ---- library state ------------------------------------------------------------------------- */
+ACFB200_API const char* acfb200_version(void);
+ACFB200_API const char* acfb200_last_error(void);
+ACFB200_API int acfb200_device_count(int* count);
+ACFB200_API int acfb200_set_device(int device);
+/* kernels launched by this library since load (bench.py's "gpu_launches"). */
+ACFB200_API int64_t acfb200_launch_count(void);
+/* Release cached device/pinned workspaces. */
+ACFB200_API int acfb200_release(void);
+
+/* ---- the reference's functions, host buffers -------------------------------------------------
+ * calcCorrelation(double* y, int nSamples, int nCorr) -> new double[nCorr]
+ *   ACFcalculator.cpp:113-146, viscosity.cpp:38-70.
+ *   corr[k] = (sum_{i=0}^{n-1-k} y[i]*y[i+k]) / (n-k), k < ncorr.  No mean handling.  Like the
+ *   reference, k == n yields NaN (0/0) and k > n yields -0.  corr is caller-allocated [ncorr]. */
+ACFB200_API int acfb200_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr);
+
+/* Many independent series in one launch (setup.sh:6-13 runs 80 of them as separate processes;
+ * viscosity.cpp:197-215 loops over 6 tensor components).  y[s] has n[s] samples;
+ * corr is [nseries][ncorr] row-major. */
+ACFB200_API int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int nseries, int64_t ncorr,
+                                   double* corr);
+
+/* variance(double* y, int nSamples): sum(y^2)/n of a zero-mean series.  ACFcalculator.cpp:203-210. */
+ACFB200_API int acfb200_variance(const double* y, int64_t n, double* var);
+
+/* calc_subtract_average(double* y, int nSamples): mean removed in place, mean returned.
+ * ACFcalculator.cpp:213-228 (viscosity.cpp:81-93). */
+ACFB200_API int acfb200_calc_subtract_average(double* y, int64_t n, double* avg);
+
+/* velocity_series(double* y, int nSamples, double deltat) -> new double[nSamples-2]:
+ * vel[i-1] = (y[i+1]-y[i-1])/(2.0*dt), then its own mean removed.  ACFcalculator.cpp:231-244.
+ * vel is caller-allocated [n-2]. */
+ACFB200_API int acfb200_velocity_series(const double* y, int64_t n, double dt, double* vel);
+
+/* integrateCorrCutoff(double* acf, int nCorr, double deltat, double cutoff): trapezoid integral that
+ * stops at the first i with acf[i] < cutoff*acf[0] when cutoff != 0.  ACFcalculator.cpp:247-259.
+ * break_index (nullable) receives that i ("cutoff bin") or -1. */
+ACFB200_API int acfb200_integrate_corr_cutoff(const double* acf, int64_t ncorr, double dt, double cutoff, double* integral,
+                                  int64_t* break_index);
+
+/* integrateCorr(double* acf, int nCorr, double timestep): the un-cut trapezoid.  viscosity.cpp:95-110. */
+ACFB200_API int acfb200_integrate_corr(const double* acf, int64_t ncorr, double dt, double* integral);
+
+/* ---- the ACFcalculator main() sequence as one call -------------------------------------------
+ * ACFcalculator.cpp:712-725 and :775: mean over all n samples removed; velocity series (n-2 samples,
+ * own mean removed); positions truncated to the first n-2; acf and vacf over n-2 samples;
+ * var = acf[0], varVel = vacf[0] (the reference's variance() sums the same terms); cutoff integral;
+ * D = var*var/acfInt*0.1 (ACFcalculator.cpp:905).  The input series is NOT modified. */
+typedef struct acfb200_result {
+    double avg;           /* mean of the n input samples            (#avg)    */
+    double var;           /* variance of the first n-2 centred ones (#var)    */
+    double var_vel;       /*                                        (#varVel) */
+    double acf_int;       /* integrateCorrCutoff(acf)                         */
+    double vel_avg;       /* mean removed from the velocity series            */
+    double diffusivity;   /* var*var/acf_int*0.1, cm2/s             (#D (ACF)) */
+    int64_t cutoff_index; /* break index of the integral, -1 if none          */
+    int64_t n_used;       /* n-2                                              */
+} acfb200_result;
+
+ACFB200_API int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double dt, double cutoff, double* acf,
+                         double* vacf, acfb200_result* result);
+
+/* Batched windows (the setup.sh workload): series[w] has n[w] samples; acf/vacf are
+ * [nwindows][ncorr]; result is [nwindows]. */
+ACFB200_API int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, int nwindows, int64_t ncorr, double dt,
+                               double cutoff, double* acf, double* vacf, acfb200_result* result);
+
+/* Spring-constant rescale of acf/vacf in place, ACFcalculator.cpp:730-753 (host arrays; O(ncorr)).
+ * var/var_vel receive R*T/k and 1e-10*kB*T/m. */
+ACFB200_API int acfb200_spring_rescale(double* acf, double* vacf, int64_t ncorr, double k_spring, double mass_amu,
+                           double temperature, double* var, double* var_vel);
+
+/* Green-Kubo driver of viscosity.cpp:197-215: ncomp raw series (no mean removal, no truncation),
+ * acf [ncomp][ncorr], integrals [ncomp] (un-cut trapezoid), eta [ncomp] with the formula of
+ * viscosity.cpp:206 for the given box length (Angstrom) and temperature (K). */
+ACFB200_API int acfb200_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t ncorr, double dt, double box_length,
+                       double temperature, double* acf, double* integrals, double* eta);
+
+/* ---- device-resident entry points ------------------------------------------------------------
+ * Raw lag sums of one time block:  sums[k] = sum_{i < i_end, i+k < n} x[i]*x[i+k].
+ * With i_end == n this is calcCorrelation before the divide (ACFcalculator.cpp:125-137).  With
+ * i_end < n, x holds a block plus its halo and the sums of all blocks add up to the whole series'
+ * (the multi-GPU time-block path; the caller all-reduces d_sums and then normalises). */
+ACFB200_API int acfb200_lag_sums_device(const double* d_x, int64_t n, int64_t i_end, int64_t ncorr, double* d_sums,
+                            void* stream);
+
+/* d_corr[k] = d_sums[k] / (n_total - k)   (ACFcalculator.cpp:139-143). In place allowed. */
+ACFB200_API int acfb200_normalise_device(const double* d_sums, int64_t n_total, int64_t ncorr, double* d_corr, void* stream);
+
+/* calcCorrelation on device memory: d_corr [ncorr]. */
+ACFB200_API int acfb200_calc_correlation_device(const double* d_y, int64_t n, int64_t ncorr, double* d_corr, void* stream);
+
+/* Batch of device-resident series.  d_y / n / i_end are HOST arrays of nseries entries (device
+ * pointers and lengths); i_end may be NULL (= n).  d_out is [nseries][ncorr]; normalise != 0 divides
+ * by (n[s]-k), otherwise raw sums are returned. */
+ACFB200_API int acfb200_calc_correlation_batch_device(const double* const* d_y, const int64_t* n, const int64_t* i_end,
+                                          int nseries, int64_t ncorr, double* d_out, int normalise, void* stream);
+
+/* The main() sequence on a device-resident series.  d_acf/d_vacf [ncorr] are device pointers;
+ * result is a HOST struct filled after a stream synchronise. */
+ACFB200_API int acfb200_acf_pipeline_device(const double* d_series, int64_t n, int64_t ncorr, double dt, double cutoff,
+                                double* d_acf, double* d_vacf, acfb200_result* result, void* stream);
+
+/* Zero-padded Wiener-Khinchin path for maxcorr -> n (no reference implementation exists; the
+ * reference's FFT stub ACFcalculator.cpp:148-200 is dead code).  Same contract as
+ * acfb200_calc_correlation[_device]; results agree with the direct sum to ~1e-13*corr[0]. */
+ACFB200_API int acfb200_calc_correlation_fft(const double* y, int64_t n, int64_t ncorr, double* corr);
+ACFB200_API int acfb200_calc_correlation_fft_device(const double* d_y, int64_t n, int64_t ncorr, double* d_corr, void* stream);
+
+/* ---- tuning / introspection / measurement ---------------------------------------------------- */
+/* Describe the launch the planner would make: fills a NUL-terminated text line. */
+ACFB200_API int acfb200_describe_plan(int64_t n, int64_t ncorr, int nseries, char* buf, int buflen);
+/* Force a direct-kernel variant (-1 = automatic).  Also: env ACFB200_VARIANT/WARPS/TS/CHUNKS. */
+ACFB200_API int acfb200_set_variant(int variant);
+ACFB200_API int acfb200_variant_count(void);
+ACFB200_API const char* acfb200_variant_name(int variant);
+/* FP64-pipe ceiling (pure DFMA chains) and STREAM-style copy bandwidth measured on the current device. */
+ACFB200_API int acfb200_measure_dfma_peak(double* tflops, double* effective_sm_mhz);
+ACFB200_API int acfb200_measure_hbm_copy(double* gb_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACF_B200_H */

@@ -1,0 +1,83 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/acf_b200.h declares, plans launches sanely, and refuses to compute without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "acf_b200.h")).read()
+    return sorted(set(re.findall(r"\b(acfb200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(acf):
+    lib = ctypes.CDLL(acf._lib.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/acf_b200.h but not exported"
+    assert set(names) == set(acf._lib.SIGNATURES), "python binding and header disagree"
+
+
+def test_no_torch_types_in_the_abi():
+    text = open(os.path.join(ROOT, "include", "acf_b200.h")).read()
+    assert "torch" not in text.lower() and "at::" not in text and "#include <cuda" not in text
+
+
+def test_version_and_variants(acf):
+    assert "sm_100a" in acf.version()
+    assert len(acf.variants()) >= 4
+
+
+def _plan(acf, n, m, s=1):
+    d = dict(kv.split("=") for kv in acf.describe_plan(n, m, s).split())
+    return {k: (float(v) if "." in v else v) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("n,m,s", [(10**7, 10**4, 1), (10**6 - 2, 5000, 128), (10**8, 2 * 10**4, 3),
+                                   (4999, 1000, 2), (100, 7, 1), (50, 60, 1)])
+def test_planner_geometry(acf, n, m, s):
+    p = _plan(acf, n, m, s)
+    warps, ti, bsz = int(p["warps"]), int(p["ti"]), int(p["bsz"])
+    assert warps in (4, 8, 12, 16) and int(p["block"]) == 32 * warps
+    assert int(p["mpad"]) >= m and int(p["lag_tiles"]) * (int(p["mpad"]) // int(p["lag_tiles"])) == int(p["mpad"])
+    assert int(p["smem"]) <= 227 * 1024 and int(p["smem"]) == (ti + bsz) * 8 + 16
+    assert ti % 2 == 0 and bsz % 2 == 0  # 16-byte TMA bulk copies
+    assert 1 <= int(p["chunks"]) <= 65535
+    if m >= 1000:
+        assert p["useful_lag_frac"] > 0.85
+
+
+def test_no_cpu_fallback(acf):
+    """Without a usable GPU every compute entry point must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(acf._lib.AcfError) as e:
+        acf.calcCorrelation(np.arange(10.0), nCorr=3)
+    assert e.value.code == acf._lib.ERR_CUDA
+    with pytest.raises(acf._lib.AcfError):
+        acf.acf_pipeline(np.arange(10.0), 3, 1.0)
+
+
+def test_spring_rescale_is_host_arithmetic(acf, oracle):
+    acf_in = np.array([2.0, 1.0, 0.5])
+    vacf_in = np.array([4.0, -1.0, 0.25])
+    got = acf.spring_rescale(acf_in, vacf_in, 10.0, 18.0, 298.15)
+    want = oracle.spring_rescale(acf_in, vacf_in, 10.0, 18.0, 298.15)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2:] == want[2:]
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure; nothing under acfcalculator_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "acfcalculator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.lower(), f"{f} mentions the oracle"
