@@ -9,6 +9,9 @@ namespace acfb200 {
 constexpr int kChains = 16;
 constexpr int kInner = 64;
 
+// MODE 0: acc = fma(acc, a, b)   (accumulator as multiplicand, two loop-invariant operands)
+// MODE 1: acc = fma(a, b, acc)   (accumulator as addend, the shape of the lag kernel's inner loop)
+template <int MODE>
 __global__ void __launch_bounds__(512, 1) dfma_peak_kernel(double* out, int outer, double a, double b)
 {
     double acc[kChains];
@@ -18,7 +21,7 @@ __global__ void __launch_bounds__(512, 1) dfma_peak_kernel(double* out, int oute
 #pragma unroll
         for (int r = 0; r < kInner; ++r) {
 #pragma unroll
-            for (int j = 0; j < kChains; ++j) acc[j] = fma(acc[j], a, b);
+            for (int j = 0; j < kChains; ++j) acc[j] = MODE == 0 ? fma(acc[j], a, b) : fma(a, b, acc[j]);
         }
     }
     double s = 0.0;
@@ -39,12 +42,16 @@ int measure_dfma_peak(double* tflops, double* sm_mhz_effective, int iters)
     ACF_CUDA_OK(cudaEventCreate(&e1));
     const int outer = 2000;
     const int grid = sms * 2;  // 1 CTA/SM resident at a time, two waves
-    dfma_peak_kernel<<<grid, 512>>>(d_out, 50, 0.999999, 1e-9);  // warm-up
+    dfma_peak_kernel<0><<<grid, 512>>>(d_out, 50, 0.999999, 1e-9);  // warm-up
+    dfma_peak_kernel<1><<<grid, 512>>>(d_out, 50, 0.999999, 1e-9);
     ACF_CUDA_OK(cudaDeviceSynchronize());
     double best = 0.0;
-    for (int it = 0; it < (iters > 0 ? iters : 3); ++it) {
+    for (int it = 0; it < 2 * (iters > 0 ? iters : 3); ++it) {
         ACF_CUDA_OK(cudaEventRecord(e0));
-        dfma_peak_kernel<<<grid, 512>>>(d_out, outer, 0.999999, 1e-9);
+        if (it & 1)
+            dfma_peak_kernel<1><<<grid, 512>>>(d_out, outer, 0.999999, 1e-9);
+        else
+            dfma_peak_kernel<0><<<grid, 512>>>(d_out, outer, 0.999999, 1e-9);
         ACF_CUDA_OK(cudaEventRecord(e1));
         ACF_CUDA_OK(cudaEventSynchronize(e1));
         float ms = 0.f;
