@@ -1,17 +1,565 @@
-// K2 placeholder until the Wiener-Khinchin kernels land (same round): reports "not built".
+// K2: zero-padded Wiener-Khinchin autocorrelation for the maxcorr -> n regime (FP64, sm_100a, HBM-bound).
+//
+// The reference has no working FFT path (its stub, /root/reference/ACFcalculator.cpp:148-200, is dead code
+// and unpadded); the contract is that of calcCorrelation (:113-146): corr[k] = sum_i x[i]x[i+k] / (n-k).
+//
+//   L  = 2^ceil(log2(n + ncorr - 1))            (zero padding => the circular correlation has no wrap for k < ncorr)
+//   z[j] = x[2j] + i x[2j+1],  j < Nc = L/2     (real series packed as a half-length complex one)
+//   Z = DFT_Nc(z)                                (forward, decimation in frequency)
+//   X[k] = (Z[k]+conj Z[Nc-k])/2 - (i/2) W_L^k (Z[k]-conj Z[Nc-k]);   P[k] = |X[k]|^2
+//   Z'[k] = (P[k]+P[Nc-k])/2 + (i/2) conj(W_L^k) (P[k]-P[Nc-k])         (packed spectrum of the real, even r)
+//   r[2j] + i r[2j+1] = (1/Nc) IDFT_Nc(Z')[j];   corr[k] = r[k] / (n-k)
+//
+// Nc = N1*N2*N3 (each <= 512).  Every factor is a pass over HBM in which a CTA holds a tile in shared memory and
+// runs a Stockham radix-8/4/2 FFT there:
+//   col_pass  fwd step 1 (axis j1, fused: real->complex packing + zero padding on load) and step 2 (axis j2)
+//   row_pass  fwd step 3 on a row and on its mirror row (Nc-k), the |X|^2 pair operation, and inverse step 3'
+//             -- fused, so the spectrum never goes to HBM in natural order and no transpose/bit-reversal pass exists
+//   col_pass  inverse step 2' and step 1' (fused: 1/Nc, /(n-k), only the first ncorr lags are written)
+// Algorithmic bytes: 8n + 8M + 8L*(2*passes - 2) with passes = number of factors > 1, counted per series.
 #include "common.cuh"
+
 namespace acfb200 {
+
+constexpr int kLoBits = 14;
+constexpr int kLoSize = 1 << kLoBits;
+constexpr int kTileElems = 4096;  // complex doubles per column-pass tile (64 KB)
+constexpr int kColThreads = 512;
+
+struct FftGeom {
+    int b1, b2, b3;   // log2 of the factors; 0 = factor absent
+    int q;            // log2(Nc)
+    long long Nc, L;
+    long long n, ncorr;
+};
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+// multiply by -i (DIR=-1, forward) or +i (DIR=+1, inverse)
+template <int DIR>
+__device__ __forceinline__ double2 mul_i(double2 a)
+{
+    return DIR < 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x);
+}
+
+// W_L^e = exp(-2 pi i e / L), e in [0, L), from the two-level table (hi: multiples of 2^14, lo: the rest).
+__device__ __forceinline__ double2 tw_L(const double2* __restrict__ lo, const double2* __restrict__ hi,
+                                        unsigned long long e)
+{
+    const double2 a = hi[e >> kLoBits];
+    const double2 b = lo[e & (kLoSize - 1)];
+    return cmul(a, b);
+}
+
+__global__ void fft_table_kernel(double2* lo, double2* hi, long long L)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nlo = L < kLoSize ? L : kLoSize;
+    const long long nhi = L < kLoSize ? 1 : (L >> kLoBits);
+    if (t < nlo) {
+        double s, c;
+        sincospi(-2.0 * (double)t / (double)L, &s, &c);
+        lo[t] = make_double2(c, s);
+    }
+    if (t < nhi) {
+        double s, c;
+        sincospi(-2.0 * (double)(t << kLoBits) / (double)L, &s, &c);
+        hi[t] = make_double2(c, s);
+    }
+}
+
+// ---- radix butterflies (outputs in natural order) ----------------------------------------------------
+template <int DIR>
+__device__ __forceinline__ void dft8(double2* v)
+{
+    constexpr double h = 0.70710678118654752440;
+    double2 a0 = cadd(v[0], v[4]), b0 = csub(v[0], v[4]);
+    double2 a1 = cadd(v[1], v[5]), b1 = csub(v[1], v[5]);
+    double2 a2 = cadd(v[2], v[6]), b2 = csub(v[2], v[6]);
+    double2 a3 = cadd(v[3], v[7]), b3 = csub(v[3], v[7]);
+    // b1 *= W8^1, b2 *= W8^2, b3 *= W8^3 with W8 = exp(DIR * i pi/4)
+    b1 = DIR < 0 ? make_double2(h * (b1.x + b1.y), h * (b1.y - b1.x)) : make_double2(h * (b1.x - b1.y), h * (b1.y + b1.x));
+    b2 = mul_i<DIR>(b2);
+    b3 = DIR < 0 ? make_double2(h * (b3.y - b3.x), -h * (b3.x + b3.y)) : make_double2(-h * (b3.x + b3.y), h * (b3.x - b3.y));
+    double2 c0 = cadd(a0, a2), c2 = csub(a0, a2), c1 = cadd(a1, a3), c3 = mul_i<DIR>(csub(a1, a3));
+    double2 d0 = cadd(b0, b2), d2 = csub(b0, b2), d1 = cadd(b1, b3), d3 = mul_i<DIR>(csub(b1, b3));
+    v[0] = cadd(c0, c1);
+    v[4] = csub(c0, c1);
+    v[2] = cadd(c2, c3);
+    v[6] = csub(c2, c3);
+    v[1] = cadd(d0, d1);
+    v[5] = csub(d0, d1);
+    v[3] = cadd(d2, d3);
+    v[7] = csub(d2, d3);
+}
+template <int DIR>
+__device__ __forceinline__ void dft4(double2* v)
+{
+    double2 a0 = cadd(v[0], v[2]), b0 = csub(v[0], v[2]);
+    double2 a1 = cadd(v[1], v[3]), b1 = mul_i<DIR>(csub(v[1], v[3]));
+    v[0] = cadd(a0, a1);
+    v[2] = csub(a0, a1);
+    v[1] = cadd(b0, b1);
+    v[3] = csub(b0, b1);
+}
+__device__ __forceinline__ void dft2(double2* v)
+{
+    const double2 a = cadd(v[0], v[1]), b = csub(v[0], v[1]);
+    v[0] = a;
+    v[1] = b;
+}
+
+// One Stockham pass of radix R = 2^LR over a length-NB axis held in shared memory.
+//   element (row r, column c) lives at s[r * pitch + c];  `s_stride` is the Stockham stride of this pass.
+// A thread owns 8/R groups (8 complex values in registers): it reads them all, and after a barrier writes them
+// back in place -- no second buffer.  Callers guarantee (NB/R)*ncols <= (8/R)*nthreads.
+template <int DIR, int LR>
+__device__ __forceinline__ void stockham_pass(double2* s, int NB, int ncols, int pitch, int s_stride,
+                                              const double2* __restrict__ lo, const double2* __restrict__ hi,
+                                              long long L, int tid, int nthreads)
+{
+    constexpr int R = 1 << LR;
+    constexpr int GPT = 8 / R;
+    const int groups = NB / R;  // per column
+    const int total = groups * ncols;
+    double2 v[8];
+#pragma unroll
+    for (int it = 0; it < GPT; ++it) {
+        const int w = tid + it * nthreads;
+        if (w < total) {
+            const int g = w / ncols, c = w - g * ncols;
+#pragma unroll
+            for (int t = 0; t < R; ++t) v[it * R + t] = s[(g + t * groups) * pitch + c];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < GPT; ++it) {
+        const int w = tid + it * nthreads;
+        if (w < total) {
+            const int g = w / ncols, c = w - g * ncols;
+            const int qq = g % s_stride;  // q
+            const int ps = g - qq;        // p * s
+            if (LR == 3)
+                dft8<DIR>(v + it * R);
+            else if (LR == 2)
+                dft4<DIR>(v + it * R);
+            else
+                dft2(v + it * R);
+            // twiddle W_n^{p u} = W_NB^{p s u};  W_NB = W_L^{L/NB}
+            if (ps != 0) {
+                double2 w1 = tw_L(lo, hi, (unsigned long long)ps * (unsigned long long)(L / NB));
+                if (DIR > 0) w1 = cconj(w1);
+                double2 wu = w1;
+#pragma unroll
+                for (int u = 1; u < R; ++u) {
+                    v[it * R + u] = cmul(v[it * R + u], wu);
+                    if (u + 1 < R) wu = cmul(wu, w1);
+                }
+            }
+            const int base = qq + ps * R;  // q + s * R * p
+#pragma unroll
+            for (int u = 0; u < R; ++u) s[(base + s_stride * u) * pitch + c] = v[it * R + u];
+        }
+    }
+    __syncthreads();
+}
+
+// Full length-NB (= 2^b) transform of every column of the tile: radix-8 passes, then one radix-4/2 pass.
+template <int DIR>
+__device__ __forceinline__ void smem_fft(double2* s, int b, int ncols, int pitch, const double2* __restrict__ lo,
+                                         const double2* __restrict__ hi, long long L, int tid, int nthreads)
+{
+    const int NB = 1 << b;
+    int stride = 1, left = b;
+    while (left >= 3) {
+        stockham_pass<DIR, 3>(s, NB, ncols, pitch, stride, lo, hi, L, tid, nthreads);
+        stride <<= 3;
+        left -= 3;
+    }
+    if (left == 2)
+        stockham_pass<DIR, 2>(s, NB, ncols, pitch, stride, lo, hi, L, tid, nthreads);
+    else if (left == 1)
+        stockham_pass<DIR, 1>(s, NB, ncols, pitch, stride, lo, hi, L, tid, nthreads);
+}
+
+// ---- column pass --------------------------------------------------------------------------------------
+// Data viewed as [A][NB][C] complex (C contiguous).  One CTA: fixed a, NB rows x TC columns.
+//   MODE 0  forward step 1: A=1; input is the REAL series (packed + zero padded on load); twiddle W_Nc^{kb*c}
+//   MODE 1  forward step 2: twiddle W_Nc^{N1*kb*c}
+//   MODE 2  inverse step 2': conj twiddle W_Nc^{(kb*C + c)*a}
+//   MODE 3  inverse step 1': A=1; no twiddle; output = normalised lags, only k < ncorr written
+template <int MODE>
+__global__ void __launch_bounds__(kColThreads)
+col_pass_kernel(double2* __restrict__ data, const double* __restrict__ x, double* __restrict__ out, FftGeom G, int b,
+                long long C, int TC, const double2* __restrict__ lo, const double2* __restrict__ hi)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* s = reinterpret_cast<double2*>(smem_raw);
+    constexpr int DIR = (MODE <= 1) ? -1 : +1;
+    const int NB = 1 << b;
+    const int tid = threadIdx.x;
+    const long long c0 = (long long)blockIdx.x * TC;
+    const long long a = blockIdx.y;
+    const long long batch = blockIdx.z;
+    double2* base = data + batch * G.Nc + a * (long long)NB * C;
+    const int total = NB * TC;
+
+    // skip tiles that produce nothing that is ever read (inverse step 1': columns beyond the last wanted lag)
+    if (MODE == 3 && 2 * c0 >= G.ncorr) return;
+
+    if (MODE == 0) {
+        const double* xs = x + batch * G.n;
+        for (int w = tid; w < total; w += kColThreads) {
+            const int r = w / TC, c = w - r * TC;
+            const long long j = (long long)r * C + c0 + c;  // complex index; samples 2j, 2j+1
+            double2 z = make_double2(0.0, 0.0);
+            if (2 * j + 1 < G.n)
+                z = *reinterpret_cast<const double2*>(xs + 2 * j);  // n even pitch => 16-byte aligned
+            else if (2 * j < G.n)
+                z.x = xs[2 * j];
+            s[w] = z;
+        }
+    } else {
+        for (int w = tid; w < total; w += kColThreads) {
+            const int r = w / TC, c = w - r * TC;
+            s[w] = base[(long long)r * C + c0 + c];
+        }
+    }
+    __syncthreads();
+    smem_fft<DIR>(s, b, TC, TC, lo, hi, G.L, tid, kColThreads);
+
+    if (MODE == 3) {
+        // r[2j], r[2j+1] with j = kb*C + c;  corr[k] = r[k] / (Nc * (n - k))
+        double* o = out + batch * G.ncorr;
+        const double inv_nc = 1.0 / (double)G.Nc;
+        for (int w = tid; w < total; w += kColThreads) {
+            const int r = w / TC, c = w - r * TC;
+            const long long j = (long long)r * C + c0 + c;
+            const double2 z = s[w];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long k = 2 * j + h;
+                if (k < G.ncorr) {
+                    const long long m = G.n - k;
+                    double val = (h ? z.y : z.x) * inv_nc;
+                    if (m > 0)
+                        val = val / (double)m;
+                    else if (m == 0)
+                        val = __longlong_as_double(0xFFF8000000000000ull);  // reference: 0/0
+                    else
+                        val = -0.0;                                          // reference: 0/negative
+                    o[k] = val;
+                }
+            }
+        }
+        return;
+    }
+    for (int w = tid; w < total; w += kColThreads) {
+        const int kb = w / TC, c = w - kb * TC;
+        const long long cc = c0 + c;
+        unsigned long long e;  // exponent of W_Nc
+        if (MODE == 0)
+            e = (unsigned long long)kb * (unsigned long long)cc;
+        else if (MODE == 1)
+            e = ((unsigned long long)kb << G.b1) * (unsigned long long)cc;
+        else
+            e = ((unsigned long long)kb * (unsigned long long)C + (unsigned long long)cc) * (unsigned long long)a;
+        e &= (unsigned long long)(G.Nc - 1);
+        double2 v = s[w];
+        if (e) {
+            double2 t = tw_L(lo, hi, 2ull * e);  // W_Nc = W_L^2
+            if (DIR > 0) t = cconj(t);
+            v = cmul(v, t);
+        }
+        base[(long long)kb * C + cc] = v;
+    }
+}
+
+// ---- fused row pass: forward step 3, |X|^2 pair operation with the mirror row, inverse step 3' ------------
+// Rows are indexed by (k1, k2); a row holds k3 = 0..N3-1 contiguously.  The mirror of spectrum index k is Nc-k:
+//   k1 != 0:             (N1-k1, N2-1-k2),  column N3-1-k3
+//   k1 == 0, k2 != 0:    (0,     N2-k2),    column N3-1-k3
+//   k1 == 0, k2 == 0:    same row,          column (N3-k3) mod N3
+// One CTA per row; the CTA whose row index is the larger of the pair exits at once.
+__global__ void __launch_bounds__(256)
+row_pass_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict__ lo, const double2* __restrict__ hi)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N3 = 1 << G.b3;
+    double2* sa = reinterpret_cast<double2*>(smem_raw);  // this row
+    double2* sb = sa + N3;                               // mirror row (unused when self-paired)
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const long long N1 = 1ll << G.b1, N2 = 1ll << G.b2;
+    const long long row = blockIdx.x;       // = k1 * N2 + k2
+    const long long k1 = row >> G.b2, k2 = row & (N2 - 1);
+    long long m1, m2;
+    if (k1 != 0) {
+        m1 = N1 - k1;
+        m2 = N2 - 1 - k2;
+    } else {
+        m1 = 0;
+        m2 = (N2 - k2) & (N2 - 1);
+    }
+    const long long mrow = m1 * N2 + m2;
+    if (mrow < row) return;
+    const bool self = (mrow == row);
+    const bool origin = (k1 == 0 && k2 == 0);
+    double2* ga = data + (long long)blockIdx.z * G.Nc + row * N3;
+    double2* gb = data + (long long)blockIdx.z * G.Nc + mrow * N3;
+
+    // load as one [N3][ncols] tile with the two rows as two columns
+    const int ncols = self ? 1 : 2;
+    // layout: element (r, col) at s[r * ncols + col]  (interleaved rows => one smem_fft call does both)
+    double2* s = sa;
+    for (int w = tid; w < N3 * ncols; w += nth) {
+        const int r = w / ncols, col = w - r * ncols;
+        s[w] = (col == 0 ? ga : gb)[r];
+    }
+    __syncthreads();
+    smem_fft<-1>(s, G.b3, ncols, ncols, lo, hi, G.L, tid, nth);
+
+    // pair operation
+    const double2 half_i_dummy = make_double2(0.0, 0.0);
+    (void)half_i_dummy;
+    (void)sb;
+    const long long kbase = k1 + (k2 << G.b1);  // k = kbase + N1*N2*k3
+    const int shift12 = G.b1 + G.b2;
+    if (!self) {
+        // column k3 of this row pairs with column N3-1-k3 of the mirror row
+        for (int k3 = tid; k3 < N3; k3 += nth) {
+            const int p3 = N3 - 1 - k3;
+            const double2 Za = s[k3 * 2 + 0];       // Z[k]
+            const double2 Zb = s[p3 * 2 + 1];       // Z[Nc-k]
+            const unsigned long long k = (unsigned long long)kbase + ((unsigned long long)k3 << shift12);
+            const double2 W = tw_L(lo, hi, k);      // W_L^k
+            // X[k] = (Za + conj Zb)/2 - (i/2) W (Za - conj Zb);  X[Nc-k] = (Zb + conj Za)/2 - (i/2) W' (Zb - conj Za), W' = -conj W
+            const double2 S = make_double2(Za.x + Zb.x, Za.y - Zb.y);   // Za + conj Zb
+            const double2 D = make_double2(Za.x - Zb.x, Za.y + Zb.y);   // Za - conj Zb
+            const double2 WD = cmul(W, D);
+            // -(i/2) WD = (WD.y/2, -WD.x/2)
+            const double2 Xa = make_double2(0.5 * (S.x + WD.y), 0.5 * (S.y - WD.x));
+            // X[Nc-k] = conj(S)/2 - (i/2)(-conj W)(-conj D) = conj(S)/2 - (i/2) conj(WD)
+            const double2 Xb = make_double2(0.5 * (S.x - WD.y), 0.5 * (-S.y - WD.x));
+            const double Pa = Xa.x * Xa.x + Xa.y * Xa.y;
+            const double Pb = Xb.x * Xb.x + Xb.y * Xb.y;
+            const double hs = 0.5 * (Pa + Pb), hd = 0.5 * (Pa - Pb);
+            // Z'[k] = hs + i conj(W) hd ; Z'[Nc-k] = hs + i W hd
+            s[k3 * 2 + 0] = make_double2(hs + W.y * hd, W.x * hd);
+            s[p3 * 2 + 1] = make_double2(hs - W.y * hd, W.x * hd);
+        }
+    } else {
+        // pairs inside one row: k3 <-> N3-1-k3 (mirror row == row) or k3 <-> (N3-k3) mod N3 (origin row)
+        for (int k3 = tid; k3 < N3; k3 += nth) {
+            const int p3 = origin ? ((N3 - k3) & (N3 - 1)) : (N3 - 1 - k3);
+            if (p3 < k3) continue;
+            const double2 Za = s[k3];
+            const double2 Zb = s[p3];
+            if (origin && k3 == 0) {
+                // k = 0 pairs with the Nyquist bin: X[0] = Re+Im, X[Nc] = Re-Im
+                const double P0 = (Za.x + Za.y) * (Za.x + Za.y), PN = (Za.x - Za.y) * (Za.x - Za.y);
+                s[0] = make_double2(0.5 * (P0 + PN), 0.5 * (P0 - PN));
+                continue;
+            }
+            const unsigned long long k = (unsigned long long)kbase + ((unsigned long long)k3 << shift12);
+            const double2 W = tw_L(lo, hi, k);
+            const double2 S = make_double2(Za.x + Zb.x, Za.y - Zb.y);
+            const double2 D = make_double2(Za.x - Zb.x, Za.y + Zb.y);
+            const double2 WD = cmul(W, D);
+            const double2 Xa = make_double2(0.5 * (S.x + WD.y), 0.5 * (S.y - WD.x));
+            const double2 Xb = make_double2(0.5 * (S.x - WD.y), 0.5 * (-S.y - WD.x));
+            const double Pa = Xa.x * Xa.x + Xa.y * Xa.y;
+            const double Pb = Xb.x * Xb.x + Xb.y * Xb.y;
+            const double hs = 0.5 * (Pa + Pb), hd = 0.5 * (Pa - Pb);
+            s[k3] = make_double2(hs + W.y * hd, W.x * hd);
+            if (p3 != k3) s[p3] = make_double2(hs - W.y * hd, W.x * hd);
+        }
+    }
+    __syncthreads();
+    smem_fft<+1>(s, G.b3, ncols, ncols, lo, hi, G.L, tid, nth);
+
+    // post twiddle conj(W_Nc^{j3 * f}) with f = N1*k2 (three factors) or k1 (N2 absent); then store
+    for (int w = tid; w < N3 * ncols; w += nth) {
+        const int j3 = w / ncols, col = w - j3 * ncols;
+        const long long r1 = col == 0 ? k1 : m1, r2 = col == 0 ? k2 : m2;
+        const unsigned long long f = (G.b2 > 0) ? ((unsigned long long)r2 << G.b1) : (unsigned long long)r1;
+        unsigned long long e = ((unsigned long long)j3 * f) & (unsigned long long)(G.Nc - 1);
+        double2 v = s[w];
+        if (e) v = cmul(v, cconj(tw_L(lo, hi, 2ull * e)));
+        (col == 0 ? ga : gb)[j3] = v;
+    }
+}
+
+// Tiny problems (Nc == N3, one factor): the row pass output is already r; this writes the lags.
+__global__ void fft_finish_kernel(const double2* __restrict__ data, double* __restrict__ out, FftGeom G)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= G.Nc) return;
+    const double2 z = data[(long long)blockIdx.y * G.Nc + j];
+    const double inv_nc = 1.0 / (double)G.Nc;
+    double* o = out + (long long)blockIdx.y * G.ncorr;
+    for (int h = 0; h < 2; ++h) {
+        const long long k = 2 * j + h;
+        if (k < G.ncorr) {
+            const long long m = G.n - k;
+            double val = (h ? z.y : z.x) * inv_nc;
+            if (m > 0)
+                val = val / (double)m;
+            else if (m == 0)
+                val = __longlong_as_double(0xFFF8000000000000ull);
+            else
+                val = -0.0;
+            o[k] = val;
+        }
+    }
+}
+// Packs the real series into the complex work array (only used by the one-factor path).
+__global__ void fft_pack_kernel(const double* __restrict__ x, double2* __restrict__ data, FftGeom G)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= G.Nc) return;
+    const double* xs = x + (long long)blockIdx.y * G.n;
+    double2 z = make_double2(0.0, 0.0);
+    if (2 * j < G.n) z.x = xs[2 * j];
+    if (2 * j + 1 < G.n) z.y = xs[2 * j + 1];
+    data[(long long)blockIdx.y * G.Nc + j] = z;
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+static int make_geom(long long n, long long ncorr, FftGeom* g)
+{
+    if (n < 1 || ncorr < 1) {
+        set_error("fft_acf: n and ncorr must be positive");
+        return 1;
+    }
+    long long need = n + ncorr - 1;
+    if (need < 16) need = 16;
+    int lq = 0;
+    while ((1ll << lq) < need) ++lq;
+    const int q = lq - 1;  // Nc = L/2
+    if (q > 27) {
+        set_error("fft_acf: n + ncorr - 1 = %lld needs a transform of 2^%d points; this build handles up to 2^28", need,
+                  lq);
+        return 1;
+    }
+    g->q = q;
+    g->L = 1ll << lq;
+    g->Nc = 1ll << q;
+    g->n = n;
+    g->ncorr = ncorr;
+    if (q <= 9) {
+        g->b1 = 0;
+        g->b2 = 0;
+        g->b3 = q;
+    } else if (q <= 18) {
+        g->b3 = (q - 9 >= 3) ? 9 : q - 3;
+        g->b1 = q - g->b3;
+        g->b2 = 0;
+    } else {
+        g->b3 = 9;
+        g->b2 = (q - 9 - 3 >= 9) ? 9 : q - 9 - 3;
+        g->b1 = q - 9 - g->b2;
+    }
+    return 0;
+}
+
 int fft_acf_workspace_bytes(long long n, long long ncorr, size_t* bytes, long long* L)
 {
-    (void)n; (void)ncorr;
-    if (bytes) *bytes = 0;
-    if (L) *L = 0;
-    set_error("the FFT path is not built yet");
-    return 1;
+    FftGeom g;
+    if (make_geom(n, ncorr, &g)) return 1;
+    const long long nhi = g.L < kLoSize ? 1 : (g.L >> kLoBits);
+    if (bytes) *bytes = (size_t)g.Nc * 16 + (size_t)(kLoSize + nhi) * 16 + 256;
+    if (L) *L = g.L;
+    return 0;
 }
-int launch_fft_acf(const double*, long long, long long, double*, int, void*, size_t, cudaStream_t)
+
+// Returns the number of kernels launched (>= 0) or -(error code).
+int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_out, int normalise, void* d_work,
+                   size_t work_bytes, cudaStream_t st)
 {
-    set_error("the FFT path is not built yet");
-    return -1;
+    (void)normalise;
+    FftGeom g;
+    if (make_geom(n, ncorr, &g)) return -1;
+    size_t need = 0;
+    fft_acf_workspace_bytes(n, ncorr, &need, nullptr);
+    if (work_bytes < need) {
+        set_error("fft_acf: workspace too small (%zu < %zu)", work_bytes, need);
+        return -1;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0 && g.b1 > 0) {
+        set_error("fft_acf: the series must be 16-byte aligned");
+        return -1;
+    }
+    double2* data = reinterpret_cast<double2*>(d_work);
+    double2* lo = data + g.Nc;
+    double2* hi = lo + kLoSize;
+    int launches = 0;
+    fft_table_kernel<<<kLoSize / 256, 256, 0, st>>>(lo, hi, g.L);
+    ++launches;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(col_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
+        cudaFuncSetAttribute(col_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
+        cudaFuncSetAttribute(col_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
+        cudaFuncSetAttribute(col_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
+        attr = true;
+    }
+    const long long N1 = 1ll << g.b1, N2 = 1ll << g.b2, N3 = 1ll << g.b3;
+    auto tc_for = [](int b, long long C) {
+        long long tc = kTileElems >> b;
+        if (tc > C) tc = C;
+        return (int)tc;
+    };
+    if (g.b1 > 0) {
+        const long long C = N2 * N3;
+        const int TC = tc_for(g.b1, C);
+        col_pass_kernel<0><<<dim3((unsigned)(C / TC), 1, 1), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
+            data, d_x, nullptr, g, g.b1, C, TC, lo, hi);
+        ++launches;
+    } else {
+        fft_pack_kernel<<<dim3((unsigned)((g.Nc + 255) / 256), 1), 256, 0, st>>>(d_x, data, g);
+        ++launches;
+    }
+    if (g.b2 > 0) {
+        const int TC = tc_for(g.b2, N3);
+        col_pass_kernel<1><<<dim3((unsigned)(N3 / TC), (unsigned)N1, 1), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
+            data, nullptr, nullptr, g, g.b2, N3, TC, lo, hi);
+        ++launches;
+    }
+    {
+        int threads = (int)(N3 / 8) * 2;
+        if (threads < 32) threads = 32;
+        if (threads > 256) threads = 256;
+        row_pass_kernel<<<dim3((unsigned)(N1 * N2), 1, 1), threads, (size_t)N3 * 2 * 16, st>>>(data, g, lo, hi);
+        ++launches;
+    }
+    if (g.b2 > 0) {
+        const int TC = tc_for(g.b2, N3);
+        col_pass_kernel<2><<<dim3((unsigned)(N3 / TC), (unsigned)N1, 1), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
+            data, nullptr, nullptr, g, g.b2, N3, TC, lo, hi);
+        ++launches;
+    }
+    if (g.b1 > 0) {
+        const long long C = N2 * N3;
+        const int TC = tc_for(g.b1, C);
+        col_pass_kernel<3><<<dim3((unsigned)(C / TC), 1, 1), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
+            data, nullptr, d_out, g, g.b1, C, TC, lo, hi);
+        ++launches;
+    } else {
+        fft_finish_kernel<<<dim3((unsigned)((g.Nc + 255) / 256), 1), 256, 0, st>>>(data, d_out, g);
+        ++launches;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("fft_acf launch failed: %s", cudaGetErrorString(e));
+        return -2;
+    }
+    return launches;
 }
+
 }  // namespace acfb200

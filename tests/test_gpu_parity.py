@@ -207,3 +207,44 @@ def test_errors_are_reported_not_swallowed(acf):
     assert e.value.code == acf._lib.ERR_ARG
     with pytest.raises(acf._lib.AcfError):
         acf.acf_pipeline(np.arange(2.0), 3, 1.0)
+
+
+# ---- K2: zero-padded Wiener-Khinchin path --------------------------------------------------------------
+@pytest.mark.parametrize("n,m", [(7, 3), (100, 100), (500, 13), (513, 512), (5001, 1000), (40000, 30000),
+                                 (100000, 99999), (262144, 1), (300000, 262144)])
+def test_fft_path_matches_oracle(acf, oracle, n, m):
+    """One-, two- and three-factor transform plans against the direct-sum oracle."""
+    x = ou_series(n, 30.0, mu=0.25, seed=n + 3 * m)
+    if n * m <= 4 * 10**9:
+        lags = np.arange(m)
+        ref = oracle.calc_correlation(x, m, threads=0)
+    else:
+        lags = np.unique(np.concatenate([np.arange(32), np.geomspace(32, m - 1, 200).astype(np.int64), [m - 1]]))
+        ref = oracle.calc_correlation_lags(x, lags)
+    got = acf.calcCorrelationFFT(x, m)
+    assert got.shape == (m,)
+    c0 = oracle.calc_correlation(x, 1)[0]
+    assert rel_to_c0(got[lags], ref, c0) <= TOL
+
+
+def test_fft_maxcorr_beyond_n(acf):
+    g = golden("f4_edges.npz")
+    c9 = acf.calcCorrelationFFT(g["y"], 9)
+    assert np.allclose(c9[:6], g["corr9"][:6], rtol=1e-13, atol=0)
+    assert np.isnan(c9[6]) and np.signbit(c9[6])
+    assert np.all(c9[7:] == 0) and np.all(np.signbit(c9[7:]))
+
+
+def test_fft_equals_direct_kernel_long_lag(acf, oracle):
+    """Long-lag regime (config 5, reduced to N=2^20, maxcorr=N/2): the FFT path against the direct-lag kernel
+    on the same device buffer, all lags, and a lag subset against the oracle."""
+    import torch
+    n, m = 1 << 20, 1 << 19
+    x = ou_series(n, 1.0e4, seed=20260301)
+    d = torch.from_numpy(x).cuda()
+    f = acf.calc_correlation_fft_device(d, m).cpu().numpy()
+    k = acf.calc_correlation_device(d, m).cpu().numpy()
+    assert rel_to_c0(f, k, k[0]) <= TOL
+    lags = np.unique(np.concatenate([np.arange(16), np.geomspace(16, m - 1, 240).astype(np.int64)]))
+    ref = oracle.calc_correlation_lags(x, lags)
+    assert rel_to_c0(f[lags], ref, ref[0]) <= TOL
