@@ -1,0 +1,172 @@
+#include "options.hpp"
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+
+namespace acfhost {
+
+const OptionSpec* Options::find_long(const std::string& name, bool allow_prefix) const
+{
+    const OptionSpec* hit = nullptr;
+    int hits = 0;
+    for (const auto& s : specs_) {
+        if (name == s.long_name) return &s;
+        if (allow_prefix && !name.empty() && std::strncmp(s.long_name, name.c_str(), name.size()) == 0) {
+            hit = &s;
+            ++hits;
+        }
+    }
+    return hits == 1 ? hit : nullptr;
+}
+
+const OptionSpec* Options::find_short(char c) const
+{
+    for (const auto& s : specs_)
+        if (s.short_name == c) return &s;
+    return nullptr;
+}
+
+// lexical_cast-like conversions: the whole token must be consumed, no surrounding blanks
+static bool to_double(const std::string& t, double* out)
+{
+    if (t.empty() || t[0] == ' ' || t[0] == '\t') return false;
+    errno = 0;
+    char* end = nullptr;
+    const double v = std::strtod(t.c_str(), &end);
+    if (end == t.c_str() || *end != '\0') return false;
+    if (t.find_first_of("xXpP") != std::string::npos) return false;  // no hex floats in lexical_cast
+    *out = v;
+    return true;
+}
+
+static bool to_int(const std::string& t, int* out)
+{
+    if (t.empty()) return false;
+    size_t i = (t[0] == '-' || t[0] == '+') ? 1 : 0;
+    if (i == t.size()) return false;
+    for (size_t j = i; j < t.size(); ++j)
+        if (t[j] < '0' || t[j] > '9') return false;
+    errno = 0;
+    const long v = std::strtol(t.c_str(), nullptr, 10);
+    if (errno != 0 || v > 2147483647L || v < -2147483647L - 1) return false;
+    *out = (int)v;
+    return true;
+}
+
+void Options::parse(int argc, const char* const* argv)
+{
+    struct Seen {
+        const OptionSpec* spec;
+        std::string value;
+    };
+    std::vector<Seen> seen;
+    bool only_positional = false;
+    for (int i = 1; i < argc; ++i) {
+        const std::string tok = argv[i];
+        if (only_positional || tok.size() < 2 || tok[0] != '-') continue;  // positionals are ignored
+        if (tok == "--") {
+            only_positional = true;
+            continue;
+        }
+        const OptionSpec* spec = nullptr;
+        std::string value;
+        bool have_value = false;
+        if (tok[1] == '-') {
+            const size_t eq = tok.find('=');
+            const std::string name = tok.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+            spec = find_long(name, true);
+            if (!spec) throw OptionError("unrecognised option '" + tok + "'");
+            if (eq != std::string::npos) {
+                value = tok.substr(eq + 1);
+                have_value = true;
+            }
+        } else {
+            spec = find_short(tok[1]);
+            if (!spec) throw OptionError("unrecognised option '" + tok.substr(0, 2) + "'");
+            if (tok.size() > 2) {
+                value = tok.substr(2);
+                have_value = true;
+            }
+        }
+        if (spec->kind == OptionSpec::Flag) {
+            seen.push_back({spec, ""});
+            continue;
+        }
+        if (!have_value) {
+            if (i + 1 >= argc)
+                throw OptionError(std::string("the required argument for option '--") + spec->long_name + "' is missing");
+            value = argv[++i];
+        }
+        seen.push_back({spec, value});
+    }
+    // store phase
+    for (const auto& s : seen) {
+        const std::string key = s.spec->long_name;
+        if (values_.count(key) && s.spec->kind != OptionSpec::Flag)
+            throw OptionError("option '--" + key + "' cannot be specified more than once");
+        double d;
+        int n;
+        if ((s.spec->kind == OptionSpec::Double && !to_double(s.value, &d)) ||
+            (s.spec->kind == OptionSpec::Int && !to_int(s.value, &n)))
+            throw OptionError("the argument ('" + s.value + "') for option '--" + key + "' is invalid");
+        values_[key] = s.value;
+    }
+}
+
+void Options::notify() const
+{
+    std::vector<std::string> req;
+    for (const auto& s : specs_)
+        if (s.required) req.push_back(s.long_name);
+    std::sort(req.begin(), req.end());
+    for (const auto& r : req)
+        if (!values_.count(r)) throw OptionError("the option '--" + r + "' is required but missing");
+}
+
+double Options::get_double(const std::string& n, double dflt) const
+{
+    auto it = values_.find(n);
+    double v = dflt;
+    if (it != values_.end()) to_double(it->second, &v);
+    return v;
+}
+
+int Options::get_int(const std::string& n, int dflt) const
+{
+    auto it = values_.find(n);
+    int v = dflt;
+    if (it != values_.end()) to_int(it->second, &v);
+    return v;
+}
+
+std::string Options::help_text() const
+{
+    // boost::program_options layout: two spaces, "-x [ --name ] arg (=dflt)", padded to the widest entry + 1
+    std::vector<std::string> left;
+    size_t width = 0;
+    for (const auto& s : specs_) {
+        if (s.hidden) {
+            left.push_back("");
+            continue;
+        }
+        std::string l = std::string("  -") + s.short_name + " [ --" + s.long_name + " ]";
+        if (s.kind != OptionSpec::Flag) {
+            l += " arg";
+            if (s.default_text) l += std::string(" (=") + s.default_text + ")";
+        }
+        left.push_back(l);
+        if (l.size() > width) width = l.size();
+    }
+    std::ostringstream os;
+    os << "Allowed options:\n";
+    for (size_t i = 0; i < specs_.size(); ++i) {
+        if (specs_[i].hidden) continue;
+        os << left[i] << std::string(width + 1 - left[i].size(), ' ') << specs_[i].description << "\n";
+    }
+    return os.str();
+}
+
+}  // namespace acfhost

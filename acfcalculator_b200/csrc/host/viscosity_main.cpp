@@ -1,0 +1,77 @@
+// viscosity -- Green-Kubo shear viscosity from the off-diagonal pressure tensor in a NAMD log, drop-in for
+// /root/reference/viscosity.cpp (main, :171-224): same reader (including its ten-leading-zeros quirk), the six
+// off-diagonal components (i % 4 != 0), maxcorr 1000, 2 fs, box length and temperature as hard-coded there,
+// and the same stdout grammar.  The correlations and integrals run on the GPU through libacf_b200.so.
+//
+//   viscosity <namd.log> [--maxcorr M] [--timestep fs] [--box A] [--temperature K] [--exact-reader]
+// The optional switches are extensions; without them the output is the reference's.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../../include/acf_b200.h"
+#include "readers.hpp"
+
+int main(int argc, char* argv[])
+{
+    int ncorr = 1000;                   // viscosity.cpp:173
+    double timestep = 2.0;              // :180
+    double box_length = 31.0399376148;  // :186
+    double temperature = 298.15;        // :188
+    bool quirk = true;
+    if (argc < 2) return 1;
+    const char* fname = argv[1];
+    for (int i = 2; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "--exact-reader")
+            quirk = false;
+        else if (i + 1 < argc && a == "--maxcorr")
+            ncorr = atoi(argv[++i]);
+        else if (i + 1 < argc && a == "--timestep")
+            timestep = atof(argv[++i]);
+        else if (i + 1 < argc && a == "--box")
+            box_length = atof(argv[++i]);
+        else if (i + 1 < argc && a == "--temperature")
+            temperature = atof(argv[++i]);
+        else {
+            std::cerr << "viscosity: unknown argument " << a << std::endl;
+            return 1;
+        }
+    }
+    int num_samples = 0;
+    const std::vector<std::vector<double> > comps = acfhost::read_pressure_namd(fname, num_samples, quirk);
+
+    std::vector<const double*> ptrs;
+    std::vector<int> which;
+    for (int i = 0; i < 9; ++i) {
+        if (i % 4 == 0) continue;  // off-diagonal components only (:200)
+        ptrs.push_back(comps[i].data());
+        which.push_back(i);
+    }
+    const int nc = (int)ptrs.size();
+    std::vector<double> acf((size_t)nc * ncorr), integrals(nc), eta(nc);
+    if (acfb200_green_kubo(ptrs.data(), nc, num_samples, ncorr, timestep, box_length, temperature, acf.data(),
+                           integrals.data(), eta.data()) != ACFB200_OK) {
+        std::cerr << "viscosity: " << acfb200_last_error() << std::endl;
+        return 2;
+    }
+    std::vector<double> all;
+    for (int c = 0; c < nc; ++c) {
+        std::cout << "#" << integrals[c] << std::endl;
+        std::cout << "#eta " << which[c] << " " << eta[c] << std::endl;
+        all.push_back(eta[c]);
+        for (int j = 0; j < ncorr; ++j) std::cout << j << " " << acf[(size_t)c * ncorr + j] << std::endl;
+        std::cout << std::endl;
+    }
+    // mean and population standard deviation over the components (:217-222)
+    const double sum = std::accumulate(all.begin(), all.end(), 0.0);
+    const double mean = sum / all.size();
+    const double sq_sum = std::inner_product(all.begin(), all.end(), all.begin(), 0.0);
+    const double stdev = sqrt(sq_sum / all.size() - mean * mean);
+    std::cout << "#eta = " << mean << " " << stdev << std::endl;
+    return 0;
+}

@@ -1,0 +1,44 @@
+"""Deterministic text renderings of a series in the four input formats ACFcalculator reads
+(shared by tests/golden/make_cli_golden.py and the CLI tests; printf-style formatting only, so the files are
+identical wherever they are regenerated)."""
+
+
+def write_input(path, series, fmt):
+    with open(path, "w") as f:
+        if fmt in ("general", "general_blank"):
+            f.write("# step solute1\n")
+            for i, v in enumerate(series):
+                if fmt == "general_blank" and i == 10:
+                    f.write("\n")
+                f.write("%11d % .14e\n" % (i, v))
+        elif fmt == "general_tab":
+            f.write("# time\tvalue\n")
+            for i, v in enumerate(series):
+                f.write("%.4f\t%.10g\n" % (2.0 * i, v))
+        elif fmt == "gromacs":
+            f.write("# This file was created by a test\n@    title \"Pull COM\"\n@TYPE xy\n")
+            for i, v in enumerate(series):
+                f.write("%.4f\t%.9g\n" % (2.0 * i, v / 10.0))  # nm; the reader multiplies by 10
+        elif fmt == "namd":
+            f.write("# step         solute1               solute2\n")
+            for i, v in enumerate(series):
+                # 11-char step, 4 blanks, then 21-char fields separated by 2 blanks: value k starts at 23*(k-1)+15
+                f.write("%11d    %21.14e  %21.14e\n" % (i, v, -v))
+        elif fmt in ("charmm", "charmm_blank"):
+            f.write("# charmm time series\n")
+            for i, v in enumerate(series):
+                if fmt == "charmm_blank" and i == 10:
+                    f.write("\n")
+                f.write("%.12f  %d\n" % (v, i))
+        else:
+            raise ValueError(fmt)
+
+
+def write_pressure_log(path, pressure):
+    """A NAMD-log look-alike: PRESSURE: <step> <9 tensor components>, with other lines in between."""
+    with open(path, "w") as f:
+        f.write("Info: synthetic NAMD log for tests\n")
+        for i, row in enumerate(pressure):
+            f.write("ENERGY: %d 0 0 0\n" % i)
+            f.write("PRESSURE: %d " % i + " ".join("%.6f" % v for v in row) + "\n")
+            f.write("GPRESSURE: %d " % i + " ".join("%.6f" % (v + 1) for v in row) + "\n")

@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""End-to-end CLI fixtures: runs the shipped reference binary (oracle/_ref/ACFcalculator_ref) and the
+reference's viscosity program (oracle/_ref/viscosity_ref) on synthetic inputs and records stdout, exit status,
+the ACF file and the .out file in tests/golden/cli_cases.json (+ the series in cli_series.npz).
+Build-container only; the tests read just the two files written here.
+
+    python tests/golden/make_cli_golden.py
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+OUT_DIR = os.path.join(ROOT, "tests", "golden")
+from oracle import oracle as O  # noqa: E402
+from cli_inputs import write_input, write_pressure_log  # noqa: E402
+sys.path.insert(0, OUT_DIR)
+from make_golden import langevin  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = [
+    # name, series key, file format, extra CLI args
+    ("general_langevin1", "lv1", "general", ["-t", "general", "-f", "1", "-s", "1", "-m", "1000"]),
+    ("general_langevin1_cutoff", "lv1", "general", ["-t", "general", "-f", "1", "-s", "1", "-m", "1000", "-c", "0.05"]),
+    ("general_default_type", "lv1", "general", ["-f", "1", "--maxcorr=500", "--timestep", "1"]),
+    ("general_langevin3_m500", "lv3", "general", ["-t", "general", "-f", "1", "-s", "1", "-m", "500"]),
+    ("general_langevin2_aborts", "lv2", "general", ["-t", "general", "-f", "1", "-s", "1", "-m", "1000"]),
+    ("general_spring", "lv1", "general", ["-t", "general", "-f", "1", "-s", "1", "-m", "1000", "-k", "10", "-e", "298.15",
+                                          "-w", "18"]),
+    ("general_spring_no_temperature", "lv1", "general", ["-t", "general", "-f", "1", "-s", "1", "-m", "200", "-k", "10"]),
+    ("general_pfactor", "lv1", "general", ["-t", "general", "-f", "1", "-s", "1", "-m", "500", "-p", "10"]),
+    ("general_tabs_field2", "lv3", "general_tab", ["-t", "general", "-f", "2", "-s", "1", "-m", "500"]),
+    ("general_tabs_field1_zero", "short", "general_tab", ["-t", "general", "-f", "1", "-s", "1", "-m", "20"]),
+    ("gromacs_field2", "lv3", "gromacs", ["-t", "gromacs", "-f", "2", "-s", "2", "-m", "500"]),
+    ("gromacs_field_beyond_columns", "short", "gromacs", ["-t", "gromacs", "-f", "5", "-s", "2", "-m", "20"]),
+    ("namd_field1", "lv1", "namd", ["-t", "namd", "-f", "1", "-s", "1", "-m", "1000"]),
+    ("namd_field0_empty", "short", "namd", ["-t", "namd", "-f", "0", "-s", "1", "-m", "20"]),
+    ("charmm", "lv3", "charmm", ["-t", "charmm", "-s", "1", "-m", "500"]),
+    ("maxcorr_beyond_n", "short", "general", ["-t", "general", "-f", "1", "-s", "1", "-m", "60"]),
+    ("blank_line_general", "short", "general_blank", ["-t", "general", "-f", "1", "-m", "20"]),
+    ("blank_line_charmm", "short", "charmm_blank", ["-t", "charmm", "-m", "20"]),
+]
+
+
+def main():
+    O.build()
+    series = {"lv1": langevin(20000, 1), "lv2": langevin(20000, 2), "lv3": langevin(20000, 3),
+              "short": langevin(50, 5)}
+    np.savez_compressed(os.path.join(OUT, "cli_series.npz"), **series)
+    ref = O.ref_path("ACFcalculator_ref")
+    out = {}
+    with tempfile.TemporaryDirectory() as t:
+        for name, key, fmt, args in CASES:
+            inp = os.path.join(t, name + ".in")
+            write_input(inp, series[key], fmt)
+            acf_f, out_f = os.path.join(t, name + ".acf"), os.path.join(t, name + ".out")
+            p = subprocess.run([ref, "-i", inp, "-a", acf_f, "-o", out_f] + args, capture_output=True, text=True, cwd=t)
+            rec = {"series": key, "format": fmt, "args": args, "returncode": p.returncode,
+                   "stdout": p.stdout.replace(out_f, "<OUT>"), "stderr_head": p.stderr.splitlines()[:1],
+                   "acf_file": open(acf_f).read() if os.path.exists(acf_f) else None,
+                   "out_file": open(out_f).read() if os.path.exists(out_f) else None}
+            out[name] = rec
+            print("%-32s rc=%4d acf=%s out=%r" % (name, p.returncode, "yes" if rec["acf_file"] else "no",
+                                                  (rec["out_file"] or "")[:40]))
+        # viscosity: reference program on a synthetic NAMD log
+        rng = np.random.default_rng(20260201)
+        pres = rng.standard_normal((1500, 9)) * 50.0
+        for i in range(1, 1500):
+            pres[i] = 0.9 * pres[i - 1] + np.sqrt(1 - 0.81) * pres[i]
+        np.savez_compressed(os.path.join(OUT, "cli_pressure.npz"), pressure=pres)
+        log = os.path.join(t, "namd.log")
+        write_pressure_log(log, pres)
+        p = subprocess.run([O.ref_path("viscosity_ref"), log], capture_output=True, text=True)
+        out["viscosity_log"] = {"returncode": p.returncode, "stdout": p.stdout}
+        print("viscosity rc=%d, %d stdout lines, last: %s" % (p.returncode, len(p.stdout.splitlines()),
+                                                             p.stdout.splitlines()[-1]))
+    json.dump(out, open(os.path.join(OUT, "cli_cases.json"), "w"), indent=0)
+
+
+if __name__ == "__main__":
+    main()

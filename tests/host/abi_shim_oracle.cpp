@@ -1,0 +1,71 @@
+// TEST INFRASTRUCTURE: a stand-in for libacf_b200.so that answers the few C-ABI calls the C++ front-ends
+// make by calling the CPU oracle (oracle/acf_oracle.c).  Linked ONLY into tests/_build/*_oracle, the
+// CPU-side builds of the front-ends used by tests/test_cli.py to check options, readers, the GLE stage and
+// the output formats against the reference binary's recorded output without a GPU.  Never shipped.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/acf_b200.h"
+
+extern "C" {
+typedef struct {
+    double avg, var, var_vel, acf_int, vel_avg;
+    int64_t cutoff_index;
+    int64_t n_used;
+} oracle_pipeline_result;
+void oracle_acf_pipeline(double* series, int64_t n, int64_t ncorr, double dt, double cutoff, double* acf,
+                         double* vacf, oracle_pipeline_result* out, int nthreads);
+void oracle_spring_rescale(double* acf, double* vacf, int64_t ncorr, double k_spring, double mass_amu,
+                           double temperature, double* var, double* var_vel);
+double oracle_integrate_corr_cutoff(const double* acf, int64_t ncorr, double dt, double cutoff, int64_t* brk);
+double oracle_integrate_corr(const double* acf, int64_t ncorr, double dt);
+void oracle_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr);
+double oracle_viscosity_eta(double box_length, double temperature, double integral);
+
+const char* acfb200_last_error(void) { return "oracle shim"; }
+
+int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double dt, double cutoff, double* acf,
+                         double* vacf, acfb200_result* r)
+{
+    std::vector<double> s(series, series + n);
+    oracle_pipeline_result o;
+    oracle_acf_pipeline(s.data(), n, ncorr, dt, cutoff, acf, vacf, &o, 1);
+    r->avg = o.avg;
+    r->var = o.var;
+    r->var_vel = o.var_vel;
+    r->acf_int = o.acf_int;
+    r->vel_avg = o.vel_avg;
+    r->cutoff_index = o.cutoff_index;
+    r->n_used = o.n_used;
+    r->diffusivity = o.var * o.var / o.acf_int * 0.1;
+    return 0;
+}
+
+int acfb200_spring_rescale(double* acf, double* vacf, int64_t ncorr, double k, double mass, double temperature,
+                           double* var, double* var_vel)
+{
+    oracle_spring_rescale(acf, vacf, ncorr, k, mass, temperature, var, var_vel);
+    return 0;
+}
+
+int acfb200_integrate_corr_cutoff(const double* acf, int64_t ncorr, double dt, double cutoff, double* integral,
+                                  int64_t* brk)
+{
+    int64_t b;
+    *integral = oracle_integrate_corr_cutoff(acf, ncorr, dt, cutoff, &b);
+    if (brk) *brk = b;
+    return 0;
+}
+
+int acfb200_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t ncorr, double dt, double box_length,
+                       double temperature, double* acf, double* integrals, double* eta)
+{
+    for (int c = 0; c < ncomp; ++c) {
+        oracle_calc_correlation(comps[c], n, ncorr, acf + (size_t)c * ncorr);
+        integrals[c] = oracle_integrate_corr(acf + (size_t)c * ncorr, ncorr, dt);
+        eta[c] = oracle_viscosity_eta(box_length, temperature, integrals[c]);
+    }
+    return 0;
+}
+}
