@@ -278,6 +278,23 @@ def acf_pipeline_device(series, ncorr, timestep, cutoff=0.0, stream=None):
     return acf, vacf, r.as_dict()
 
 
+def acf_pipeline_batch_device(windows, ncorr, timestep, cutoff=0.0, want_results=True, stream=None):
+    """Main() sequence for a list of device tensors in one launch set -> (acf [W,ncorr], vacf [W,ncorr], [dict])."""
+    import torch
+    nw = len(windows)
+    for t in windows:
+        _check_dev(t)
+    ptrs = (C.c_void_p * nw)(*[t.data_ptr() for t in windows])
+    lens = (C.c_int64 * nw)(*[t.numel() for t in windows])
+    acf = torch.empty((nw, int(ncorr)), dtype=torch.float64, device=windows[0].device)
+    vacf = torch.empty((nw, int(ncorr)), dtype=torch.float64, device=windows[0].device)
+    res = (Result * nw)() if want_results else None
+    check(_lib.load().acfb200_acf_pipeline_batch_device(ptrs, lens, nw, int(ncorr), float(timestep), float(cutoff),
+                                                        C.c_void_p(acf.data_ptr()), C.c_void_p(vacf.data_ptr()),
+                                                        res, _stream_ptr(stream)))
+    return acf, vacf, ([r.as_dict() for r in res] if want_results else None)
+
+
 def measure_dfma_peak():
     """(TFLOP/s of pure DFMA chains, SM clock in MHz at which 64 DFMA/clk/SM gives that rate)."""
     tf = C.c_double(0)

@@ -180,53 +180,74 @@ static int check_common(const void* p, long long n, long long ncorr, const char*
     return 0;
 }
 
-// The main() sequence on a device-resident series; d_acf/d_vacf device [ncorr].
-static int pipeline_device(Workspace* ws, const double* d_series, long long n, long long ncorr, double dt,
-                           double cutoff, double* d_acf, double* d_vacf, acfb200_result* res, cudaStream_t st)
+// The main() sequence (ACFcalculator.cpp:712-725,:775) for nw device-resident windows in one go:
+// per window mean / centre+velocity / velocity-mean kernels, then ONE direct-lag launch over the 2*nw
+// centred series, one integral kernel per window.  d_acf/d_vacf (nullable) are device [nw][ncorr].
+static int pipeline_batch_device(Workspace* ws, const double* const* d_series, const int64_t* n, int nw,
+                                 long long ncorr, double dt, double cutoff, double* d_acf, double* d_vacf,
+                                 acfb200_result* res, cudaStream_t st)
 {
-    if (n < 3) {
-        set_error("acf_pipeline: need n >= 3 samples (velocity series has n-2), got %lld", n);
-        return ACFB200_ERR_ARG;
+    size_t total = 0;
+    for (int w = 0; w < nw; ++w) {
+        if (n[w] < 3) {
+            set_error("acf_pipeline: window %d has %lld samples; need n >= 3 (the velocity series has n-2)", w,
+                      (long long)n[w]);
+            return ACFB200_ERR_ARG;
+        }
+        total += even_up(n[w]);
     }
-    ACF_TRY(ws->y.ensure(even_up(n) * 8));
-    ACF_TRY(ws->vel.ensure(even_up(n) * 8));
-    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch), true));
-    ACF_TRY(ws->small.ensure(64));
+    ACF_TRY(ws->y.ensure(total * 8));
+    ACF_TRY(ws->vel.ensure(total * 8));
+    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch) * (size_t)nw, true));
+    ACF_TRY(ws->out.ensure((size_t)2 * nw * ncorr * 8));
+    ACF_TRY(ws->small.ensure((size_t)16 * nw));
     ReduceScratch* sc = ws->scratch.as<ReduceScratch>();
-    double* d_y = ws->y.as<double>();
-    double* d_v = ws->vel.as<double>();
-    ACF_TRY(launch_sum(d_series, n, sc, st));
-    ACF_TRY(launch_center_velocity(d_series, n, sc, d_y, d_v, dt, st));
-    ACF_TRY(launch_subtract_mean(d_v, n - 2, &sc->vel_sum, &sc->vel_mean, st));
-    g_launches += 3;
-    const long long m = n - 2;  // ACFcalculator.cpp:718
-    std::vector<SeriesDesc> descs = {{d_y, m, m}, {d_v, m, m}};
-    ACF_TRY(ws->out.ensure((size_t)2 * ncorr * 8));
-    double* d_o = ws->out.as<double>();
+    std::vector<SeriesDesc> descs(2 * (size_t)nw);
+    size_t off = 0;
+    for (int w = 0; w < nw; ++w) {
+        double* d_y = ws->y.as<double>() + off;
+        double* d_v = ws->vel.as<double>() + off;
+        ACF_TRY(launch_sum(d_series[w], n[w], sc + w, st));
+        ACF_TRY(launch_center_velocity(d_series[w], n[w], sc + w, d_y, d_v, dt, st));
+        ACF_TRY(launch_subtract_mean(d_v, n[w] - 2, &sc[w].vel_sum, &sc[w].vel_mean, st));
+        g_launches += 3;
+        const long long m = n[w] - 2;  // ACFcalculator.cpp:718
+        descs[2 * w] = {d_y, m, m};
+        descs[2 * w + 1] = {d_v, m, m};
+        off += even_up(n[w]);
+    }
+    double* d_o = ws->out.as<double>();  // [window][acf|vacf][ncorr]
     ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
-    double* d_int = ws->small.as<double>();
-    long long* d_brk = reinterpret_cast<long long*>(d_int + 1);
-    ACF_TRY(launch_integrate_cutoff(d_o, ncorr, dt, cutoff, d_int, d_brk, nullptr, st));
-    g_launches += 1;
-    if (d_acf) ACF_CUDA_OK(cudaMemcpyAsync(d_acf, d_o, ncorr * 8, cudaMemcpyDeviceToDevice, st));
-    if (d_vacf) ACF_CUDA_OK(cudaMemcpyAsync(d_vacf, d_o + ncorr, ncorr * 8, cudaMemcpyDeviceToDevice, st));
+    double* d_small = ws->small.as<double>();
+    for (int w = 0; w < nw; ++w) {
+        ACF_TRY(launch_integrate_cutoff(d_o + (size_t)2 * w * ncorr, ncorr, dt, cutoff, d_small + 2 * w,
+                                        reinterpret_cast<long long*>(d_small + 2 * w + 1), nullptr, st));
+        g_launches += 1;
+    }
+    if (d_acf)
+        ACF_CUDA_OK(cudaMemcpy2DAsync(d_acf, ncorr * 8, d_o, 2 * ncorr * 8, ncorr * 8, nw, cudaMemcpyDeviceToDevice, st));
+    if (d_vacf)
+        ACF_CUDA_OK(cudaMemcpy2DAsync(d_vacf, ncorr * 8, d_o + ncorr, 2 * ncorr * 8, ncorr * 8, nw,
+                                      cudaMemcpyDeviceToDevice, st));
     if (res) {
-        double h_sc[4], h_int[2], h_a0 = 0, h_v0 = 0;
-        ACF_CUDA_OK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
-        ACF_CUDA_OK(cudaMemcpyAsync(h_int, d_int, sizeof(h_int), cudaMemcpyDeviceToHost, st));
-        ACF_CUDA_OK(cudaMemcpyAsync(&h_a0, d_o, 8, cudaMemcpyDeviceToHost, st));
-        ACF_CUDA_OK(cudaMemcpyAsync(&h_v0, d_o + ncorr, 8, cudaMemcpyDeviceToHost, st));
+        std::vector<double> h_small(2 * (size_t)nw), h_means(4 * (size_t)nw), h_c0(2 * (size_t)nw);
+        ACF_CUDA_OK(cudaMemcpyAsync(h_small.data(), d_small, h_small.size() * 8, cudaMemcpyDeviceToHost, st));
+        ACF_CUDA_OK(cudaMemcpy2DAsync(h_means.data(), 32, sc, sizeof(ReduceScratch), 32, nw, cudaMemcpyDeviceToHost, st));
+        ACF_CUDA_OK(cudaMemcpy2DAsync(h_c0.data(), 8, d_o, ncorr * 8, 8, 2 * (size_t)nw, cudaMemcpyDeviceToHost, st));
         ACF_CUDA_OK(cudaStreamSynchronize(st));
-        res->avg = h_sc[1];
-        res->vel_avg = h_sc[3];
-        res->var = h_a0;
-        res->var_vel = h_v0;
-        res->acf_int = h_int[0];
-        long long brk;
-        memcpy(&brk, &h_int[1], 8);
-        res->cutoff_index = brk;
-        res->n_used = m;
-        res->diffusivity = res->var * res->var / res->acf_int * 0.1;  // ACFcalculator.cpp:905
+        for (int w = 0; w < nw; ++w) {
+            acfb200_result& r = res[w];
+            r.avg = h_means[4 * w + 1];
+            r.vel_avg = h_means[4 * w + 3];
+            r.var = h_c0[2 * w];          // == variance(timeSeries, n-2): same terms as lag 0 (:724)
+            r.var_vel = h_c0[2 * w + 1];
+            r.acf_int = h_small[2 * w];
+            long long brk;
+            memcpy(&brk, &h_small[2 * w + 1], 8);
+            r.cutoff_index = brk;
+            r.n_used = n[w] - 2;
+            r.diffusivity = r.var * r.var / r.acf_int * 0.1;  // ACFcalculator.cpp:905
+        }
     }
     return 0;
 }
@@ -449,79 +470,30 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
         set_error("acf_pipeline_batch: null argument or nwindows < 1");
         return ACFB200_ERR_ARG;
     }
-    for (int w = 0; w < nwindows; ++w) {
-        ACF_TRY(check_common(series[w], n[w], ncorr, "acf_pipeline"));
-        if (n[w] < 3) {
-            set_error("acf_pipeline: window %d has %lld samples, need >= 3", w, (long long)n[w]);
-            return ACFB200_ERR_ARG;
-        }
-    }
+    for (int w = 0; w < nwindows; ++w) ACF_TRY(check_common(series[w], n[w], ncorr, "acf_pipeline"));
     Workspace* ws;
     ACF_TRY(get_ws(&ws));
     cudaStream_t st = ws->stream;
-    size_t total = 0, max_n = 0;
-    for (int w = 0; w < nwindows; ++w) {
-        total += even_up(n[w]);
-        if ((size_t)n[w] > max_n) max_n = (size_t)n[w];
-    }
-    ACF_TRY(ws->series.ensure(even_up((long long)max_n) * 8));
-    ACF_TRY(ws->y.ensure(total * 8));
-    ACF_TRY(ws->vel.ensure(total * 8));
-    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch) * (size_t)nwindows, true));
-    ACF_TRY(ws->out.ensure((size_t)2 * nwindows * ncorr * 8));
-    ACF_TRY(ws->small.ensure((size_t)16 * nwindows));
-    ReduceScratch* sc = ws->scratch.as<ReduceScratch>();
-    std::vector<SeriesDesc> descs(2 * (size_t)nwindows);
+    size_t total = 0;
+    for (int w = 0; w < nwindows; ++w) total += even_up(n[w]);
+    ACF_TRY(ws->series.ensure(total * 8));
+    std::vector<const double*> d_ptr(nwindows);
     size_t off = 0;
     for (int w = 0; w < nwindows; ++w) {
-        double* d_x = ws->series.as<double>();
-        double* d_y = ws->y.as<double>() + off;
-        double* d_v = ws->vel.as<double>() + off;
-        // the staging buffer is reused window to window: stream order keeps the copies behind the kernels
-        ACF_CUDA_OK(cudaMemcpyAsync(d_x, series[w], (size_t)n[w] * 8, cudaMemcpyHostToDevice, st));
-        ACF_TRY(launch_sum(d_x, n[w], sc + w, st));
-        ACF_TRY(launch_center_velocity(d_x, n[w], sc + w, d_y, d_v, dt, st));
-        ACF_TRY(launch_subtract_mean(d_v, n[w] - 2, &sc[w].vel_sum, &sc[w].vel_mean, st));
-        g_launches += 3;
-        const long long m = n[w] - 2;
-        descs[2 * w] = {d_y, m, m};
-        descs[2 * w + 1] = {d_v, m, m};
+        double* d = ws->series.as<double>() + off;
+        ACF_CUDA_OK(cudaMemcpyAsync(d, series[w], (size_t)n[w] * 8, cudaMemcpyHostToDevice, st));
+        d_ptr[w] = d;
         off += even_up(n[w]);
     }
-    double* d_o = ws->out.as<double>();  // [window][acf|vacf][ncorr]
-    ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
-    double* d_small = ws->small.as<double>();
-    for (int w = 0; w < nwindows; ++w) {
-        ACF_TRY(launch_integrate_cutoff(d_o + (size_t)2 * w * ncorr, ncorr, dt, cutoff, d_small + 2 * w,
-                                        reinterpret_cast<long long*>(d_small + 2 * w + 1), nullptr, st));
-        g_launches += 1;
-    }
-    std::vector<double> h_o((size_t)2 * nwindows * ncorr), h_small(2 * (size_t)nwindows);
-    std::vector<ReduceScratch> h_sc;  // only the 4 leading doubles of each are needed
-    std::vector<double> h_means(4 * (size_t)nwindows);
-    ACF_CUDA_OK(cudaMemcpyAsync(h_o.data(), d_o, h_o.size() * 8, cudaMemcpyDeviceToHost, st));
-    ACF_CUDA_OK(cudaMemcpyAsync(h_small.data(), d_small, h_small.size() * 8, cudaMemcpyDeviceToHost, st));
-    ACF_CUDA_OK(cudaMemcpy2DAsync(h_means.data(), 32, sc, sizeof(ReduceScratch), 32, nwindows, cudaMemcpyDeviceToHost,
-                                  st));
+    ACF_TRY(pipeline_batch_device(ws, d_ptr.data(), n, nwindows, ncorr, dt, cutoff, nullptr, nullptr, result, st));
+    // results live in ws->out as [window][acf|vacf][ncorr]
+    const double* d_o = ws->out.as<double>();
+    if (acf)
+        ACF_CUDA_OK(cudaMemcpy2DAsync(acf, ncorr * 8, d_o, 2 * ncorr * 8, ncorr * 8, nwindows, cudaMemcpyDeviceToHost, st));
+    if (vacf)
+        ACF_CUDA_OK(cudaMemcpy2DAsync(vacf, ncorr * 8, d_o + ncorr, 2 * ncorr * 8, ncorr * 8, nwindows,
+                                      cudaMemcpyDeviceToHost, st));
     ACF_CUDA_OK(cudaStreamSynchronize(st));
-    for (int w = 0; w < nwindows; ++w) {
-        const double* a = h_o.data() + (size_t)2 * w * ncorr;
-        if (acf) memcpy(acf + (size_t)w * ncorr, a, (size_t)ncorr * 8);
-        if (vacf) memcpy(vacf + (size_t)w * ncorr, a + ncorr, (size_t)ncorr * 8);
-        if (result) {
-            acfb200_result& r = result[w];
-            r.avg = h_means[4 * w + 1];
-            r.vel_avg = h_means[4 * w + 3];
-            r.var = a[0];
-            r.var_vel = a[ncorr];
-            r.acf_int = h_small[2 * w];
-            long long brk;
-            memcpy(&brk, &h_small[2 * w + 1], 8);
-            r.cutoff_index = brk;
-            r.n_used = n[w] - 2;
-            r.diffusivity = r.var * r.var / r.acf_int * 0.1;  // ACFcalculator.cpp:905
-        }
-    }
     return 0;
 }
 
@@ -640,14 +612,26 @@ int acfb200_normalise_device(const double* d_sums, int64_t n_total, int64_t ncor
     return 0;
 }
 
+int acfb200_acf_pipeline_batch_device(const double* const* d_series, const int64_t* n, int nwindows, int64_t ncorr,
+                                      double dt, double cutoff, double* d_acf, double* d_vacf, acfb200_result* result,
+                                      void* stream)
+{
+    Lock lk(g_mu);
+    if (!d_series || !n || nwindows < 1) {
+        set_error("acf_pipeline_batch_device: null argument or nwindows < 1");
+        return ACFB200_ERR_ARG;
+    }
+    for (int w = 0; w < nwindows; ++w) ACF_TRY(check_common(d_series[w], n[w], ncorr, "acf_pipeline_device"));
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    return pipeline_batch_device(ws, d_series, n, nwindows, ncorr, dt, cutoff, d_acf, d_vacf, result,
+                                 (cudaStream_t)stream);
+}
+
 int acfb200_acf_pipeline_device(const double* d_series, int64_t n, int64_t ncorr, double dt, double cutoff,
                                 double* d_acf, double* d_vacf, acfb200_result* result, void* stream)
 {
-    Lock lk(g_mu);
-    ACF_TRY(check_common(d_series, n, ncorr, "acf_pipeline_device"));
-    Workspace* ws;
-    ACF_TRY(get_ws(&ws));
-    return pipeline_device(ws, d_series, n, ncorr, dt, cutoff, d_acf, d_vacf, result, (cudaStream_t)stream);
+    return acfb200_acf_pipeline_batch_device(&d_series, &n, 1, ncorr, dt, cutoff, d_acf, d_vacf, result, stream);
 }
 
 int acfb200_calc_correlation_fft_device(const double* d_y, int64_t n, int64_t ncorr, double* d_corr, void* stream)

@@ -228,13 +228,14 @@ def run_native(args):
         d_w = [h.to(dev, non_blocking=True) for h in h_w]
         products_rank = 2.0 * len(mine) * (n - 2) * m
         fmas_rank = 2.0 * len(mine) * (float(m) * (n - 2) - m * (m - 1) / 2.0)
-        launches_per_step = len(mine) * 6
+        launches_per_step = len(mine) * 4 + 2
         plan = A.describe_plan(n - 2, m, 2 * max(1, len(mine)))
         res = {}
 
         def step():
-            for d in d_w:
-                res["last"] = A.acf_pipeline_device(d, m, 2.0, 0.05, stream=stream)
+            # all local windows: per-window mean/velocity kernels, ONE direct-lag launch over 2*len(mine) series,
+            # per-window integrals; the scalars (avg, var, D, cutoff bin) come back to the host each step
+            res["last"] = A.acf_pipeline_batch_device(d_w, m, 2.0, 0.05, stream=stream)
 
         def e2e_step():
             A.acf_pipeline_batch([h.numpy() for h in h_w], m, 2.0, 0.05)
@@ -242,9 +243,9 @@ def run_native(args):
         scaling = "strong"
         total_products = 2.0 * nw * (n - 2) * m
     elif args.workload == "viscosity":
+        from acfcalculator_b200 import parallel as P
         comps = int(wl["comps"])
-        lo, hi = n * rank // world, n * (rank + 1) // world
-        halo_end = min(n, hi + m - 1)
+        lo, hi, halo_end = P.time_block(n, m, world, rank)
         # every rank synthesises only its block + halo (stationary OU started at the block edge)
         blocks = [ou_series(halo_end - lo, 500.0, sigma=50.0, seed=20260201 + c + 1000 * rank) for c in range(comps)]
         h_b = [torch.from_numpy(b).pin_memory() for b in blocks]
@@ -257,12 +258,14 @@ def run_native(args):
         plan = A.describe_plan(hi - lo, m, comps)
         i_end = [hi - lo] * comps
 
+        def batch_fn(blocks, i_count, mm):
+            return A.calc_correlation_batch_device(blocks, mm, i_end=[i_count] * len(blocks), normalise=False,
+                                                   out=d_sums, stream=stream)
+
         def step():
-            A.calc_correlation_batch_device(d_b, m, i_end=i_end, normalise=False, out=d_sums, stream=stream)
-            if world > 1:
-                dist.all_reduce(d_sums)  # one NCCL all-reduce of comps*m doubles (480 KB)
-            for c in range(comps):
-                A.normalise_device(d_sums[c], n, out=d_corr[c], stream=stream)
+            # per-block raw lag sums -> ONE NCCL all-reduce of comps*m doubles (480 KB) -> divide by (n-k)
+            P.time_block_correlation_batch(d_b, hi - lo, n, m, batch_fn,
+                                           lambda s_, nt: A.normalise_device(s_, nt, stream=stream))
 
         e2e_step = None
         h2d, d2h = 8 * (halo_end - lo) * comps, 8 * m * comps

@@ -142,6 +142,12 @@ ACFB200_API int acfb200_calc_correlation_batch_device(const double* const* d_y, 
 ACFB200_API int acfb200_acf_pipeline_device(const double* d_series, int64_t n, int64_t ncorr, double dt, double cutoff,
                                 double* d_acf, double* d_vacf, acfb200_result* result, void* stream);
 
+/* Batched form: d_series / n are HOST arrays of nwindows device pointers / lengths; d_acf / d_vacf are device
+ * [nwindows][ncorr] (nullable); result is a HOST array [nwindows] (nullable: then nothing synchronises). */
+ACFB200_API int acfb200_acf_pipeline_batch_device(const double* const* d_series, const int64_t* n, int nwindows, int64_t ncorr,
+                                      double dt, double cutoff, double* d_acf, double* d_vacf, acfb200_result* result,
+                                      void* stream);
+
 /* Zero-padded Wiener-Khinchin path for maxcorr -> n (no reference implementation exists; the
  * reference's FFT stub ACFcalculator.cpp:148-200 is dead code).  Same contract as
  * acfb200_calc_correlation[_device]; results agree with the direct sum to ~1e-13*corr[0]. */

@@ -58,6 +58,14 @@ def run_case(exe, name, tmp_path):
 NUM = re.compile(r"^[-+]?(\d+\.?\d*|\.\d+)([eE][-+]?\d+)?$")
 
 
+# Lines produced by the host-side GLE extrapolation (ACFcalculator.cpp:778-906).  Its discrete segment search
+# amplifies 1e-15 perturbations of vacf (second finite differences + argmin) into the
+# 3rd-4th printed digit, so with the GPU backend these lines are held to GLE_REL; the hot-path quantities
+# (#avg, #var, #varVel, #D (ACF), every ACF-file row) stay at the tight tolerance.
+GLE_LINES = ("#m=", "#b=", "#r2=", "#ddDs_min", "#Ds (VACF)", "#s1", "#s2", "#Ds_min")
+GLE_REL = 5e-3
+
+
 def same_text(got, want, rel):
     """Token-wise comparison: numbers within `rel` (0 = identical text), everything else identical."""
     if rel == 0:
@@ -66,6 +74,7 @@ def same_text(got, want, rel):
     if len(g) != len(w):
         return False
     for lg, lw in zip(g, w):
+        line_rel = GLE_REL if lw.startswith(GLE_LINES) else rel
         tg, tw = lg.split(" "), lw.split(" ")
         if len(tg) != len(tw):
             return False
@@ -75,7 +84,7 @@ def same_text(got, want, rel):
             if not (NUM.match(a) and NUM.match(b)):
                 return False
             fa, fb = float(a), float(b)
-            if abs(fa - fb) > rel * max(abs(fa), abs(fb)):
+            if abs(fa - fb) > line_rel * max(abs(fa), abs(fb)):
                 return False
     return True
 

@@ -248,3 +248,12 @@ def test_fft_equals_direct_kernel_long_lag(acf, oracle):
     lags = np.unique(np.concatenate([np.arange(16), np.geomspace(16, m - 1, 240).astype(np.int64)]))
     ref = oracle.calc_correlation_lags(x, lags)
     assert rel_to_c0(f[lags], ref, ref[0]) <= TOL
+
+
+def test_batch_device_pipeline_equals_host_batch(acf):
+    import torch
+    wins = [ou_series(60000 + 11 * w, 30.0 + w, sigma=0.25, mu=-3.0 + w, seed=900 + w) for w in range(5)]
+    a, v, res = acf.acf_pipeline_batch(wins, 800, 2.0, 0.05)
+    da, dv, dres = acf.acf_pipeline_batch_device([torch.from_numpy(w).cuda() for w in wins], 800, 2.0, 0.05)
+    assert np.array_equal(da.cpu().numpy(), a) and np.array_equal(dv.cpu().numpy(), v)
+    assert dres == res
