@@ -71,6 +71,7 @@ SIGNATURES = {
     "acfb200_variant_name": (C.c_char_p, [C.c_int]),
     "acfb200_measure_dfma_peak": (C.c_int, [_P, _P]),
     "acfb200_measure_hbm_copy": (C.c_int, [_P]),
+    "acfb200_measure_dfma_probe": (C.c_int, [C.c_int, _P]),
 }
 
 _lib = None

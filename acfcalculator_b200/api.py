@@ -307,3 +307,10 @@ def measure_hbm_copy():
     g = C.c_double(0)
     check(_lib.load().acfb200_measure_hbm_copy(C.byref(g)))
     return g.value
+
+
+def measure_dfma_probe(probe):
+    """DFMA TFLOP/s with the lag kernel's operand pattern: probe 0 without loads, 1 with its LDS ratio."""
+    tf = C.c_double(0)
+    check(_lib.load().acfb200_measure_dfma_probe(int(probe), C.byref(tf)))
+    return tf.value

@@ -76,7 +76,7 @@ struct Workspace {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    Buf series, y, vel, desc, partials, out, scratch, small, fftwork;
+    Buf series, y, vel, desc, partials, out, scratch, small, fftwork, queue;
     void release()
     {
         series.release();
@@ -88,6 +88,7 @@ struct Workspace {
         scratch.release();
         small.release();
         fftwork.release();
+        queue.release();
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
         device = -1;
@@ -156,7 +157,9 @@ static int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long 
     ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, ns) * sizeof(double)));
     // pageable source: the runtime stages it before returning, so `descs` may die right after
     ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * (size_t)ns, cudaMemcpyHostToDevice, st));
-    ACF_TRY(launch_direct(plan, ws->desc.as<SeriesDesc>(), ns, ncorr, ws->partials.as<double>(), st));
+    ACF_TRY(ws->queue.ensure(64, true));
+    ACF_TRY(launch_direct(plan, ws->desc.as<SeriesDesc>(), ns, ncorr, ws->partials.as<double>(),
+                          ws->queue.as<unsigned int>(), ws->sm_count, st));
     ACF_TRY(launch_reduce_partials(plan, ws->desc.as<SeriesDesc>(), ns, ncorr, ws->partials.as<double>(), d_out,
                                    normalise, st));
     g_launches += 2;
@@ -321,10 +324,12 @@ int acfb200_describe_plan(int64_t n, int64_t ncorr, int nseries, char* buf, int 
     ACF_TRY(plan_direct(n, ncorr, nseries, sms, g_force_variant, &p));
     if (buf && buflen > 0)
         snprintf(buf, buflen,
-                 "variant=%s warps=%d ts=%d ti=%d bsz=%d lag_tiles=%d chunks=%d nseries=%d grid=%dx%dx%d block=%d "
+                 "mode=%s variant=%s warps=%d ts=%d ti=%d bsz=%d lag_tiles=%d chunks=%d nseries=%d grid=%dx%dx%d block=%d "
                  "smem=%zu mpad=%d useful_lag_frac=%.4f",
-                 direct_variant_name(p.variant), p.warps, p.ts, p.ti, p.bsz, p.lag_tiles, p.chunks, nseries,
-                 p.lag_tiles, p.chunks, nseries, p.warps * 32, p.smem_bytes, p.mpad, (double)ncorr / p.mpad);
+                 p.mode ? "stream" : "tiled",
+                 p.mode ? stream_variant_name(p.variant) : direct_variant_name(p.variant), p.warps, p.ts, p.ti, p.bsz,
+                 p.lag_tiles, p.chunks, nseries, p.lag_tiles, p.chunks, nseries, p.warps * 32, p.smem_bytes, p.mpad,
+                 (double)ncorr / p.mpad);
     return 0;
 }
 
@@ -682,6 +687,14 @@ int acfb200_measure_dfma_peak(double* tflops, double* effective_sm_mhz)
     Workspace* ws;
     ACF_TRY(get_ws(&ws));
     return measure_dfma_peak(tflops, effective_sm_mhz, 3);
+}
+
+int acfb200_measure_dfma_probe(int probe, double* tflops)
+{
+    Lock lk(g_mu);
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    return measure_dfma_probe(probe, tflops);
 }
 
 int acfb200_measure_hbm_copy(double* gb_per_s)

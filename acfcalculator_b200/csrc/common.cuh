@@ -16,13 +16,14 @@ struct SeriesDesc {
 
 // Launch geometry chosen on the host for one direct-lag launch (see plan_direct()).
 struct DirectPlan {
-    int variant;        // index into the kernel-variant table
+    int mode;           // 0 = tiled CTA kernel (direct_lag.cu), 1 = per-warp streaming kernel (direct_stream.cu)
+    int variant;        // index into the kernel-variant table of that mode
     int rk, lk, pf;     // lags per thread, lag lanes per warp, prefetch distance (pairs)
     int warps;          // warps per CTA == lag blocks per CTA
     int ts;             // i-steps per lane group per tile (multiple of the ring size)
-    int ti;             // i values per tile = (32/lk) * ts
+    int ti;             // i values per tile = (32/lk) * ts     (mode 1: samples per work unit)
     int bsz;            // doubles staged for the shifted operand
-    int lag_tiles;      // gridDim.x
+    int lag_tiles;      // gridDim.x                           (mode 1: lag blocks of 32*rk lags)
     int chunks;         // gridDim.y  (time chunks per series)
     int mpad;           // lag_tiles * warps * lk * rk  (row pitch of the partial-sum buffer)
     size_t smem_bytes;
@@ -37,14 +38,24 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
 size_t direct_partial_elems(const DirectPlan& p, int nseries);
 // Raw lag sums per (series, chunk) into `partials`; then reduce_partials folds the chunks in fixed order.
 int launch_direct(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
-                  double* d_partials, cudaStream_t st);
+                  double* d_partials, unsigned int* d_queue, int sm_count, cudaStream_t st);
 // out[s*ncorr + k] = sum_c partials[s][c][k]  (normalise=0)  or that / (n_s - k)  (normalise=1)
 int launch_reduce_partials(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
                            const double* d_partials, double* d_out, int normalise, cudaStream_t st);
 // out[k] = sums[k] / (n - k) with the reference's k >= n behaviour (NaN at k == n, -0 beyond).
 int launch_normalise(const double* d_sums, long long n, long long ncorr, double* d_out, cudaStream_t st);
-int direct_variant_count();
+int direct_variant_count();                 // tiled variants followed by streaming variants
 const char* direct_variant_name(int v);
+
+// direct_stream.cu
+int stream_variant_count();
+const char* stream_variant_name(int v);
+int stream_variant_rk(int v);
+int stream_variant_piece(int v);  // samples per TMA piece; work units are multiples of it
+double stream_variant_quality(int v);
+size_t stream_smem_bytes();
+int launch_direct_stream(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
+                         double* d_partials, unsigned int* d_queue, int sm_count, cudaStream_t st);
 
 // series_ops.cu
 constexpr int kReduceBlocks = 592;  // 4 per SM on a 148-SM part; partial sums are folded in fixed order
@@ -78,6 +89,7 @@ int launch_rescale(double* d_acf, long long ncorr, double target, cudaStream_t s
 // peaks.cu
 int measure_dfma_peak(double* tflops, double* sm_mhz_effective, int iters);
 int measure_hbm_copy(double* gbs, size_t bytes, int iters);
+int measure_dfma_probe(int probe, double* tflops);
 
 // fft_acf.cu
 int fft_acf_workspace_bytes(long long n, long long ncorr, size_t* bytes, long long* L);

@@ -20,56 +20,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace acfb200 {
-
-// ------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: UBLKCP / SYNCS)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-{
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ double2 lds2(const double* p)
-{
-    return *reinterpret_cast<const double2*>(p);
-}
 
 // ------------------------------------------------------------------------------------------------
 // The kernel
@@ -242,16 +195,30 @@ struct Variant {
 };
 
 #define ACF_VARIANT(RK, LK, PF, Q) {RK, LK, PF, direct_lag_kernel<RK, LK, PF>, "rk" #RK "_lk" #LK "_pf" #PF, Q}
+// quality = inner-loop DFMA efficiency relative to the best variant, measured on B200 at N=1e8, maxcorr=1e4
+// (profiles/r1_sweep_*.jsonl: time / useful-lag fraction).  More lags per thread = fewer LDS per DFMA.
 static const Variant kVariants[] = {
-    ACF_VARIANT(18, 32, 1, 1.00), ACF_VARIANT(18, 16, 1, 0.99), ACF_VARIANT(18, 8, 1, 0.98),
-    ACF_VARIANT(14, 32, 1, 0.97), ACF_VARIANT(22, 32, 1, 1.00), ACF_VARIANT(10, 32, 1, 0.93),
-    ACF_VARIANT(18, 32, 0, 0.95), ACF_VARIANT(18, 32, 2, 1.00),
+    ACF_VARIANT(18, 32, 1, 0.985), ACF_VARIANT(18, 16, 1, 0.985), ACF_VARIANT(18, 8, 1, 0.985),
+    ACF_VARIANT(14, 32, 1, 0.960), ACF_VARIANT(22, 32, 1, 1.000), ACF_VARIANT(10, 32, 1, 0.920),
+    ACF_VARIANT(18, 32, 0, 0.970), ACF_VARIANT(18, 32, 2, 0.985),
+    ACF_VARIANT(22, 8, 1, 1.000),  ACF_VARIANT(22, 16, 1, 1.000), ACF_VARIANT(18, 8, 0, 0.975), ACF_VARIANT(18, 8, 2, 0.985),
+    ACF_VARIANT(22, 8, 0, 0.990),  ACF_VARIANT(26, 8, 0, 0.993),
 };
+// CTA width: 1- and 2-warp CTAs have (almost) no barrier skew; 16 warps leave the tile load unoverlapped
+static double warps_quality(int w)
+{
+    return w == 1 ? 0.994 : w == 2 ? 1.0 : w == 4 ? 0.985 : w == 8 ? 0.980 : w == 12 ? 0.95 : 0.90;
+}
 static const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 static bool g_attr_set[sizeof(kVariants) / sizeof(kVariants[0])] = {false};
 
-int direct_variant_count() { return kNumVariants; }
-const char* direct_variant_name(int v) { return (v >= 0 && v < kNumVariants) ? kVariants[v].name : "?"; }
+// Public variant numbering: [0, kNumVariants) tiled kernels, then the streaming kernels.
+int direct_variant_count() { return kNumVariants + stream_variant_count(); }
+const char* direct_variant_name(int v)
+{
+    if (v >= 0 && v < kNumVariants) return kVariants[v].name;
+    return stream_variant_name(v - kNumVariants);
+}
 
 static int env_int(const char* name, int dflt)
 {
@@ -273,21 +240,77 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
     int fw = env_int("ACFB200_WARPS", 0);
     int fts = env_int("ACFB200_TS", 0);
     int fch = env_int("ACFB200_CHUNKS", 0);
+    if (nseries > 65535) {
+        set_error("plan_direct: at most 65535 series per launch (got %d)", nseries);
+        return 1;
+    }
+
+    // ---- streaming kernel: default; a forced variant index >= kNumVariants selects one explicitly -------
+    // mode 0 (tiled CTAs) is the default: measured faster than the streaming form
+    const int mode = env_int("ACFB200_MODE", fv >= kNumVariants ? 1 : 0);
+    if (mode == 1) {
+        int best = -1;
+        double best_score = -1.0;
+        for (int v = 0; v < stream_variant_count(); ++v) {
+            if (fv >= kNumVariants && v != fv - kNumVariants) continue;
+            if (fv < kNumVariants && stream_variant_quality(v) < 0.96) continue;
+            const long long w = 32ll * stream_variant_rk(v);
+            const long long lb = (ncorr + w - 1) / w;
+            const double score = (double)ncorr / (double)(lb * w) * stream_variant_quality(v);
+            if (score > best_score) {
+                best_score = score;
+                best = v;
+            }
+        }
+        if (best < 0) {
+            set_error("plan_direct: no streaming variant matches ACFB200_VARIANT");
+            return 1;
+        }
+        DirectPlan p;
+        p.mode = 1;
+        p.variant = best;
+        p.rk = stream_variant_rk(best);
+        p.lk = 32;
+        p.pf = 1;
+        p.warps = 16;
+        p.ts = 0;
+        p.bsz = 0;
+        const long long w = 32ll * p.rk;
+        p.lag_tiles = (int)((ncorr + w - 1) / w);
+        p.mpad = (int)(p.lag_tiles * w);
+        // work units: ~`upw` units per resident warp so that the dynamic queue evens out the SMSPs' different
+        // speeds; never shorter than 2048 samples (the 32*rk-sample halo and the pipeline fill are per unit)
+        const int upw = fch > 0 ? 0 : env_int("ACFB200_UNITS_PER_WARP", 8);
+        const long long slots = (long long)sm_count * 16;
+        const long long groups = (long long)nseries * p.lag_tiles;
+        long long chunks = fch > 0 ? fch : (slots * upw + groups - 1) / groups;
+        if (chunks < 1) chunks = 1;
+        long long unit = (max_i_end + chunks - 1) / chunks;
+        if (fts > 0) unit = fts;
+        if (unit < 2048 && fts <= 0) unit = 2048;
+        const long long piece = stream_variant_piece(best);
+        unit = (unit + piece - 1) / piece * piece;
+        chunks = (max_i_end + unit - 1) / unit;
+        if (chunks < 1) chunks = 1;
+        p.ti = (int)unit;
+        p.chunks = (int)chunks;
+        p.smem_bytes = stream_smem_bytes();
+        *plan = p;
+        return 0;
+    }
 
     double best_score = -1.0;
     int best_v = 0, best_w = 4;
     for (int v = 0; v < kNumVariants; ++v) {
         if (fv >= 0 && v != fv) continue;
-        if (fv < 0 && kVariants[v].quality < 0.96) continue;  // tuning-only variants
+        if (fv < 0 && kVariants[v].quality < 0.95) continue;  // tuning-only variants
         const long long lkrk = (long long)kVariants[v].lk * kVariants[v].rk;
         const long long lb = (ncorr + lkrk - 1) / lkrk;
-        for (int w = 4; w <= kMaxWarps; w += 4) {
+        for (int w = 1; w <= kMaxWarps; w = (w < 4 ? w * 2 : w + 4)) {
             if (fw > 0 && w != fw) continue;
             const long long lt = (lb + w - 1) / w;
             const double useful = (double)ncorr / (double)(lt * w * lkrk);
-            // prefer 8 warps (two CTAs per SM overlap one's tile load with the other's math)
-            const double pref = (w == 8) ? 1.0 : (w == 4 ? 0.999 : (w == 16 ? 0.998 : 0.990));
-            const double score = useful * kVariants[v].quality * pref;
+            const double score = useful * kVariants[v].quality * warps_quality(w);
             if (score > best_score) {
                 best_score = score;
                 best_v = v;
@@ -301,6 +324,7 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
     }
     const Variant& V = kVariants[best_v];
     DirectPlan p;
+    p.mode = 0;
     p.variant = best_v;
     p.rk = V.rk;
     p.lk = V.lk;
@@ -346,10 +370,6 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
     if (fch > 0) chunks = fch;
     if (chunks < 1) chunks = 1;
     p.chunks = (int)chunks;
-    if (nseries > 65535) {
-        set_error("plan_direct: at most 65535 series per launch (got %d)", nseries);
-        return 1;
-    }
     *plan = p;
     return 0;
 }
@@ -360,8 +380,9 @@ size_t direct_partial_elems(const DirectPlan& p, int nseries)
 }
 
 int launch_direct(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
-                  double* d_partials, cudaStream_t st)
+                  double* d_partials, unsigned int* d_queue, int sm_count, cudaStream_t st)
 {
+    if (p.mode == 1) return launch_direct_stream(p, d_desc, nseries, ncorr, d_partials, d_queue, sm_count, st);
     const Variant& V = kVariants[p.variant];
     if (!g_attr_set[p.variant]) {
         ACF_CUDA_OK(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -30,6 +30,116 @@ __global__ void __launch_bounds__(512, 1) dfma_peak_kernel(double* out, int oute
     if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
 }
 
+// Probes of what limits the lag kernel's inner loop (tools/probe_dfma.py), not used for the roofline peak:
+//   PROBE 0: acc[j] = fma(a, w[j], acc[j])  -- three register operands per DFMA, only `a` reusable (the lag kernel's
+//            operand pattern) -- no loads
+//   PROBE 1: the same with one 16-byte shared-memory load per 18 DFMAs (the lag kernel's LDS:DFMA ratio)
+template <int PROBE>
+__global__ void __launch_bounds__(512, 1) dfma_probe_kernel(double* out, int outer, double a0)
+{
+    __shared__ double2 sh[512];
+    sh[threadIdx.x] = make_double2(1.0 + threadIdx.x * 1e-9, 1.0 - threadIdx.x * 1e-9);
+    __syncthreads();
+    double acc[18], w[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {
+        acc[j] = (double)(threadIdx.x + j);
+        w[j] = 1.0 + 1e-12 * (threadIdx.x + 3 * j);
+    }
+    double a = a0;
+    for (int o = 0; o < outer; ++o) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+#pragma unroll
+            for (int j = 0; j < 18; ++j) acc[j] = fma(a, w[j], acc[j]);
+            if (PROBE == 1) {          // 16-byte load, distinct address per lane (4 wavefronts)
+                const double2 v = sh[(threadIdx.x + r + o) & 511];
+                w[r % 18] = v.x;
+                a = v.y;
+            } else if (PROBE == 2) {   // 16-byte load, same address for the whole warp (broadcast)
+                const double2 v = sh[(r + o) & 511];
+                w[r % 18] = v.x;
+                a = v.y;
+            } else if (PROBE == 3) {   // 8-byte load, distinct addresses
+                const double v = reinterpret_cast<const double*>(sh)[(threadIdx.x + r + o) & 1023];
+                w[r % 18] = v;
+                a = a * 0.9999999;
+            } else if (PROBE == 4) {   // two 8-byte loads, distinct addresses
+                const double v = reinterpret_cast<const double*>(sh)[(threadIdx.x + r + o) & 1023];
+                const double v2 = reinterpret_cast<const double*>(sh)[(threadIdx.x + 2 * r + o + 37) & 1023];
+                w[r % 18] = v;
+                a = v2;
+            } else if (PROBE == 5) {   // 16-byte load whose result is not consumed by the DFMAs of this round
+                const double2 v = sh[(threadIdx.x + r + o) & 511];
+                w[(r + 9) % 18] = v.x + v.y;
+                a = a * 0.9999999;
+            } else if (PROBE == 6) {   // warp shuffle instead of a load (64-bit = 2 SHFL)
+                a = __shfl_sync(0xffffffffu, w[r % 18], (r + o) & 31);
+            } else {
+                a = a * 0.9999999;  // keeps `a` changing without a load (1 extra DMUL per 18 DFMA is counted)
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 18; ++j) s += acc[j];
+    if (s == 12345.678) out[0] = s;
+}
+
+int measure_dfma_probe(int probe, double* tflops)
+{
+    // probe = kind + 10 * (warps per SMSP: 1, 2 or 4; 0 = 4): one CTA per SM is forced with 200 KB of dynamic smem
+    const int wps = (probe / 10) ? (probe / 10) : 4;
+    probe %= 10;
+    const int threads = 128 * wps;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(dfma_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dfma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dfma_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dfma_probe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dfma_probe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dfma_probe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dfma_probe_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    int dev = 0, sms = 0;
+    ACF_CUDA_OK(cudaGetDevice(&dev));
+    ACF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* d_out = nullptr;
+    ACF_CUDA_OK(cudaMalloc(&d_out, 8));
+    cudaEvent_t e0, e1;
+    ACF_CUDA_OK(cudaEventCreate(&e0));
+    ACF_CUDA_OK(cudaEventCreate(&e1));
+    const int outer = 2000 * 4 / wps / 2, grid = sms * 2;
+    double best = 0.0;
+    for (int it = 0; it < 3; ++it) {
+        ACF_CUDA_OK(cudaEventRecord(e0));
+        switch (probe) {
+            case 0: dfma_probe_kernel<0><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+            case 1: dfma_probe_kernel<1><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+            case 2: dfma_probe_kernel<2><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+            case 3: dfma_probe_kernel<3><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+            case 4: dfma_probe_kernel<4><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+            case 5: dfma_probe_kernel<5><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+            default: dfma_probe_kernel<6><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+        }
+        ACF_CUDA_OK(cudaEventRecord(e1));
+        ACF_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        ACF_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        const double fmas = (double)grid * threads * outer * 32 * ((probe == 0 || probe == 3 || probe == 5) ? 19 : 18);
+        const double tf = 2.0 * fmas / (ms * 1e-3) / 1e12;
+        if (it > 0 && tf > best) best = tf;
+    }
+    ACF_CUDA_OK(cudaGetLastError());
+    if (tflops) *tflops = best;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return 0;
+}
+
 int measure_dfma_peak(double* tflops, double* sm_mhz_effective, int iters)
 {
     int dev = 0, sms = 0;

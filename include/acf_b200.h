@@ -164,6 +164,9 @@ ACFB200_API const char* acfb200_variant_name(int variant);
 /* FP64-pipe ceiling (pure DFMA chains) and STREAM-style copy bandwidth measured on the current device. */
 ACFB200_API int acfb200_measure_dfma_peak(double* tflops, double* effective_sm_mhz);
 ACFB200_API int acfb200_measure_hbm_copy(double* gb_per_s);
+/* Inner-loop probes (tuning aid): DFMA rate with the lag kernel's operand pattern, without (0) / with (1) its
+ * shared-memory load ratio. */
+ACFB200_API int acfb200_measure_dfma_probe(int probe, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -39,18 +39,38 @@ def _plan(acf, n, m, s=1):
     return {k: (float(v) if "." in v else v) for k, v in d.items()}
 
 
-@pytest.mark.parametrize("n,m,s", [(10**7, 10**4, 1), (10**6 - 2, 5000, 128), (10**8, 2 * 10**4, 3),
-                                   (4999, 1000, 2), (100, 7, 1), (50, 60, 1)])
-def test_planner_geometry(acf, n, m, s):
+SIZES = [(10**7, 10**4, 1), (10**6 - 2, 5000, 128), (10**8, 2 * 10**4, 3), (4999, 1000, 2), (100, 7, 1), (50, 60, 1)]
+
+
+@pytest.mark.parametrize("n,m,s", SIZES)
+def test_planner_geometry_streaming(acf, n, m, s):
+    """The per-warp streaming kernel (selectable): one 16-warp CTA per SM, work units of whole ~1 KB pieces."""
+    try:
+        acf.set_variant(acf.variants().index("stream_rk18_pf1"))
+        p = _plan(acf, n, m, s)
+    finally:
+        acf.set_variant(-1)
+    assert p["mode"] == "stream" and int(p["block"]) == 512
+    rk = int(p["variant"].split("_")[1][2:])
+    assert int(p["mpad"]) == int(p["lag_tiles"]) * 32 * rk >= m
+    assert int(p["ti"]) % 132 == 0 and int(p["ti"]) * int(p["chunks"]) >= n      # units tile the series
+    assert int(p["smem"]) <= 227 * 1024
+    if m >= 1000:
+        assert p["useful_lag_frac"] > 0.85
+
+
+@pytest.mark.parametrize("n,m,s", SIZES)
+def test_planner_geometry_tiled(acf, n, m, s):
+    """Default plan: the CTA-tiled kernel."""
     p = _plan(acf, n, m, s)
     warps, ti, bsz = int(p["warps"]), int(p["ti"]), int(p["bsz"])
-    assert warps in (4, 8, 12, 16) and int(p["block"]) == 32 * warps
-    assert int(p["mpad"]) >= m and int(p["lag_tiles"]) * (int(p["mpad"]) // int(p["lag_tiles"])) == int(p["mpad"])
+    assert p["mode"] == "tiled" and warps in (1, 2, 4, 8, 12, 16) and int(p["block"]) == 32 * warps
+    assert int(p["mpad"]) >= m
     assert int(p["smem"]) <= 227 * 1024 and int(p["smem"]) == (ti + bsz) * 8 + 16
     assert ti % 2 == 0 and bsz % 2 == 0  # 16-byte TMA bulk copies
     assert 1 <= int(p["chunks"]) <= 65535
     if m >= 1000:
-        assert p["useful_lag_frac"] > 0.85
+        assert p["useful_lag_frac"] > 0.97
 
 
 def test_no_cpu_fallback(acf):
