@@ -17,6 +17,7 @@
 //             -- fused, so the spectrum never goes to HBM in natural order and no transpose/bit-reversal pass exists
 //   col_pass  inverse step 2' and step 1' (fused: 1/Nc, /(n-k), only the first ncorr lags are written)
 // Algorithmic bytes: 8n + 8M + 8L*(2*passes - 2) with passes = number of factors > 1, counted per series.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace acfb200 {
@@ -281,6 +282,204 @@ col_pass_kernel(double2* __restrict__ data, const double* __restrict__ x, double
     }
 }
 
+// ---- column pass, pipelined form ---------------------------------------------------------------------------
+// Same transform and modes as col_pass_kernel, restructured after the first ncu pass over the FFT path
+// (profiles/r1_fft_launches.csv: every pass sat at 2-2.8 TB/s and ~1800 instructions per thread and tile -- issue
+// bound on index arithmetic, not on HBM or the FP64 pipe):
+//   * NB = 2^B and the tile width TC = 4096/NB are compile-time, so all tile/row/column arithmetic is shifts and
+//     masks in 32 bits (every twiddle exponent is < 2^28);
+//   * persistent CTAs (one per SM) walk their tiles; the butterfly twiddles W_NB^m sit in a shared-memory table built
+//     once per CTA, and all seven powers of a radix-8 twiddle are table look-ups instead of six complex multiplies;
+//   * the 8 inputs a thread needs for radix pass 1 of the NEXT tile are loaded from HBM into registers before the
+//     current tile is computed; radix pass 1 runs on registers and the last radix pass stores straight to HBM
+//     (inter-step twiddle / normalisation fused), so only the middle hand-offs go through shared memory.
+template <int MODE, int B>
+__global__ void __launch_bounds__(kColThreads, 1)
+col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, double* __restrict__ out, FftGeom G,
+                 int logC, int A, const double2* __restrict__ lo, const double2* __restrict__ hi)
+{
+    constexpr int DIR = (MODE <= 1) ? -1 : +1;
+    constexpr int NB = 1 << B;
+    constexpr int LTC = 12 - B, TC = 1 << LTC;     // tile = NB rows x TC columns = 4096 elements
+    constexpr int NB8 = NB >> 3;                   // radix-8 groups per column (>= 1)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* s = reinterpret_cast<double2*>(smem_raw);
+    double2* tw = s + NB * TC;                     // W_NB^m (conjugated for the inverse), m < NB
+    const int tid = threadIdx.x;
+    const int g = tid >> LTC, c = tid & (TC - 1);  // pass-1 role: group g of column c; NB8 * TC == 512 threads
+    const unsigned int tiles_c_log = logC - LTC;
+    unsigned int tiles = (unsigned int)A << tiles_c_log;
+    if (MODE == 3) {
+        // inverse step 1' (A == 1): columns beyond the last wanted lag produce nothing that is read
+        const long long need = (G.ncorr + 1) / 2;  // complex outputs j < need
+        if (need < (1ll << logC)) tiles = (unsigned int)((need + TC - 1) >> LTC);
+    }
+    const long long batch = blockIdx.y;
+    double2* bdata = data + batch * G.Nc;
+    const double* xs = (MODE == 0) ? x + batch * G.n : nullptr;
+    {
+        const unsigned int wstep = (unsigned int)(G.L >> B);   // W_NB = W_L^wstep
+        for (int m = tid; m < NB; m += kColThreads) {
+            const double2 w = tw_L(lo, hi, (unsigned long long)m * wstep);
+            tw[m] = DIR > 0 ? cconj(w) : w;
+        }
+    }
+    const unsigned int nc_mask = (unsigned int)(G.Nc - 1);
+
+    auto load_tile = [&](unsigned int tile, double2 (&v)[8]) {
+        const unsigned int a = tile >> tiles_c_log, c0 = (tile & ((1u << tiles_c_log) - 1)) << LTC;
+        if (MODE == 0) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const long long j = ((long long)(g + t * NB8) << logC) + c0 + c;   // complex index: samples 2j, 2j+1
+                double2 z = make_double2(0.0, 0.0);
+                if (2 * j + 1 < G.n)
+                    z = *reinterpret_cast<const double2*>(xs + 2 * j);
+                else if (2 * j < G.n)
+                    z.x = xs[2 * j];
+                v[t] = z;
+            }
+        } else {
+            const double2* base = bdata + (((size_t)a << B) << logC) + c0 + c;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = base[(size_t)(g + t * NB8) << logC];
+        }
+    };
+
+    // one output of the last radix pass: index kb along this axis, column cc of slab a
+    auto store_out = [&](unsigned int a, unsigned int cc, unsigned int kb, double2 v) {
+        if (MODE == 3) {
+            double* o = out + batch * G.ncorr;
+            const long long j = ((long long)kb << logC) + cc;
+            const double inv_nc = 1.0 / (double)G.Nc;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long k = 2 * j + h;
+                if (k < G.ncorr) {
+                    const long long m = G.n - k;
+                    double val = (h ? v.y : v.x) * inv_nc;
+                    if (m > 0)
+                        val = val / (double)m;
+                    else if (m == 0)
+                        val = __longlong_as_double(0xFFF8000000000000ull);  // reference: 0/0
+                    else
+                        val = -0.0;                                          // reference: 0/negative
+                    o[k] = val;
+                }
+            }
+            return;
+        }
+        unsigned int e;  // exponent of W_Nc, all products < 2^28
+        if (MODE == 0)
+            e = kb * cc;
+        else if (MODE == 1)
+            e = (kb << G.b1) * cc;
+        else
+            e = ((kb << logC) + cc) * a;
+        e &= nc_mask;
+        if (e) {
+            const double2 t = tw_L(lo, hi, 2ull * e);  // W_Nc = W_L^2
+            v = cmul(v, DIR > 0 ? cconj(t) : t);
+        }
+        bdata[(((size_t)a << B) << logC) + ((size_t)kb << logC) + cc] = v;
+    };
+
+    double2 nxt[8];
+    unsigned int tile = blockIdx.x;
+    if (tile < tiles) load_tile(tile, nxt);
+    __syncthreads();  // twiddle table ready
+    for (; tile < tiles; tile += gridDim.x) {
+        const unsigned int a = tile >> tiles_c_log, c0 = (tile & ((1u << tiles_c_log) - 1)) << LTC;
+        double2 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = nxt[t];
+        if (tile + gridDim.x < tiles) load_tile(tile + gridDim.x, nxt);   // in flight during the math below
+
+        // ---- radix pass 1 (Stockham stride 1, p = g) on registers
+        dft8<DIR>(v);
+        if (g != 0) {
+#pragma unroll
+            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], tw[g * u]);
+        }
+        if (B == 3) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) store_out(a, c0 + c, u, v[u]);
+            continue;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[((8 * g + u) << LTC) + c] = v[u];
+        __syncthreads();
+
+        // ---- middle radix-8 pass (stride 8) through shared memory, only for NB >= 128
+        if (B > 6) {
+            double2 r[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) r[t] = s[((g + t * NB8) << LTC) + c];
+            __syncthreads();
+            dft8<DIR>(r);
+            const int qq = g & 7, ps = g - qq;
+            if (ps != 0) {
+#pragma unroll
+                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], tw[ps * u]);
+            }
+            const int base = qq + ps * 8;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[((base + 8 * u) << LTC) + c] = r[u];
+            __syncthreads();
+        }
+
+        // ---- last pass: shared memory -> registers -> HBM
+        {
+            constexpr int LEFT = (B > 6) ? B - 6 : B - 3;   // log2 of the last radix: 1, 2 or 3
+            constexpr int STRIDE = (B > 6) ? 64 : 8;
+            constexpr int R = 1 << LEFT, GPT = 8 / R;
+            constexpr int GROUPS = NB / R;                   // per column
+#pragma unroll
+            for (int it = 0; it < GPT; ++it) {
+                const int w = tid + it * kColThreads;        // GROUPS * TC == GPT * 512
+                const int gg = w >> LTC, cc = w & (TC - 1);
+                double2 r[8];
+#pragma unroll
+                for (int t = 0; t < R; ++t) r[t] = s[((gg + t * GROUPS) << LTC) + cc];
+                if (LEFT == 3)
+                    dft8<DIR>(r);
+                else if (LEFT == 2)
+                    dft4<DIR>(r);
+                else
+                    dft2(r);
+                const int qq = gg & (STRIDE - 1), ps = gg - qq;
+                if (ps != 0) {
+#pragma unroll
+                    for (int u = 1; u < R; ++u) r[u] = cmul(r[u], tw[ps * u]);
+                }
+                const int base = qq + ps * R;
+#pragma unroll
+                for (int u = 0; u < R; ++u) store_out(a, c0 + cc, base + STRIDE * u, r[u]);
+            }
+        }
+        __syncthreads();  // the next tile's pass 1 overwrites the tile
+    }
+}
+
+typedef void (*col2_fn)(double2*, const double*, double*, FftGeom, int, int, const double2*, const double2*);
+template <int MODE>
+static col2_fn col2_for(int b)
+{
+    switch (b) {
+        case 3: return col_pass2_kernel<MODE, 3>;
+        case 4: return col_pass2_kernel<MODE, 4>;
+        case 5: return col_pass2_kernel<MODE, 5>;
+        case 6: return col_pass2_kernel<MODE, 6>;
+        case 7: return col_pass2_kernel<MODE, 7>;
+        case 8: return col_pass2_kernel<MODE, 8>;
+        default: return col_pass2_kernel<MODE, 9>;
+    }
+}
+static col2_fn col2_select(int mode, int b)
+{
+    return mode == 0 ? col2_for<0>(b) : mode == 1 ? col2_for<1>(b) : mode == 2 ? col2_for<2>(b) : col2_for<3>(b);
+}
+
 // ---- fused row pass: forward step 3, |X|^2 pair operation with the mirror row, inverse step 3' ------------
 // Rows are indexed by (k1, k2); a row holds k3 = 0..N3-1 contiguously.  The mirror of spectrum index k is Nc-k:
 //   k1 != 0:             (N1-k1, N2-1-k2),  column N3-1-k3
@@ -392,6 +591,231 @@ row_pass_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict
         double2 v = s[w];
         if (e) v = cmul(v, cconj(tw_L(lo, hi, 2ull * e)));
         (col == 0 ? ga : gb)[j3] = v;
+    }
+}
+
+// ---- fused row pass, pipelined form --------------------------------------------------------------------------
+// Same mathematics as row_pass_kernel (forward axis-3 transform of a row and of its mirror row Nc-k, |X|^2 pair
+// operation, inverse axis-3 transform, post twiddle), restructured like col_pass2_kernel: persistent 512-thread CTAs,
+// a 4096-element tile = 4096/N3 rows kept as (row, mirror) pairs in adjacent slots, compile-time N3, butterfly
+// twiddles from a shared-memory table, next tile prefetched into registers, first forward / last inverse radix pass
+// on registers.  Each row thread evaluates the pair formula for its own 8 spectrum points (the mirror thread
+// evaluates it again from its side) so that the inverse transform starts from registers without another exchange.
+// Work list: one entry per unordered row pair {(k1,k2), mirror}; self-mirrored rows fill both slots of their pair.
+template <int B3>
+__global__ void __launch_bounds__(kColThreads, 1)
+row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict__ lo, const double2* __restrict__ hi)
+{
+    constexpr int N3 = 1 << B3;
+    constexpr int G8 = N3 >> 3;                       // radix-8 groups per row
+    constexpr int LG8 = B3 - 3;
+    constexpr int ROWS = 4096 >> B3, PAIRS = ROWS / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* s = reinterpret_cast<double2*>(smem_raw);
+    double2* twf = s + 4096;                          // W_N3^m
+    const int tid = threadIdx.x;
+    const int rs = tid >> LG8, g = tid & (G8 - 1);    // row slot, radix group
+    double2* row_s = s + (rs << B3);
+    const double2* mir_s = s + ((rs ^ 1) << B3);
+    const unsigned int N1 = 1u << G.b1, N2 = 1u << G.b2;
+    // pair list: k1 = 0 -> k2 in [0, N2/2];  0 < k1 < N1/2 -> every k2;  k1 = N1/2 -> k2 in [0, max(N2/2,1))
+    const unsigned int cnt0 = N2 / 2 + 1, cntm = (N1 / 2 - 1) * N2, cnth = N2 >= 2 ? N2 / 2 : 1;
+    const unsigned int npairs = cnt0 + cntm + cnth;
+    const unsigned int ntiles = (npairs + PAIRS - 1) / PAIRS;
+    double2* bdata = data + (long long)blockIdx.y * G.Nc;
+    {
+        const unsigned int wstep = (unsigned int)(G.L >> B3);
+        for (int m = tid; m < N3; m += kColThreads) twf[m] = tw_L(lo, hi, (unsigned long long)m * wstep);
+    }
+    const unsigned int nc_mask = (unsigned int)(G.Nc - 1);
+    const int shift12 = G.b1 + G.b2;
+
+    // digits (k1, k2) of the row held by slot `rs` of tile `tile`; false past the end of the list
+    auto slot_row = [&](unsigned int tile, unsigned int& r1, unsigned int& r2, bool& origin) -> bool {
+        const unsigned int pidx = tile * PAIRS + (rs >> 1);
+        if (pidx >= npairs) return false;
+        unsigned int k1, k2;
+        if (pidx < cnt0) {
+            k1 = 0;
+            k2 = pidx;
+        } else if (pidx < cnt0 + cntm) {
+            const unsigned int t = pidx - cnt0;
+            k1 = 1 + (t >> G.b2);
+            k2 = t & (N2 - 1);
+        } else {
+            k1 = N1 / 2;
+            k2 = pidx - cnt0 - cntm;
+        }
+        origin = (k1 == 0 && k2 == 0);
+        if (rs & 1) {  // mirror row
+            if (k1 != 0) {
+                r1 = N1 - k1;
+                r2 = N2 - 1 - k2;
+            } else {
+                r1 = 0;
+                r2 = (N2 - k2) & (N2 - 1);
+            }
+        } else {
+            r1 = k1;
+            r2 = k2;
+        }
+        return true;
+    };
+    auto load_row = [&](unsigned int tile, double2 (&v)[8]) {
+        unsigned int r1, r2;
+        bool origin;
+        if (slot_row(tile, r1, r2, origin)) {
+            const double2* src = bdata + ((size_t)((r1 << G.b2) + r2) << B3) + g;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = src[t * G8];
+        }
+    };
+    auto sw = [](int i) { return i ^ ((i >> 3) & 7); };
+
+    double2 nxt[8];
+    unsigned int tile = blockIdx.x;
+    if (tile < ntiles) load_row(tile, nxt);
+    __syncthreads();
+    for (; tile < ntiles; tile += gridDim.x) {
+        unsigned int r1 = 0, r2 = 0;
+        bool origin = false;
+        const bool valid = slot_row(tile, r1, r2, origin);
+        double2 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = valid ? nxt[t] : make_double2(0.0, 0.0);
+        if (tile + gridDim.x < ntiles) load_row(tile + gridDim.x, nxt);
+
+        // ================= forward transform along the row (DIR = -1) =================
+        dft8<-1>(v);
+        if (g != 0) {
+#pragma unroll
+            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], twf[g * u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) row_s[sw(8 * g + u)] = v[u];
+        __syncthreads();
+        {   // middle pass: radix 8, stride 8
+            double2 r[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) r[t] = row_s[sw(g + t * G8)];
+            __syncthreads();
+            dft8<-1>(r);
+            const int qq = g & 7, ps = g - qq;
+            if (ps != 0) {
+#pragma unroll
+                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], twf[ps * u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) row_s[sw(qq + ps * 8 + 8 * u)] = r[u];
+            __syncthreads();
+        }
+        {   // last forward pass: radix 2^(B3-6), stride 64, back to shared memory in natural order
+            constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
+            double2 r[8];
+#pragma unroll
+            for (int it = 0; it < GPT; ++it) {
+                const int gg = g + it * G8;
+#pragma unroll
+                for (int t = 0; t < R; ++t) r[it * R + t] = row_s[sw(gg + t * GROUPS)];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < GPT; ++it) {
+                const int gg = g + it * G8;
+                if (LEFT == 3)
+                    dft8<-1>(r + it * R);
+                else if (LEFT == 2)
+                    dft4<-1>(r + it * R);
+                else
+                    dft2(r + it * R);
+                const int qq = gg & 63, ps = gg - qq;
+                if (ps != 0) {
+#pragma unroll
+                    for (int u = 1; u < R; ++u) r[it * R + u] = cmul(r[it * R + u], twf[ps * u]);
+                }
+#pragma unroll
+                for (int u = 0; u < R; ++u) row_s[sw(qq + ps * R + 64 * u)] = r[it * R + u];
+            }
+            __syncthreads();
+        }
+
+        // ================= |X|^2 pair operation for this thread's 8 spectrum points =================
+        const unsigned int kbase = r1 + (r2 << G.b1);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int k3 = g + t * G8;
+            const int p3 = origin ? ((N3 - k3) & (N3 - 1)) : (N3 - 1 - k3);
+            const double2 Za = row_s[sw(k3)];
+            const double2 Zb = mir_s[sw(p3)];
+            const double2 W = tw_L(lo, hi, (unsigned long long)(kbase + ((unsigned int)k3 << shift12)));
+            const double2 S = make_double2(Za.x + Zb.x, Za.y - Zb.y);   // Za + conj Zb
+            const double2 D = make_double2(Za.x - Zb.x, Za.y + Zb.y);   // Za - conj Zb
+            const double2 WD = cmul(W, D);
+            const double2 Xa = make_double2(0.5 * (S.x + WD.y), 0.5 * (S.y - WD.x));
+            const double2 Xb = make_double2(0.5 * (S.x - WD.y), 0.5 * (-S.y - WD.x));
+            const double Pa = Xa.x * Xa.x + Xa.y * Xa.y;
+            const double Pb = Xb.x * Xb.x + Xb.y * Xb.y;
+            const double hs = 0.5 * (Pa + Pb), hd = 0.5 * (Pa - Pb);
+            v[t] = make_double2(hs + W.y * hd, W.x * hd);               // Z'[k] = hs + i conj(W) hd
+        }
+        __syncthreads();  // every thread has read both rows before they are overwritten
+
+        // ================= inverse transform along the row (DIR = +1, conjugated table) =================
+        dft8<+1>(v);
+        if (g != 0) {
+#pragma unroll
+            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], cconj(twf[g * u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) row_s[sw(8 * g + u)] = v[u];
+        __syncthreads();
+        {
+            double2 r[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) r[t] = row_s[sw(g + t * G8)];
+            __syncthreads();
+            dft8<+1>(r);
+            const int qq = g & 7, ps = g - qq;
+            if (ps != 0) {
+#pragma unroll
+                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], cconj(twf[ps * u]));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) row_s[sw(qq + ps * 8 + 8 * u)] = r[u];
+            __syncthreads();
+        }
+        {   // last inverse pass -> post twiddle conj(W_Nc^{j3 * f}) -> HBM
+            constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
+            const unsigned int f = (G.b2 > 0) ? (r2 << G.b1) : r1;
+            double2* dst = bdata + ((size_t)((r1 << G.b2) + r2) << B3);
+#pragma unroll
+            for (int it = 0; it < GPT; ++it) {
+                const int gg = g + it * G8;
+                double2 r[8];
+#pragma unroll
+                for (int t = 0; t < R; ++t) r[t] = row_s[sw(gg + t * GROUPS)];
+                if (LEFT == 3)
+                    dft8<+1>(r);
+                else if (LEFT == 2)
+                    dft4<+1>(r);
+                else
+                    dft2(r);
+                const int qq = gg & 63, ps = gg - qq;
+                if (ps != 0) {
+#pragma unroll
+                    for (int u = 1; u < R; ++u) r[u] = cmul(r[u], cconj(twf[ps * u]));
+                }
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    const unsigned int j3 = qq + ps * R + 64 * u;
+                    const unsigned int e = (j3 * f) & nc_mask;
+                    double2 o = r[u];
+                    if (e) o = cmul(o, cconj(tw_L(lo, hi, 2ull * e)));
+                    if (valid) dst[j3] = o;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -507,9 +931,26 @@ int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_ou
         cudaFuncSetAttribute(col_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 512) * 16);
+        for (int mode = 0; mode < 4; ++mode)
+            for (int bb = 3; bb <= 9; ++bb)
+                cudaFuncSetAttribute(col2_select(mode, bb), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (kTileElems + 512) * 16);
         attr = true;
     }
     const long long N1 = 1ll << g.b1, N2 = 1ll << g.b2, N3 = 1ll << g.b3;
+    const char* env = getenv("ACFB200_FFT_PIPELINED");
+    bool pipelined = !(env && env[0] == '0');
+    // the pipelined kernels use fixed 4096-element tiles: every pass must offer at least one full tile width
+    if (g.b1 > 0 && g.b2 + g.b3 < 12 - g.b1) pipelined = false;
+    if (g.b2 > 0 && g.b3 < 12 - g.b2) pipelined = false;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto pgrid = [sms](long long tiles) { return (unsigned)(tiles < sms ? tiles : sms); };
+    const size_t smem2 = (size_t)(kTileElems + 512) * 16;
     auto tc_for = [](int b, long long C) {
         long long tc = kTileElems >> b;
         if (tc > C) tc = C;
@@ -518,8 +959,12 @@ int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_ou
     if (g.b1 > 0) {
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
-        col_pass_kernel<0><<<dim3((unsigned)(C / TC), 1, 1), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
-            data, d_x, nullptr, g, g.b1, C, TC, lo, hi);
+        if (pipelined)
+            col2_select(0, g.b1)<<<dim3(pgrid(C >> (12 - g.b1)), 1, 1), kColThreads, smem2, st>>>(
+                data, d_x, nullptr, g, g.b2 + g.b3, 1, lo, hi);
+        else
+            col_pass_kernel<0><<<dim3((unsigned)(C / TC), 1, 1), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
+                data, d_x, nullptr, g, g.b1, C, TC, lo, hi);
         ++launches;
     } else {
         fft_pack_kernel<<<dim3((unsigned)((g.Nc + 255) / 256), 1), 256, 0, st>>>(d_x, data, g);
@@ -527,11 +972,24 @@ int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_ou
     }
     if (g.b2 > 0) {
         const int TC = tc_for(g.b2, N3);
-        col_pass_kernel<1><<<dim3((unsigned)(N3 / TC), (unsigned)N1, 1), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
-            data, nullptr, nullptr, g, g.b2, N3, TC, lo, hi);
+        if (pipelined)
+            col2_select(1, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), 1, 1), kColThreads, smem2, st>>>(
+                data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
+        else
+            col_pass_kernel<1><<<dim3((unsigned)(N3 / TC), (unsigned)N1, 1), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
+                data, nullptr, nullptr, g, g.b2, N3, TC, lo, hi);
         ++launches;
     }
-    {
+    if (pipelined && g.b1 > 0 && g.b3 >= 7) {
+        const size_t smem = (size_t)(4096 + N3) * 16;
+        if (g.b3 == 9)
+            row_pass2_kernel<9><<<dim3(sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+        else if (g.b3 == 8)
+            row_pass2_kernel<8><<<dim3(sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+        else
+            row_pass2_kernel<7><<<dim3(sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+        ++launches;
+    } else {
         int threads = (int)(N3 / 8) * 2;
         if (threads < 32) threads = 32;
         if (threads > 256) threads = 256;
@@ -540,15 +998,23 @@ int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_ou
     }
     if (g.b2 > 0) {
         const int TC = tc_for(g.b2, N3);
-        col_pass_kernel<2><<<dim3((unsigned)(N3 / TC), (unsigned)N1, 1), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
-            data, nullptr, nullptr, g, g.b2, N3, TC, lo, hi);
+        if (pipelined)
+            col2_select(2, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), 1, 1), kColThreads, smem2, st>>>(
+                data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
+        else
+            col_pass_kernel<2><<<dim3((unsigned)(N3 / TC), (unsigned)N1, 1), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
+                data, nullptr, nullptr, g, g.b2, N3, TC, lo, hi);
         ++launches;
     }
     if (g.b1 > 0) {
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
-        col_pass_kernel<3><<<dim3((unsigned)(C / TC), 1, 1), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
-            data, nullptr, d_out, g, g.b1, C, TC, lo, hi);
+        if (pipelined)
+            col2_select(3, g.b1)<<<dim3(pgrid(C >> (12 - g.b1)), 1, 1), kColThreads, smem2, st>>>(
+                data, nullptr, d_out, g, g.b2 + g.b3, 1, lo, hi);
+        else
+            col_pass_kernel<3><<<dim3((unsigned)(C / TC), 1, 1), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
+                data, nullptr, d_out, g, g.b1, C, TC, lo, hi);
         ++launches;
     } else {
         fft_finish_kernel<<<dim3((unsigned)((g.Nc + 255) / 256), 1), 256, 0, st>>>(data, d_out, g);
