@@ -346,42 +346,56 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
         }
     };
 
-    // one output of the last radix pass: index kb along this axis, column cc of slab a
-    auto store_out = [&](unsigned int a, unsigned int cc, unsigned int kb, double2 v) {
+    // The R outputs of one last-pass group: indices kb_u = base + stride*u along this axis, column cc of slab a.
+    // Their inter-step twiddles W_Nc^{e_u} have exponents in arithmetic progression (e_u = e_0 + u*de), so two
+    // table look-ups (W^{e_0}, W^{de}) and R-1 complex multiplies replace R look-ups: the look-ups are L2-latency
+    // loads and were the top stall of the first version (profiles/r1_fft_ncu.md).
+    auto store_group = [&](unsigned int a, unsigned int cc, unsigned int base, unsigned int stride, int R, double2* r) {
         if (MODE == 3) {
             double* o = out + batch * G.ncorr;
-            const long long j = ((long long)kb << logC) + cc;
             const double inv_nc = 1.0 / (double)G.Nc;
+            for (int u = 0; u < R; ++u) {
+                const long long j = ((long long)(base + stride * u) << logC) + cc;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const long long k = 2 * j + h;
-                if (k < G.ncorr) {
-                    const long long m = G.n - k;
-                    double val = (h ? v.y : v.x) * inv_nc;
-                    if (m > 0)
-                        val = val / (double)m;
-                    else if (m == 0)
-                        val = __longlong_as_double(0xFFF8000000000000ull);  // reference: 0/0
-                    else
-                        val = -0.0;                                          // reference: 0/negative
-                    o[k] = val;
+                for (int h = 0; h < 2; ++h) {
+                    const long long k = 2 * j + h;
+                    if (k < G.ncorr) {
+                        const long long m = G.n - k;
+                        double val = (h ? r[u].y : r[u].x) * inv_nc;
+                        if (m > 0)
+                            val = val / (double)m;
+                        else if (m == 0)
+                            val = __longlong_as_double(0xFFF8000000000000ull);  // reference: 0/0
+                        else
+                            val = -0.0;                                          // reference: 0/negative
+                        o[k] = val;
+                    }
                 }
             }
             return;
         }
-        unsigned int e;  // exponent of W_Nc, all products < 2^28
-        if (MODE == 0)
-            e = kb * cc;
-        else if (MODE == 1)
-            e = (kb << G.b1) * cc;
-        else
-            e = ((kb << logC) + cc) * a;
-        e &= nc_mask;
-        if (e) {
-            const double2 t = tw_L(lo, hi, 2ull * e);  // W_Nc = W_L^2
-            v = cmul(v, DIR > 0 ? cconj(t) : t);
+        unsigned int e0, de;  // exponents of W_Nc; every product stays below 2^28
+        if (MODE == 0) {
+            e0 = base * cc;
+            de = stride * cc;
+        } else if (MODE == 1) {
+            e0 = (base << G.b1) * cc;
+            de = (stride << G.b1) * cc;
+        } else {
+            e0 = ((base << logC) + cc) * a;
+            de = (stride << logC) * a;
         }
-        bdata[(((size_t)a << B) << logC) + ((size_t)kb << logC) + cc] = v;
+        double2 t = tw_L(lo, hi, 2ull * (e0 & nc_mask));  // W_Nc = W_L^2
+        double2 d = tw_L(lo, hi, 2ull * (de & nc_mask));
+        if (DIR > 0) {
+            t = cconj(t);
+            d = cconj(d);
+        }
+        double2* dst = bdata + (((size_t)a << B) << logC) + cc;
+        for (int u = 0; u < R; ++u) {
+            dst[(size_t)(base + stride * u) << logC] = cmul(r[u], t);
+            t = cmul(t, d);
+        }
     };
 
     double2 nxt[8];
@@ -402,8 +416,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], tw[g * u]);
         }
         if (B == 3) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) store_out(a, c0 + c, u, v[u]);
+            store_group(a, c0 + c, 0, 1, 8, v);
             continue;
         }
 #pragma unroll
@@ -452,9 +465,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
 #pragma unroll
                     for (int u = 1; u < R; ++u) r[u] = cmul(r[u], tw[ps * u]);
                 }
-                const int base = qq + ps * R;
-#pragma unroll
-                for (int u = 0; u < R; ++u) store_out(a, c0 + cc, base + STRIDE * u, r[u]);
+                store_group(a, c0 + cc, qq + ps * R, STRIDE, R, r);
             }
         }
         __syncthreads();  // the next tile's pass 1 overwrites the tile
@@ -740,14 +751,16 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         }
 
         // ================= |X|^2 pair operation for this thread's 8 spectrum points =================
+        // W_L^k for k = kbase + N1*N2*(g + t*N3/8): successive t differ by W_L^{Nc/8} = exp(-i pi/8), a constant
         const unsigned int kbase = r1 + (r2 << G.b1);
+        double2 W = tw_L(lo, hi, (unsigned long long)(kbase + ((unsigned int)g << shift12)));
+        const double2 rot = make_double2(0.92387953251128675613, -0.38268343236508977173);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             const int k3 = g + t * G8;
             const int p3 = origin ? ((N3 - k3) & (N3 - 1)) : (N3 - 1 - k3);
             const double2 Za = row_s[sw(k3)];
             const double2 Zb = mir_s[sw(p3)];
-            const double2 W = tw_L(lo, hi, (unsigned long long)(kbase + ((unsigned int)k3 << shift12)));
             const double2 S = make_double2(Za.x + Zb.x, Za.y - Zb.y);   // Za + conj Zb
             const double2 D = make_double2(Za.x - Zb.x, Za.y + Zb.y);   // Za - conj Zb
             const double2 WD = cmul(W, D);
@@ -757,6 +770,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             const double Pb = Xb.x * Xb.x + Xb.y * Xb.y;
             const double hs = 0.5 * (Pa + Pb), hd = 0.5 * (Pa - Pb);
             v[t] = make_double2(hs + W.y * hd, W.x * hd);               // Z'[k] = hs + i conj(W) hd
+            W = cmul(W, rot);
         }
         __syncthreads();  // every thread has read both rows before they are overwritten
 
@@ -805,13 +819,14 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
 #pragma unroll
                     for (int u = 1; u < R; ++u) r[u] = cmul(r[u], cconj(twf[ps * u]));
                 }
+                // post twiddle conj(W_Nc^{j3*f}), j3 = j0 + 64u: exponents in arithmetic progression
+                const unsigned int j0 = qq + ps * R;
+                double2 tq = cconj(tw_L(lo, hi, 2ull * ((j0 * f) & nc_mask)));
+                const double2 dq = cconj(tw_L(lo, hi, 2ull * ((64u * f) & nc_mask)));
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
-                    const unsigned int j3 = qq + ps * R + 64 * u;
-                    const unsigned int e = (j3 * f) & nc_mask;
-                    double2 o = r[u];
-                    if (e) o = cmul(o, cconj(tw_L(lo, hi, 2ull * e)));
-                    if (valid) dst[j3] = o;
+                    if (valid) dst[j0 + 64 * u] = cmul(r[u], tq);
+                    tq = cmul(tq, dq);
                 }
             }
         }
