@@ -317,10 +317,21 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     const long long batch = blockIdx.y;
     double2* bdata = data + batch * G.Nc;
     const double* xs = (MODE == 0) ? x + batch * G.n : nullptr;
+    // butterfly twiddles, laid out so that a warp reads consecutive entries (no bank conflicts):
+    //   tw[(u-1)*NB8 + g]            = W_NB^{g*u}     pass 1 (Stockham stride 1, p = g)
+    //   tw2[(u-1)*(NB8/8) + p]       = W_NB^{8*p*u}   middle pass (stride 8, p = g >> 3)
+    // the last pass of a Stockham transform has p = 0: no twiddles
+    double2* tw2 = tw + 7 * NB8;
     {
         const unsigned int wstep = (unsigned int)(G.L >> B);   // W_NB = W_L^wstep
-        for (int m = tid; m < NB; m += kColThreads) {
-            const double2 w = tw_L(lo, hi, (unsigned long long)m * wstep);
+        for (int m = tid; m < 7 * NB8 + 7 * (NB8 / 8); m += kColThreads) {
+            unsigned int e;
+            if (m < 7 * NB8)
+                e = (unsigned int)(m % NB8) * (unsigned int)(m / NB8 + 1);
+            else
+                e = 8u * (unsigned int)((m - 7 * NB8) % (NB8 / 8 > 0 ? NB8 / 8 : 1)) *
+                    (unsigned int)((m - 7 * NB8) / (NB8 / 8 > 0 ? NB8 / 8 : 1) + 1);
+            const double2 w = tw_L(lo, hi, (unsigned long long)e * wstep);
             tw[m] = DIR > 0 ? cconj(w) : w;
         }
     }
@@ -413,7 +424,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
         dft8<DIR>(v);
         if (g != 0) {
 #pragma unroll
-            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], tw[g * u]);
+            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], tw[(u - 1) * NB8 + g]);
         }
         if (B == 3) {
             store_group(a, c0 + c, 0, 1, 8, v);
@@ -433,7 +444,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             const int qq = g & 7, ps = g - qq;
             if (ps != 0) {
 #pragma unroll
-                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], tw[ps * u]);
+                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], tw2[(u - 1) * (NB8 / 8) + (g >> 3)]);
             }
             const int base = qq + ps * 8;
 #pragma unroll
@@ -460,12 +471,8 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
                     dft4<DIR>(r);
                 else
                     dft2(r);
-                const int qq = gg & (STRIDE - 1), ps = gg - qq;
-                if (ps != 0) {
-#pragma unroll
-                    for (int u = 1; u < R; ++u) r[u] = cmul(r[u], tw[ps * u]);
-                }
-                store_group(a, c0 + cc, qq + ps * R, STRIDE, R, r);
+                static_assert(GROUPS <= STRIDE, "last Stockham pass: p == 0, no twiddles");
+                store_group(a, c0 + cc, gg, STRIDE, R, r);
             }
         }
         __syncthreads();  // the next tile's pass 1 overwrites the tile
@@ -614,7 +621,7 @@ row_pass_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict
 // evaluates it again from its side) so that the inverse transform starts from registers without another exchange.
 // Work list: one entry per unordered row pair {(k1,k2), mirror}; self-mirrored rows fill both slots of their pair.
 template <int B3>
-__global__ void __launch_bounds__(kColThreads, 1)
+__global__ void __launch_bounds__(kColThreads, 2)
 row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict__ lo, const double2* __restrict__ hi)
 {
     constexpr int N3 = 1 << B3;
@@ -634,9 +641,18 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     const unsigned int npairs = cnt0 + cntm + cnth;
     const unsigned int ntiles = (npairs + PAIRS - 1) / PAIRS;
     double2* bdata = data + (long long)blockIdx.y * G.Nc;
+    // butterfly twiddles in warp-contiguous layout: twf[(u-1)*G8 + g] = W_N3^{g*u}, twm[(u-1)*(G8/8) + p] = W_N3^{8pu}
+    double2* twm = twf + 7 * G8;
     {
         const unsigned int wstep = (unsigned int)(G.L >> B3);
-        for (int m = tid; m < N3; m += kColThreads) twf[m] = tw_L(lo, hi, (unsigned long long)m * wstep);
+        for (int m = tid; m < 7 * G8 + 7 * (G8 / 8); m += kColThreads) {
+            unsigned int e;
+            if (m < 7 * G8)
+                e = (unsigned int)(m % G8) * (unsigned int)(m / G8 + 1);
+            else
+                e = 8u * (unsigned int)((m - 7 * G8) % (G8 / 8)) * (unsigned int)((m - 7 * G8) / (G8 / 8) + 1);
+            twf[m] = tw_L(lo, hi, (unsigned long long)e * wstep);
+        }
     }
     const unsigned int nc_mask = (unsigned int)(G.Nc - 1);
     const int shift12 = G.b1 + G.b2;
@@ -683,24 +699,22 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     };
     auto sw = [](int i) { return i ^ ((i >> 3) & 7); };
 
-    double2 nxt[8];
-    unsigned int tile = blockIdx.x;
-    if (tile < ntiles) load_row(tile, nxt);
+    // two CTAs per SM (<= 64 registers/thread): one loads its next tile while the other transforms
     __syncthreads();
-    for (; tile < ntiles; tile += gridDim.x) {
+    for (unsigned int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         unsigned int r1 = 0, r2 = 0;
         bool origin = false;
         const bool valid = slot_row(tile, r1, r2, origin);
         double2 v[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = valid ? nxt[t] : make_double2(0.0, 0.0);
-        if (tile + gridDim.x < ntiles) load_row(tile + gridDim.x, nxt);
+        for (int t = 0; t < 8; ++t) v[t] = make_double2(0.0, 0.0);
+        load_row(tile, v);
 
         // ================= forward transform along the row (DIR = -1) =================
         dft8<-1>(v);
         if (g != 0) {
 #pragma unroll
-            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], twf[g * u]);
+            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], twf[(u - 1) * G8 + g]);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) row_s[sw(8 * g + u)] = v[u];
@@ -714,7 +728,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             const int qq = g & 7, ps = g - qq;
             if (ps != 0) {
 #pragma unroll
-                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], twf[ps * u]);
+                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], twm[(u - 1) * (G8 / 8) + (g >> 3)]);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) row_s[sw(qq + ps * 8 + 8 * u)] = r[u];
@@ -739,13 +753,9 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                     dft4<-1>(r + it * R);
                 else
                     dft2(r + it * R);
-                const int qq = gg & 63, ps = gg - qq;
-                if (ps != 0) {
+                static_assert(GROUPS == 64, "last Stockham pass: p == 0, no twiddles");
 #pragma unroll
-                    for (int u = 1; u < R; ++u) r[it * R + u] = cmul(r[it * R + u], twf[ps * u]);
-                }
-#pragma unroll
-                for (int u = 0; u < R; ++u) row_s[sw(qq + ps * R + 64 * u)] = r[it * R + u];
+                for (int u = 0; u < R; ++u) row_s[sw(gg + 64 * u)] = r[it * R + u];
             }
             __syncthreads();
         }
@@ -778,7 +788,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         dft8<+1>(v);
         if (g != 0) {
 #pragma unroll
-            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], cconj(twf[g * u]));
+            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], cconj(twf[(u - 1) * G8 + g]));
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) row_s[sw(8 * g + u)] = v[u];
@@ -792,7 +802,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             const int qq = g & 7, ps = g - qq;
             if (ps != 0) {
 #pragma unroll
-                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], cconj(twf[ps * u]));
+                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], cconj(twm[(u - 1) * (G8 / 8) + (g >> 3)]));
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) row_s[sw(qq + ps * 8 + 8 * u)] = r[u];
@@ -814,13 +824,8 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                     dft4<+1>(r);
                 else
                     dft2(r);
-                const int qq = gg & 63, ps = gg - qq;
-                if (ps != 0) {
-#pragma unroll
-                    for (int u = 1; u < R; ++u) r[u] = cmul(r[u], cconj(twf[ps * u]));
-                }
                 // post twiddle conj(W_Nc^{j3*f}), j3 = j0 + 64u: exponents in arithmetic progression
-                const unsigned int j0 = qq + ps * R;
+                const unsigned int j0 = gg;
                 double2 tq = cconj(tw_L(lo, hi, 2ull * ((j0 * f) & nc_mask)));
                 const double2 dq = cconj(tw_L(lo, hi, 2ull * ((64u * f) & nc_mask)));
 #pragma unroll
@@ -998,11 +1003,11 @@ int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_ou
     if (pipelined && g.b1 > 0 && g.b3 >= 7) {
         const size_t smem = (size_t)(4096 + N3) * 16;
         if (g.b3 == 9)
-            row_pass2_kernel<9><<<dim3(sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+            row_pass2_kernel<9><<<dim3(2 * sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         else if (g.b3 == 8)
-            row_pass2_kernel<8><<<dim3(sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+            row_pass2_kernel<8><<<dim3(2 * sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         else
-            row_pass2_kernel<7><<<dim3(sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+            row_pass2_kernel<7><<<dim3(2 * sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         ++launches;
     } else {
         int threads = (int)(N3 / 8) * 2;
