@@ -141,17 +141,29 @@ direct_lag_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int ts, 
     }
 }
 
-// out[s][k] = (sum over chunks, ascending) [/ (n_s - k)]
-__global__ void reduce_partials_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int chunks, int mpad,
-                                       const double* __restrict__ partials, double* __restrict__ out,
-                                       int normalise)
+// out[s][k] = (sum over chunks) [/ (n_s - k)].  A CTA covers KL lags x CL chunk lanes: lane c sums the chunks
+// c, c+CL, c+2CL, ... in ascending order, then the CL lane sums are folded in lane order -- a fixed tree, so the
+// result does not depend on which CTA of the lag kernel produced which partial, nor on the run.
+template <int KL, int CL>
+__global__ void __launch_bounds__(KL * CL)
+reduce_partials_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int chunks, int mpad,
+                       const double* __restrict__ partials, double* __restrict__ out, int normalise)
 {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ncorr) return;
+    __shared__ double sh[CL][KL];
+    const int kl = threadIdx.x % KL, cl = threadIdx.x / KL;
+    const long long k = (long long)blockIdx.x * KL + kl;
     const int s = blockIdx.y;
-    const double* p = partials + (size_t)s * chunks * (size_t)mpad + k;
     double sum = 0.0;
-    for (int c = 0; c < chunks; ++c) sum += p[(size_t)c * mpad];
+    if (k < ncorr) {
+        const double* p = partials + (size_t)s * chunks * (size_t)mpad + k;
+        for (int c = cl; c < chunks; c += CL) sum += p[(size_t)c * mpad];
+    }
+    sh[cl][kl] = sum;
+    __syncthreads();
+    if (cl != 0 || k >= ncorr) return;
+    sum = sh[0][kl];
+#pragma unroll
+    for (int c = 1; c < CL; ++c) sum += sh[c][kl];
     if (normalise) {
         const long long m = desc[s].n - k;
         // k == n: 0/0 (the x86 default NaN has the sign bit set, the reference prints "-nan");
@@ -397,8 +409,13 @@ int launch_direct(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, lo
 int launch_reduce_partials(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
                            const double* d_partials, double* d_out, int normalise, cudaStream_t st)
 {
-    dim3 grid((unsigned)((ncorr + 255) / 256), nseries), block(256);
-    reduce_partials_kernel<<<grid, block, 0, st>>>(d_desc, ncorr, p.chunks, p.mpad, d_partials, d_out, normalise);
+    if (ncorr >= 4096) {
+        dim3 grid((unsigned)((ncorr + 31) / 32), nseries);
+        reduce_partials_kernel<32, 8><<<grid, 256, 0, st>>>(d_desc, ncorr, p.chunks, p.mpad, d_partials, d_out, normalise);
+    } else {
+        dim3 grid((unsigned)((ncorr + 7) / 8), nseries);
+        reduce_partials_kernel<8, 32><<<grid, 256, 0, st>>>(d_desc, ncorr, p.chunks, p.mpad, d_partials, d_out, normalise);
+    }
     ACF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -104,6 +104,8 @@ sum_kernel(const double* __restrict__ x, long long n, double* __restrict__ parti
 
 // y[i] = x[i] - mean for i in [0,n);  vel[i-1] = (y[i+1] - y[i-1]) / (2.0*dt) for i in [1,n-1).
 // The subtraction is redone for the neighbours instead of re-reading y: x - mean rounds identically.
+// A thread handles an aligned pair (i, i+1) per step with one 16-byte load and one 16-byte store of y; the two
+// neighbours x[i-1], x[i+2] are 8-byte loads that hit L1 (their lines are fetched by the adjacent threads).
 __global__ void __launch_bounds__(kThreads)
 center_velocity_kernel(const double* __restrict__ x, long long n, const double* __restrict__ sum, double* mean_out,
                        double* __restrict__ y, double* __restrict__ vel, double dt, double* __restrict__ partial,
@@ -113,16 +115,59 @@ center_velocity_kernel(const double* __restrict__ x, long long n, const double* 
     const double mean = sum[0] / (double)n;
     if (blockIdx.x == 0 && threadIdx.x == 0 && mean_out) mean_out[0] = mean;
     long long lo, hi;
-    cta_slice(n, &lo, &hi);
+    cta_slice(n, &lo, &hi);  // [lo, hi) with lo even
     const double den = 2.0 * dt;
     double vs = 0.0;
-    for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
-        const double yi = x[i] - mean;
-        y[i] = yi;
-        if (vel && i >= 1 && i < n - 1) {
-            const double v = ((x[i + 1] - mean) - (x[i - 1] - mean)) / den;
-            vel[i - 1] = v;
-            vs += v;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                       reinterpret_cast<uintptr_t>(vel)) & 15) == 0;
+    if (vec) {
+        // thread step: samples j, j+1 (j even) -> y[j], y[j+1] and vel[j], vel[j+1] (centres j+1, j+2), every
+        // load and store a 16-byte access; the second load re-reads the pair the next thread owns (L1 hit)
+        const long long full = lo + ((hi - lo) & ~1ll);
+        auto do_pair = [&](long long j, const double2 a, const double2 b, bool have_b) {
+            const double y0 = a.x - mean, y1 = a.y - mean;
+            *reinterpret_cast<double2*>(y + j) = make_double2(y0, y1);
+            if (vel) {
+                if (have_b) {
+                    const double w0 = ((b.x - mean) - y0) / den, w1 = ((b.y - mean) - y1) / den;
+                    *reinterpret_cast<double2*>(vel + j) = make_double2(w0, w1);
+                    vs += w0;
+                    vs += w1;
+                } else if (j + 2 < n) {
+                    const double w0 = ((x[j + 2] - mean) - y0) / den;
+                    vel[j] = w0;
+                    vs += w0;
+                }
+            }
+        };
+        const double2 zero2 = make_double2(0.0, 0.0);
+        long long j = lo + 2ll * threadIdx.x;
+        for (; j + 2ll * kThreads < full; j += 4ll * kThreads) {   // two pairs per step: four loads in flight
+            const long long j2 = j + 2ll * kThreads;
+            const bool hb1 = j + 3 < n, hb2 = j2 + 3 < n;
+            const double2 a1 = *reinterpret_cast<const double2*>(x + j);
+            const double2 a2 = *reinterpret_cast<const double2*>(x + j2);
+            const double2 b1 = hb1 ? *reinterpret_cast<const double2*>(x + j + 2) : zero2;
+            const double2 b2 = hb2 ? *reinterpret_cast<const double2*>(x + j2 + 2) : zero2;
+            do_pair(j, a1, b1, hb1);
+            do_pair(j2, a2, b2, hb2);
+        }
+        for (; j < full; j += 2ll * kThreads) {
+            const bool hb = j + 3 < n;
+            const double2 a = *reinterpret_cast<const double2*>(x + j);
+            const double2 b = hb ? *reinterpret_cast<const double2*>(x + j + 2) : zero2;
+            do_pair(j, a, b, hb);
+        }
+        if (threadIdx.x == 0 && full < hi) y[full] = x[full] - mean;  // odd last sample: no velocity centred there
+    } else {
+        for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
+            const double yi = x[i] - mean;
+            y[i] = yi;
+            if (vel && i >= 1 && i < n - 1) {
+                const double v = ((x[i + 1] - mean) - (x[i - 1] - mean)) / den;
+                vel[i - 1] = v;
+                vs += v;
+            }
         }
     }
     if (vel) {
@@ -137,7 +182,30 @@ subtract_mean_kernel(double* __restrict__ x, long long n, const double* __restri
     const double mean = sum[0] / (double)n;
     if (blockIdx.x == 0 && threadIdx.x == 0 && mean_out) mean_out[0] = mean;
     const long long stride = (long long)gridDim.x * kThreads;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) x[i] -= mean;
+    const long long t0 = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const long long pairs = n >> 1;
+        double2* x2 = reinterpret_cast<double2*>(x);
+        long long p = t0;
+        for (; p + stride < pairs; p += 2 * stride) {      // two independent 16-byte loads in flight per thread
+            double2 a = x2[p], b = x2[p + stride];
+            a.x -= mean;
+            a.y -= mean;
+            b.x -= mean;
+            b.y -= mean;
+            x2[p] = a;
+            x2[p + stride] = b;
+        }
+        for (; p < pairs; p += stride) {
+            double2 a = x2[p];
+            a.x -= mean;
+            a.y -= mean;
+            x2[p] = a;
+        }
+        if ((n & 1) && t0 == 0) x[n - 1] -= mean;
+    } else {
+        for (long long i = t0; i < n; i += stride) x[i] -= mean;
+    }
 }
 
 int launch_sum(const double* d_x, long long n, ReduceScratch* sc, cudaStream_t st)
