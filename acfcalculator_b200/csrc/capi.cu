@@ -76,6 +76,7 @@ struct Workspace {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of the next window group while the current one computes
     Buf series, y, vel, desc, partials, out, scratch, small, fftwork, queue;
     void release()
     {
@@ -90,7 +91,9 @@ struct Workspace {
         fftwork.release();
         queue.release();
         if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         stream = nullptr;
+        copy_stream = nullptr;
         device = -1;
     }
 };
@@ -125,6 +128,7 @@ static int get_ws(Workspace** out)
         }
         w->sm_count = prop.multiProcessorCount;
         e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
             set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
             delete w;
@@ -483,23 +487,54 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
     for (int w = 0; w < nwindows; ++w) total += even_up(n[w]);
     ACF_TRY(ws->series.ensure(total * 8));
     std::vector<const double*> d_ptr(nwindows);
+    // Window groups: all uploads are queued on the copy stream up front, one event per group; the compute stream
+    // starts group g as soon as its windows have landed, so the H2D of group g+1 overlaps the kernels of group g
+    // (with pageable host memory the copies degrade to synchronous staging and nothing is lost).
+    const int ngroups = nwindows >= 8 ? 4 : 1;
+    std::vector<cudaEvent_t> landed(ngroups);
+    std::vector<int> gbeg(ngroups + 1);
+    for (int g = 0; g <= ngroups; ++g) gbeg[g] = (int)((long long)nwindows * g / ngroups);
     size_t off = 0;
-    for (int w = 0; w < nwindows; ++w) {
-        double* d = ws->series.as<double>() + off;
-        ACF_CUDA_OK(cudaMemcpyAsync(d, series[w], (size_t)n[w] * 8, cudaMemcpyHostToDevice, st));
-        d_ptr[w] = d;
-        off += even_up(n[w]);
+    for (int g = 0; g < ngroups; ++g) {
+        for (int w = gbeg[g]; w < gbeg[g + 1]; ++w) {
+            double* d = ws->series.as<double>() + off;
+            ACF_CUDA_OK(cudaMemcpyAsync(d, series[w], (size_t)n[w] * 8, cudaMemcpyHostToDevice, ws->copy_stream));
+            d_ptr[w] = d;
+            off += even_up(n[w]);
+        }
+        ACF_CUDA_OK(cudaEventCreateWithFlags(&landed[g], cudaEventDisableTiming));
+        ACF_CUDA_OK(cudaEventRecord(landed[g], ws->copy_stream));
     }
-    ACF_TRY(pipeline_batch_device(ws, d_ptr.data(), n, nwindows, ncorr, dt, cutoff, nullptr, nullptr, result, st));
-    // results live in ws->out as [window][acf|vacf][ncorr]
-    const double* d_o = ws->out.as<double>();
-    if (acf)
-        ACF_CUDA_OK(cudaMemcpy2DAsync(acf, ncorr * 8, d_o, 2 * ncorr * 8, ncorr * 8, nwindows, cudaMemcpyDeviceToHost, st));
-    if (vacf)
-        ACF_CUDA_OK(cudaMemcpy2DAsync(vacf, ncorr * 8, d_o + ncorr, 2 * ncorr * 8, ncorr * 8, nwindows,
-                                      cudaMemcpyDeviceToHost, st));
-    ACF_CUDA_OK(cudaStreamSynchronize(st));
-    return 0;
+    int rc = 0;
+    for (int g = 0; g < ngroups && rc == 0; ++g) {
+        const int w0 = gbeg[g], cnt = gbeg[g + 1] - gbeg[g];
+        if (cnt == 0) continue;
+        cudaStreamWaitEvent(st, landed[g], 0);
+        rc = pipeline_batch_device(ws, d_ptr.data() + w0, n + w0, cnt, ncorr, dt, cutoff, nullptr, nullptr,
+                                   result ? result + w0 : nullptr, st);
+        if (rc != 0) break;
+        // this group's results sit in ws->out as [window][acf|vacf][ncorr]; copy them out before the next group runs
+        const double* d_o = ws->out.as<double>();
+        cudaError_t e = cudaSuccess;
+        if (acf)
+            e = cudaMemcpy2DAsync(acf + (size_t)w0 * ncorr, ncorr * 8, d_o, 2 * ncorr * 8, ncorr * 8, cnt,
+                                  cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && vacf)
+            e = cudaMemcpy2DAsync(vacf + (size_t)w0 * ncorr, ncorr * 8, d_o + ncorr, 2 * ncorr * 8, ncorr * 8, cnt,
+                                  cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) {
+            set_error("result copy failed: %s", cudaGetErrorString(e));
+            rc = ACFB200_ERR_CUDA;
+        }
+    }
+    cudaError_t es = cudaStreamSynchronize(st);
+    cudaStreamSynchronize(ws->copy_stream);
+    for (auto& ev : landed) cudaEventDestroy(ev);
+    if (rc == 0 && es != cudaSuccess) {
+        set_error("stream synchronize failed: %s", cudaGetErrorString(es));
+        rc = ACFB200_ERR_CUDA;
+    }
+    return rc;
 }
 
 int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double dt, double cutoff, double* acf,
