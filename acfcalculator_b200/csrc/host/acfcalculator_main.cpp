@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../../include/acf_b200.h"
+#include "fast_readers.hpp"
 #include "gle.hpp"
 #include "options.hpp"
 #include "readers.hpp"
@@ -116,7 +117,20 @@ int main(int argc, char* argv[])
     std::vector<double> series;
     int num_samples = 0;
     char* fname_c = const_cast<char*>(fname.c_str());
-    if (type == gromacs)
+    // mapped, multi-threaded reader for files the reference reads without incident; anything unusual falls back to
+    // the line-by-line readers below (ACFB200_FAST_READER=0 disables it, ACFB200_READER_DEBUG=1 says which ran)
+    const char* fr = getenv("ACFB200_FAST_READER");
+    const bool dbg = getenv("ACFB200_READER_DEBUG") != nullptr;
+    bool fast_done = false;
+    if (!(fr && fr[0] == '0')) {
+        const FastFormat ff = type == gromacs ? FAST_GROMACS : type == charmm ? FAST_CHARMM : type == namd ? FAST_NAMD
+                                                                                                           : FAST_GENERAL;
+        fast_done = fast_read_series(fname_c, ff, field, p_factor, series);
+        if (fast_done) num_samples = (int)series.size();
+    }
+    if (dbg) std::cerr << "#reader: " << (fast_done ? "fast" : "line-by-line") << std::endl;
+    if (fast_done) {
+    } else if (type == gromacs)
         series = read_series_gromacs(fname_c, num_samples, field);
     else if (type == charmm)
         series = read_series_charmm(fname_c, num_samples);

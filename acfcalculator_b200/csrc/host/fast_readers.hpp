@@ -1,0 +1,18 @@
+// Fast path for the four time-series readers: the file is mapped once, cut into
+// per-thread pieces at line boundaries and parsed with strtod on bounded copies -- the same correctly-rounded
+// conversion atof / sscanf("%lf") perform in /root/reference/ACFcalculator.cpp:265-415, so the doubles are
+// bit-identical.  Only files the reference reads without incident are handled here: any line that would make
+// the reference stop early, throw, or hit its undefined behaviour (blank line, short NAMD line, missing column,
+// field out of range, ...) makes fast_read_series() return false and the caller falls back to the faithful
+// line-by-line readers in readers.cpp, which reproduce that behaviour exactly.
+#pragma once
+#include <vector>
+
+namespace acfhost {
+
+enum FastFormat { FAST_NAMD, FAST_CHARMM, FAST_GROMACS, FAST_GENERAL };
+
+// true: `out` holds the whole series.  false: nothing usable was produced, use the faithful reader.
+bool fast_read_series(const char* fname, FastFormat fmt, int field, double p_factor, std::vector<double>& out);
+
+}  // namespace acfhost

@@ -31,8 +31,9 @@ def oracle_frontends(oracle):
     """ACFcalculator / viscosity front-ends linked against the oracle shim (CPU only)."""
     os.makedirs(BUILD, exist_ok=True)
     shim = os.path.join(ROOT, "tests", "host", "abi_shim_oracle.cpp")
-    common = [os.path.join(HOST, f) for f in ("options.cpp", "readers.cpp", "gle.cpp")]
-    link = ["-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"]
+    common = [os.path.join(HOST, f) for f in ("options.cpp", "readers.cpp", "fast_readers.cpp", "gle.cpp")]
+    link = ["-pthread", "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"),
+            "-fopenmp"]
     exe = {}
     for name, main in (("ACFcalculator", "acfcalculator_main.cpp"), ("viscosity", "viscosity_main.cpp")):
         out = os.path.join(BUILD, name + "_oracle")
@@ -114,6 +115,35 @@ def test_viscosity_frontend_with_oracle_backend(oracle_frontends, tmp_path):
     p = subprocess.run([oracle_frontends["viscosity"], log], capture_output=True, text=True)
     assert p.returncode == CASES["viscosity_log"]["returncode"]
     assert p.stdout == CASES["viscosity_log"]["stdout"]
+
+
+FAST_READER_CASES = {  # case -> does the mapped reader handle it (True) or defer to the line-by-line one (False)
+    "general_langevin1": True, "general_tabs_field2": True, "gromacs_field2": True, "namd_field1": True, "charmm": True,
+    "general_pfactor": True, "gromacs_field_beyond_columns": False, "namd_field0_empty": False,
+    "blank_line_general": False, "blank_line_charmm": False, "general_tabs_field1_zero": True,
+}
+
+
+@pytest.mark.parametrize("name", sorted(FAST_READER_CASES))
+def test_fast_reader_is_used_only_on_clean_files_and_changes_nothing(oracle_frontends, name, tmp_path):
+    """Both readers give byte-identical program output on every recorded case; the mapped one steps aside whenever
+    the reference would stop early, throw or run into its undefined behaviour."""
+    c = CASES[name]
+    inp = str(tmp_path / (name + ".in"))
+    write_input(inp, SERIES[c["series"]], c["format"])
+    outs = {}
+    for mode in ("1", "0"):
+        env = dict(os.environ, ACFB200_FAST_READER=mode, ACFB200_READER_DEBUG="1")
+        acf_f, out_f = str(tmp_path / (mode + ".acf")), str(tmp_path / (mode + ".out"))
+        p = subprocess.run([oracle_frontends["ACFcalculator"], "-i", inp, "-a", acf_f, "-o", out_f] + c["args"],
+                           capture_output=True, text=True, env=env, cwd=str(tmp_path))
+        which = [l for l in p.stderr.splitlines() if l.startswith("#reader:")]
+        outs[mode] = (p.returncode, p.stdout.replace(out_f, "<OUT>"),
+                      open(acf_f).read() if os.path.exists(acf_f) else None, which)
+    assert outs["1"][:3] == outs["0"][:3]
+    assert outs["0"][3] == ["#reader: line-by-line"]
+    assert outs["1"][3] == ["#reader: " + ("fast" if FAST_READER_CASES[name] else "line-by-line")]
+    assert outs["1"][0] == c["returncode"]
 
 
 OPTION_ERRORS = [
