@@ -67,6 +67,7 @@ SIGNATURES = {
     "acfb200_calc_correlation_fft_device": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p, C.c_void_p]),
     "acfb200_describe_plan": (C.c_int, [_I64, _I64, C.c_int, C.c_char_p, C.c_int]),
     "acfb200_set_variant": (C.c_int, [C.c_int]),
+    "acfb200_set_method": (C.c_int, [C.c_int]),
     "acfb200_variant_count": (C.c_int, []),
     "acfb200_variant_name": (C.c_char_p, [C.c_int]),
     "acfb200_measure_dfma_peak": (C.c_int, [_P, _P]),

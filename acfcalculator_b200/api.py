@@ -54,6 +54,11 @@ def set_variant(v):
     check(_lib.load().acfb200_set_variant(int(v)))
 
 
+def set_method(method):
+    """'direct' (reference summation, default), 'fft' (Wiener-Khinchin) or 'auto' (cost model)."""
+    check(_lib.load().acfb200_set_method({"direct": 0, "fft": 1, "auto": 2}[method]))
+
+
 def variants():
     L = _lib.load()
     return [L.acfb200_variant_name(i).decode() for i in range(L.acfb200_variant_count())]

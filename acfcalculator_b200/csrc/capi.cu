@@ -25,6 +25,7 @@ void set_error(const char* fmt, ...)
 static std::recursive_mutex g_mu;
 static std::atomic<long long> g_launches{0};
 static int g_force_variant = -1;
+static int g_method = 0;  // 0 direct (default), 1 fft, 2 auto
 
 #define ACF_TRY(expr)            \
     do {                         \
@@ -154,6 +155,36 @@ static int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long 
             return ACFB200_ERR_ARG;
         }
         if (d.i_end > max_i_end) max_i_end = d.i_end;
+    }
+    // Method selection (acfb200_set_method): the Wiener-Khinchin path gives the same numbers to ~1e-14*C(0) and costs
+    // O(L log L) instead of O(n*ncorr).  It only serves whole, 16-byte aligned series with the divide included.
+    if (g_method != 0 && normalise) {
+        bool eligible = true;
+        double t_direct = 0.0, t_fft = 0.0;
+        for (const auto& d : descs) {
+            size_t wb = 0;
+            long long L = 0;
+            if (d.i_end != d.n || (reinterpret_cast<uintptr_t>(d.x) & 15) != 0 ||
+                fft_acf_workspace_bytes(d.n, ncorr, &wb, &L) != 0) {
+                eligible = false;
+                break;
+            }
+            t_direct += (double)d.n * (double)ncorr / 1.5e13;            // measured direct-lag rate (lag-products/s)
+            t_fft += (8.0 * d.n + 64.0 * (double)L) / 3.5e12 + 4.0e-5;  // measured FFT-path HBM rate + launches
+        }
+        if (eligible && (g_method == 1 || t_fft < t_direct)) {
+            for (int s = 0; s < ns; ++s) {
+                size_t wb = 0;
+                long long L = 0;
+                ACF_TRY(fft_acf_workspace_bytes(descs[s].n, ncorr, &wb, &L));
+                ACF_TRY(ws->fftwork.ensure(wb));
+                const int launches = launch_fft_acf(descs[s].x, descs[s].n, ncorr, d_out + (size_t)s * ncorr, 1,
+                                                    ws->fftwork.p, ws->fftwork.cap, st);
+                if (launches < 0) return ACFB200_ERR_CUDA;
+                g_launches += launches;
+            }
+            return 0;
+        }
     }
     DirectPlan plan;
     ACF_TRY(plan_direct(max_i_end, ncorr, ns, ws->sm_count, g_force_variant, &plan));
@@ -314,6 +345,15 @@ int acfb200_set_variant(int variant)
         return ACFB200_ERR_ARG;
     }
     g_force_variant = variant < 0 ? -1 : variant;
+    return 0;
+}
+int acfb200_set_method(int method)
+{
+    if (method < 0 || method > 2) {
+        set_error("method must be 0 (direct), 1 (fft) or 2 (auto), got %d", method);
+        return ACFB200_ERR_ARG;
+    }
+    g_method = method;
     return 0;
 }
 int acfb200_variant_count(void) { return direct_variant_count(); }

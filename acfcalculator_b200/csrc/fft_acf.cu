@@ -510,7 +510,6 @@ row_pass_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N3 = 1 << G.b3;
     double2* sa = reinterpret_cast<double2*>(smem_raw);  // this row
-    double2* sb = sa + N3;                               // mirror row (unused when self-paired)
     const int tid = threadIdx.x, nth = blockDim.x;
     const long long N1 = 1ll << G.b1, N2 = 1ll << G.b2;
     const long long row = blockIdx.x;       // = k1 * N2 + k2
@@ -542,9 +541,6 @@ row_pass_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict
     smem_fft<-1>(s, G.b3, ncols, ncols, lo, hi, G.L, tid, nth);
 
     // pair operation
-    const double2 half_i_dummy = make_double2(0.0, 0.0);
-    (void)half_i_dummy;
-    (void)sb;
     const long long kbase = k1 + (k2 << G.b1);  // k = kbase + N1*N2*k3
     const int shift12 = G.b1 + G.b2;
     if (!self) {

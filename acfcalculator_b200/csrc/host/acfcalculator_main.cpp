@@ -47,6 +47,7 @@ std::vector<OptionSpec> option_table()
         {"mass", 'w', O::Double, false, "0", "mass of the solute (units amu, optional)", false},
         {"temperature", 'e', O::Double, false, "0", "temperature (optional)", false},
         {"factor", 'r', O::Double, false, "1", "alias of --p_factor (README.md:14)", true},
+        {"fft", '\0', O::String, false, nullptr, "use fft to calculate correlation functions (ACFcalculator.cpp:571)", true},
     };
 }
 
@@ -99,6 +100,10 @@ int main(int argc, char* argv[])
         k = opt.get_double("spring", 0.0);
         mass = opt.get_double("mass", 0.0);
         temperature = opt.get_double("temperature", 0.0);
+        if (opt.count("fft")) {  // the reference's FFTW-only switch (:644-651); here it selects the GPU FFT path
+            std::cout << "#Correlation functions will be calculated using FFT" << std::endl;
+            acfb200_set_method(1);
+        }
         std::cout << "#Time step of " << timestep << " fs will be used." << std::endl;
         cutoff = opt.get_double("cutoff", 0.0);
         if (cutoff > 0.0)

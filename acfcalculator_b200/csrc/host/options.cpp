@@ -25,7 +25,7 @@ const OptionSpec* Options::find_long(const std::string& name, bool allow_prefix)
 const OptionSpec* Options::find_short(char c) const
 {
     for (const auto& s : specs_)
-        if (s.short_name == c) return &s;
+        if (s.short_name != '\0' && s.short_name == c) return &s;
     return nullptr;
 }
 

@@ -378,6 +378,23 @@ def run_native(args):
     if world == 1 and not args.no_cpu:
         cpu = cpu_reference_rate(args.workload, 1, 0)
         cpu.pop("ms_per_step", None)
+    # informational: the same step with acfb200_set_method("auto") (the cost model sends config 2 through the
+    # Wiener-Khinchin path); NOT the headline, which is the direct-lag kernel BASELINE.json names
+    alt = None
+    if args.workload == "ou":
+        A.set_method("auto")
+        try:
+            step()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(5):
+                step()
+            a1.record(stream)
+            torch.cuda.synchronize()
+            alt = {"method": "auto (cost model -> FFT path)", "ms_per_step": a0.elapsed_time(a1) / 5}
+        finally:
+            A.set_method("direct")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
@@ -388,6 +405,7 @@ def run_native(args):
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
         "dfma_peak": {"tflops": peak_tf, "effective_sm_mhz": eff_mhz},
+        "alt_method": alt,
     }
     if world == 1 and not args.no_cpu and args.allcores:
         line["cpu_baseline_allcores"] = cpu_allcores_rate(args.workload)

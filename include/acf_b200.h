@@ -159,6 +159,10 @@ ACFB200_API int acfb200_calc_correlation_fft_device(const double* d_y, int64_t n
 ACFB200_API int acfb200_describe_plan(int64_t n, int64_t ncorr, int nseries, char* buf, int buflen);
 /* Force a direct-kernel variant (-1 = automatic).  Also: env ACFB200_VARIANT/WARPS/TS/CHUNKS. */
 ACFB200_API int acfb200_set_variant(int variant);
+/* How calcCorrelation-type entry points (including the pipelines) compute their lags: 0 = direct summation, the
+ * reference's method (default); 1 = zero-padded Wiener-Khinchin FFT; 2 = whichever the built-in cost model expects
+ * to be faster.  Results agree to ~1e-14*C(0).  Raw lag sums of time blocks always use direct summation. */
+ACFB200_API int acfb200_set_method(int method);
 ACFB200_API int acfb200_variant_count(void);
 ACFB200_API const char* acfb200_variant_name(int variant);
 /* FP64-pipe ceiling (pure DFMA chains) and STREAM-style copy bandwidth measured on the current device. */

@@ -24,6 +24,7 @@ void oracle_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* 
 double oracle_viscosity_eta(double box_length, double temperature, double integral);
 
 const char* acfb200_last_error(void) { return "oracle shim"; }
+int acfb200_set_method(int) { return 0; }
 
 int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double dt, double cutoff, double* acf,
                          double* vacf, acfb200_result* r)

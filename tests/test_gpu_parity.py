@@ -257,3 +257,21 @@ def test_batch_device_pipeline_equals_host_batch(acf):
     da, dv, dres = acf.acf_pipeline_batch_device([torch.from_numpy(w).cuda() for w in wins], 800, 2.0, 0.05)
     assert np.array_equal(da.cpu().numpy(), a) and np.array_equal(dv.cpu().numpy(), v)
     assert dres == res
+
+
+def test_method_selection_fft_and_auto(acf, oracle):
+    """acfb200_set_method: the pipelines and calcCorrelation through the FFT path agree with direct summation."""
+    x = ou_series(200000, 300.0, mu=2.0, seed=77)
+    d = acf.acf_pipeline(x, 20000, 2.0, 0.05)
+    try:
+        acf.set_method("fft")
+        f = acf.acf_pipeline(x, 20000, 2.0, 0.05)
+        acf.set_method("auto")
+        a = acf.acf_pipeline(x, 20000, 2.0, 0.05)          # cost model picks the FFT here
+        s = acf.calcCorrelation(x[:5000], nCorr=8)          # ... and direct summation here
+    finally:
+        acf.set_method("direct")
+    for r in (f, a):
+        assert rel_to_c0(r["acf"], d["acf"], d["var"]) <= TOL and rel_to_c0(r["vacf"], d["vacf"], d["var_vel"]) <= TOL
+        assert r["cutoff_index"] == d["cutoff_index"] and _close(r["acf_int"], d["acf_int"]) and r["avg"] == d["avg"]
+    assert np.array_equal(s, acf.calcCorrelation(x[:5000], nCorr=8))
