@@ -173,6 +173,43 @@ static int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long 
             t_fft += (8.0 * d.n + 64.0 * (double)L) / 3.5e12 + 4.0e-5;  // measured FFT-path HBM rate + launches
         }
         if (eligible && (g_method == 1 || t_fft < t_direct)) {
+            // Batches: series of one length whose addresses form an arithmetic progression go out as one set of
+            // launches.  The two shapes that occur: every series (a [S][pitch] tensor), or the pipeline's
+            // interleaving y_0, v_0, y_1, v_1, ... (two progressions, outputs interleaved the same way).
+            auto progression = [&](int first, int step, int count, long long* stride) {
+                if (count < 2) return false;
+                const long long st0 = descs[first + step].x - descs[first].x;
+                if (st0 <= 0 || (st0 & 1)) return false;
+                for (int i = 0; i < count; ++i) {
+                    const SeriesDesc& d = descs[first + i * step];
+                    if (d.n != descs[first].n || d.x != descs[first].x + (long long)i * st0) return false;
+                }
+                *stride = st0;
+                return true;
+            };
+            auto run_batch = [&](int first, int step, int count, long long stride) -> int {
+                const int max_batch = 64;  // bounds the work array (count * 8L bytes)
+                for (int b0 = 0; b0 < count; b0 += max_batch) {
+                    const int nb = count - b0 < max_batch ? count - b0 : max_batch;
+                    size_t wb = 0;
+                    long long L = 0;
+                    ACF_TRY(fft_acf_workspace_bytes_batch(descs[first].n, ncorr, nb, &wb, &L));
+                    ACF_TRY(ws->fftwork.ensure(wb));
+                    const int launches = launch_fft_acf_batch(
+                        descs[first + b0 * step].x, descs[first].n, stride, nb, ncorr,
+                        d_out + (size_t)(first + b0 * step) * ncorr, (long long)step * ncorr, 1, ws->fftwork.p,
+                        ws->fftwork.cap, st);
+                    if (launches < 0) return ACFB200_ERR_CUDA;
+                    g_launches += launches;
+                }
+                return 0;
+            };
+            long long stride = 0, stride2 = 0;
+            if (progression(0, 1, ns, &stride)) return run_batch(0, 1, ns, stride);
+            if (ns >= 4 && ns % 2 == 0 && progression(0, 2, ns / 2, &stride) && progression(1, 2, ns / 2, &stride2)) {
+                ACF_TRY(run_batch(0, 2, ns / 2, stride));
+                return run_batch(1, 2, ns / 2, stride2);
+            }
             for (int s = 0; s < ns; ++s) {
                 size_t wb = 0;
                 long long L = 0;

@@ -32,6 +32,7 @@ struct FftGeom {
     int q;            // log2(Nc)
     long long Nc, L;
     long long n, ncorr;
+    long long x_stride, out_stride;  // batch: series b starts at x + b*x_stride, its lags go to out + b*out_stride
 };
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -215,7 +216,7 @@ col_pass_kernel(double2* __restrict__ data, const double* __restrict__ x, double
     if (MODE == 3 && 2 * c0 >= G.ncorr) return;
 
     if (MODE == 0) {
-        const double* xs = x + batch * G.n;
+        const double* xs = x + batch * G.x_stride;
         for (int w = tid; w < total; w += kColThreads) {
             const int r = w / TC, c = w - r * TC;
             const long long j = (long long)r * C + c0 + c;  // complex index; samples 2j, 2j+1
@@ -237,7 +238,7 @@ col_pass_kernel(double2* __restrict__ data, const double* __restrict__ x, double
 
     if (MODE == 3) {
         // r[2j], r[2j+1] with j = kb*C + c;  corr[k] = r[k] / (Nc * (n - k))
-        double* o = out + batch * G.ncorr;
+        double* o = out + batch * G.out_stride;
         const double inv_nc = 1.0 / (double)G.Nc;
         for (int w = tid; w < total; w += kColThreads) {
             const int r = w / TC, c = w - r * TC;
@@ -316,7 +317,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     }
     const long long batch = blockIdx.y;
     double2* bdata = data + batch * G.Nc;
-    const double* xs = (MODE == 0) ? x + batch * G.n : nullptr;
+    const double* xs = (MODE == 0) ? x + batch * G.x_stride : nullptr;
     // butterfly twiddles, laid out so that a warp reads consecutive entries (no bank conflicts):
     //   tw[(u-1)*NB8 + g]            = W_NB^{g*u}     pass 1 (Stockham stride 1, p = g)
     //   tw2[(u-1)*(NB8/8) + p]       = W_NB^{8*p*u}   middle pass (stride 8, p = g >> 3)
@@ -363,7 +364,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     // loads and were the top stall of the first version (profiles/r1_fft_ncu.md).
     auto store_group = [&](unsigned int a, unsigned int cc, unsigned int base, unsigned int stride, int R, double2* r) {
         if (MODE == 3) {
-            double* o = out + batch * G.ncorr;
+            double* o = out + batch * G.out_stride;
             const double inv_nc = 1.0 / (double)G.Nc;
             for (int u = 0; u < R; ++u) {
                 const long long j = ((long long)(base + stride * u) << logC) + cc;
@@ -842,7 +843,7 @@ __global__ void fft_finish_kernel(const double2* __restrict__ data, double* __re
     if (j >= G.Nc) return;
     const double2 z = data[(long long)blockIdx.y * G.Nc + j];
     const double inv_nc = 1.0 / (double)G.Nc;
-    double* o = out + (long long)blockIdx.y * G.ncorr;
+    double* o = out + (long long)blockIdx.y * G.out_stride;
     for (int h = 0; h < 2; ++h) {
         const long long k = 2 * j + h;
         if (k < G.ncorr) {
@@ -863,7 +864,7 @@ __global__ void fft_pack_kernel(const double* __restrict__ x, double2* __restric
 {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= G.Nc) return;
-    const double* xs = x + (long long)blockIdx.y * G.n;
+    const double* xs = x + (long long)blockIdx.y * G.x_stride;
     double2 z = make_double2(0.0, 0.0);
     if (2 * j < G.n) z.x = xs[2 * j];
     if (2 * j + 1 < G.n) z.y = xs[2 * j + 1];
@@ -892,6 +893,8 @@ static int make_geom(long long n, long long ncorr, FftGeom* g)
     g->Nc = 1ll << q;
     g->n = n;
     g->ncorr = ncorr;
+    g->x_stride = n;
+    g->out_stride = ncorr;
     if (q <= 9) {
         g->b1 = 0;
         g->b2 = 0;
@@ -910,10 +913,15 @@ static int make_geom(long long n, long long ncorr, FftGeom* g)
 
 int fft_acf_workspace_bytes(long long n, long long ncorr, size_t* bytes, long long* L)
 {
+    return fft_acf_workspace_bytes_batch(n, ncorr, 1, bytes, L);
+}
+
+int fft_acf_workspace_bytes_batch(long long n, long long ncorr, int nbatch, size_t* bytes, long long* L)
+{
     FftGeom g;
     if (make_geom(n, ncorr, &g)) return 1;
     const long long nhi = g.L < kLoSize ? 1 : (g.L >> kLoBits);
-    if (bytes) *bytes = (size_t)g.Nc * 16 + (size_t)(kLoSize + nhi) * 16 + 256;
+    if (bytes) *bytes = (size_t)g.Nc * 16 * (size_t)(nbatch > 0 ? nbatch : 1) + (size_t)(kLoSize + nhi) * 16 + 256;
     if (L) *L = g.L;
     return 0;
 }
@@ -922,11 +930,26 @@ int fft_acf_workspace_bytes(long long n, long long ncorr, size_t* bytes, long lo
 int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_out, int normalise, void* d_work,
                    size_t work_bytes, cudaStream_t st)
 {
+    return launch_fft_acf_batch(d_x, n, n, 1, ncorr, d_out, ncorr, normalise, d_work, work_bytes, st);
+}
+
+// nbatch series of n samples each, series b at d_x + b*x_stride (x_stride even, d_x 16-byte aligned); lags of series b
+// go to d_out + b*out_stride.  One set of launches for the whole batch (grid.y / grid.z = series).
+int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int nbatch, long long ncorr, double* d_out,
+                         long long out_stride, int normalise, void* d_work, size_t work_bytes, cudaStream_t st)
+{
     (void)normalise;
     FftGeom g;
     if (make_geom(n, ncorr, &g)) return -1;
+    if (nbatch < 1 || nbatch > 65535 || (nbatch > 1 && (x_stride & 1))) {
+        set_error("fft_acf: batch of %d series with stride %lld is not supported (1..65535 series, even stride)", nbatch,
+                  x_stride);
+        return -1;
+    }
+    g.x_stride = x_stride;
+    g.out_stride = out_stride;
     size_t need = 0;
-    fft_acf_workspace_bytes(n, ncorr, &need, nullptr);
+    fft_acf_workspace_bytes_batch(n, ncorr, nbatch, &need, nullptr);
     if (work_bytes < need) {
         set_error("fft_acf: workspace too small (%zu < %zu)", work_bytes, need);
         return -1;
@@ -936,7 +959,8 @@ int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_ou
         return -1;
     }
     double2* data = reinterpret_cast<double2*>(d_work);
-    double2* lo = data + g.Nc;
+    double2* lo = data + g.Nc * nbatch;
+    const unsigned nb = (unsigned)nbatch;
     double2* hi = lo + kLoSize;
     int launches = 0;
     fft_table_kernel<<<kLoSize / 256, 256, 0, st>>>(lo, hi, g.L);
@@ -976,49 +1000,49 @@ int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_ou
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
         if (pipelined)
-            col2_select(0, g.b1)<<<dim3(pgrid(C >> (12 - g.b1)), 1, 1), kColThreads, smem2, st>>>(
+            col2_select(0, g.b1)<<<dim3(pgrid(C >> (12 - g.b1)), nb, 1), kColThreads, smem2, st>>>(
                 data, d_x, nullptr, g, g.b2 + g.b3, 1, lo, hi);
         else
-            col_pass_kernel<0><<<dim3((unsigned)(C / TC), 1, 1), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
+            col_pass_kernel<0><<<dim3((unsigned)(C / TC), 1, nb), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
                 data, d_x, nullptr, g, g.b1, C, TC, lo, hi);
         ++launches;
     } else {
-        fft_pack_kernel<<<dim3((unsigned)((g.Nc + 255) / 256), 1), 256, 0, st>>>(d_x, data, g);
+        fft_pack_kernel<<<dim3((unsigned)((g.Nc + 255) / 256), nb), 256, 0, st>>>(d_x, data, g);
         ++launches;
     }
     if (g.b2 > 0) {
         const int TC = tc_for(g.b2, N3);
         if (pipelined)
-            col2_select(1, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), 1, 1), kColThreads, smem2, st>>>(
+            col2_select(1, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), nb, 1), kColThreads, smem2, st>>>(
                 data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
         else
-            col_pass_kernel<1><<<dim3((unsigned)(N3 / TC), (unsigned)N1, 1), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
+            col_pass_kernel<1><<<dim3((unsigned)(N3 / TC), (unsigned)N1, nb), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
                 data, nullptr, nullptr, g, g.b2, N3, TC, lo, hi);
         ++launches;
     }
     if (pipelined && g.b1 > 0 && g.b3 >= 7) {
         const size_t smem = (size_t)(4096 + N3) * 16;
         if (g.b3 == 9)
-            row_pass2_kernel<9><<<dim3(2 * sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+            row_pass2_kernel<9><<<dim3(2 * sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         else if (g.b3 == 8)
-            row_pass2_kernel<8><<<dim3(2 * sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+            row_pass2_kernel<8><<<dim3(2 * sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         else
-            row_pass2_kernel<7><<<dim3(2 * sms, 1, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+            row_pass2_kernel<7><<<dim3(2 * sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         ++launches;
     } else {
         int threads = (int)(N3 / 8) * 2;
         if (threads < 32) threads = 32;
         if (threads > 256) threads = 256;
-        row_pass_kernel<<<dim3((unsigned)(N1 * N2), 1, 1), threads, (size_t)N3 * 2 * 16, st>>>(data, g, lo, hi);
+        row_pass_kernel<<<dim3((unsigned)(N1 * N2), 1, nb), threads, (size_t)N3 * 2 * 16, st>>>(data, g, lo, hi);
         ++launches;
     }
     if (g.b2 > 0) {
         const int TC = tc_for(g.b2, N3);
         if (pipelined)
-            col2_select(2, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), 1, 1), kColThreads, smem2, st>>>(
+            col2_select(2, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), nb, 1), kColThreads, smem2, st>>>(
                 data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
         else
-            col_pass_kernel<2><<<dim3((unsigned)(N3 / TC), (unsigned)N1, 1), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
+            col_pass_kernel<2><<<dim3((unsigned)(N3 / TC), (unsigned)N1, nb), kColThreads, (size_t)(N2 * TC) * 16, st>>>(
                 data, nullptr, nullptr, g, g.b2, N3, TC, lo, hi);
         ++launches;
     }
@@ -1026,14 +1050,14 @@ int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_ou
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
         if (pipelined)
-            col2_select(3, g.b1)<<<dim3(pgrid(C >> (12 - g.b1)), 1, 1), kColThreads, smem2, st>>>(
+            col2_select(3, g.b1)<<<dim3(pgrid(C >> (12 - g.b1)), nb, 1), kColThreads, smem2, st>>>(
                 data, nullptr, d_out, g, g.b2 + g.b3, 1, lo, hi);
         else
-            col_pass_kernel<3><<<dim3((unsigned)(C / TC), 1, 1), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
+            col_pass_kernel<3><<<dim3((unsigned)(C / TC), 1, nb), kColThreads, (size_t)(N1 * TC) * 16, st>>>(
                 data, nullptr, d_out, g, g.b1, C, TC, lo, hi);
         ++launches;
     } else {
-        fft_finish_kernel<<<dim3((unsigned)((g.Nc + 255) / 256), 1), 256, 0, st>>>(data, d_out, g);
+        fft_finish_kernel<<<dim3((unsigned)((g.Nc + 255) / 256), nb), 256, 0, st>>>(data, d_out, g);
         ++launches;
     }
     cudaError_t e = cudaGetLastError();

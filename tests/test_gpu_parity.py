@@ -275,3 +275,26 @@ def test_method_selection_fft_and_auto(acf, oracle):
         assert rel_to_c0(r["acf"], d["acf"], d["var"]) <= TOL and rel_to_c0(r["vacf"], d["vacf"], d["var_vel"]) <= TOL
         assert r["cutoff_index"] == d["cutoff_index"] and _close(r["acf_int"], d["acf_int"]) and r["avg"] == d["avg"]
     assert np.array_equal(s, acf.calcCorrelation(x[:5000], nCorr=8))
+
+
+def test_fft_batches_equal_direct(acf):
+    """Batched Wiener-Khinchin launches: a stack of equal-length series (one progression) and the window pipeline
+    (y/vel interleaved, two progressions) give what direct summation gives."""
+    import torch
+    rows = torch.from_numpy(np.stack([ou_series(70000, 40.0 + s, seed=500 + s) for s in range(5)])).cuda()
+    direct = acf.calc_correlation_batch_device(list(rows), 6000).cpu().numpy()
+    wins = [ou_series(50000, 30.0 + w, mu=1.0 + w, seed=600 + w) for w in range(6)]
+    a0, v0, r0 = acf.acf_pipeline_batch(wins, 5000, 2.0, 0.05)
+    try:
+        acf.set_method("fft")
+        before = acf.launch_count()
+        batched = acf.calc_correlation_batch_device(list(rows), 6000).cpu().numpy()
+        assert acf.launch_count() - before <= 8          # one set of launches for the five series
+        a1, v1, r1 = acf.acf_pipeline_batch(wins, 5000, 2.0, 0.05)
+    finally:
+        acf.set_method("direct")
+    for s in range(5):
+        assert rel_to_c0(batched[s], direct[s], direct[s][0]) <= TOL
+    for w in range(6):
+        assert rel_to_c0(a1[w], a0[w], a0[w][0]) <= TOL and rel_to_c0(v1[w], v0[w], v0[w][0]) <= TOL
+        assert r1[w]["cutoff_index"] == r0[w]["cutoff_index"] and _close(r1[w]["acf_int"], r0[w]["acf_int"])
