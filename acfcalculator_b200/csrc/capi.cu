@@ -381,6 +381,7 @@ int acfb200_set_variant(int variant)
         set_error("variant %d out of range (0..%d)", variant, direct_variant_count() - 1);
         return ACFB200_ERR_ARG;
     }
+    Lock lk(g_mu);
     g_force_variant = variant < 0 ? -1 : variant;
     return 0;
 }
@@ -390,6 +391,7 @@ int acfb200_set_method(int method)
         set_error("method must be 0 (direct), 1 (fft) or 2 (auto), got %d", method);
         return ACFB200_ERR_ARG;
     }
+    Lock lk(g_mu);
     g_method = method;
     return 0;
 }

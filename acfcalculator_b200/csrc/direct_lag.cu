@@ -222,7 +222,9 @@ static double warps_quality(int w)
     return w == 1 ? 0.994 : w == 2 ? 1.0 : w == 4 ? 0.985 : w == 8 ? 0.980 : w == 12 ? 0.95 : 0.90;
 }
 static const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-static bool g_attr_set[sizeof(kVariants) / sizeof(kVariants[0])] = {false};
+// opt-in to > 48 KB dynamic shared memory is per device: one flag per (device, variant)
+constexpr int kMaxDevices = 64;
+static bool g_attr_set[kMaxDevices][sizeof(kVariants) / sizeof(kVariants[0])] = {{false}};
 
 // Public variant numbering: [0, kNumVariants) tiled kernels, then the streaming kernels.
 int direct_variant_count() { return kNumVariants + stream_variant_count(); }
@@ -396,9 +398,11 @@ int launch_direct(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, lo
 {
     if (p.mode == 1) return launch_direct_stream(p, d_desc, nseries, ncorr, d_partials, d_queue, sm_count, st);
     const Variant& V = kVariants[p.variant];
-    if (!g_attr_set[p.variant]) {
+    int dev = 0;
+    ACF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= kMaxDevices || !g_attr_set[dev][p.variant]) {
         ACF_CUDA_OK(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        g_attr_set[p.variant] = true;
+        if (dev < kMaxDevices) g_attr_set[dev][p.variant] = true;
     }
     dim3 grid(p.lag_tiles, p.chunks, nseries), block(p.warps * 32);
     V.fn<<<grid, block, p.smem_bytes, st>>>(d_desc, ncorr, p.ts, p.bsz, p.chunks, p.mpad, d_partials);

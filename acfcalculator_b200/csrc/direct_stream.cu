@@ -212,7 +212,7 @@ static const StreamVariant kStream[] = {
     ACF_SVARIANT(18, 2, 1.00),
 };
 static const int kNumStream = (int)(sizeof(kStream) / sizeof(kStream[0]));
-static bool g_stream_attr[sizeof(kStream) / sizeof(kStream[0])] = {false};
+static bool g_stream_attr[64][sizeof(kStream) / sizeof(kStream[0])] = {{false}};  // per (device, variant)
 
 int stream_variant_count() { return kNumStream; }
 const char* stream_variant_name(int v) { return (v >= 0 && v < kNumStream) ? kStream[v].name : "?"; }
@@ -229,9 +229,11 @@ int launch_direct_stream(const DirectPlan& p, const SeriesDesc* d_desc, int nser
                          double* d_partials, unsigned int* d_queue, int sm_count, cudaStream_t st)
 {
     const StreamVariant& V = kStream[p.variant];
-    if (!g_stream_attr[p.variant]) {
+    int dev = 0;
+    ACF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 64 || !g_stream_attr[dev][p.variant]) {
         ACF_CUDA_OK(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        g_stream_attr[p.variant] = true;
+        if (dev < 64) g_stream_attr[dev][p.variant] = true;
     }
     ACF_CUDA_OK(cudaMemsetAsync(d_queue, 0, sizeof(unsigned int), st));
     StreamParams P;

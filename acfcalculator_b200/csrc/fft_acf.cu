@@ -965,7 +965,11 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     int launches = 0;
     fft_table_kernel<<<kLoSize / 256, 256, 0, st>>>(lo, hi, g.L);
     ++launches;
-    static bool attr = false;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static bool attr_done[64] = {false};  // the > 48 KB shared-memory opt-in is per device
+    const bool attr = dev < 64 && attr_done[dev];
     if (!attr) {
         cudaFuncSetAttribute(col_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
@@ -978,7 +982,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
             for (int bb = 3; bb <= 9; ++bb)
                 cudaFuncSetAttribute(col2_select(mode, bb), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (kTileElems + 512) * 16);
-        attr = true;
+        if (dev < 64) attr_done[dev] = true;
     }
     const long long N1 = 1ll << g.b1, N2 = 1ll << g.b2, N3 = 1ll << g.b3;
     const char* env = getenv("ACFB200_FFT_PIPELINED");
@@ -986,9 +990,6 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     // the pipelined kernels use fixed 4096-element tiles: every pass must offer at least one full tile width
     if (g.b1 > 0 && g.b2 + g.b3 < 12 - g.b1) pipelined = false;
     if (g.b2 > 0 && g.b3 < 12 - g.b2) pipelined = false;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     auto pgrid = [sms](long long tiles) { return (unsigned)(tiles < sms ? tiles : sms); };
     const size_t smem2 = (size_t)(kTileElems + 512) * 16;
     auto tc_for = [](int b, long long C) {
