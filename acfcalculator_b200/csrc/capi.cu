@@ -448,8 +448,75 @@ int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int
     return 0;
 }
 
+// One long host series, direct summation: the upload is cut into pieces on the copy stream and the lag kernel of
+// piece p (a time block whose halo lies in piece p+1, SeriesDesc.i_end < n) starts as soon as piece p+1 has landed, so
+// only the first two pieces' transfer time is exposed.  All pieces share one plan; their per-chunk partial sums are
+// folded by one reduce launch in fixed order, exactly as for a single launch.
+static int calc_correlation_pipelined(Workspace* ws, const double* y, long long n, long long ncorr, double* corr)
+{
+    const int kPieces = 8;
+    long long piece = ((n + kPieces - 1) / kPieces + 1) & ~1ll;
+    if (piece < ncorr + 2) piece = (ncorr + 3) & ~1ll;  // the halo of a piece must lie inside the next one
+    const int np = (int)((n + piece - 1) / piece);
+    cudaStream_t st = ws->stream;
+    ACF_TRY(ws->series.ensure(even_up(n) * 8));
+    ACF_TRY(ws->out.ensure((size_t)ncorr * 8));
+    double* d = ws->series.as<double>();
+    DirectPlan plan;
+    ACF_TRY(plan_direct(piece, ncorr, 1, ws->sm_count, g_force_variant, &plan));
+    ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, 1) * (size_t)np * sizeof(double)));
+    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)(np + 1)));
+    ACF_TRY(ws->queue.ensure(64, true));
+    std::vector<SeriesDesc> descs(np + 1);
+    std::vector<cudaEvent_t> landed(np);
+    for (int p = 0; p < np; ++p) {
+        const long long b = (long long)p * piece, e = b + piece < n ? b + piece : n;
+        ACF_CUDA_OK(cudaMemcpyAsync(d + b, y + b, (size_t)(e - b) * 8, cudaMemcpyHostToDevice, ws->copy_stream));
+        ACF_CUDA_OK(cudaEventCreateWithFlags(&landed[p], cudaEventDisableTiming));
+        ACF_CUDA_OK(cudaEventRecord(landed[p], ws->copy_stream));
+        const long long reach = e + ncorr < n ? e + ncorr : n;  // last sample a pair starting in this piece can touch
+        descs[p] = {d + b, reach - b, e - b};
+    }
+    descs[np] = {d, n, n};  // the whole series, for the divide by (n - k)
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * descs.size(), cudaMemcpyHostToDevice, st));
+    const size_t per_piece = direct_partial_elems(plan, 1);
+    int rc = 0;
+    for (int p = 0; p < np && rc == 0; ++p) {
+        cudaStreamWaitEvent(st, landed[p + 1 < np ? p + 1 : p], 0);
+        rc = launch_direct(plan, ws->desc.as<SeriesDesc>() + p, 1, ncorr, ws->partials.as<double>() + per_piece * p,
+                           ws->queue.as<unsigned int>(), ws->sm_count, st);
+        g_launches += 1;
+    }
+    if (rc == 0) {
+        DirectPlan all = plan;
+        all.chunks = plan.chunks * np;
+        rc = launch_reduce_partials(all, ws->desc.as<SeriesDesc>() + np, 1, ncorr, ws->partials.as<double>(),
+                                    ws->out.as<double>(), 1, st);
+        g_launches += 1;
+    }
+    cudaError_t e = cudaSuccess;
+    if (rc == 0) e = cudaMemcpyAsync(corr, ws->out.p, (size_t)ncorr * 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t es = cudaStreamSynchronize(st);
+    cudaStreamSynchronize(ws->copy_stream);
+    for (auto& ev : landed) cudaEventDestroy(ev);
+    if (rc == 0 && (e != cudaSuccess || es != cudaSuccess)) {
+        set_error("pipelined calc_correlation failed: %s", cudaGetErrorString(e != cudaSuccess ? e : es));
+        rc = ACFB200_ERR_CUDA;
+    }
+    return rc;
+}
+
 int acfb200_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr)
 {
+    {
+        Lock lk(g_mu);
+        // long series, direct summation, lags short enough for 8 pieces: overlap the upload with the kernels
+        if (y && corr && g_method == 0 && n >= (1 << 22) && ncorr >= 1 && ncorr * 16 <= n) {
+            Workspace* ws;
+            ACF_TRY(get_ws(&ws));
+            return calc_correlation_pipelined(ws, y, n, ncorr, corr);
+        }
+    }
     return acfb200_calc_correlation_batch(&y, &n, 1, ncorr, corr);
 }
 

@@ -298,3 +298,17 @@ def test_fft_batches_equal_direct(acf):
     for w in range(6):
         assert rel_to_c0(a1[w], a0[w], a0[w][0]) <= TOL and rel_to_c0(v1[w], v0[w], v0[w][0]) <= TOL
         assert r1[w]["cutoff_index"] == r0[w]["cutoff_index"] and _close(r1[w]["acf_int"], r0[w]["acf_int"])
+
+
+def test_host_entry_pipelined_upload_matches_device_entry(acf, oracle):
+    """acfb200_calc_correlation cuts a long host series into time blocks so that upload and kernels overlap; the
+    result must be what one launch over the resident series gives (same chunk partials, different grouping)."""
+    import torch
+    n, m = (1 << 22) + 12345, 3000
+    x = ou_series(n, 150.0, seed=4242)
+    host = acf.calcCorrelation(x, nCorr=m)
+    dev = acf.calc_correlation_device(torch.from_numpy(x).cuda(), m).cpu().numpy()
+    assert rel_to_c0(host, dev, dev[0]) <= 1e-13
+    lags = np.array([0, 1, 2, 17, 1000, 2999])
+    ref = oracle.calc_correlation_lags(x, lags)
+    assert rel_to_c0(host[lags], ref, ref[0]) <= TOL
