@@ -360,7 +360,10 @@ def run_native(args):
     if achieved_tf is not None:
         roofline = {
             "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / peak_tf, "traffic": None,
+            "frac": achieved_tf / peak_tf,
+            # DRAM bytes of one direct_lag_kernel launch from the committed ncu capture of this command
+            # (profiles/r1b_direct_lag_ncu_raw.csv: 80.03 MB read + 7.06 MB written); irrelevant to an FP64-bound kernel
+            "traffic": 87.08e6 if (args.workload == "ou" and n == 10**7 and m == 10**4) else None,
             "peak_source": "DFMA-chain micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
             "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS, "nominal_peak": FP64_NOMINAL_TFLOPS,
             "kernel": "direct_lag_kernel (step time includes the ~us reduce_partials epilogue)",
@@ -376,7 +379,7 @@ def run_native(args):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        cpu = cpu_reference_rate(args.workload, 1, 0)
+        cpu = cpu_reference_rate(args.workload, 1, 0, sample_products=5.0e10)  # ~10 s of one host core
         cpu.pop("ms_per_step", None)
     # informational: the same step with acfb200_set_method("auto") (the cost model sends config 2 through the
     # Wiener-Khinchin path); NOT the headline, which is the direct-lag kernel BASELINE.json names
