@@ -122,6 +122,7 @@ def cpu_reference_rate(workload, steps, warmup, sample_products=1.0e10):
     from oracle import oracle as O
     w = WORKLOADS[workload]
     m = min(w["m"], 20000) if workload != "fft" else 20000
+    sample_products = float(os.environ.get("ACFB200_BENCH_CPU_PRODUCTS", sample_products))  # tests shrink the sample
     ns = int(min(w["n"], max(4 * m, sample_products / m)))
     x = ou_series(ns, 200.0, mu=0.0, seed=1)
     if O.ref_available("libref_acf_fast.so"):
