@@ -78,7 +78,7 @@ struct Workspace {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of the next window group while the current one computes
-    Buf series, y, vel, desc, partials, out, scratch, small, fftwork, queue;
+    Buf series, y, vel, desc, partials, out, scratch, small, fftwork, queue, wins;
     void release()
     {
         series.release();
@@ -91,6 +91,7 @@ struct Workspace {
         small.release();
         fftwork.release();
         queue.release();
+        wins.release();
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         stream = nullptr;
@@ -278,27 +279,27 @@ static int pipeline_batch_device(Workspace* ws, const double* const* d_series, c
     ACF_TRY(ws->small.ensure((size_t)16 * nw));
     ReduceScratch* sc = ws->scratch.as<ReduceScratch>();
     std::vector<SeriesDesc> descs(2 * (size_t)nw);
+    std::vector<WindowDesc> wins(nw);
     size_t off = 0;
     for (int w = 0; w < nw; ++w) {
         double* d_y = ws->y.as<double>() + off;
         double* d_v = ws->vel.as<double>() + off;
-        ACF_TRY(launch_sum(d_series[w], n[w], sc + w, st));
-        ACF_TRY(launch_center_velocity(d_series[w], n[w], sc + w, d_y, d_v, dt, st));
-        ACF_TRY(launch_subtract_mean(d_v, n[w] - 2, &sc[w].vel_sum, &sc[w].vel_mean, st));
-        g_launches += 3;
+        wins[w] = {d_series[w], d_y, d_v, (long long)n[w]};
         const long long m = n[w] - 2;  // ACFcalculator.cpp:718
         descs[2 * w] = {d_y, m, m};
         descs[2 * w + 1] = {d_v, m, m};
         off += even_up(n[w]);
     }
+    // mean -> centre + velocity -> velocity mean, all windows per launch
+    ACF_TRY(ws->wins.ensure(sizeof(WindowDesc) * (size_t)nw));
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->wins.p, wins.data(), sizeof(WindowDesc) * (size_t)nw, cudaMemcpyHostToDevice, st));
+    ACF_TRY(launch_window_prep(ws->wins.as<WindowDesc>(), nw, sc, dt, st));
+    g_launches += 3;
     double* d_o = ws->out.as<double>();  // [window][acf|vacf][ncorr]
     ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
     double* d_small = ws->small.as<double>();
-    for (int w = 0; w < nw; ++w) {
-        ACF_TRY(launch_integrate_cutoff(d_o + (size_t)2 * w * ncorr, ncorr, dt, cutoff, d_small + 2 * w,
-                                        reinterpret_cast<long long*>(d_small + 2 * w + 1), nullptr, st));
-        g_launches += 1;
-    }
+    ACF_TRY(launch_integrate_cutoff_batch(d_o, 2 * ncorr, nw, ncorr, dt, cutoff, d_small, st));
+    g_launches += 1;
     if (d_acf)
         ACF_CUDA_OK(cudaMemcpy2DAsync(d_acf, ncorr * 8, d_o, 2 * ncorr * 8, ncorr * 8, nw, cudaMemcpyDeviceToDevice, st));
     if (d_vacf)

@@ -70,6 +70,14 @@ struct ReduceScratch {
     double partial[kReduceBlocks];
     unsigned int ticket[4];
 };
+// One window of the batched pre-processing: input series, centred copy, velocity series (n-2 samples)
+struct WindowDesc {
+    const double* x;
+    double* y;
+    double* vel;
+    long long n;
+};
+int launch_window_prep(const WindowDesc* d_wins, int nw, ReduceScratch* d_sc, double dt, cudaStream_t st);
 int launch_sum(const double* d_x, long long n, ReduceScratch* sc, cudaStream_t st);
 // y[i] = x[i] - sum/n, and (d_vel != null) vel_raw[i-1] = (y[i+1]-y[i-1])/(2.0*dt) with sc->vel_sum = sum(vel_raw)
 int launch_center_velocity(const double* d_x, long long n, ReduceScratch* sc, double* d_y,
@@ -83,6 +91,9 @@ int launch_sumsq(const double* d_x, long long n, ReduceScratch* sc, cudaStream_t
 //   d_out[0] = integral, d_brk[0] = break index or -1; d_cum (nullable) = cumulative integral, ncorr entries
 int launch_integrate_cutoff(const double* d_acf, long long ncorr, double dt, double cutoff, double* d_out,
                             long long* d_brk, double* d_cum, cudaStream_t st);
+// nb correlation functions `acf_stride` doubles apart; results: d_small[2*b] = integral, d_small[2*b+1] = break index
+int launch_integrate_cutoff_batch(const double* d_acf, long long acf_stride, int nb, long long ncorr, double dt,
+                                  double cutoff, double* d_small, cudaStream_t st);
 // acf[i] *= target / acf[0]  (spring rescale, ACFcalculator.cpp:740-742 / :746-749)
 int launch_rescale(double* d_acf, long long ncorr, double target, cudaStream_t st);
 

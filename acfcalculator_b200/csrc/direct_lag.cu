@@ -248,7 +248,7 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
         return 1;
     }
     if (max_i_end < 1) max_i_end = 1;
-    const int warps_per_sm = 16;  // 128 registers/thread
+    const int warps_per_sm = env_int("ACFB200_WARPS_PER_SM", 16);  // 16 = the 128-registers/thread limit
     const int smem_per_sm = 228 * 1024;
     int fv = env_int("ACFB200_VARIANT", force_variant);
     int fw = env_int("ACFB200_WARPS", 0);
@@ -354,7 +354,7 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
         return 1;
     }
     long long ts = ts_max;
-    const long long ts_cap = (4096 / LI) / R * R;  // tiles of <= ~4096 samples keep the chunks balanced
+    const long long ts_cap = (env_int("ACFB200_TI_CAP", 4096) / LI) / R * R;  // tiles of <= ~4096 samples keep the chunks balanced
     if (ts > ts_cap) ts = ts_cap;
     const long long ts_need = ((max_i_end + LI - 1) / LI + R - 1) / R * R;  // short series: one small tile
     if (ts > ts_need) ts = ts_need;

@@ -16,8 +16,14 @@ constexpr int kIntThreads = 1024;
 
 __global__ void __launch_bounds__(kIntThreads)
 integrate_cutoff_kernel(const double* __restrict__ acf, long long ncorr, double dt, double cutoff,
-                        double* __restrict__ out, long long* __restrict__ brk_out, double* __restrict__ cum)
+                        double* __restrict__ out, long long* __restrict__ brk_out, double* __restrict__ cum,
+                        long long acf_stride)
 {
+    if (acf_stride > 0) {  // batched form: function blockIdx.x, results packed as (integral, break index) pairs
+        acf += (long long)blockIdx.x * acf_stride;
+        out += 2 * blockIdx.x;
+        brk_out = reinterpret_cast<long long*>(out + 1);
+    }
     __shared__ long long sh_min[32];
     __shared__ double sh_sum[32];
     __shared__ long long sh_brk;
@@ -86,14 +92,14 @@ integrate_cutoff_kernel(const double* __restrict__ acf, long long ncorr, double 
         if (i == stop) out[0] = run;
         run += 0.5 * (acf[i] + acf[i + 1]) * dt;
     }
-    if (hi == nterm && lo <= nterm && (lo < hi || tid == 0 || lo == nterm)) {
-        // the thread that owns the end of the range publishes I(t_{ncorr-1})
-        if (hi == nterm && (lo < nterm ? true : (tid == 0 || (lo - per) < nterm))) {
-            if (lo < hi || nterm == 0 || (lo == nterm && lo - per < nterm)) {
-                if (cum && ncorr > 0) cum[nterm] = run;
-                if (stop == nterm) out[0] = run;
-            }
-        }
+    if (nterm > 0 && tid == (int)((nterm - 1) / per)) {
+        // exactly one thread -- the owner of the last trapezoid -- publishes I(t_{ncorr-1})
+        if (cum) cum[nterm] = run;
+        if (stop == nterm) out[0] = run;
+    }
+    if (nterm == 0 && tid == 0) {
+        if (cum && ncorr > 0) cum[0] = 0.0;
+        out[0] = 0.0;
     }
     if (tid == 0) brk_out[0] = (stop == nterm) ? -1 : stop;
 }
@@ -110,7 +116,15 @@ rescale_kernel(double* __restrict__ acf, long long ncorr, double target)
 int launch_integrate_cutoff(const double* d_acf, long long ncorr, double dt, double cutoff, double* d_out,
                             long long* d_brk, double* d_cum, cudaStream_t st)
 {
-    integrate_cutoff_kernel<<<1, kIntThreads, 0, st>>>(d_acf, ncorr, dt, cutoff, d_out, d_brk, d_cum);
+    integrate_cutoff_kernel<<<1, kIntThreads, 0, st>>>(d_acf, ncorr, dt, cutoff, d_out, d_brk, d_cum, 0);
+    ACF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_integrate_cutoff_batch(const double* d_acf, long long acf_stride, int nb, long long ncorr, double dt,
+                                  double cutoff, double* d_small, cudaStream_t st)
+{
+    integrate_cutoff_kernel<<<nb, kIntThreads, 0, st>>>(d_acf, ncorr, dt, cutoff, d_small, nullptr, nullptr, acf_stride);
     ACF_CUDA_OK(cudaGetLastError());
     return 0;
 }

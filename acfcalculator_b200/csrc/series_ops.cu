@@ -80,9 +80,18 @@ __device__ __forceinline__ void cta_slice(long long n, long long* lo, long long*
 template <bool SQUARE>
 __global__ void __launch_bounds__(kThreads)
 sum_kernel(const double* __restrict__ x, long long n, double* __restrict__ partial, double* __restrict__ out,
-           double den, unsigned int* ticket)
+           double den, unsigned int* ticket, const WindowDesc* __restrict__ wins, ReduceScratch* __restrict__ scs)
 {
     __shared__ double sh[32];
+    if (wins) {  // batched form: one window per blockIdx.y
+        const WindowDesc w = wins[blockIdx.y];
+        ReduceScratch* sc = scs + blockIdx.y;
+        x = w.x;
+        n = w.n;
+        partial = sc->partial;
+        out = &sc->sum;
+        ticket = &sc->ticket[0];
+    }
     long long lo, hi;
     cta_slice(n, &lo, &hi);
     const bool vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
@@ -109,9 +118,23 @@ sum_kernel(const double* __restrict__ x, long long n, double* __restrict__ parti
 __global__ void __launch_bounds__(kThreads)
 center_velocity_kernel(const double* __restrict__ x, long long n, const double* __restrict__ sum, double* mean_out,
                        double* __restrict__ y, double* __restrict__ vel, double dt, double* __restrict__ partial,
-                       double* __restrict__ vel_sum, unsigned int* ticket)
+                       double* __restrict__ vel_sum, unsigned int* ticket, const WindowDesc* __restrict__ wins,
+                       ReduceScratch* __restrict__ scs)
 {
     __shared__ double sh[32];
+    if (wins) {  // batched form: one window per blockIdx.y
+        const WindowDesc w = wins[blockIdx.y];
+        ReduceScratch* sc = scs + blockIdx.y;
+        x = w.x;
+        n = w.n;
+        y = w.y;
+        vel = w.vel;
+        sum = &sc->sum;
+        mean_out = &sc->mean;
+        partial = sc->partial;
+        vel_sum = &sc->vel_sum;
+        ticket = &sc->ticket[2];
+    }
     const double mean = sum[0] / (double)n;
     if (blockIdx.x == 0 && threadIdx.x == 0 && mean_out) mean_out[0] = mean;
     long long lo, hi;
@@ -177,8 +200,17 @@ center_velocity_kernel(const double* __restrict__ x, long long n, const double* 
 }
 
 __global__ void __launch_bounds__(kThreads)
-subtract_mean_kernel(double* __restrict__ x, long long n, const double* __restrict__ sum, double* mean_out)
+subtract_mean_kernel(double* __restrict__ x, long long n, const double* __restrict__ sum, double* mean_out,
+                     const WindowDesc* __restrict__ wins, ReduceScratch* __restrict__ scs)
 {
+    if (wins) {  // batched form: the velocity series of window blockIdx.y (n-2 samples)
+        const WindowDesc w = wins[blockIdx.y];
+        ReduceScratch* sc = scs + blockIdx.y;
+        x = w.vel;
+        n = w.n - 2;
+        sum = &sc->vel_sum;
+        mean_out = &sc->vel_mean;
+    }
     const double mean = sum[0] / (double)n;
     if (blockIdx.x == 0 && threadIdx.x == 0 && mean_out) mean_out[0] = mean;
     const long long stride = (long long)gridDim.x * kThreads;
@@ -210,14 +242,16 @@ subtract_mean_kernel(double* __restrict__ x, long long n, const double* __restri
 
 int launch_sum(const double* d_x, long long n, ReduceScratch* sc, cudaStream_t st)
 {
-    sum_kernel<false><<<kReduceBlocks, kThreads, 0, st>>>(d_x, n, sc->partial, &sc->sum, 0.0, &sc->ticket[0]);
+    sum_kernel<false><<<kReduceBlocks, kThreads, 0, st>>>(d_x, n, sc->partial, &sc->sum, 0.0, &sc->ticket[0], nullptr,
+                                                           nullptr);
     ACF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int launch_sumsq(const double* d_x, long long n, ReduceScratch* sc, cudaStream_t st)
 {
-    sum_kernel<true><<<kReduceBlocks, kThreads, 0, st>>>(d_x, n, sc->partial, &sc->meansq, (double)n, &sc->ticket[1]);
+    sum_kernel<true><<<kReduceBlocks, kThreads, 0, st>>>(d_x, n, sc->partial, &sc->meansq, (double)n, &sc->ticket[1],
+                                                          nullptr, nullptr);
     ACF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -226,14 +260,32 @@ int launch_center_velocity(const double* d_x, long long n, ReduceScratch* sc, do
                            cudaStream_t st)
 {
     center_velocity_kernel<<<kReduceBlocks, kThreads, 0, st>>>(d_x, n, &sc->sum, &sc->mean, d_y, d_vel, dt, sc->partial,
-                                                                &sc->vel_sum, &sc->ticket[2]);
+                                                                &sc->vel_sum, &sc->ticket[2], nullptr, nullptr);
     ACF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int launch_subtract_mean(double* d_x, long long n, const double* d_sum, double* d_mean_out, cudaStream_t st)
 {
-    subtract_mean_kernel<<<kReduceBlocks, kThreads, 0, st>>>(d_x, n, d_sum, d_mean_out);
+    subtract_mean_kernel<<<kReduceBlocks, kThreads, 0, st>>>(d_x, n, d_sum, d_mean_out, nullptr, nullptr);
+    ACF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// The three per-window steps of the main() sequence for nw windows in three launches (grid.y = window):
+// mean -> centre + velocity (+ its sum) -> velocity mean removed.  Blocks per window shrink with the window count so
+// that the grid stays a few waves; the slice/ticket logic is per window, so results do not depend on nw.
+int launch_window_prep(const WindowDesc* d_wins, int nw, ReduceScratch* d_sc, double dt, cudaStream_t st)
+{
+    if (nw < 1 || nw > 65535) {
+        set_error("launch_window_prep: 1..65535 windows per launch (got %d)", nw);
+        return 1;
+    }
+    const dim3 grid(kReduceBlocks, nw);
+    sum_kernel<false><<<grid, kThreads, 0, st>>>(nullptr, 0, nullptr, nullptr, 0.0, nullptr, d_wins, d_sc);
+    center_velocity_kernel<<<grid, kThreads, 0, st>>>(nullptr, 0, nullptr, nullptr, nullptr, nullptr, dt, nullptr, nullptr,
+                                                       nullptr, d_wins, d_sc);
+    subtract_mean_kernel<<<grid, kThreads, 0, st>>>(nullptr, 0, nullptr, nullptr, d_wins, d_sc);
     ACF_CUDA_OK(cudaGetLastError());
     return 0;
 }

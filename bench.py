@@ -229,7 +229,7 @@ def run_native(args):
         d_w = [h.to(dev, non_blocking=True) for h in h_w]
         products_rank = 2.0 * len(mine) * (n - 2) * m
         fmas_rank = 2.0 * len(mine) * (float(m) * (n - 2) - m * (m - 1) / 2.0)
-        launches_per_step = len(mine) * 4 + 2
+        launches_per_step = 6
         plan = A.describe_plan(n - 2, m, 2 * max(1, len(mine)))
         res = {}
 
