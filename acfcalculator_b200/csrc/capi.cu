@@ -693,21 +693,32 @@ int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double 
 int acfb200_spring_rescale(double* acf, double* vacf, int64_t ncorr, double k_spring, double mass_amu,
                            double temperature, double* var, double* var_vel)
 {
+    Lock lk(g_mu);
     if (!acf || !vacf || ncorr < 1) {
         set_error("spring_rescale: null argument or ncorr < 1");
         return ACFB200_ERR_ARG;
     }
-    // ACFcalculator.cpp:730-753, constants :37 (kB) and :42 (R); O(ncorr) host arithmetic in the
-    // same evaluation order, so the result is bit-identical to the reference's.
+    // ACFcalculator.cpp:730-753, constants :37 (kB) and :42 (R).  The two target variances are scalars; the
+    // element-wise rescale acf[i] *= target/acf[0] runs on the device (IEEE divide and multiply: the same bits the
+    // reference's loop produces).
     const double kB = 1.38064852E-23, R = 8.314;
     const double mass = 1.66054e-27 * mass_amu;
     const double k = k_spring * 4184.0;
     const double v = R * temperature / k;
-    double factor = v / acf[0];
-    for (int64_t i = 0; i < ncorr; ++i) acf[i] *= factor;
     const double vv = 1.0E-10 * kB * temperature / mass;
-    factor = vv / vacf[0];
-    for (int64_t i = 0; i < ncorr; ++i) vacf[i] *= factor;
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    cudaStream_t st = ws->stream;
+    ACF_TRY(ws->out.ensure((size_t)2 * ncorr * 8));
+    double* d = ws->out.as<double>();
+    ACF_CUDA_OK(cudaMemcpyAsync(d, acf, (size_t)ncorr * 8, cudaMemcpyHostToDevice, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(d + ncorr, vacf, (size_t)ncorr * 8, cudaMemcpyHostToDevice, st));
+    ACF_TRY(launch_rescale(d, ncorr, v, st));
+    ACF_TRY(launch_rescale(d + ncorr, ncorr, vv, st));
+    g_launches += 2;
+    ACF_CUDA_OK(cudaMemcpyAsync(acf, d, (size_t)ncorr * 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(vacf, d + ncorr, (size_t)ncorr * 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
     if (var) *var = v;
     if (var_vel) *var_vel = vv;
     return 0;

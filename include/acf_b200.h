@@ -106,7 +106,7 @@ ACFB200_API int acfb200_acf_pipeline(const double* series, int64_t n, int64_t nc
 ACFB200_API int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, int nwindows, int64_t ncorr, double dt,
                                double cutoff, double* acf, double* vacf, acfb200_result* result);
 
-/* Spring-constant rescale of acf/vacf in place, ACFcalculator.cpp:730-753 (host arrays; O(ncorr)).
+/* Spring-constant rescale of acf/vacf in place, ACFcalculator.cpp:730-753 (host arrays, rescaled on the device).
  * var/var_vel receive R*T/k and 1e-10*kB*T/m. */
 ACFB200_API int acfb200_spring_rescale(double* acf, double* vacf, int64_t ncorr, double k_spring, double mass_amu,
                            double temperature, double* var, double* var_vel);

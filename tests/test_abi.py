@@ -85,14 +85,6 @@ def test_no_cpu_fallback(acf):
         acf.acf_pipeline(np.arange(10.0), 3, 1.0)
 
 
-def test_spring_rescale_is_host_arithmetic(acf, oracle):
-    acf_in = np.array([2.0, 1.0, 0.5])
-    vacf_in = np.array([4.0, -1.0, 0.25])
-    got = acf.spring_rescale(acf_in, vacf_in, 10.0, 18.0, 298.15)
-    want = oracle.spring_rescale(acf_in, vacf_in, 10.0, 18.0, 298.15)
-    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2:] == want[2:]
-
-
 def test_product_does_not_import_oracle():
     """The oracle is test infrastructure; nothing under acfcalculator_b200/ may reference it."""
     pkg = os.path.join(ROOT, "acfcalculator_b200")

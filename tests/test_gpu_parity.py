@@ -312,3 +312,12 @@ def test_host_entry_pipelined_upload_matches_device_entry(acf, oracle):
     lags = np.array([0, 1, 2, 17, 1000, 2999])
     ref = oracle.calc_correlation_lags(x, lags)
     assert rel_to_c0(host[lags], ref, ref[0]) <= TOL
+
+
+def test_spring_rescale_is_bit_identical(acf, oracle):
+    """ACFcalculator.cpp:730-753 on the device: one IEEE divide and one multiply per element -> the oracle's bits."""
+    x = ou_series(50000, 30.0, seed=12)
+    r = oracle.acf_pipeline(x, 700, 1.0, 0.0)
+    got = acf.spring_rescale(r["acf"], r["vacf"], 10.0, 18.0, 298.15)
+    want = oracle.spring_rescale(r["acf"], r["vacf"], 10.0, 18.0, 298.15)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2:] == want[2:]
