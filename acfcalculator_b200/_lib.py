@@ -63,6 +63,11 @@ SIGNATURES = {
                                               C.c_void_p, C.POINTER(Result), C.c_void_p]),
     "acfb200_acf_pipeline_batch_device": (C.c_int, [_PP, _PI64, C.c_int, _I64, C.c_double, C.c_double, C.c_void_p,
                                                     C.c_void_p, C.POINTER(Result), C.c_void_p]),
+    "acfb200_multi_gpu_calc_correlation": (C.c_int, [_PP, _PI64, C.c_int, _I64, C.c_void_p, C.c_int]),
+    "acfb200_multi_gpu_pipeline_batch": (C.c_int, [_PP, _PI64, C.c_int, _I64, C.c_double, C.c_double, C.c_void_p,
+                                                   C.c_void_p, C.POINTER(Result), C.c_int]),
+    "acfb200_multi_gpu_green_kubo": (C.c_int, [_PP, C.c_int, _I64, _I64, C.c_double, C.c_double, C.c_double,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "acfb200_calc_correlation_fft": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p]),
     "acfb200_calc_correlation_fft_device": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p, C.c_void_p]),
     "acfb200_describe_plan": (C.c_int, [_I64, _I64, C.c_int, C.c_char_p, C.c_int]),

@@ -319,3 +319,42 @@ def measure_dfma_probe(probe):
     tf = C.c_double(0)
     check(_lib.load().acfb200_measure_dfma_probe(int(probe), C.byref(tf)))
     return tf.value
+
+
+# ---------------------------------------------------------------------------------------------------
+# several GPUs of one box from a single process (host threads + NCCL inside the library)
+# ---------------------------------------------------------------------------------------------------
+def multi_gpu_calc_correlation(series, nCorr, ngpus=0):
+    arrs = [_f64(s) for s in series]
+    ns = len(arrs)
+    ptrs = (C.c_void_p * ns)(*[a.ctypes.data for a in arrs])
+    lens = (C.c_int64 * ns)(*[a.size for a in arrs])
+    out = np.empty((ns, int(nCorr)), dtype=np.float64)
+    check(_lib.load().acfb200_multi_gpu_calc_correlation(ptrs, lens, ns, int(nCorr), _vp(out), int(ngpus)))
+    return out
+
+
+def multi_gpu_pipeline_batch(windows, nCorr, timestep, cutoff=0.0, ngpus=0):
+    arrs = [_f64(s) for s in windows]
+    nw = len(arrs)
+    ptrs = (C.c_void_p * nw)(*[a.ctypes.data for a in arrs])
+    lens = (C.c_int64 * nw)(*[a.size for a in arrs])
+    acf = np.empty((nw, int(nCorr)), dtype=np.float64)
+    vacf = np.empty((nw, int(nCorr)), dtype=np.float64)
+    res = (Result * nw)()
+    check(_lib.load().acfb200_multi_gpu_pipeline_batch(ptrs, lens, nw, int(nCorr), float(timestep), float(cutoff),
+                                                       _vp(acf), _vp(vacf), res, int(ngpus)))
+    return acf, vacf, [r.as_dict() for r in res]
+
+
+def multi_gpu_green_kubo(components, nCorr, timestep, box_length=31.0399376148, temperature=298.15, ngpus=0):
+    arrs = [_f64(c) for c in components]
+    nc = len(arrs)
+    n = arrs[0].size
+    ptrs = (C.c_void_p * nc)(*[a.ctypes.data for a in arrs])
+    acf = np.empty((nc, int(nCorr)), dtype=np.float64)
+    integ = np.empty(nc, dtype=np.float64)
+    eta = np.empty(nc, dtype=np.float64)
+    check(_lib.load().acfb200_multi_gpu_green_kubo(ptrs, nc, n, int(nCorr), float(timestep), float(box_length),
+                                                   float(temperature), _vp(acf), _vp(integ), _vp(eta), int(ngpus)))
+    return acf, integ, eta

@@ -3,7 +3,7 @@
 // off-diagonal components (i % 4 != 0), maxcorr 1000, 2 fs, box length and temperature as hard-coded there,
 // and the same stdout grammar.  The correlations and integrals run on the GPU through libacf_b200.so.
 //
-//   viscosity <namd.log> [--maxcorr M] [--timestep fs] [--box A] [--temperature K] [--exact-reader]
+//   viscosity <namd.log> [--maxcorr M] [--timestep fs] [--box A] [--temperature K] [--exact-reader] [--gpus G]
 // The optional switches are extensions; without them the output is the reference's.
 #include <cmath>
 #include <cstdlib>
@@ -23,6 +23,7 @@ int main(int argc, char* argv[])
     double box_length = 31.0399376148;  // :186
     double temperature = 298.15;        // :188
     bool quirk = true;
+    int gpus = 1;  // --gpus G: spread the components (or time blocks of them) over G devices of this box
     if (argc < 2) return 1;
     const char* fname = argv[1];
     for (int i = 2; i < argc; ++i) {
@@ -37,6 +38,8 @@ int main(int argc, char* argv[])
             box_length = atof(argv[++i]);
         else if (i + 1 < argc && a == "--temperature")
             temperature = atof(argv[++i]);
+        else if (i + 1 < argc && a == "--gpus")
+            gpus = atoi(argv[++i]);
         else {
             std::cerr << "viscosity: unknown argument " << a << std::endl;
             return 1;
@@ -54,8 +57,11 @@ int main(int argc, char* argv[])
     }
     const int nc = (int)ptrs.size();
     std::vector<double> acf((size_t)nc * ncorr), integrals(nc), eta(nc);
-    if (acfb200_green_kubo(ptrs.data(), nc, num_samples, ncorr, timestep, box_length, temperature, acf.data(),
-                           integrals.data(), eta.data()) != ACFB200_OK) {
+    const int rc = gpus == 1 ? acfb200_green_kubo(ptrs.data(), nc, num_samples, ncorr, timestep, box_length, temperature,
+                                                  acf.data(), integrals.data(), eta.data())
+                             : acfb200_multi_gpu_green_kubo(ptrs.data(), nc, num_samples, ncorr, timestep, box_length,
+                                                            temperature, acf.data(), integrals.data(), eta.data(), gpus);
+    if (rc != ACFB200_OK) {
         std::cerr << "viscosity: " << acfb200_last_error() << std::endl;
         return 2;
     }

@@ -148,6 +148,19 @@ ACFB200_API int acfb200_acf_pipeline_batch_device(const double* const* d_series,
                                       double dt, double cutoff, double* d_acf, double* d_vacf, acfb200_result* result,
                                       void* stream);
 
+/* ---- several GPUs of one box, one process (one host thread per device) ----------------------------------------
+ * nseries >= devices: series s on device s mod G, no communication.  Fewer series: every series is cut into G time
+ * blocks (block g plus its (ncorr-1)-sample halo on device g), raw lag sums per block, ONE ncclAllReduce(sum) of
+ * nseries*ncorr doubles over NVLink (NCCL is dlopen()ed on first use), divide by (n-k) on device 0.
+ * ngpus <= 0 means "all visible devices".  Same outputs as the single-device entry points. */
+ACFB200_API int acfb200_multi_gpu_calc_correlation(const double* const* y, const int64_t* n, int nseries, int64_t ncorr, double* corr,
+                                       int ngpus);
+ACFB200_API int acfb200_multi_gpu_pipeline_batch(const double* const* series, const int64_t* n, int nwindows, int64_t ncorr, double dt,
+                                     double cutoff, double* acf, double* vacf, acfb200_result* result, int ngpus);
+ACFB200_API int acfb200_multi_gpu_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t ncorr, double dt,
+                                 double box_length, double temperature, double* acf, double* integrals, double* eta,
+                                 int ngpus);
+
 /* Zero-padded Wiener-Khinchin path for maxcorr -> n (no reference implementation exists; the
  * reference's FFT stub ACFcalculator.cpp:148-200 is dead code).  Same contract as
  * acfb200_calc_correlation[_device]; results agree with the direct sum to ~1e-13*corr[0]. */

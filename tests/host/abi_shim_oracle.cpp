@@ -60,6 +60,14 @@ int acfb200_integrate_corr_cutoff(const double* acf, int64_t ncorr, double dt, d
 }
 
 int acfb200_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t ncorr, double dt, double box_length,
+                       double temperature, double* acf, double* integrals, double* eta);
+int acfb200_multi_gpu_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t ncorr, double dt,
+                                 double box_length, double temperature, double* acf, double* integrals, double* eta, int)
+{
+    return acfb200_green_kubo(comps, ncomp, n, ncorr, dt, box_length, temperature, acf, integrals, eta);
+}
+
+int acfb200_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t ncorr, double dt, double box_length,
                        double temperature, double* acf, double* integrals, double* eta)
 {
     for (int c = 0; c < ncomp; ++c) {

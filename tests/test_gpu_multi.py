@@ -1,0 +1,70 @@
+"""Multi-GPU entry points of the C library (host threads + NCCL inside one process).  Need >= 2 visible GPUs;
+the single-GPU round-end run skips them, `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu` runs them."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cli_inputs import write_pressure_log
+from conftest import GOLDEN, ROOT, ou_series, rel_to_c0
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ngpus(acf):
+    n = acf.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    return n
+
+
+def test_series_sharding(acf, ngpus):
+    """Series s on device s mod G.  The time-chunk count of a launch depends on how many series it holds, so the
+    partial sums are grouped differently than in the one-device launch: agreement to rounding, not bit identity."""
+    series = [ou_series(80000 + 13 * s, 20.0 + s, seed=300 + s) for s in range(2 * ngpus + 1)]
+    one = acf.calcCorrelationBatch(series, 900)
+    many = acf.multi_gpu_calc_correlation(series, 900, ngpus)
+    for a, b in zip(one, many):
+        assert rel_to_c0(b, a, a[0]) <= 1e-13
+    assert np.array_equal(many, acf.multi_gpu_calc_correlation(series, 900, ngpus))   # reproducible
+
+
+def test_time_blocks_with_nccl_allreduce(acf, oracle, ngpus):
+    """Fewer series than devices: every series is cut into time blocks, one ncclAllReduce combines the lag sums."""
+    x = ou_series(3_000_001, 200.0, sigma=50.0, seed=20260201)
+    one = acf.calcCorrelation(x, nCorr=4000)
+    many = acf.multi_gpu_calc_correlation([x], 4000, ngpus)[0]
+    assert rel_to_c0(many, one, one[0]) <= 1e-13
+    lags = np.array([0, 1, 7, 100, 3999])
+    ref = oracle.calc_correlation_lags(x, lags)
+    assert rel_to_c0(many[lags], ref, ref[0]) <= 1e-10
+    again = acf.multi_gpu_calc_correlation([x], 4000, ngpus)[0]
+    assert np.array_equal(many, again)         # reproducible run to run
+
+
+def test_window_pipeline_sharding(acf, ngpus):
+    wins = [ou_series(60000 + 5 * w, 30.0 + w, sigma=0.25, mu=-3.0 + w, seed=900 + w) for w in range(2 * ngpus + 1)]
+    a1, v1, r1 = acf.acf_pipeline_batch(wins, 700, 2.0, 0.05)
+    a2, v2, r2 = acf.multi_gpu_pipeline_batch(wins, 700, 2.0, 0.05, ngpus)
+    for w in range(len(wins)):
+        assert rel_to_c0(a2[w], a1[w], a1[w][0]) <= 1e-13 and rel_to_c0(v2[w], v1[w], v1[w][0]) <= 1e-13
+        assert r1[w]["avg"] == r2[w]["avg"] and r1[w]["cutoff_index"] == r2[w]["cutoff_index"]
+        assert abs(r1[w]["acf_int"] - r2[w]["acf_int"]) <= 1e-12 * abs(r1[w]["acf_int"])
+
+
+def test_green_kubo_and_viscosity_cli(acf, ngpus, tmp_path):
+    g = np.load(os.path.join(GOLDEN, "f3_viscosity.npz"))
+    a1, i1, e1 = acf.green_kubo(list(g["comps"]), 1000, 2.0)
+    a2, i2, e2 = acf.multi_gpu_green_kubo(list(g["comps"]), 1000, 2.0, ngpus=ngpus)
+    assert rel_to_c0(a2, a1, a1[0][0]) <= 1e-13 and np.allclose(i1, i2, rtol=1e-12) and np.allclose(e1, e2, rtol=1e-12)
+    pres = np.load(os.path.join(GOLDEN, "cli_pressure.npz"))["pressure"]
+    log = str(tmp_path / "namd.log")
+    write_pressure_log(log, pres)
+    exe = os.path.join(ROOT, "acfcalculator_b200", "bin", "viscosity")
+    one = subprocess.run([exe, log], capture_output=True, text=True)
+    many = subprocess.run([exe, log, "--gpus", str(ngpus)], capture_output=True, text=True)
+    assert one.returncode == 0 and many.returncode == 0, many.stderr
+    assert len(one.stdout.splitlines()) == len(many.stdout.splitlines())
+    assert one.stdout.splitlines()[-1].split()[:2] == many.stdout.splitlines()[-1].split()[:2]
