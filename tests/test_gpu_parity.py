@@ -210,8 +210,8 @@ def test_errors_are_reported_not_swallowed(acf):
 
 
 # ---- K2: zero-padded Wiener-Khinchin path --------------------------------------------------------------
-@pytest.mark.parametrize("n,m", [(7, 3), (100, 100), (500, 13), (513, 512), (5001, 1000), (40000, 30000),
-                                 (100000, 99999), (262144, 1), (300000, 262144)])
+@pytest.mark.parametrize("n,m", [(7, 3), (100, 100), (500, 13), (513, 512), (1500, 500), (3000, 1000), (5001, 1000),
+                                 (40000, 30000), (100000, 99999), (262144, 1), (300000, 262144)])
 def test_fft_path_matches_oracle(acf, oracle, n, m):
     """One-, two- and three-factor transform plans against the direct-sum oracle."""
     x = ou_series(n, 30.0, mu=0.25, seed=n + 3 * m)
@@ -385,3 +385,18 @@ def test_full_size_config5_fft(acf, oracle):
     assert rel_to_c0(got[lags], ref, ref[0]) <= TOL
     assert _close(got[0], float(np.dot(x, x)) / n, 1e-12)
     assert np.all(np.isfinite(got))
+
+
+def test_fft_small_batches_use_the_simple_kernels(acf):
+    """Windows short enough for the one- and two-factor plans (non-pipelined kernels, series index = grid.z)."""
+    for n, m in ((400, 100), (1500, 500), (3000, 900)):
+        wins = [ou_series(n, 8.0 + w, mu=0.5 * w, seed=40 + w) for w in range(5)]
+        a0, v0, r0 = acf.acf_pipeline_batch(wins, m, 1.0, 0.05)
+        try:
+            acf.set_method("fft")
+            a1, v1, r1 = acf.acf_pipeline_batch(wins, m, 1.0, 0.05)
+        finally:
+            acf.set_method("direct")
+        for w in range(5):
+            assert rel_to_c0(a1[w], a0[w], a0[w][0]) <= TOL and rel_to_c0(v1[w], v0[w], v0[w][0]) <= TOL
+            assert r1[w]["cutoff_index"] == r0[w]["cutoff_index"]
