@@ -26,6 +26,14 @@ class Result(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class MsdResult(C.Structure):
+    """struct acfb200_msd_result"""
+    _fields_ = [("sum", C.c_double), ("slope", C.c_double), ("diffusivity", C.c_double), ("nframes", _I64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class AcfError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libacf_b200 error {code}: {msg}")
@@ -70,6 +78,15 @@ SIGNATURES = {
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "acfb200_calc_correlation_fft": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p]),
     "acfb200_calc_correlation_fft_device": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p, C.c_void_p]),
+    "acfb200_msd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, _I64, _I64, C.c_void_p, C.c_void_p]),
+    "acfb200_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, C.c_double]),
+    "acfb200_msd_slope": (C.c_int, [C.c_void_p, _I64, _P, _P]),
+    "acfb200_traj2diffusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, _I64, _I64, C.c_double, C.c_double,
+                                         C.c_int, C.c_void_p, C.c_void_p, C.POINTER(MsdResult)]),
+    "acfb200_msd_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, _I64, _I64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "acfb200_image_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, C.c_double, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
     "acfb200_describe_plan": (C.c_int, [_I64, _I64, C.c_int, C.c_char_p, C.c_int]),
     "acfb200_set_variant": (C.c_int, [C.c_int]),
     "acfb200_set_method": (C.c_int, [C.c_int]),

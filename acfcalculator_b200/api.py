@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Result, check
+from ._lib import MsdResult, Result, check
 
 _P = C.POINTER(C.c_double)
 
@@ -195,6 +195,57 @@ def green_kubo(components, nCorr, timestep, box_length=31.0399376148, temperatur
 
 
 # ---------------------------------------------------------------------------------------------------
+# traj2diffusion (names after /root/reference/traj2diffusion.cpp: image :275, slope :342, main :497-552)
+# ---------------------------------------------------------------------------------------------------
+def _axes(x, y=None, z=None):
+    """Three float64 arrays; y/z omitted = the same array three times (what the general reader yields, :186-231)."""
+    x = _f64(x)
+    y = x if y is None else _f64(y)
+    z = x if z is None else _f64(z)
+    if not (x.size == y.size == z.size):
+        raise ValueError("x, y and z must have the same length")
+    return x, y, z
+
+
+def msd(x, y=None, z=None, stride=1, max_s=1000):
+    """(msd[max_s], msd_counter[max_s]) of traj2diffusion.cpp:530-545."""
+    x, y, z = _axes(x, y, z)
+    out = np.empty(int(max_s), dtype=np.float64)
+    cnt = np.empty(int(max_s), dtype=np.int32)
+    check(_lib.load().acfb200_msd(_vp(x), _vp(y), _vp(z), x.size, int(stride), int(max_s), _vp(out), _vp(cnt)))
+    return out, cnt
+
+
+def image(x, y, z, L):
+    """Unwrapped copies of the coordinate arrays (image(), traj2diffusion.cpp:275-340)."""
+    x, y, z = (_f64(a).copy() for a in (x, y, z))
+    check(_lib.load().acfb200_image(_vp(x), _vp(y), _vp(z), x.size, float(L)))
+    return x, y, z
+
+
+def slope(msd_arr):
+    """(slope, sum) of slope() (:342-355)."""
+    m = _f64(msd_arr)
+    sl, sm = C.c_double(), C.c_double()
+    check(_lib.load().acfb200_msd_slope(_vp(m), m.size, C.byref(sl), C.byref(sm)))
+    return sl.value, sm.value
+
+
+def traj2diffusion(x, y=None, z=None, stride=1, max_s=1000, timestep=1.0, cell=None):
+    """main() of traj2diffusion after the reader: dict(msd, counter, sum, slope, diffusivity [A^2/fs], nframes)."""
+    x, y, z = _axes(x, y, z)
+    out = np.empty(int(max_s), dtype=np.float64)
+    cnt = np.empty(int(max_s), dtype=np.int32)
+    res = MsdResult()
+    check(_lib.load().acfb200_traj2diffusion(_vp(x), _vp(y), _vp(z), x.size, int(stride), int(max_s), float(timestep),
+                                             0.0 if cell is None else float(cell), 0 if cell is None else 1,
+                                             _vp(out), _vp(cnt), C.byref(res)))
+    d = res.as_dict()
+    d.update(msd=out, counter=cnt)
+    return d
+
+
+# ---------------------------------------------------------------------------------------------------
 # device-resident (torch CUDA tensors; torch is plumbing: memory + streams)
 # ---------------------------------------------------------------------------------------------------
 def _stream_ptr(stream=None):
@@ -298,6 +349,30 @@ def acf_pipeline_batch_device(windows, ncorr, timestep, cutoff=0.0, want_results
                                                         C.c_void_p(acf.data_ptr()), C.c_void_p(vacf.data_ptr()),
                                                         res, _stream_ptr(stream)))
     return acf, vacf, ([r.as_dict() for r in res] if want_results else None)
+
+
+def msd_device(x, y, z, stride=1, max_s=1000, stream=None):
+    """Device tensors x, y, z -> (msd float64[max_s], counter int32[max_s]) device tensors."""
+    import torch
+    for t in (x, y, z):
+        _check_dev(t)
+    out = torch.empty(int(max_s), dtype=torch.float64, device=x.device)
+    cnt = torch.empty(int(max_s), dtype=torch.int32, device=x.device)
+    check(_lib.load().acfb200_msd_device(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(z.data_ptr()),
+                                         x.numel(), int(stride), int(max_s), C.c_void_p(out.data_ptr()),
+                                         C.c_void_p(cnt.data_ptr()), _stream_ptr(stream)))
+    return out, cnt
+
+
+def image_device(x, y, z, L, stream=None):
+    import torch
+    for t in (x, y, z):
+        _check_dev(t)
+    outs = [torch.empty_like(t) for t in (x, y, z)]
+    check(_lib.load().acfb200_image_device(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(z.data_ptr()),
+                                           x.numel(), float(L), *[C.c_void_p(o.data_ptr()) for o in outs],
+                                           _stream_ptr(stream)))
+    return outs
 
 
 def measure_dfma_peak():

@@ -39,6 +39,8 @@ size_t direct_partial_elems(const DirectPlan& p, int nseries);
 // Raw lag sums per (series, chunk) into `partials`; then reduce_partials folds the chunks in fixed order.
 int launch_direct(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
                   double* d_partials, unsigned int* d_queue, int sm_count, cudaStream_t st);
+int launch_direct_msd(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
+                      double* d_partials, cudaStream_t st);
 // out[s*ncorr + k] = sum_c partials[s][c][k]  (normalise=0)  or that / (n_s - k)  (normalise=1)
 int launch_reduce_partials(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
                            const double* d_partials, double* d_out, int normalise, cudaStream_t st);
@@ -96,6 +98,20 @@ int launch_integrate_cutoff_batch(const double* d_acf, long long acf_stride, int
                                   double cutoff, double* d_small, cudaStream_t st);
 // acf[i] *= target / acf[0]  (spring rescale, ACFcalculator.cpp:740-742 / :746-749)
 int launch_rescale(double* d_acf, long long ncorr, double target, cudaStream_t st);
+
+// msd.cu (traj2diffusion)
+int plan_msd_strided(long long n, long long stride, long long ncorr, int sm_count, DirectPlan* plan);
+int launch_msd_strided(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long stride, long long ncorr,
+                       double* d_partials, cudaStream_t st);
+// msd[j] = (Sx+Sy+Sz)[j] / cnt_j from d_sums (axes axis_pitch doubles apart; 0 = one array for all three);
+// d_counter (nullable) = cnt_j
+int launch_msd_finalize(const double* d_sums, long long axis_pitch, long long n, long long stride, long long ncorr,
+                        double* d_msd, int* d_counter, cudaStream_t st);
+// d_out[0] = sum_{i>=1} msd[i]/i, d_out[1] = d_out[0]/n
+int launch_msd_slope(const double* d_msd, long long n, double* d_out, cudaStream_t st);
+size_t image_workspace_bytes(long long n);
+int launch_image(const double* const d_in[3], double* const d_out[3], long long n, double L, void* d_work,
+                 cudaStream_t st);
 
 // peaks.cu
 int measure_dfma_peak(double* tflops, double* sm_mhz_effective, int iters);

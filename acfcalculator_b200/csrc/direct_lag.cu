@@ -29,7 +29,10 @@ namespace acfb200 {
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxWarps = 16;
 
-template <int RK, int LK, int PF>
+// MSD = false: S[k] += x[i]*x[i+k].   MSD = true: S[k] += (x[i+k]-x[i])^2 -- the displacement sums of
+// traj2diffusion.cpp:530-541 for unit origin stride; same staging, ring and partial-sum layout, one extra
+// DADD per term (so the FP64 pipe runs two instructions per displacement instead of one per product).
+template <int RK, int LK, int PF, bool MSD = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 direct_lag_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int ts, int bsz, int chunks, int mpad,
                   double* __restrict__ partials)
@@ -77,7 +80,8 @@ direct_lag_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int ts, 
         const long long it = t * ti;
         const long long jb = it + K0;
         if (t != t0) __syncthreads();  // everyone is done reading the previous tile
-        const bool fast = aligned && (it + ti <= d.i_end) && (jb + bsz <= d.n);
+        const bool full = (it + ti <= d.i_end) && (jb + bsz <= d.n);  // every staged pair is inside the series
+        const bool fast = aligned && full;
         if (fast) {
             if (threadIdx.x == 0) {
                 fence_proxy_async();
@@ -101,6 +105,25 @@ direct_lag_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int ts, 
         }
         if (!warp_active) continue;
 
+        if constexpr (MSD) {
+            // zero fill does not neutralise a displacement, so ragged tiles are walked pair by pair
+            if (!full) {
+                for (int s = 0; s < ts; ++s) {
+                    const long long i = it + li * ts + s;
+                    if (i >= d.i_end) break;
+                    const double a = ap[s];
+#pragma unroll
+                    for (int j = 0; j < RK; ++j) {
+                        if (i + kb + lk * RK + j < d.n) {
+                            const double dd = bp[s + j] - a;
+                            acc[j] = fma(dd, dd, acc[j]);
+                        }
+                    }
+                }
+                continue;
+            }
+        }
+
         // sliding window in a register ring: element e of the window stream lives in win[e % R]
         double win[R];
 #pragma unroll
@@ -118,10 +141,23 @@ direct_lag_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int ts, 
                 const double2 nw = lds2(bp + s + u + RK + 2 * PF);
                 win[(u + RK + 2 * PF) % R] = nw.x;
                 win[(u + RK + 2 * PF + 1) % R] = nw.y;
+                if constexpr (MSD) {
 #pragma unroll
-                for (int j = 0; j < RK; ++j) acc[j] = fma(a.x, win[(u + j) % R], acc[j]);
+                    for (int j = 0; j < RK; ++j) {
+                        const double dd = win[(u + j) % R] - a.x;
+                        acc[j] = fma(dd, dd, acc[j]);
+                    }
 #pragma unroll
-                for (int j = 0; j < RK; ++j) acc[j] = fma(a.y, win[(u + 1 + j) % R], acc[j]);
+                    for (int j = 0; j < RK; ++j) {
+                        const double dd = win[(u + 1 + j) % R] - a.y;
+                        acc[j] = fma(dd, dd, acc[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < RK; ++j) acc[j] = fma(a.x, win[(u + j) % R], acc[j]);
+#pragma unroll
+                    for (int j = 0; j < RK; ++j) acc[j] = fma(a.y, win[(u + 1 + j) % R], acc[j]);
+                }
             }
         }
     }
@@ -202,11 +238,13 @@ typedef void (*direct_fn)(const SeriesDesc*, long long, int, int, int, int, doub
 struct Variant {
     int rk, lk, pf;
     direct_fn fn;
+    direct_fn fn_msd;  // displacement-square form of the same geometry
     const char* name;
     double quality;  // relative DFMA-pipe efficiency of the inner loop (measured; 1.0 = best)
 };
 
-#define ACF_VARIANT(RK, LK, PF, Q) {RK, LK, PF, direct_lag_kernel<RK, LK, PF>, "rk" #RK "_lk" #LK "_pf" #PF, Q}
+#define ACF_VARIANT(RK, LK, PF, Q) \
+    {RK, LK, PF, direct_lag_kernel<RK, LK, PF, false>, direct_lag_kernel<RK, LK, PF, true>, "rk" #RK "_lk" #LK "_pf" #PF, Q}
 // quality = inner-loop DFMA efficiency relative to the best variant, measured on B200 at N=1e8, maxcorr=1e4
 // (profiles/r1_sweep_*.jsonl: time / useful-lag fraction).  More lags per thread = fewer LDS per DFMA.
 static const Variant kVariants[] = {
@@ -224,7 +262,7 @@ static double warps_quality(int w)
 static const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 // opt-in to > 48 KB dynamic shared memory is per device: one flag per (device, variant)
 constexpr int kMaxDevices = 64;
-static bool g_attr_set[kMaxDevices][sizeof(kVariants) / sizeof(kVariants[0])] = {{false}};
+static bool g_attr_set[kMaxDevices][2 * sizeof(kVariants) / sizeof(kVariants[0])] = {{false}};
 
 // Public variant numbering: [0, kNumVariants) tiled kernels, then the streaming kernels.
 int direct_variant_count() { return kNumVariants + stream_variant_count(); }
@@ -393,21 +431,40 @@ size_t direct_partial_elems(const DirectPlan& p, int nseries)
     return (size_t)nseries * (size_t)p.chunks * (size_t)p.mpad;
 }
 
+static int launch_tiled(const DirectPlan& p, bool msd, const SeriesDesc* d_desc, int nseries, long long ncorr,
+                        double* d_partials, cudaStream_t st)
+{
+    const Variant& V = kVariants[p.variant];
+    const direct_fn fn = msd ? V.fn_msd : V.fn;
+    const int slot = p.variant + (msd ? kNumVariants : 0);
+    int dev = 0;
+    ACF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= kMaxDevices || !g_attr_set[dev][slot]) {
+        ACF_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (dev < kMaxDevices) g_attr_set[dev][slot] = true;
+    }
+    dim3 grid(p.lag_tiles, p.chunks, nseries), block(p.warps * 32);
+    fn<<<grid, block, p.smem_bytes, st>>>(d_desc, ncorr, p.ts, p.bsz, p.chunks, p.mpad, d_partials);
+    ACF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_direct(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
                   double* d_partials, unsigned int* d_queue, int sm_count, cudaStream_t st)
 {
     if (p.mode == 1) return launch_direct_stream(p, d_desc, nseries, ncorr, d_partials, d_queue, sm_count, st);
-    const Variant& V = kVariants[p.variant];
-    int dev = 0;
-    ACF_CUDA_OK(cudaGetDevice(&dev));
-    if (dev >= kMaxDevices || !g_attr_set[dev][p.variant]) {
-        ACF_CUDA_OK(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        if (dev < kMaxDevices) g_attr_set[dev][p.variant] = true;
+    return launch_tiled(p, false, d_desc, nseries, ncorr, d_partials, st);
+}
+
+// Displacement sums  sum_i (x[i+k]-x[i])^2  per (series, chunk); the plan must be a tiled one (mode 0).
+int launch_direct_msd(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,
+                      double* d_partials, cudaStream_t st)
+{
+    if (p.mode != 0) {
+        set_error("launch_direct_msd: the displacement kernel exists for tiled plans only");
+        return 1;
     }
-    dim3 grid(p.lag_tiles, p.chunks, nseries), block(p.warps * 32);
-    V.fn<<<grid, block, p.smem_bytes, st>>>(d_desc, ncorr, p.ts, p.bsz, p.chunks, p.mpad, d_partials);
-    ACF_CUDA_OK(cudaGetLastError());
-    return 0;
+    return launch_tiled(p, true, d_desc, nseries, ncorr, d_partials, st);
 }
 
 int launch_reduce_partials(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,

@@ -1,0 +1,346 @@
+// traj2diffusion on the GPU (FP64, sm_100a): the kernels around the displacement-sum kernel
+// (direct_lag_kernel<.., MSD=true> in direct_lag.cu), SURVEY 8f rank 4.
+//
+//   msd_strided_kernel   origins every `stride` frames (traj2diffusion.cpp:530 `i+=stride`), stride > 1
+//   msd_finalize_kernel  add the three axes, divide by the origin count (:545), write msd_counter
+//   msd_slope_kernel     slope() (:342-355): sum_{i>=1} msd[i]/i and that / n
+//   image_*_kernel       periodic-image unwrapping, image() (:275-340), bit-exact: the reference accumulates
+//                        the +-L shifts frame after frame in FP64, which is path dependent when k*L is not
+//                        representable; the crossings are therefore compacted (flag -> scan -> scatter),
+//                        chained by ONE thread per axis in frame order, and looked up per frame.
+// All of them are HBM- or latency-bound helpers; the FP64-bound part is the displacement kernel.
+#include "common.cuh"
+
+namespace acfb200 {
+
+// ------------------------------------------------------------------------------------------------
+// Strided origins.  One thread per lag, origins of one chunk walked in order; x[i] is a warp-wide
+// broadcast load, x[i+j] a coalesced one (L1/L2 resident: consecutive origins overlap by ncorr-stride).
+// Work is n/stride * ncorr terms -- `stride` times less than the unit-stride kernel's.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStrideThreads = 256;
+
+__global__ void __launch_bounds__(kStrideThreads)
+msd_strided_kernel(const SeriesDesc* __restrict__ desc, long long stride, long long ncorr, int chunks, int mpad,
+                   double* __restrict__ partials)
+{
+    const SeriesDesc d = desc[blockIdx.z];
+    const long long j = (long long)blockIdx.x * kStrideThreads + threadIdx.x;
+    const long long origins = (d.i_end + stride - 1) / stride;  // i = 0, stride, ... < i_end
+    const long long o0 = origins * blockIdx.y / chunks, o1 = origins * (blockIdx.y + 1) / chunks;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (j < ncorr) {
+        const double* __restrict__ x = d.x;
+        long long o = o0;
+        for (; o + 1 < o1; o += 2) {
+            const long long ia = o * stride, ib = ia + stride;
+            if (ib + j >= d.n) break;
+            const double da = x[ia + j] - x[ia], db = x[ib + j] - x[ib];
+            acc0 = fma(da, da, acc0);
+            acc1 = fma(db, db, acc1);
+        }
+        for (; o < o1; ++o) {
+            const long long ia = o * stride;
+            if (ia + j >= d.n) break;
+            const double da = x[ia + j] - x[ia];
+            acc0 = fma(da, da, acc0);
+        }
+    }
+    if (j < mpad) partials[((size_t)blockIdx.z * chunks + blockIdx.y) * (size_t)mpad + j] = acc0 + acc1;
+}
+
+int plan_msd_strided(long long n, long long stride, long long ncorr, int sm_count, DirectPlan* plan)
+{
+    DirectPlan p = {};
+    p.mode = 2;
+    p.variant = -1;
+    p.lag_tiles = (int)((ncorr + kStrideThreads - 1) / kStrideThreads);
+    p.mpad = p.lag_tiles * kStrideThreads;
+    const long long origins = (n + stride - 1) / stride;
+    long long chunks = ((long long)sm_count * 8) / ((long long)p.lag_tiles * 3);
+    if (chunks > origins / 8) chunks = origins / 8;
+    if (chunks > 65535) chunks = 65535;
+    if (chunks < 1) chunks = 1;
+    p.chunks = (int)chunks;
+    *plan = p;
+    return 0;
+}
+
+int launch_msd_strided(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long stride, long long ncorr,
+                       double* d_partials, cudaStream_t st)
+{
+    dim3 grid(p.lag_tiles, p.chunks, nseries);
+    msd_strided_kernel<<<grid, kStrideThreads, 0, st>>>(d_desc, stride, ncorr, p.chunks, p.mpad, d_partials);
+    ACF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// msd[j] = (Sx[j] + Sy[j] + Sz[j]) / cnt_j,  cnt_j = #{i = 0, stride, ... : i + j < n}
+// cnt_j == 0 (j >= n): the reference divides 0.0 by int 0 -> the x86 default NaN (sign bit set, "-nan").
+// ------------------------------------------------------------------------------------------------
+__global__ void msd_finalize_kernel(const double* __restrict__ sums, long long axis_pitch, long long n, long long stride,
+                                    long long ncorr, double* __restrict__ msd, int* __restrict__ counter)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncorr) return;
+    const long long cnt = j < n ? (n - 1 - j) / stride + 1 : 0;
+    const double s = (sums[j] + sums[axis_pitch + j]) + sums[2 * axis_pitch + j];  // pitch 0: one array serves all axes
+    msd[j] = cnt > 0 ? s / (double)cnt : __longlong_as_double(0xFFF8000000000000ull);
+    if (counter) counter[j] = (int)cnt;
+}
+
+int launch_msd_finalize(const double* d_sums, long long axis_pitch, long long n, long long stride, long long ncorr,
+                        double* d_msd, int* d_counter, cudaStream_t st)
+{
+    msd_finalize_kernel<<<(unsigned)((ncorr + 255) / 256), 256, 0, st>>>(d_sums, axis_pitch, n, stride, ncorr, d_msd,
+                                                                        d_counter);
+    ACF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// slope(): out[0] = sum_{i=1}^{n-1} msd[i]/i, out[1] = out[0]/n.  One CTA; contiguous slices per thread
+// folded in thread order (fixed tree => reproducible).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSlopeThreads = 1024;
+
+__global__ void __launch_bounds__(kSlopeThreads)
+msd_slope_kernel(const double* __restrict__ msd, long long n, double* __restrict__ out)
+{
+    __shared__ double sh[kSlopeThreads];
+    const int tid = threadIdx.x;
+    const long long terms = n > 1 ? n - 1 : 0;
+    const long long per = (terms + kSlopeThreads - 1) / kSlopeThreads;
+    const long long lo = 1 + (long long)tid * per;
+    const long long hi = lo + per < n ? lo + per : n;
+    double s = 0.0;
+    for (long long i = lo; i < hi; ++i) s += msd[i] / (double)i;
+    sh[tid] = s;
+    __syncthreads();
+    if (tid < 32) {
+        double w = 0.0;
+        for (int k = 0; k < kSlopeThreads / 32; ++k) w += sh[tid * (kSlopeThreads / 32) + k];
+        sh[tid] = w;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 32; ++k) t += sh[k];
+        out[0] = t;
+        out[1] = t / (double)n;
+    }
+}
+
+int launch_msd_slope(const double* d_msd, long long n, double* d_out, cudaStream_t st)
+{
+    msd_slope_kernel<<<1, kSlopeThreads, 0, st>>>(d_msd, n, d_out);
+    ACF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Imaging
+// ------------------------------------------------------------------------------------------------
+constexpr int kImgThreads = 256;
+constexpr int kImgItems = 8;
+constexpr int kImgTile = kImgThreads * kImgItems;
+
+// crossing of frame i (i >= 1): -1 if x[i]-x[i-1] > L/2 (:301), +1 if < -L/2 (:306), both (L < 0) cancel exactly
+__device__ __forceinline__ int crossing(const double* __restrict__ x, long long i, long long n, double half)
+{
+    if (i < 1 || i >= n) return 0;
+    const double delta = x[i] - x[i - 1];
+    int c = 0;
+    if (delta > half) c -= 1;
+    if (delta < -half) c += 1;
+    return c;
+}
+
+// Inclusive scan of per-thread counts over the CTA; returns the CTA total, `excl` = exclusive prefix of this thread.
+__device__ __forceinline__ int block_scan(int mine, int* excl, int* sh /*[kImgThreads/32]*/)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+    }
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kImgThreads / 32; ++w) {
+        const int v = sh[w];
+        if (w < warp) base += v;
+        total += v;
+    }
+    __syncthreads();
+    *excl = base + incl - mine;
+    return total;
+}
+
+// phase 1: number of crossings per tile.  grid (tiles, 3 axes)
+__global__ void __launch_bounds__(kImgThreads)
+image_count_kernel(const double* const* __restrict__ axes, long long n, double L, int tiles,
+                   unsigned int* __restrict__ tile_count)
+{
+    __shared__ int sh[kImgThreads / 32];
+    const double* __restrict__ x = axes[blockIdx.y];
+    const double half = L / 2;
+    const long long base = (long long)blockIdx.x * kImgTile + (long long)threadIdx.x * kImgItems;
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < kImgItems; ++k) mine += crossing(x, base + k, n, half) != 0;
+    int excl;
+    const int total = block_scan(mine, &excl, sh);
+    if (threadIdx.x == 0) tile_count[(size_t)blockIdx.y * tiles + blockIdx.x] = (unsigned)total;
+}
+
+// phase 2: exclusive scan of the tile counts of one axis (one CTA per axis), total into totals[axis]
+__global__ void __launch_bounds__(1024)
+image_scan_tiles_kernel(unsigned int* __restrict__ tile_count, int tiles, unsigned int* __restrict__ totals)
+{
+    __shared__ unsigned int sh[1024];
+    unsigned int* c = tile_count + (size_t)blockIdx.x * tiles;
+    const int tid = threadIdx.x;
+    const int per = (tiles + 1023) / 1024;
+    const int lo = tid * per, hi = lo + per < tiles ? lo + per : tiles;
+    unsigned int s = 0;
+    for (int i = lo; i < hi; ++i) s += c[i];
+    sh[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int run = 0;
+        for (int k = 0; k < 1024; ++k) {
+            const unsigned int v = sh[k];
+            sh[k] = run;
+            run += v;
+        }
+        totals[blockIdx.x] = run;
+    }
+    __syncthreads();
+    unsigned int run = sh[tid];
+    for (int i = lo; i < hi; ++i) {
+        const unsigned int v = c[i];
+        c[i] = run;
+        run += v;
+    }
+}
+
+// phase 3: scatter the crossings in frame order: ev[axis][e] = -1 / +1
+__global__ void __launch_bounds__(kImgThreads)
+image_scatter_kernel(const double* const* __restrict__ axes, long long n, double L, int tiles,
+                     const unsigned int* __restrict__ tile_offset, signed char* __restrict__ ev, long long ev_pitch)
+{
+    __shared__ int sh[kImgThreads / 32];
+    const double* __restrict__ x = axes[blockIdx.y];
+    const double half = L / 2;
+    const long long base = (long long)blockIdx.x * kImgTile + (long long)threadIdx.x * kImgItems;
+    int c[kImgItems], mine = 0;
+#pragma unroll
+    for (int k = 0; k < kImgItems; ++k) {
+        c[k] = crossing(x, base + k, n, half);
+        mine += c[k] != 0;
+    }
+    int excl;
+    block_scan(mine, &excl, sh);
+    size_t pos = (size_t)blockIdx.y * ev_pitch + tile_offset[(size_t)blockIdx.y * tiles + blockIdx.x] + excl;
+#pragma unroll
+    for (int k = 0; k < kImgItems; ++k)
+        if (c[k] != 0) ev[pos++] = (signed char)c[k];
+}
+
+// phase 4: the reference's running sum of image shifts (:316-323), one thread per axis, frame order:
+// shift_e = (+-L) + shift_{e-1}, every addition rounded exactly as on the host.
+__global__ void image_chain_kernel(const signed char* __restrict__ ev, long long ev_pitch,
+                                   const unsigned int* __restrict__ totals, double L, double* __restrict__ shift)
+{
+    const int axis = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const signed char* e = ev + (size_t)axis * ev_pitch;
+    double* s = shift + (size_t)axis * ev_pitch;
+    const unsigned int cnt = totals[axis];
+    double run = 0.0;
+    for (unsigned int k = 0; k < cnt; ++k) {
+        const double step = e[k] < 0 ? 0.0 - L : 0.0 + L;  // pbc_images starts at 0.0: "-= L" / "+= L" (:303, :308)
+        run = step + run;                                  // pbc_images[i] += pbc_images[i-1] (:321)
+        s[k] = run;
+    }
+}
+
+// phase 5: out[i] = x[i] + shift(number of crossings up to and including frame i)   (:325-332; frame 0 untouched)
+__global__ void __launch_bounds__(kImgThreads)
+image_apply_kernel(const double* const* __restrict__ axes, double* const* __restrict__ outs, long long n, double L,
+                   int tiles, const unsigned int* __restrict__ tile_offset, const double* __restrict__ shift,
+                   long long ev_pitch)
+{
+    __shared__ int sh[kImgThreads / 32];
+    const double* __restrict__ x = axes[blockIdx.y];
+    double* __restrict__ out = outs[blockIdx.y];
+    const double half = L / 2;
+    const long long base = (long long)blockIdx.x * kImgTile + (long long)threadIdx.x * kImgItems;
+    int c[kImgItems], mine = 0;
+#pragma unroll
+    for (int k = 0; k < kImgItems; ++k) {
+        c[k] = crossing(x, base + k, n, half) != 0;
+        mine += c[k];
+    }
+    int excl;
+    block_scan(mine, &excl, sh);
+    long long seen = (long long)tile_offset[(size_t)blockIdx.y * tiles + blockIdx.x] + excl;
+    const double* s = shift + (size_t)blockIdx.y * ev_pitch;
+#pragma unroll
+    for (int k = 0; k < kImgItems; ++k) {
+        const long long i = base + k;
+        if (i >= n) break;
+        seen += c[k];
+        const double v = x[i];
+        out[i] = i == 0 ? v : v + (seen > 0 ? s[seen - 1] : 0.0);
+    }
+}
+
+// header (6 pointers, 3 totals) | tile counts | running shifts (double) | crossings (int8)
+size_t image_workspace_bytes(long long n)
+{
+    const size_t tiles = (size_t)((n + kImgTile - 1) / kImgTile);
+    const size_t pitch = (size_t)((n + 15) & ~15ll);
+    return 128 + ((3 * tiles * 4 + 63) & ~(size_t)63) + 3 * pitch * 8 + 3 * pitch;
+}
+
+// d_in / d_out: three device arrays each (out may not alias in).  d_work: image_workspace_bytes(n) bytes.
+// Returns the number of kernel launches (5) or -1.
+int launch_image(const double* const d_in[3], double* const d_out[3], long long n, double L, void* d_work,
+                 cudaStream_t st)
+{
+    if (n < 1) return 0;
+    const int tiles = (int)((n + kImgTile - 1) / kImgTile);
+    const long long pitch = (n + 15) & ~15ll;
+    unsigned char* w = static_cast<unsigned char*>(d_work);
+    const double** d_axes = reinterpret_cast<const double**>(w);
+    double** d_outs = reinterpret_cast<double**>(w + 24);
+    unsigned int* totals = reinterpret_cast<unsigned int*>(w + 64);
+    unsigned int* tile_count = reinterpret_cast<unsigned int*>(w + 128);
+    size_t off = 128 + (((size_t)3 * tiles * 4 + 63) & ~(size_t)63);
+    double* shift = reinterpret_cast<double*>(w + off);
+    signed char* ev = reinterpret_cast<signed char*>(w + off + 3 * (size_t)pitch * 8);
+    const void* ptrs[6] = {d_in[0], d_in[1], d_in[2], d_out[0], d_out[1], d_out[2]};
+    if (cudaMemcpyAsync(w, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        set_error("launch_image: pointer upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    dim3 grid(tiles, 3);
+    image_count_kernel<<<grid, kImgThreads, 0, st>>>(d_axes, n, L, tiles, tile_count);
+    image_scan_tiles_kernel<<<3, 1024, 0, st>>>(tile_count, tiles, totals);
+    image_scatter_kernel<<<grid, kImgThreads, 0, st>>>(d_axes, n, L, tiles, tile_count, ev, pitch);
+    image_chain_kernel<<<3, 32, 0, st>>>(ev, pitch, totals, L, shift);
+    image_apply_kernel<<<grid, kImgThreads, 0, st>>>(d_axes, d_outs, n, L, tiles, tile_count, shift, pitch);
+    if (cudaGetLastError() != cudaSuccess) {
+        set_error("launch_image: kernel launch failed");
+        return -1;
+    }
+    return 5;
+}
+
+}  // namespace acfb200

@@ -52,7 +52,21 @@ WORKLOADS = {
     "viscosity": dict(n=10**8, m=2 * 10**4, comps=3,
                       desc="config4: 3 Green-Kubo components N=1e8, maxcorr=2e4, time blocks + allreduce"),
     "fft": dict(n=2**27, m=2**26, desc="config5: N=2^27, maxcorr=N/2, zero-padded Wiener-Khinchin FFT"),
+    "msd": dict(n=10**7, m=1000, desc="traj2diffusion: 3-D random walk, 1e7 frames, stride 1, max 1000 (the program's "
+                                      "default), displacement kernel", metric="msd_frame_lag_pairs_per_s",
+                unit="frame-lag pairs/s"),
 }
+
+
+def metric_of(workload):
+    w = WORKLOADS[workload]
+    return w.get("metric", METRIC), w.get("unit", UNIT)
+
+
+def walk_xyz(n, seed):
+    """Unwrapped 3-D random walk, one contiguous array per axis."""
+    rng = np.random.default_rng(seed)
+    return [np.cumsum(rng.standard_normal(n) * 0.3) + 50.0 for _ in range(3)]
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -123,6 +137,24 @@ def cpu_reference_rate(workload, steps, warmup, sample_products=1.0e10):
     w = WORKLOADS[workload]
     m = min(w["m"], 20000) if workload != "fft" else 20000
     sample_products = float(os.environ.get("ACFB200_BENCH_CPU_PRODUCTS", sample_products))  # tests shrink the sample
+    if workload == "msd":
+        # the reference's own MSD loop (traj2diffusion.cpp:530-541, oracle/_ref/libref_msd_fast.so), 1 core
+        ns = int(min(w["n"], max(4 * m, sample_products / 4 / m)))
+        xyz = np.ascontiguousarray(np.stack(walk_xyz(ns, 1), axis=1))
+        if O.ref_available("libref_msd_fast.so"):
+            kind, fn = "reference", (lambda: O.ref_msd(xyz, 1, m, "libref_msd_fast.so"))
+        else:
+            cols = [np.ascontiguousarray(xyz[:, a]) for a in range(3)]
+            kind, fn = "port", (lambda: O.msd(cols[0], cols[1], cols[2], 1, m))
+        for _ in range(warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (time.perf_counter() - t0) / steps
+        return dict(value=ns * m / dt, unit=w["unit"], cores=1, kind=kind, ms_per_step=dt * 1e3,
+                    sample="MSD loop on the first %d frames, stride 1, max %d (%.1e frame-lag pairs per step)" % (
+                        ns, m, ns * m))
     ns = int(min(w["n"], max(4 * m, sample_products / m)))
     x = ou_series(ns, 200.0, mu=0.0, seed=1)
     if O.ref_available("libref_acf_fast.so"):
@@ -162,10 +194,11 @@ def run_reference(args):
         return
     r = cpu_reference_rate(args.workload, args.steps, args.warmup)
     w = WORKLOADS[args.workload]
+    METRIC, UNIT = metric_of(args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak" if args.workload == "ou" else "strong", "vs_baseline": None, "dtype": "f64",
+        "scaling": "weak" if args.workload in ("ou", "fft", "msd") else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": w["desc"], "sample": r["sample"]},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -193,8 +226,10 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     wl = WORKLOADS[args.workload]
+    METRIC, UNIT = metric_of(args.workload)
     n, m = int(args.n or wl["n"]), int(args.m or wl["m"])
     stream = torch.cuda.current_stream()
+    fp64_instr_rank = None
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
 
     # ---- workload set-up: returns step(), e2e_step(), accounting --------------------------------------
@@ -272,6 +307,26 @@ def run_native(args):
         h2d, d2h = 8 * (halo_end - lo) * comps, 8 * m * comps
         scaling = "strong"
         total_products = float(comps) * n * m
+    elif args.workload == "msd":
+        axes = walk_xyz(n, 20260401 + rank)
+        h_a = [torch.from_numpy(a).pin_memory() for a in axes]
+        d_a = [h.to(dev, non_blocking=True) for h in h_a]
+        pairs = float(m) * n - m * (m - 1) / 2.0  # frame-lag pairs actually summed (i + j < n)
+        products_rank = float(n) * m
+        fmas_rank = 0.0
+        fp64_instr_rank = 6.0 * pairs  # per pair and axis: one DADD (difference) + one DFMA (square-accumulate)
+        launches_per_step = 3
+        plan = A.describe_plan(n, m, 3)
+        res = {}
+
+        def step():
+            res["msd"] = A.msd_device(d_a[0], d_a[1], d_a[2], stride=1, max_s=m, stream=stream)
+
+        def e2e_step():
+            A.traj2diffusion(h_a[0].numpy(), h_a[1].numpy(), h_a[2].numpy(), stride=1, max_s=m, timestep=1.0)
+        h2d, d2h = 3 * 8 * n, 12 * m
+        scaling = "weak"
+        total_products = products_rank * world
     else:  # fft
         x = ou_series(n, 1.0e4, seed=20260301 + rank)
         h_x = torch.from_numpy(x).pin_memory()
@@ -363,12 +418,23 @@ def run_native(args):
             "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf,
             # DRAM bytes of one direct_lag_kernel launch from the committed ncu capture of this command
-            # (profiles/r1b_direct_lag_ncu_raw.csv: 80.03 MB read + 7.06 MB written); irrelevant to an FP64-bound kernel
-            "traffic": 87.08e6 if (args.workload == "ou" and n == 10**7 and m == 10**4) else None,
+            # (profiles/r1c_direct_lag_ncu_raw.csv: 80.25 MB read + 8.42 MB written); irrelevant to an FP64-bound kernel
+            "traffic": 88.67e6 if (args.workload == "ou" and n == 10**7 and m == 10**4) else None,
             "peak_source": "DFMA-chain micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
             "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS, "nominal_peak": FP64_NOMINAL_TFLOPS,
             "kernel": "direct_lag_kernel (step time includes the ~us reduce_partials epilogue)",
             "algorithmic_flops_per_launch": 2.0 * fmas_rank,
+        }
+    if fp64_instr_rank is not None:
+        # displacement kernel: DADD + DFMA per axis term = 3 flops in 2 FP64-pipe slots, so the pipe can deliver at
+        # most 0.75 of the DFMA peak in flops; both fractions are reported
+        ach = 1.5 * fp64_instr_rank / (ms_per_step * 1e-3) / 1e12
+        roofline = {
+            "bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            "frac_of_pipe_slots": (fp64_instr_rank / (ms_per_step * 1e-3)) / (peak_tf * 1e12 / 2.0),
+            "traffic": None, "peak_source": "DFMA-chain micro-benchmark measured in this run",
+            "kernel": "direct_lag_kernel<MSD> x 3 axes (step includes reduce_partials + msd_finalize)",
+            "algorithmic_flops_per_launch": 1.5 * fp64_instr_rank,
         }
     if args.workload == "fft":
         hbm_peak = peaks.get("hbm_gbs") or 6650.0

@@ -167,6 +167,40 @@ ACFB200_API int acfb200_multi_gpu_green_kubo(const double* const* comps, int nco
 ACFB200_API int acfb200_calc_correlation_fft(const double* y, int64_t n, int64_t ncorr, double* corr);
 ACFB200_API int acfb200_calc_correlation_fft_device(const double* d_y, int64_t n, int64_t ncorr, double* d_corr, void* stream);
 
+/* ---- traj2diffusion: mean-square displacement (traj2diffusion.cpp) --------------------------------
+ * Coordinates are three separate arrays (the reference holds crd[frame][0..2], :59-121, :145-260).
+ *
+ * acfb200_msd            msd[j] = (1/cnt_j) sum_{i = 0, stride, 2*stride, ... ; i + j < n} |r(i+j) - r(i)|^2 and
+ *                        counter[j] = cnt_j for j < max_s: the loop traj2diffusion.cpp:530-541 with calcmsd (:43-53)
+ *                        and the divide at :545.  j >= n gives NaN ("-nan") like the reference's 0.0/0.
+ *                        counter may be NULL.  Summation order differs from the reference (per axis, tiled):
+ *                        results agree to ~1e-13 relative.
+ * acfb200_image          in-place periodic-image unwrapping of image() (:275-340); bit-exact, including the
+ *                        frame-by-frame FP64 accumulation of the +-L shifts (:316-323).
+ * acfb200_msd_slope      slope() (:342-355): *sum = sum_{i=1}^{n-1} msd[i]/i (the "#sum" line), *slope = *sum / n.
+ * acfb200_traj2diffusion the body of main() after the reader (:497-552): optional imaging (on the device copy; the
+ *                        caller's arrays are left alone), MSD, slope, D = slope/(dt*stride)/6 in A^2/fs. */
+typedef struct acfb200_msd_result {
+    double sum;          /* "#sum = ..."  (:353)                      */
+    double slope;        /* slope(msd, max_s)  (:354)                  */
+    double diffusivity;  /* D in A^2/fs (:549); *1e-1 cm2/s, *1e-5 m2/s */
+    int64_t nframes;
+} acfb200_msd_result;
+ACFB200_API int acfb200_msd(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s,
+                            double* msd, int32_t* counter);
+ACFB200_API int acfb200_image(double* x, double* y, double* z, int64_t n, double cell);
+ACFB200_API int acfb200_msd_slope(const double* msd, int64_t n, double* slope, double* sum);
+ACFB200_API int acfb200_traj2diffusion(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s, double dt,
+                                       double cell, int imaging, double* msd, int32_t* counter,
+                                       acfb200_msd_result* result);
+/* Device-resident forms (stream: a cudaStream_t passed as void*, like the other *_device calls; the out arrays of
+ * acfb200_image_device must not alias its inputs).  Passing the same pointer for x, y and z (what the reference's
+ * general reader effectively produces, :186-231) is recognised and computed once. */
+ACFB200_API int acfb200_msd_device(const double* d_x, const double* d_y, const double* d_z, int64_t n, int64_t stride,
+                                   int64_t max_s, double* d_msd, int32_t* d_counter, void* stream);
+ACFB200_API int acfb200_image_device(const double* d_x, const double* d_y, const double* d_z, int64_t n, double cell,
+                                     double* d_xo, double* d_yo, double* d_zo, void* stream);
+
 /* ---- tuning / introspection / measurement ---------------------------------------------------- */
 /* Describe the launch the planner would make: fills a NUL-terminated text line. */
 ACFB200_API int acfb200_describe_plan(int64_t n, int64_t ncorr, int nseries, char* buf, int buflen);

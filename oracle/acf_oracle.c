@@ -230,6 +230,87 @@ void oracle_acf_pipeline(double *series, int64_t n, int64_t ncorr, double dt, do
     free(vel);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * traj2diffusion: mean-square displacement over strided time origins.
+ * Coordinates are taken as three separate arrays (the reference holds crd[i][0..2]).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* msd[j] = (1/cnt_j) * sum over origins i = 0, stride, 2*stride, ... with i + j < n of
+ *          (x[i+j]-x[i])^2 + (y[i+j]-y[i])^2 + (z[i+j]-z[i])^2,     cnt_j = number of such origins.
+ * Restates traj2diffusion.cpp:530-541 (accumulation, i outermost, j innermost, break at i+j >= n)
+ * with calcmsd :43-53 (dx*dx + dy*dy + dz*dz, left to right) and the divide at :545
+ * (cnt_j == 0 gives 0.0/0 = NaN exactly like the reference's double/int division). */
+void oracle_msd(const double *x, const double *y, const double *z, int64_t n, int64_t stride, int64_t max_s,
+                double *msd, int32_t *counter)
+{
+    memset(msd, 0, sizeof(double) * (size_t)max_s);
+    memset(counter, 0, sizeof(int32_t) * (size_t)max_s);
+    for (int64_t i = 0; i < n; i += stride) {
+        for (int64_t j = 0; j < max_s; ++j) {
+            if (i + j >= n) break;
+            const double dx = x[i + j] - x[i], dy = y[i + j] - y[i], dz = z[i + j] - z[i];
+            msd[j] += dx * dx + dy * dy + dz * dz;
+            counter[j] += 1;
+        }
+    }
+    for (int64_t j = 0; j < max_s; ++j) msd[j] /= counter[j];
+}
+
+/* The same sums lag-parallel (per-lag order of additions unchanged => bit-identical), for timing the
+ * "best honest CPU" figure and for full-size parity runs. */
+void oracle_msd_lagpar(const double *x, const double *y, const double *z, int64_t n, int64_t stride,
+                       int64_t max_s, double *msd, int32_t *counter, int nthreads)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nthreads > 0 ? nthreads : omp_get_max_threads())
+#endif
+    for (int64_t j = 0; j < max_s; ++j) {
+        double acc = 0.0;
+        int32_t cnt = 0;
+        for (int64_t i = 0; i + j < n; i += stride) {
+            const double dx = x[i + j] - x[i], dy = y[i + j] - y[i], dz = z[i + j] - z[i];
+            acc += dx * dx + dy * dy + dz * dz;
+            ++cnt;
+        }
+        msd[j] = acc / cnt;
+        counter[j] = cnt;
+    }
+}
+
+/* Periodic-image unwrapping, traj2diffusion.cpp:275-340: a frame whose step from the previous
+ * frame (of the ORIGINAL, still wrapped coordinates) exceeds L/2 gets an image shift of -L
+ * (:301-304), below -L/2 of +L (:306-309); the shifts are accumulated frame after frame as
+ * doubles (:316-323) and added to the coordinates (:325-332).  One axis per call. */
+void oracle_image_axis(double *c, int64_t n, double L)
+{
+    if (n < 1) return;
+    double *img = (double *)calloc((size_t)n, sizeof(double));
+    for (int64_t i = 1; i < n; ++i) {
+        const double delta = c[i] - c[i - 1];
+        if (delta > L / 2) img[i] -= L;
+        if (delta < -L / 2) img[i] += L;
+    }
+    for (int64_t i = 1; i < n; ++i) img[i] += img[i - 1];
+    for (int64_t i = 1; i < n; ++i) c[i] += img[i];
+    free(img);
+}
+
+/* slope(), traj2diffusion.cpp:342-355: (sum_{i=1}^{n-1} msd[i]/i) / n; *sum_out receives the "#sum" value. */
+double oracle_msd_slope(const double *msd, int64_t n, double *sum_out)
+{
+    double sum = 0.0;
+    for (int64_t i = 1; i < n; ++i) sum += (msd[i] / i);
+    if (sum_out) *sum_out = sum;
+    return sum / n;
+}
+
+/* D in A^2/fs, traj2diffusion.cpp:549 with spaceSeries = dt*stride (:497). */
+double oracle_msd_diffusivity(const double *msd, int64_t max_s, double dt, int64_t stride)
+{
+    const double space_series = dt * stride;
+    return oracle_msd_slope(msd, max_s, NULL) / space_series / 6.0;
+}
+
 int oracle_max_threads(void)
 {
 #ifdef _OPENMP

@@ -66,6 +66,13 @@ def lib():
         L.oracle_viscosity_eta.restype = C.c_double
         L.oracle_acf_pipeline.argtypes = [_P, _I64, _I64, C.c_double, C.c_double, _P, _P,
                                           C.POINTER(_Result), C.c_int]
+        L.oracle_msd.argtypes = [_P, _P, _P, _I64, _I64, _I64, _P, _P]
+        L.oracle_msd_lagpar.argtypes = [_P, _P, _P, _I64, _I64, _I64, _P, _P, C.c_int]
+        L.oracle_image_axis.argtypes = [_P, _I64, C.c_double]
+        L.oracle_msd_slope.argtypes = [_P, _I64, _P]
+        L.oracle_msd_slope.restype = C.c_double
+        L.oracle_msd_diffusivity.argtypes = [_P, _I64, C.c_double, _I64]
+        L.oracle_msd_diffusivity.restype = C.c_double
         L.oracle_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -158,6 +165,40 @@ def acf_pipeline(series, ncorr, dt, cutoff, threads=1):
                 cutoff_index=r.cutoff_index, n_used=r.n_used, acf=acf, vacf=vacf)
 
 
+def msd(x, y, z, stride, max_s, threads=1):
+    """(msd[max_s], counter[max_s]) -- traj2diffusion.cpp:530-545."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    out = np.empty(max_s, dtype=np.float64)
+    cnt = np.empty(max_s, dtype=np.int32)
+    if threads == 1:
+        lib().oracle_msd(_ptr(x), _ptr(y), _ptr(z), x.size, stride, max_s, _ptr(out), _ptr(cnt))
+    else:
+        lib().oracle_msd_lagpar(_ptr(x), _ptr(y), _ptr(z), x.size, stride, max_s, _ptr(out), _ptr(cnt), threads)
+    return out, cnt
+
+
+def image(x, y, z, L):
+    """Unwrapped copies of the three coordinate arrays -- traj2diffusion.cpp:275-340."""
+    out = []
+    for c in (x, y, z):
+        c = _f64(c).copy()
+        lib().oracle_image_axis(_ptr(c), c.size, L)
+        out.append(c)
+    return out
+
+
+def msd_slope(msd_arr):
+    m = _f64(msd_arr)
+    s = C.c_double()
+    v = lib().oracle_msd_slope(_ptr(m), m.size, C.byref(s))
+    return v, s.value
+
+
+def msd_diffusivity(msd_arr, dt, stride):
+    m = _f64(msd_arr)
+    return lib().oracle_msd_diffusivity(_ptr(m), m.size, dt, stride)
+
+
 def max_threads():
     return lib().oracle_max_threads()
 
@@ -179,7 +220,14 @@ def ref_available(name="libref_acf.so"):
 def ref_lib(name="libref_acf.so"):
     if name not in _ref:
         L = C.CDLL(ref_path(name))
-        if "viscosity" in name:
+        if "msd" in name:
+            L.ref_msd.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P]
+            L.ref_image.argtypes = [_P, C.c_int, C.c_double]
+            L.ref_slope.argtypes = [_P, C.c_int]
+            L.ref_slope.restype = C.c_double
+            L.ref_read_series.argtypes = [C.c_char_p, C.c_int, _P, C.c_int]
+            L.ref_read_series.restype = C.c_int
+        elif "viscosity" in name:
             L.refv_calc_correlation.argtypes = [_P, C.c_int, C.c_int, _P]
             L.refv_variance.argtypes = [_P, C.c_int]
             L.refv_variance.restype = C.c_double
@@ -217,3 +265,30 @@ def ref_acf_pipeline(series, ncorr, dt, cutoff, name="libref_acf.so"):
     sc = np.empty(4, dtype=np.float64)
     ref_lib(name).ref_acf_pipeline(_ptr(s), s.size, ncorr, dt, cutoff, _ptr(acf), _ptr(vacf), _ptr(sc))
     return dict(avg=sc[0], var=sc[1], var_vel=sc[2], acf_int=sc[3], acf=acf, vacf=vacf)
+
+
+def ref_msd(xyz, stride, max_s, name="libref_msd.so"):
+    """The reference's own MSD loop on an (n, 3) array; returns (msd, counter)."""
+    a = _f64(xyz)
+    out = np.empty(max_s, dtype=np.float64)
+    cnt = np.empty(max_s, dtype=np.int32)
+    ref_lib(name).ref_msd(_ptr(a), a.shape[0], stride, max_s, _ptr(out), _ptr(cnt))
+    return out, cnt
+
+
+def ref_image(xyz, L, name="libref_msd.so"):
+    a = _f64(xyz).copy()
+    ref_lib(name).ref_image(_ptr(a), a.shape[0], L)
+    return a
+
+
+def ref_slope(msd_arr, name="libref_msd.so"):
+    m = _f64(msd_arr).copy()
+    return ref_lib(name).ref_slope(_ptr(m), m.size)
+
+
+def ref_read_series(path, kind, cap=1 << 22, name="libref_msd.so"):
+    """kind: 'namd' or 'general' -- the reference's traj2diffusion readers; returns an (n, 3) array."""
+    buf = np.empty((cap, 3), dtype=np.float64)
+    n = ref_lib(name).ref_read_series(os.fsencode(path), 0 if kind == "namd" else 1, _ptr(buf), cap)
+    return buf[:min(n, cap)].copy()

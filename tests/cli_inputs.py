@@ -42,3 +42,35 @@ def write_pressure_log(path, pressure):
             f.write("ENERGY: %d 0 0 0\n" % i)
             f.write("PRESSURE: %d " % i + " ".join("%.6f" % v for v in row) + "\n")
             f.write("GPRESSURE: %d " % i + " ".join("%.6f" % (v + 1) for v in row) + "\n")
+
+
+def write_traj(path, xyz, fmt):
+    """A trajectory (n, 3) in the layouts traj2diffusion reads (traj2diffusion.cpp:59-121, :145-260)."""
+    with open(path, "w") as f:
+        if fmt in ("general", "general_blank"):
+            f.write("# step x y z\n")
+            for i, r in enumerate(xyz):
+                if fmt == "general_blank" and i == 7:
+                    f.write("\n")
+                f.write("%d %.10f %.10f %.10f\n" % (10 * i, r[0], r[1], r[2]))
+        elif fmt == "general_sci":
+            f.write("# step x y z\n")
+            for i, r in enumerate(xyz):
+                f.write(" %10d % .14e % .14e % .14e\n" % (i, r[0], r[1], r[2]))
+        elif fmt in ("namd", "namd_blank", "namd_short"):
+            # colvars vector layout: 11-char step, then "  ( x , y , z )" with 21-char components
+            f.write("# step         position\n")
+            for i, r in enumerate(xyz):
+                if fmt == "namd_blank" and i == 7:
+                    f.write("\n")
+                line = "%11d  ( %21.14e , %21.14e , %21.14e )" % (10 * i, r[0], r[1], r[2])
+                if fmt == "namd_short" and i == 25:
+                    line = line[:50]
+                f.write(line + "\n")
+        elif fmt == "namd_cols":
+            # columns placed where the reader looks: x at 15..36, y at 37..59, z at 61..83
+            f.write("# step         x y z\n")
+            for i, r in enumerate(xyz):
+                f.write("%15d%22.14e%23.14e %23.14e\n" % (10 * i, r[0], r[1], r[2]))
+        else:
+            raise ValueError(fmt)

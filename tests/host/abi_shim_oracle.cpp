@@ -23,7 +23,26 @@ double oracle_integrate_corr(const double* acf, int64_t ncorr, double dt);
 void oracle_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr);
 double oracle_viscosity_eta(double box_length, double temperature, double integral);
 
+void oracle_msd(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s, double* msd,
+                int32_t* counter);
+void oracle_image_axis(double* c, int64_t n, double L);
+double oracle_msd_slope(const double* msd, int64_t n, double* sum_out);
+
 const char* acfb200_last_error(void) { return "oracle shim"; }
+
+int acfb200_traj2diffusion(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s,
+                           double dt, double cell, int imaging, double* msd, int32_t* counter, acfb200_msd_result* r)
+{
+    std::vector<double> c[3] = {std::vector<double>(x, x + n), std::vector<double>(y, y + n), std::vector<double>(z, z + n)};
+    if (imaging)
+        for (auto& a : c) oracle_image_axis(a.data(), n, cell);
+    std::vector<int32_t> cnt(max_s);
+    oracle_msd(c[0].data(), c[1].data(), c[2].data(), n, stride, max_s, msd, counter ? counter : cnt.data());
+    r->slope = oracle_msd_slope(msd, max_s, &r->sum);
+    r->diffusivity = r->slope / (dt * stride) / 6.0;
+    r->nframes = n;
+    return 0;
+}
 int acfb200_set_method(int) { return 0; }
 
 int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double dt, double cutoff, double* acf,

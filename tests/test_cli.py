@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from cli_inputs import write_input, write_pressure_log
+from cli_inputs import write_input, write_pressure_log, write_traj
 from conftest import GOLDEN, ROOT
 
 HOST = os.path.join(ROOT, "acfcalculator_b200", "csrc", "host")
@@ -20,6 +20,10 @@ BUILD = os.path.join(ROOT, "tests", "_build")
 CASES = json.load(open(os.path.join(GOLDEN, "cli_cases.json")))
 SERIES = np.load(os.path.join(GOLDEN, "cli_series.npz"))
 ACF_CASES = [k for k in CASES if k != "viscosity_log"]
+T2D = json.load(open(os.path.join(GOLDEN, "t2d_cases.json")))
+T2D_TRAJ = np.load(os.path.join(GOLDEN, "t2d_traj.npz"))
+T2D_CASES = [k for k in T2D if not k.startswith("opt_")]
+T2D_OPT = [k for k in T2D if k.startswith("opt_")]
 
 
 def _cxx():
@@ -35,9 +39,12 @@ def oracle_frontends(oracle):
     link = ["-pthread", "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"),
             "-fopenmp"]
     exe = {}
-    for name, main in (("ACFcalculator", "acfcalculator_main.cpp"), ("viscosity", "viscosity_main.cpp")):
+    for name, main in (("ACFcalculator", "acfcalculator_main.cpp"), ("viscosity", "viscosity_main.cpp"),
+                       ("traj2diffusion", "traj2diffusion_main.cpp")):
         out = os.path.join(BUILD, name + "_oracle")
         srcs = [os.path.join(HOST, main), shim] + common
+        if name == "traj2diffusion":
+            srcs.append(os.path.join(HOST, "t2d_readers.cpp"))
         if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
             subprocess.run([_cxx(), "-O2", "-std=c++14", "-ffp-contract=off", "-o", out] + srcs + link, check=True)
         exe[name] = out
@@ -192,6 +199,49 @@ def test_factor_alias_equals_p_factor(oracle_frontends, tmp_path):
     assert a["acf_file"] == b["acf_file"] and a["out_file"] == b["out_file"] and a["returncode"] == b["returncode"]
 
 
+# ---- traj2diffusion (reference: oracle/_ref/traj2diffusion_ref, see tests/golden/make_t2d_golden.py) ------------
+def run_t2d(exe, name, tmp_path):
+    c = T2D[name]
+    if name.startswith("opt_"):
+        p = subprocess.run([exe] + c["args"], capture_output=True, text=True, cwd=str(tmp_path))
+        return p, None
+    inp = str(tmp_path / (name + ".traj"))
+    if c["format"] != "none":
+        write_traj(inp, T2D_TRAJ[c["traj"]], c["format"])
+    return subprocess.run([exe, "-t", inp] + c["args"], capture_output=True, text=True, cwd=str(tmp_path)), inp
+
+
+def check_t2d(p, inp, name, rel):
+    want = T2D[name]
+    assert p.returncode == want["returncode"], (name, p.stderr[-300:])
+    assert same_text(p.stdout, want["stdout"], rel), (name, p.stdout[-400:], want["stdout"][-400:])
+    head = [s.replace(inp, "<TRAJ>") if inp else s for s in p.stderr.splitlines()[:1]]
+    if want["returncode"] >= 0:  # after an abort the first stderr line is the C++ runtime's
+        assert head == want["stderr_head"], (name, head)
+
+
+@pytest.mark.parametrize("name", T2D_CASES)
+def test_traj2diffusion_frontend_with_oracle_backend_is_byte_identical(oracle_frontends, name, tmp_path):
+    p, inp = run_t2d(oracle_frontends["traj2diffusion"], name, tmp_path)
+    check_t2d(p, inp, name, rel=0)
+
+
+@pytest.mark.parametrize("name", T2D_OPT)
+def test_traj2diffusion_option_handling(oracle_frontends, name, tmp_path):
+    """Help layout, the required-option message, unknown options and bad values.  The recorded text comes from
+    oracle/boost_stub (Boost's documented wording); the front-end's parser was pinned against the real Boost
+    wording of the shipped ACFcalculator binary, and the two agree."""
+    p, _ = run_t2d(oracle_frontends["traj2diffusion"], name, tmp_path)
+    check_t2d(p, None, name, rel=0)
+
+
+def test_traj2diffusion_refuses_nonpositive_stride(oracle_frontends, tmp_path):
+    inp = str(tmp_path / "t.traj")
+    write_traj(inp, T2D_TRAJ["short"], "general")
+    p = subprocess.run([oracle_frontends["traj2diffusion"], "-t", inp, "-s", "0"], capture_output=True, text=True)
+    assert p.returncode == 1 and "stride" in p.stderr
+
+
 # ---- GPU: the shipped binaries end to end -----------------------------------------------------------------
 GPU_BIN = os.path.join(ROOT, "acfcalculator_b200", "bin")
 
@@ -214,3 +264,10 @@ def test_gpu_viscosity_matches_reference_program(tmp_path):
     p = subprocess.run([os.path.join(GPU_BIN, "viscosity"), log], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert same_text(p.stdout, CASES["viscosity_log"]["stdout"], 2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", T2D_CASES)
+def test_gpu_traj2diffusion_matches_reference_program(name, tmp_path):
+    p, inp = run_t2d(os.path.join(GPU_BIN, "traj2diffusion"), name, tmp_path)
+    check_t2d(p, inp, name, rel=2e-6)

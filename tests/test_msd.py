@@ -1,0 +1,243 @@
+"""traj2diffusion path: MSD over strided origins, imaging, slope, D.
+
+CPU tests pin the oracle restatement (oracle/acf_oracle.c: oracle_msd, oracle_image_axis, oracle_msd_slope)
+bit for bit against tests/golden/f5_msd.npz -- values produced by the reference's own object code
+(tests/golden/make_t2d_golden.py) -- and, when oracle/_ref is built, against that object code directly.
+GPU tests compare libacf_b200.so (through the C ABI) with the oracle.
+
+Tolerance (written here once): MSD(j), the slope sum and D within 1e-10 RELATIVE to their own value -- MSD has
+no sign changes, so a per-lag relative bound is meaningful (unlike C(k), SURVEY section 8 notes).  Counters and
+the NaN pattern (j >= n) identical.  Imaging: bit-identical coordinates.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+REL = 1e-10
+
+
+def walk(n, seed, step=0.45, origin=3.0):
+    rng = np.random.default_rng(seed)
+    return origin + np.cumsum(rng.standard_normal((n, 3)) * step, axis=0)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = np.isfinite(b) & (b != 0)
+    worst = float(np.max(np.abs(a[m] - b[m]) / np.abs(b[m]))) if m.any() else 0.0
+    z = np.isfinite(b) & (b == 0)
+    assert np.all(a[z] == 0)
+    return worst
+
+
+KEYS = [("walk", 1, 500), ("walk", 7, 300), ("walk", 100, 64), ("short", 1, 60), ("short", 3, 45)]
+
+
+# ---- oracle vs the reference's recorded values (CPU) --------------------------------------------------
+@pytest.mark.parametrize("key,stride,max_s", KEYS)
+def test_oracle_msd_bit_exact_against_reference(oracle, key, stride, max_s):
+    g, t = golden("f5_msd.npz"), golden("t2d_traj.npz")
+    r = t[key]
+    msd, cnt = oracle.msd(r[:, 0], r[:, 1], r[:, 2], stride, max_s)
+    want = g["msd_%s_s%d" % (key, stride)]
+    assert np.array_equal(msd, want, equal_nan=True)
+    assert np.array_equal(np.signbit(msd), np.signbit(want))  # 0.0/0 is "-nan" in the reference's output
+    assert np.array_equal(cnt, g["cnt_%s_s%d" % (key, stride)])
+    msd2, cnt2 = oracle.msd(r[:, 0], r[:, 1], r[:, 2], stride, max_s, threads=4)
+    assert np.array_equal(msd2, msd, equal_nan=True) and np.array_equal(cnt2, cnt)
+    sl, _ = oracle.msd_slope(msd)
+    want_sl = float(g["slope_%s_s%d" % (key, stride)])
+    assert sl == want_sl or (np.isnan(sl) and np.isnan(want_sl))
+
+
+def test_oracle_image_bit_exact_against_reference(oracle):
+    g, t = golden("f5_msd.npz"), golden("t2d_traj.npz")
+    for key, box, name in (("wrapped", float(g["box"]), "image_wrapped"),
+                           ("wrapped_odd", float(g["box_odd"]), "image_wrapped_odd"),
+                           ("wrapped", -float(g["box"]), "image_negative_box")):
+        r = t[key]
+        got = oracle.image(r[:, 0], r[:, 1], r[:, 2], box)
+        for a in range(3):
+            assert np.array_equal(got[a], g[name][:, a]), (name, a)
+    # the unwrapped trajectory no longer jumps by more than half a box
+    un = g["image_wrapped"]
+    assert np.max(np.abs(np.diff(un, axis=0))) <= float(g["box"]) / 2
+    assert np.max(np.abs(np.diff(t["wrapped"], axis=0))) > float(g["box"]) / 2
+
+
+def test_oracle_msd_of_imaged_trajectory(oracle):
+    g = golden("f5_msd.npz")
+    r = g["image_wrapped_odd"]
+    msd, _ = oracle.msd(r[:, 0], r[:, 1], r[:, 2], 1, 400)
+    assert np.array_equal(msd, g["msd_imaged_odd_s1"])
+
+
+def test_oracle_counter_formula_and_properties(oracle):
+    r = walk(257, 3)
+    for stride in (1, 2, 5, 64, 300):
+        msd, cnt = oracle.msd(r[:, 0], r[:, 1], r[:, 2], stride, 300)
+        j = np.arange(300)
+        want = np.where(j < 257, (257 - 1 - j) // stride + 1, 0)
+        assert np.array_equal(cnt, want)
+        assert msd[0] == 0.0 and np.all(np.isnan(msd[257:])) and np.all(msd[1:257] > 0)
+    # translation invariance (exact for a power-of-two shift that keeps the spacing representable)
+    a, _ = oracle.msd(r[:, 0], r[:, 1], r[:, 2], 1, 100)
+    b, _ = oracle.msd(r[:, 0] + 64.0, r[:, 1] - 32.0, r[:, 2] + 16.0, 1, 100)
+    assert np.allclose(a, b, rtol=1e-12, atol=0)
+    assert oracle.msd_diffusivity(a, 2.0, 1) == oracle.msd_slope(a)[0] / 2.0 / 6.0
+
+
+@pytest.mark.skipif(not __import__("oracle.oracle", fromlist=["x"]).ref_available("libref_msd.so"),
+                    reason="oracle/_ref not built (no /root/reference on this box)")
+def test_oracle_against_reference_object_code(oracle):
+    for n, stride, max_s, seed in ((300, 1, 50, 1), (300, 7, 64, 2), (100, 3, 150, 3), (5, 1, 8, 4), (1000, 100, 20, 5),
+                                   (1, 1, 3, 6)):
+        r = walk(n, seed, step=1.3, origin=100.0)
+        a, c = oracle.msd(r[:, 0], r[:, 1], r[:, 2], stride, max_s)
+        b, d = oracle.ref_msd(r, stride, max_s)
+        assert np.array_equal(a, b, equal_nan=True) and np.array_equal(c, d)
+    for box in (7.0, 3.3333333333333335, -7.0, 0.1):
+        r = walk(2000, 9, step=2.0)
+        w = r - abs(box) * np.floor(r / abs(box))
+        got = oracle.image(w[:, 0], w[:, 1], w[:, 2], box)
+        want = oracle.ref_image(w, box)
+        assert all(np.array_equal(got[a], want[:, a]) for a in range(3))
+
+
+# ---- GPU vs oracle -------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("key,stride,max_s", KEYS)
+def test_gpu_msd_matches_golden(acf, key, stride, max_s):
+    g, t = golden("f5_msd.npz"), golden("t2d_traj.npz")
+    r = t[key]
+    msd, cnt = acf.msd(r[:, 0], r[:, 1], r[:, 2], stride=stride, max_s=max_s)
+    want = g["msd_%s_s%d" % (key, stride)]
+    assert rel_err(msd, want) <= REL
+    assert np.array_equal(np.signbit(msd), np.signbit(want))
+    assert np.array_equal(cnt, g["cnt_%s_s%d" % (key, stride)])
+    sl, sm = acf.slope(want)
+    want_sl = float(g["slope_%s_s%d" % (key, stride)])
+    assert (np.isnan(sl) and np.isnan(want_sl)) or abs(sl - want_sl) <= REL * abs(want_sl)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,stride,max_s", [(1, 1, 4), (2, 1, 2), (3, 2, 5), (1000, 1, 1), (4097, 1, 4097), (5000, 1, 177),
+                                            (5000, 1, 2500), (20000, 1, 1000), (20001, 3, 999), (20000, 17, 1300),
+                                            (50000, 50000, 10), (300000, 1, 2000), (300000, 100, 3000)])
+def test_gpu_msd_shapes_against_oracle(acf, oracle, n, stride, max_s):
+    r = walk(n, n + stride, step=0.8, origin=-40.0)
+    x, y, z = (np.ascontiguousarray(r[:, a]) for a in range(3))
+    want, wcnt = oracle.msd(x, y, z, stride, max_s, threads=0)
+    msd, cnt = acf.msd(x, y, z, stride=stride, max_s=max_s)
+    assert rel_err(msd, want) <= REL
+    assert np.array_equal(cnt, wcnt)
+
+
+@pytest.mark.gpu
+def test_gpu_msd_same_array_three_times(acf, oracle):
+    """What the general reader produces (y = z = x): recognised and computed once, same numbers."""
+    x = np.ascontiguousarray(walk(30000, 77)[:, 0])
+    want, wcnt = oracle.msd(x, x, x, 1, 800, threads=0)
+    a, ca = acf.msd(x, max_s=800)
+    b, cb = acf.msd(x, x.copy(), x.copy(), max_s=800)
+    assert rel_err(a, want) <= REL and rel_err(b, want) <= REL
+    assert np.array_equal(ca, wcnt) and np.array_equal(cb, wcnt)
+    assert np.array_equal(a, b)  # (S+S)+S is the same whichever way the three sums were obtained
+
+
+@pytest.mark.gpu
+def test_gpu_image_is_bit_identical(acf, oracle):
+    g, t = golden("f5_msd.npz"), golden("t2d_traj.npz")
+    for key, box, name in (("wrapped", float(g["box"]), "image_wrapped"),
+                           ("wrapped_odd", float(g["box_odd"]), "image_wrapped_odd"),
+                           ("wrapped", -float(g["box"]), "image_negative_box")):
+        r = t[key]
+        got = acf.image(r[:, 0], r[:, 1], r[:, 2], box)
+        for a in range(3):
+            assert np.array_equal(got[a], g[name][:, a]), (name, a)
+    # many tiles, many crossings, a box whose multiples are not representable
+    box = 0.7853981633974483
+    r = walk(300001, 5, step=0.5)
+    w = r - box * np.floor(r / box)
+    x, y, z = (np.ascontiguousarray(w[:, a]) for a in range(3))
+    got = acf.image(x, y, z, box)
+    want = oracle.image(x, y, z, box)
+    for a in range(3):
+        assert np.array_equal(got[a], want[a])
+    # no crossings at all, and a single frame
+    got = acf.image(r[:, 0], r[:, 1], r[:, 2], 1e9)
+    assert all(np.array_equal(got[a], r[:, a]) for a in range(3))
+    one = acf.image(np.array([1.0]), np.array([2.0]), np.array([3.0]), 1.0)
+    assert [float(v[0]) for v in one] == [1.0, 2.0, 3.0]
+
+
+@pytest.mark.gpu
+def test_gpu_traj2diffusion_pipeline(acf, oracle):
+    g, t = golden("f5_msd.npz"), golden("t2d_traj.npz")
+    r, box = t["wrapped_odd"], float(g["box_odd"])
+    d = acf.traj2diffusion(r[:, 0], r[:, 1], r[:, 2], stride=1, max_s=400, timestep=2.0, cell=box)
+    want = g["msd_imaged_odd_s1"]
+    assert rel_err(d["msd"], want) <= REL
+    sl, sm = oracle.msd_slope(want)
+    assert abs(d["sum"] - sm) <= REL * abs(sm) and abs(d["slope"] - sl) <= REL * abs(sl)
+    assert abs(d["diffusivity"] - oracle.msd_diffusivity(want, 2.0, 1)) <= REL * abs(d["diffusivity"])
+    assert d["nframes"] == r.shape[0]
+    # strided, no imaging
+    r = t["walk"]
+    d = acf.traj2diffusion(r[:, 0], r[:, 1], r[:, 2], stride=7, max_s=300, timestep=0.5)
+    want = g["msd_walk_s7"]
+    assert rel_err(d["msd"], want) <= REL
+    assert abs(d["diffusivity"] - oracle.msd_diffusivity(want, 0.5, 7)) <= REL * abs(d["diffusivity"])
+
+
+@pytest.mark.gpu
+def test_gpu_msd_device_entry_points(acf, oracle):
+    import torch
+    r = walk(100000, 21)
+    xs = [torch.from_numpy(np.ascontiguousarray(r[:, a])).cuda() for a in range(3)]
+    msd, cnt = acf.msd_device(*xs, stride=1, max_s=1500)
+    torch.cuda.synchronize()
+    want, wcnt = oracle.msd(r[:, 0].copy(), r[:, 1].copy(), r[:, 2].copy(), 1, 1500, threads=0)
+    assert rel_err(msd.cpu().numpy(), want) <= REL and np.array_equal(cnt.cpu().numpy(), wcnt)
+    box = 3.7
+    w = r - box * np.floor(r / box)
+    ws = [torch.from_numpy(np.ascontiguousarray(w[:, a])).cuda() for a in range(3)]
+    outs = acf.image_device(*ws, box)
+    torch.cuda.synchronize()
+    want = oracle.image(w[:, 0].copy(), w[:, 1].copy(), w[:, 2].copy(), box)
+    for a in range(3):
+        assert np.array_equal(outs[a].cpu().numpy(), want[a])
+
+
+@pytest.mark.gpu
+def test_gpu_msd_full_size_properties(acf, oracle):
+    """N = 1e7 frames, max_s = 2000 (6e10 displacement terms): a lag subset against per-lag oracle sums, the
+    counters, monotone growth of a diffusive MSD, and run-to-run bit reproducibility."""
+    n, max_s = 10_000_000, 2000
+    rng = np.random.default_rng(20260401)
+    r = np.cumsum(rng.standard_normal((3, n)) * 0.3, axis=1) + 50.0
+    a, ca = acf.msd(r[0], r[1], r[2], stride=1, max_s=max_s)
+    b, _ = acf.msd(r[0], r[1], r[2], stride=1, max_s=max_s)
+    assert np.array_equal(a, b)
+    lags = sorted(set(list(range(8)) + [17, 100, 999, 1024, 1500, 1998, 1999]))
+    for j in lags:
+        acc = 0.0
+        for c in range(3):
+            d = r[c, j:] - r[c, :n - j]
+            acc += float(np.dot(d, d))
+        want = acc / (n - j)
+        assert a[j] == 0.0 if j == 0 else abs(a[j] - want) <= 1e-11 * want, j
+    assert np.array_equal(ca, n - np.arange(max_s))
+    # <|dr|^2> of a random walk grows like 3*0.09*j
+    j = np.arange(1, max_s)
+    assert np.max(np.abs(a[1:] / (0.27 * j) - 1)) < 0.05
+
+
+@pytest.mark.gpu
+def test_gpu_msd_argument_errors(acf):
+    x = np.zeros(10)
+    for kw in (dict(stride=0), dict(max_s=0)):
+        with pytest.raises(acf._lib.AcfError):
+            acf.msd(x, x, x, **{**dict(stride=1, max_s=4), **kw})
