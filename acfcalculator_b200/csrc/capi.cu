@@ -930,10 +930,7 @@ static int msd_device(Workspace* ws, const double* d_x, const double* d_y, const
     SeriesDesc descs[3] = {{d_x, n, n}, {d_y, n, n}, {d_z, n, n}};
     DirectPlan plan;
     if (stride == 1) {
-        ACF_TRY(plan_direct(n, max_s, ns, ws->sm_count, g_force_variant < direct_variant_count() - stream_variant_count()
-                                                            ? g_force_variant
-                                                            : -1,
-                            &plan));
+        ACF_TRY(plan_direct(n, max_s, ns, ws->sm_count, -1, &plan, true));
         if (plan.mode != 0) {
             set_error("msd: the displacement kernel needs a tiled plan (unset ACFB200_MODE)");
             return ACFB200_ERR_ARG;

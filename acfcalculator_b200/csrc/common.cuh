@@ -34,7 +34,7 @@ void set_error(const char* fmt, ...);
 
 // direct_lag.cu
 int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count, int force_variant,
-                DirectPlan* plan);
+                DirectPlan* plan, bool msd = false);
 size_t direct_partial_elems(const DirectPlan& p, int nseries);
 // Raw lag sums per (series, chunk) into `partials`; then reduce_partials folds the chunks in fixed order.
 int launch_direct(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long ncorr,

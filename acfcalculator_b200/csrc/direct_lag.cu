@@ -32,8 +32,9 @@ constexpr int kMaxWarps = 16;
 // MSD = false: S[k] += x[i]*x[i+k].   MSD = true: S[k] += (x[i+k]-x[i])^2 -- the displacement sums of
 // traj2diffusion.cpp:530-541 for unit origin stride; same staging, ring and partial-sum layout, one extra
 // DADD per term (so the FP64 pipe runs two instructions per displacement instead of one per product).
-template <int RK, int LK, int PF, bool MSD = false>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+// MAXW bounds the CTA width: the wide-RK variants run as 1-warp CTAs only, which lifts the 128-register cap.
+template <int RK, int LK, int PF, bool MSD = false, int MAXW = kMaxWarps>
+__global__ void __launch_bounds__(MAXW * 32, 1)
 direct_lag_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int ts, int bsz, int chunks, int mpad,
                   double* __restrict__ partials)
 {
@@ -239,20 +240,34 @@ struct Variant {
     int rk, lk, pf;
     direct_fn fn;
     direct_fn fn_msd;  // displacement-square form of the same geometry
+    int max_warps;     // widest CTA the instantiation was compiled for
     const char* name;
     double quality;  // relative DFMA-pipe efficiency of the inner loop (measured; 1.0 = best)
 };
 
 #define ACF_VARIANT(RK, LK, PF, Q) \
-    {RK, LK, PF, direct_lag_kernel<RK, LK, PF, false>, direct_lag_kernel<RK, LK, PF, true>, "rk" #RK "_lk" #LK "_pf" #PF, Q}
+    {RK, LK, PF, direct_lag_kernel<RK, LK, PF, false>, direct_lag_kernel<RK, LK, PF, true>, kMaxWarps, \
+     "rk" #RK "_lk" #LK "_pf" #PF, Q}
+// one-warp CTAs only (up to 255 registers per thread): more lags per thread = fewer LDS per DFMA
+// (no displacement form: with two FP64 instructions per term the LDS share is already halved, and measured on
+// B200 the wide geometries run the displacement loop slower -- 4.57 ms vs 3.44 ms at 1e7 frames x 1000 lags)
+#define ACF_VARIANT_W1(RK, LK, PF, Q) \
+    {RK, LK, PF, direct_lag_kernel<RK, LK, PF, false, 1>, nullptr, 1, "rk" #RK "_lk" #LK "_pf" #PF "_w1", Q}
 // quality = inner-loop DFMA efficiency relative to the best variant, measured on B200 at N=1e8, maxcorr=1e4
-// (profiles/r1_sweep_*.jsonl: time / useful-lag fraction).  More lags per thread = fewer LDS per DFMA.
+// (profiles/r1_sweep_*.jsonl: time / useful-lag fraction).  More lags per thread = fewer LDS per DFMA: every LDS costs
+// the FP64 dispatch port ~4-5 cycles, so 2 LDS per 2*RK DFMAs bound the loop at ~RK/(RK+2.5) of the DFMA peak.
+// The _w1 variants trade occupancy (9-12 warps/SM at 150-220 registers) for that ratio; one warp per SMSP already
+// saturates the pipe.  Past RK = 42 the register allocation tips over (rk46: 0.916, rk50: 0.905 inner efficiency).
 static const Variant kVariants[] = {
-    ACF_VARIANT(18, 32, 1, 0.985), ACF_VARIANT(18, 16, 1, 0.985), ACF_VARIANT(18, 8, 1, 0.985),
-    ACF_VARIANT(14, 32, 1, 0.960), ACF_VARIANT(22, 32, 1, 1.000), ACF_VARIANT(10, 32, 1, 0.920),
-    ACF_VARIANT(18, 32, 0, 0.970), ACF_VARIANT(18, 32, 2, 0.985),
-    ACF_VARIANT(22, 8, 1, 1.000),  ACF_VARIANT(22, 16, 1, 1.000), ACF_VARIANT(18, 8, 0, 0.975), ACF_VARIANT(18, 8, 2, 0.985),
-    ACF_VARIANT(22, 8, 0, 0.990),  ACF_VARIANT(26, 8, 0, 0.993),
+    ACF_VARIANT(18, 32, 1, 0.931), ACF_VARIANT(18, 16, 1, 0.931), ACF_VARIANT(18, 8, 1, 0.931),
+    ACF_VARIANT(14, 32, 1, 0.907), ACF_VARIANT(22, 32, 1, 0.945), ACF_VARIANT(10, 32, 1, 0.869),
+    ACF_VARIANT(18, 32, 0, 0.917), ACF_VARIANT(18, 32, 2, 0.931),
+    ACF_VARIANT(22, 8, 1, 0.945),  ACF_VARIANT(22, 16, 1, 0.945), ACF_VARIANT(18, 8, 0, 0.921), ACF_VARIANT(18, 8, 2, 0.931),
+    ACF_VARIANT(22, 8, 0, 0.935),  ACF_VARIANT(26, 8, 0, 0.938),
+    ACF_VARIANT_W1(30, 8, 1, 0.973), ACF_VARIANT_W1(36, 8, 1, 0.979), ACF_VARIANT_W1(34, 8, 1, 0.979),
+    ACF_VARIANT_W1(38, 8, 1, 0.987), ACF_VARIANT_W1(40, 8, 1, 0.962), ACF_VARIANT_W1(42, 8, 1, 0.994),
+    ACF_VARIANT_W1(36, 16, 1, 0.986), ACF_VARIANT_W1(42, 16, 1, 1.000), ACF_VARIANT_W1(46, 8, 1, 0.964),
+    ACF_VARIANT_W1(50, 8, 1, 0.952), ACF_VARIANT_W1(42, 32, 1, 0.995), ACF_VARIANT_W1(46, 16, 1, 0.971),
 };
 // CTA width: 1- and 2-warp CTAs have (almost) no barrier skew; 16 warps leave the tile load unoverlapped
 static double warps_quality(int w)
@@ -279,14 +294,14 @@ static int env_int(const char* name, int dflt)
 }
 
 int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count, int force_variant,
-                DirectPlan* plan)
+                DirectPlan* plan, bool msd)
 {
     if (ncorr <= 0 || nseries <= 0) {
         set_error("plan_direct: ncorr (%lld) and nseries (%d) must be positive", ncorr, nseries);
         return 1;
     }
     if (max_i_end < 1) max_i_end = 1;
-    const int warps_per_sm = env_int("ACFB200_WARPS_PER_SM", 16);  // 16 = the 128-registers/thread limit
+    const int warps_per_sm_cap = env_int("ACFB200_WARPS_PER_SM", 16);  // 16 = the 128-registers/thread limit
     const int smem_per_sm = 228 * 1024;
     int fv = env_int("ACFB200_VARIANT", force_variant);
     int fw = env_int("ACFB200_WARPS", 0);
@@ -355,11 +370,12 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
     int best_v = 0, best_w = 4;
     for (int v = 0; v < kNumVariants; ++v) {
         if (fv >= 0 && v != fv) continue;
-        if (fv < 0 && kVariants[v].quality < 0.95) continue;  // tuning-only variants
+        if (fv < 0 && kVariants[v].quality < 0.86) continue;  // tuning-only variants
+        if (msd && !kVariants[v].fn_msd) continue;            // displacement form: the 16-warp-capable geometries only
         const long long lkrk = (long long)kVariants[v].lk * kVariants[v].rk;
         const long long lb = (ncorr + lkrk - 1) / lkrk;
-        for (int w = 1; w <= kMaxWarps; w = (w < 4 ? w * 2 : w + 4)) {
-            if (fw > 0 && w != fw) continue;
+        for (int w = 1; w <= kVariants[v].max_warps; w = (w < 4 ? w * 2 : w + 4)) {
+            if (fw > 0 && w != fw && kVariants[v].max_warps > 1) continue;
             const long long lt = (lb + w - 1) / w;
             const double useful = (double)ncorr / (double)(lt * w * lkrk);
             const double score = useful * kVariants[v].quality * warps_quality(w);
@@ -375,6 +391,19 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
         return 1;
     }
     const Variant& V = kVariants[best_v];
+    // resident warps per SM: the register file holds 64K registers, allocated per warp in units of 256
+    int warps_per_sm = warps_per_sm_cap;
+    {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, msd ? V.fn_msd : V.fn) == cudaSuccess && fa.numRegs > 0) {
+            const int per_warp = (fa.numRegs * 32 + 255) / 256 * 256;
+            const int fit = 65536 / per_warp;
+            if (fit < warps_per_sm) warps_per_sm = fit;
+        } else {
+            cudaGetLastError();
+        }
+        if (warps_per_sm < best_w) warps_per_sm = best_w;
+    }
     DirectPlan p;
     p.mode = 0;
     p.variant = best_v;
@@ -413,7 +442,8 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
     if (groups < 4 * slots) {
         // fill an integer number of waves; each CTA should keep at least ~4 tiles if there are that many
         long long waves = 1;
-        while (waves < 4 && (slots * (waves + 1)) / groups <= n_tiles / 4) ++waves;
+        const int max_waves = env_int("ACFB200_MAX_WAVES", 4);
+        while (waves < max_waves && (slots * (waves + 1)) / groups <= n_tiles / 4) ++waves;
         chunks = (slots * waves) / groups;
         if (chunks < 1) chunks = 1;
     }
@@ -436,6 +466,10 @@ static int launch_tiled(const DirectPlan& p, bool msd, const SeriesDesc* d_desc,
 {
     const Variant& V = kVariants[p.variant];
     const direct_fn fn = msd ? V.fn_msd : V.fn;
+    if (!fn) {
+        set_error("variant %s has no displacement form", V.name);
+        return 1;
+    }
     const int slot = p.variant + (msd ? kNumVariants : 0);
     int dev = 0;
     ACF_CUDA_OK(cudaGetDevice(&dev));

@@ -50,8 +50,19 @@ __global__ void __launch_bounds__(512, 1) dfma_probe_kernel(double* out, int out
     for (int o = 0; o < outer; ++o) {
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
+            if (PROBE == 7) {  // pure DADD chains (are adds cheaper than FMAs on this pipe?)
 #pragma unroll
-            for (int j = 0; j < 18; ++j) acc[j] = fma(a, w[j], acc[j]);
+                for (int j = 0; j < 18; ++j) acc[j] = acc[j] + w[j];
+            } else if (PROBE == 8) {  // the displacement kernel's pair: DADD feeding a DFMA
+#pragma unroll
+                for (int j = 0; j < 18; ++j) {
+                    const double dd = w[j] - a;
+                    acc[j] = fma(dd, dd, acc[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 18; ++j) acc[j] = fma(a, w[j], acc[j]);
+            }
             if (PROBE == 1) {          // 16-byte load, distinct address per lane (4 wavefronts)
                 const double2 v = sh[(threadIdx.x + r + o) & 511];
                 w[r % 18] = v.x;
@@ -101,6 +112,8 @@ int measure_dfma_probe(int probe, double* tflops)
         cudaFuncSetAttribute(dfma_probe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(dfma_probe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(dfma_probe_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dfma_probe_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dfma_probe_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr = true;
     }
     int dev = 0, sms = 0;
@@ -122,13 +135,17 @@ int measure_dfma_probe(int probe, double* tflops)
             case 3: dfma_probe_kernel<3><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
             case 4: dfma_probe_kernel<4><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
             case 5: dfma_probe_kernel<5><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
-            default: dfma_probe_kernel<6><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+            case 6: dfma_probe_kernel<6><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+            case 7: dfma_probe_kernel<7><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
+            default: dfma_probe_kernel<8><<<grid, threads, 200 * 1024>>>(d_out, outer, 1.0); break;
         }
         ACF_CUDA_OK(cudaEventRecord(e1));
         ACF_CUDA_OK(cudaEventSynchronize(e1));
         float ms = 0.f;
         ACF_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-        const double fmas = (double)grid * threads * outer * 32 * ((probe == 0 || probe == 3 || probe == 5) ? 19 : 18);
+        // FP64-pipe instructions per round, reported as if each were a DFMA (2 flops) so the probes compare as slot rates
+        const int per_round = probe == 8 ? 37 : (probe == 0 || probe == 3 || probe == 5 || probe == 7) ? 19 : 18;
+        const double fmas = (double)grid * threads * outer * 32 * per_round;
         const double tf = 2.0 * fmas / (ms * 1e-3) / 1e12;
         if (it > 0 && tf > best) best = tf;
     }
