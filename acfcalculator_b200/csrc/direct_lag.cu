@@ -391,13 +391,14 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
         return 1;
     }
     const Variant& V = kVariants[best_v];
-    // resident warps per SM: the register file holds 64K registers, allocated per warp in units of 256
+    // resident warps per SM: the register file holds 64K registers, allocated per warp in units of 256, and warps
+    // are granted four at a time (one per SMSP): ncu reports 16 for 114 registers and 8 for 202
     int warps_per_sm = warps_per_sm_cap;
     {
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, msd ? V.fn_msd : V.fn) == cudaSuccess && fa.numRegs > 0) {
             const int per_warp = (fa.numRegs * 32 + 255) / 256 * 256;
-            const int fit = 65536 / per_warp;
+            const int fit = 65536 / per_warp / 4 * 4;
             if (fit < warps_per_sm) warps_per_sm = fit;
         } else {
             cudaGetLastError();

@@ -316,7 +316,7 @@ def run_native(args):
         fmas_rank = 0.0
         fp64_instr_rank = 6.0 * pairs  # per pair and axis: one DADD (difference) + one DFMA (square-accumulate)
         launches_per_step = 3
-        plan = A.describe_plan(n, m, 3)
+        plan = "displacement kernel (direct_lag_kernel<MSD>), geometry from the 16-warp-capable variants, 3 axes per launch"
         res = {}
 
         def step():
@@ -418,8 +418,8 @@ def run_native(args):
             "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf,
             # DRAM bytes of one direct_lag_kernel launch from the committed ncu capture of this command
-            # (profiles/r1c_direct_lag_ncu_raw.csv: 80.25 MB read + 8.42 MB written); irrelevant to an FP64-bound kernel
-            "traffic": 88.67e6 if (args.workload == "ou" and n == 10**7 and m == 10**4) else None,
+            # (profiles/r1d_direct_lag_ncu_raw.csv: 80.69 MB read + 11.15 MB written); irrelevant to an FP64-bound kernel
+            "traffic": 91.83e6 if (args.workload == "ou" and n == 10**7 and m == 10**4) else None,
             "peak_source": "DFMA-chain micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
             "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS, "nominal_peak": FP64_NOMINAL_TFLOPS,
             "kernel": "direct_lag_kernel (step time includes the ~us reduce_partials epilogue)",
