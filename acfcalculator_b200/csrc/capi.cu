@@ -469,47 +469,76 @@ int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int
 }
 
 // One long host series, direct summation: the upload is cut into pieces on the copy stream and the lag kernel of
-// piece p (a time block whose halo lies in piece p+1, SeriesDesc.i_end < n) starts as soon as piece p+1 has landed, so
-// only the first two pieces' transfer time is exposed.  All pieces share one plan; their per-chunk partial sums are
-// folded by one reduce launch in fixed order, exactly as for a single launch.
+// piece p (a time block whose halo of ncorr samples belongs to piece p+1, SeriesDesc.i_end < n) starts as soon as the
+// samples it can touch have landed.  Copy p therefore carries piece p plus the halo after it, and the pieces grow
+// geometrically (1 : 2 : 4 : 8 : rest of n/32 units): the host link is ~4x faster than the kernel consumes samples, so
+// only the first, small piece's transfer is exposed while the later launches are long enough to run at full
+// efficiency.  Every piece has its own plan (same variant and row pitch, its own chunk count); the per-chunk partial
+// sums of all pieces lie back to back and are folded by one reduce launch in fixed order, as for a single launch.
 static int calc_correlation_pipelined(Workspace* ws, const double* y, long long n, long long ncorr, double* corr)
 {
-    const int kPieces = 8;
-    long long piece = ((n + kPieces - 1) / kPieces + 1) & ~1ll;
-    if (piece < ncorr + 2) piece = (ncorr + 3) & ~1ll;  // the halo of a piece must lie inside the next one
-    const int np = (int)((n + piece - 1) / piece);
+    const int kMaxPieces = 5;
+    long long unit = (n / 32 + 1) & ~1ll;
+    if (unit < 4 * ncorr) unit = (4 * ncorr + 1) & ~1ll;  // a piece much shorter than its halo is all overhead
+    long long bounds[kMaxPieces + 1] = {0};
+    int np = 0;
+    for (long long w = 1; np < kMaxPieces && bounds[np] < n; w *= 2) {
+        long long e = bounds[np] + w * unit;
+        if (np == kMaxPieces - 1 || e + unit / 2 >= n) e = n;
+        bounds[++np] = e;
+    }
     cudaStream_t st = ws->stream;
     ACF_TRY(ws->series.ensure(even_up(n) * 8));
     ACF_TRY(ws->out.ensure((size_t)ncorr * 8));
     double* d = ws->series.as<double>();
-    DirectPlan plan;
-    ACF_TRY(plan_direct(piece, ncorr, 1, ws->sm_count, g_force_variant, &plan));
-    ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, 1) * (size_t)np * sizeof(double)));
+    std::vector<DirectPlan> plans(np);
+    std::vector<size_t> offset(np + 1, 0);
+    long long chunks_total = 0;
+    for (int p = 0; p < np; ++p) {
+        ACF_TRY(plan_direct(bounds[p + 1] - bounds[p], ncorr, 1, ws->sm_count, g_force_variant, &plans[p]));
+        if (plans[p].mode != plans[0].mode || plans[p].mpad != plans[0].mpad) {
+            set_error("pipelined calc_correlation: pieces disagree on the partial-sum layout");
+            return ACFB200_ERR_ARG;
+        }
+        offset[p + 1] = offset[p] + direct_partial_elems(plans[p], 1);
+        chunks_total += plans[p].chunks;
+    }
+    ACF_TRY(ws->partials.ensure(offset[np] * sizeof(double)));
     ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)(np + 1)));
     ACF_TRY(ws->queue.ensure(64, true));
     std::vector<SeriesDesc> descs(np + 1);
-    std::vector<cudaEvent_t> landed(np);
     for (int p = 0; p < np; ++p) {
-        const long long b = (long long)p * piece, e = b + piece < n ? b + piece : n;
-        ACF_CUDA_OK(cudaMemcpyAsync(d + b, y + b, (size_t)(e - b) * 8, cudaMemcpyHostToDevice, ws->copy_stream));
-        ACF_CUDA_OK(cudaEventCreateWithFlags(&landed[p], cudaEventDisableTiming));
-        ACF_CUDA_OK(cudaEventRecord(landed[p], ws->copy_stream));
+        const long long b = bounds[p], e = bounds[p + 1];
         const long long reach = e + ncorr < n ? e + ncorr : n;  // last sample a pair starting in this piece can touch
         descs[p] = {d + b, reach - b, e - b};
     }
     descs[np] = {d, n, n};  // the whole series, for the divide by (n - k)
     ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * descs.size(), cudaMemcpyHostToDevice, st));
-    const size_t per_piece = direct_partial_elems(plan, 1);
+    std::vector<cudaEvent_t> landed(np, nullptr);
     int rc = 0;
+    long long copied = 0;
     for (int p = 0; p < np && rc == 0; ++p) {
-        cudaStreamWaitEvent(st, landed[p + 1 < np ? p + 1 : p], 0);
-        rc = launch_direct(plan, ws->desc.as<SeriesDesc>() + p, 1, ncorr, ws->partials.as<double>() + per_piece * p,
+        // copy, then launch: with a pageable source the copy call blocks the host while the previous kernel runs
+        const long long upto = bounds[p + 1] + ncorr < n ? bounds[p + 1] + ncorr : n;
+        cudaError_t e = cudaSuccess;
+        if (upto > copied)
+            e = cudaMemcpyAsync(d + copied, y + copied, (size_t)(upto - copied) * 8, cudaMemcpyHostToDevice, ws->copy_stream);
+        copied = upto > copied ? upto : copied;
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&landed[p], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(landed[p], ws->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, landed[p], 0);
+        if (e != cudaSuccess) {
+            set_error("pipelined calc_correlation: upload of piece %d failed: %s", p, cudaGetErrorString(e));
+            rc = ACFB200_ERR_CUDA;
+            break;
+        }
+        rc = launch_direct(plans[p], ws->desc.as<SeriesDesc>() + p, 1, ncorr, ws->partials.as<double>() + offset[p],
                            ws->queue.as<unsigned int>(), ws->sm_count, st);
         g_launches += 1;
     }
     if (rc == 0) {
-        DirectPlan all = plan;
-        all.chunks = plan.chunks * np;
+        DirectPlan all = plans[0];
+        all.chunks = (int)chunks_total;
         rc = launch_reduce_partials(all, ws->desc.as<SeriesDesc>() + np, 1, ncorr, ws->partials.as<double>(),
                                     ws->out.as<double>(), 1, st);
         g_launches += 1;
@@ -518,7 +547,8 @@ static int calc_correlation_pipelined(Workspace* ws, const double* y, long long 
     if (rc == 0) e = cudaMemcpyAsync(corr, ws->out.p, (size_t)ncorr * 8, cudaMemcpyDeviceToHost, st);
     cudaError_t es = cudaStreamSynchronize(st);
     cudaStreamSynchronize(ws->copy_stream);
-    for (auto& ev : landed) cudaEventDestroy(ev);
+    for (auto& ev : landed)
+        if (ev) cudaEventDestroy(ev);
     if (rc == 0 && (e != cudaSuccess || es != cudaSuccess)) {
         set_error("pipelined calc_correlation failed: %s", cudaGetErrorString(e != cudaSuccess ? e : es));
         rc = ACFB200_ERR_CUDA;

@@ -58,7 +58,11 @@ def test_green_kubo_and_viscosity_cli(acf, ngpus, tmp_path):
     g = np.load(os.path.join(GOLDEN, "f3_viscosity.npz"))
     a1, i1, e1 = acf.green_kubo(list(g["comps"]), 1000, 2.0)
     a2, i2, e2 = acf.multi_gpu_green_kubo(list(g["comps"]), 1000, 2.0, ngpus=ngpus)
-    assert rel_to_c0(a2, a1, a1[0][0]) <= 1e-13 and np.allclose(i1, i2, rtol=1e-12) and np.allclose(e1, e2, rtol=1e-12)
+    assert rel_to_c0(a2, a1, a1[0][0]) <= 1e-13
+    # the integrals are signed sums that may nearly cancel: hold them to 1e-12 of the sum of magnitudes
+    scale = np.sum(np.abs(np.asarray(a1)), axis=1) * 2.0
+    assert np.all(np.abs(np.asarray(i1) - np.asarray(i2)) <= 1e-12 * scale)
+    assert np.all(np.abs(np.asarray(e1) - np.asarray(e2)) <= 1e-12 * scale * np.abs(np.asarray(e1) / np.asarray(i1)))
     pres = np.load(os.path.join(GOLDEN, "cli_pressure.npz"))["pressure"]
     log = str(tmp_path / "namd.log")
     write_pressure_log(log, pres)
