@@ -73,6 +73,30 @@ def test_calc_correlation_sizes(acf, oracle, n, m):
     assert rel_to_c0(got, ref, ref[0]) <= TOL
 
 
+def test_random_shapes_batches_and_time_blocks(acf, oracle):
+    """120 seeded random (n, maxcorr, batch, i_end, alignment) combinations through the device entry point: the
+    planner's choice of variant, CTA width, tile length and time chunks changes with every one of them."""
+    import torch
+    rng = np.random.default_rng(20261020)
+    for case in range(120):
+        ns = int(rng.integers(1, 5))
+        m = int(rng.choice([1, 2, 7, 41, 100, 177, 336, 337, 672, 1000, 1345, 2500, 4097]))
+        series, i_end, refs = [], [], []
+        for s in range(ns):
+            n = int(rng.choice([1, 2, 3, 50, 700, 4999, 20000, 65537, 150001]))
+            off = int(rng.integers(0, 2))  # 1: 8-byte but not 16-byte aligned -> bounds-checked loader
+            x = ou_series(n + off, float(rng.uniform(2.0, 200.0)), mu=float(rng.uniform(-1, 1)), seed=1000 * case + s)
+            d = torch.from_numpy(x).cuda()[off:]
+            ie = n if rng.random() < 0.5 else int(rng.integers(0, n + 1))
+            series.append(d)
+            i_end.append(ie)
+            refs.append(oracle.lag_sums_block(x[off:], 0, ie, m))
+        got = acf.calc_correlation_batch_device(series, m, i_end=i_end, normalise=False).cpu().numpy()
+        for s in range(ns):
+            scale = max(float(np.max(np.abs(refs[s]))), 1e-300)
+            assert np.max(np.abs(got[s] - refs[s])) <= TOL * scale, (case, s, m, series[s].numel(), i_end[s])
+
+
 def test_every_kernel_variant(acf, oracle):
     x = ou_series(300000, 100.0, mu=0.5, seed=3)
     m = 2500

@@ -136,6 +136,21 @@ def test_gpu_msd_shapes_against_oracle(acf, oracle, n, stride, max_s):
 
 
 @pytest.mark.gpu
+def test_gpu_msd_random_shapes(acf, oracle):
+    rng = np.random.default_rng(20261021)
+    for case in range(80):
+        n = int(rng.choice([1, 2, 5, 63, 704, 705, 5000, 30011, 100000]))
+        stride = int(rng.choice([1, 1, 1, 2, 3, 10, 100, 1001]))
+        max_s = int(rng.choice([1, 2, 17, 144, 145, 1000, 1009, 3000]))
+        r = walk(n, 5000 + case, step=float(rng.uniform(0.05, 3.0)), origin=float(rng.uniform(-500, 500)))
+        x, y, z = (np.ascontiguousarray(r[:, a]) for a in range(3))
+        want, wcnt = oracle.msd(x, y, z, stride, max_s, threads=0)
+        msd, cnt = acf.msd(x, y, z, stride=stride, max_s=max_s)
+        assert rel_err(msd, want) <= REL, (case, n, stride, max_s)
+        assert np.array_equal(cnt, wcnt), (case, n, stride, max_s)
+
+
+@pytest.mark.gpu
 def test_gpu_msd_same_array_three_times(acf, oracle):
     """What the general reader produces (y = z = x): recognised and computed once, same numbers."""
     x = np.ascontiguousarray(walk(30000, 77)[:, 0])
