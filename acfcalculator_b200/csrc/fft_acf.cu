@@ -304,8 +304,11 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     constexpr int LTC = 12 - B, TC = 1 << LTC;     // tile = NB rows x TC columns = 4096 elements
     constexpr int NB8 = NB >> 3;                   // radix-8 groups per column (>= 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* s = reinterpret_cast<double2*>(smem_raw);
-    double2* tw = s + NB * TC;                     // W_NB^m (conjugated for the inverse), m < NB
+    // two tile buffers: every radix pass reads one and writes the other (or alternates per tile when there is no middle
+    // pass), so a pass needs one barrier -- after its writes -- instead of a second one guarding the in-place overwrite
+    double2* s0 = reinterpret_cast<double2*>(smem_raw);
+    double2* s1 = s0 + NB * TC;
+    double2* tw = s1 + NB * TC;                    // W_NB^m (conjugated for the inverse), m < NB
     const int tid = threadIdx.x;
     const int g = tid >> LTC, c = tid & (TC - 1);  // pass-1 role: group g of column c; NB8 * TC == 512 threads
     const unsigned int tiles_c_log = logC - LTC;
@@ -414,7 +417,8 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     unsigned int tile = blockIdx.x;
     if (tile < tiles) load_tile(tile, nxt);
     __syncthreads();  // twiddle table ready
-    for (; tile < tiles; tile += gridDim.x) {
+    unsigned int parity = 0;
+    for (; tile < tiles; tile += gridDim.x, parity ^= 1) {
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & ((1u << tiles_c_log) - 1)) << LTC;
         double2 v[8];
 #pragma unroll
@@ -431,16 +435,17 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             store_group(a, c0 + c, 0, 1, 8, v);
             continue;
         }
+        // with a middle pass: pass 1 -> s0, middle s0 -> s1, last reads s1.  Without: the buffers alternate per tile.
+        double2* sa = (B > 6) ? s0 : (parity ? s1 : s0);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s[((8 * g + u) << LTC) + c] = v[u];
+        for (int u = 0; u < 8; ++u) sa[((8 * g + u) << LTC) + c] = v[u];
         __syncthreads();
 
         // ---- middle radix-8 pass (stride 8) through shared memory, only for NB >= 128
         if (B > 6) {
             double2 r[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) r[t] = s[((g + t * NB8) << LTC) + c];
-            __syncthreads();
+            for (int t = 0; t < 8; ++t) r[t] = s0[((g + t * NB8) << LTC) + c];
             dft8<DIR>(r);
             const int qq = g & 7, ps = g - qq;
             if (ps != 0) {
@@ -449,8 +454,9 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             }
             const int base = qq + ps * 8;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) s[((base + 8 * u) << LTC) + c] = r[u];
+            for (int u = 0; u < 8; ++u) s1[((base + 8 * u) << LTC) + c] = r[u];
             __syncthreads();
+            sa = s1;
         }
 
         // ---- last pass: shared memory -> registers -> HBM
@@ -465,7 +471,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
                 const int gg = w >> LTC, cc = w & (TC - 1);
                 double2 r[8];
 #pragma unroll
-                for (int t = 0; t < R; ++t) r[t] = s[((gg + t * GROUPS) << LTC) + cc];
+                for (int t = 0; t < R; ++t) r[t] = sa[((gg + t * GROUPS) << LTC) + cc];
                 if (LEFT == 3)
                     dft8<DIR>(r);
                 else if (LEFT == 2)
@@ -476,7 +482,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
                 store_group(a, c0 + cc, gg, STRIDE, R, r);
             }
         }
-        __syncthreads();  // the next tile's pass 1 overwrites the tile
+        // no barrier here: the next tile's pass 1 writes the buffer that was last READ two barriers ago
     }
 }
 
@@ -618,7 +624,7 @@ row_pass_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict
 // evaluates it again from its side) so that the inverse transform starts from registers without another exchange.
 // Work list: one entry per unordered row pair {(k1,k2), mirror}; self-mirrored rows fill both slots of their pair.
 template <int B3>
-__global__ void __launch_bounds__(kColThreads, 2)
+__global__ void __launch_bounds__(kColThreads, 1)
 row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict__ lo, const double2* __restrict__ hi)
 {
     constexpr int N3 = 1 << B3;
@@ -626,12 +632,10 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     constexpr int LG8 = B3 - 3;
     constexpr int ROWS = 4096 >> B3, PAIRS = ROWS / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* s = reinterpret_cast<double2*>(smem_raw);
-    double2* twf = s + 4096;                          // W_N3^m
+    double2* s = reinterpret_cast<double2*>(smem_raw);  // two tile buffers (ping-pong, see the loop)
+    double2* twf = s + 2 * 4096;                      // W_N3^m
     const int tid = threadIdx.x;
     const int rs = tid >> LG8, g = tid & (G8 - 1);    // row slot, radix group
-    double2* row_s = s + (rs << B3);
-    const double2* mir_s = s + ((rs ^ 1) << B3);
     const unsigned int N1 = 1u << G.b1, N2 = 1u << G.b2;
     // pair list: k1 = 0 -> k2 in [0, N2/2];  0 < k1 < N1/2 -> every k2;  k1 = N1/2 -> k2 in [0, max(N2/2,1))
     const unsigned int cnt0 = N2 / 2 + 1, cntm = (N1 / 2 - 1) * N2, cnth = N2 >= 2 ? N2 / 2 : 1;
@@ -696,16 +700,35 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     };
     auto sw = [](int i) { return i ^ ((i >> 3) & 7); };
 
-    // two CTAs per SM (<= 64 registers/thread): one loads its next tile while the other transforms
+    // Every exchange below stays inside one (row, mirror row) pair = 2^(B3-2) consecutive threads, so the pairs of a
+    // tile synchronise among themselves only: a named barrier per pair (or __syncwarp when a pair fits in a warp).
+    constexpr int PAIR_THREADS = 2 * G8;
+    auto pair_sync = [&]() {
+        if constexpr (PAIR_THREADS >= 64) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + (tid / PAIR_THREADS)), "n"(PAIR_THREADS) : "memory");
+        } else {
+            __syncwarp();
+        }
+    };
+    // One 512-thread CTA per SM (128 registers, no spills).  The tile lives in two shared-memory buffers: every radix
+    // pass reads one and writes the other, and the roles swap from tile to tile, so each of the five hand-offs of a
+    // tile needs exactly one pair barrier (the in-place version needed ten).
     __syncthreads();
-    for (unsigned int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    double2 nxt[8];  // the next tile's row, in flight while this one is transformed
+#pragma unroll
+    for (int t = 0; t < 8; ++t) nxt[t] = make_double2(0.0, 0.0);
+    if (blockIdx.x < ntiles) load_row(blockIdx.x, nxt);
+    unsigned int parity = 0;
+    for (unsigned int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+        double2* bx = s + (parity ? 4096 : 0) + (rs << B3);         // this row in buffer X
+        double2* by = s + (parity ? 0 : 4096) + (rs << B3);         // this row in buffer Y
+        const double2* mx = s + (parity ? 4096 : 0) + ((rs ^ 1) << B3);  // the mirror row in buffer X
         unsigned int r1 = 0, r2 = 0;
         bool origin = false;
         const bool valid = slot_row(tile, r1, r2, origin);
         double2 v[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = make_double2(0.0, 0.0);
-        load_row(tile, v);
+        for (int t = 0; t < 8; ++t) v[t] = nxt[t];
 
         // ================= forward transform along the row (DIR = -1) =================
         dft8<-1>(v);
@@ -714,13 +737,15 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], twf[(u - 1) * G8 + g]);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) row_s[sw(8 * g + u)] = v[u];
-        __syncthreads();
-        {   // middle pass: radix 8, stride 8
+        for (int u = 0; u < 8; ++u) bx[sw(8 * g + u)] = v[u];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) nxt[t] = make_double2(0.0, 0.0);
+        if (tile + gridDim.x < ntiles) load_row(tile + gridDim.x, nxt);
+        pair_sync();
+        {   // middle pass: radix 8, stride 8, X -> Y
             double2 r[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) r[t] = row_s[sw(g + t * G8)];
-            __syncthreads();
+            for (int t = 0; t < 8; ++t) r[t] = bx[sw(g + t * G8)];
             dft8<-1>(r);
             const int qq = g & 7, ps = g - qq;
             if (ps != 0) {
@@ -728,22 +753,17 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                 for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], twm[(u - 1) * (G8 / 8) + (g >> 3)]);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) row_s[sw(qq + ps * 8 + 8 * u)] = r[u];
-            __syncthreads();
+            for (int u = 0; u < 8; ++u) by[sw(qq + ps * 8 + 8 * u)] = r[u];
+            pair_sync();
         }
-        {   // last forward pass: radix 2^(B3-6), stride 64, back to shared memory in natural order
+        {   // last forward pass: radix 2^(B3-6), stride 64, Y -> X in natural order
             constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
             double2 r[8];
 #pragma unroll
             for (int it = 0; it < GPT; ++it) {
                 const int gg = g + it * G8;
 #pragma unroll
-                for (int t = 0; t < R; ++t) r[it * R + t] = row_s[sw(gg + t * GROUPS)];
-            }
-            __syncthreads();
-#pragma unroll
-            for (int it = 0; it < GPT; ++it) {
-                const int gg = g + it * G8;
+                for (int t = 0; t < R; ++t) r[it * R + t] = by[sw(gg + t * GROUPS)];
                 if (LEFT == 3)
                     dft8<-1>(r + it * R);
                 else if (LEFT == 2)
@@ -752,12 +772,12 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                     dft2(r + it * R);
                 static_assert(GROUPS == 64, "last Stockham pass: p == 0, no twiddles");
 #pragma unroll
-                for (int u = 0; u < R; ++u) row_s[sw(gg + 64 * u)] = r[it * R + u];
+                for (int u = 0; u < R; ++u) bx[sw(gg + 64 * u)] = r[it * R + u];
             }
-            __syncthreads();
+            pair_sync();
         }
 
-        // ================= |X|^2 pair operation for this thread's 8 spectrum points =================
+        // ================= |X|^2 pair operation for this thread's 8 spectrum points (reads X) =================
         // W_L^k for k = kbase + N1*N2*(g + t*N3/8): successive t differ by W_L^{Nc/8} = exp(-i pi/8), a constant
         const unsigned int kbase = r1 + (r2 << G.b1);
         double2 W = tw_L(lo, hi, (unsigned long long)(kbase + ((unsigned int)g << shift12)));
@@ -766,8 +786,8 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         for (int t = 0; t < 8; ++t) {
             const int k3 = g + t * G8;
             const int p3 = origin ? ((N3 - k3) & (N3 - 1)) : (N3 - 1 - k3);
-            const double2 Za = row_s[sw(k3)];
-            const double2 Zb = mir_s[sw(p3)];
+            const double2 Za = bx[sw(k3)];
+            const double2 Zb = mx[sw(p3)];
             const double2 S = make_double2(Za.x + Zb.x, Za.y - Zb.y);   // Za + conj Zb
             const double2 D = make_double2(Za.x - Zb.x, Za.y + Zb.y);   // Za - conj Zb
             const double2 WD = cmul(W, D);
@@ -779,7 +799,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             v[t] = make_double2(hs + W.y * hd, W.x * hd);               // Z'[k] = hs + i conj(W) hd
             W = cmul(W, rot);
         }
-        __syncthreads();  // every thread has read both rows before they are overwritten
 
         // ================= inverse transform along the row (DIR = +1, conjugated table) =================
         dft8<+1>(v);
@@ -788,13 +807,12 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], cconj(twf[(u - 1) * G8 + g]));
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) row_s[sw(8 * g + u)] = v[u];
-        __syncthreads();
-        {
+        for (int u = 0; u < 8; ++u) by[sw(8 * g + u)] = v[u];
+        pair_sync();
+        {   // middle pass, Y -> X (every pair-operation read of X happened before the barrier above)
             double2 r[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) r[t] = row_s[sw(g + t * G8)];
-            __syncthreads();
+            for (int t = 0; t < 8; ++t) r[t] = by[sw(g + t * G8)];
             dft8<+1>(r);
             const int qq = g & 7, ps = g - qq;
             if (ps != 0) {
@@ -802,10 +820,10 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                 for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], cconj(twm[(u - 1) * (G8 / 8) + (g >> 3)]));
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) row_s[sw(qq + ps * 8 + 8 * u)] = r[u];
-            __syncthreads();
+            for (int u = 0; u < 8; ++u) bx[sw(qq + ps * 8 + 8 * u)] = r[u];
+            pair_sync();
         }
-        {   // last inverse pass -> post twiddle conj(W_Nc^{j3 * f}) -> HBM
+        {   // last inverse pass (reads X) -> post twiddle conj(W_Nc^{j3 * f}) -> HBM
             constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
             const unsigned int f = (G.b2 > 0) ? (r2 << G.b1) : r1;
             double2* dst = bdata + ((size_t)((r1 << G.b2) + r2) << B3);
@@ -814,7 +832,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                 const int gg = g + it * G8;
                 double2 r[8];
 #pragma unroll
-                for (int t = 0; t < R; ++t) r[t] = row_s[sw(gg + t * GROUPS)];
+                for (int t = 0; t < R; ++t) r[t] = bx[sw(gg + t * GROUPS)];
                 if (LEFT == 3)
                     dft8<+1>(r);
                 else if (LEFT == 2)
@@ -832,7 +850,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                 }
             }
         }
-        __syncthreads();
+        // no barrier: the next tile starts by writing buffer Y, last read before the barrier above
     }
 }
 
@@ -975,13 +993,13 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         cudaFuncSetAttribute(col_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
-        cudaFuncSetAttribute(row_pass2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 512) * 16);
-        cudaFuncSetAttribute(row_pass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 512) * 16);
-        cudaFuncSetAttribute(row_pass2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
         for (int mode = 0; mode < 4; ++mode)
             for (int bb = 3; bb <= 9; ++bb)
                 cudaFuncSetAttribute(col2_select(mode, bb), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (kTileElems + 512) * 16);
+                                     (2 * kTileElems + 512) * 16);
         if (dev < 64) attr_done[dev] = true;
     }
     const long long N1 = 1ll << g.b1, N2 = 1ll << g.b2, N3 = 1ll << g.b3;
@@ -991,7 +1009,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     if (g.b1 > 0 && g.b2 + g.b3 < 12 - g.b1) pipelined = false;
     if (g.b2 > 0 && g.b3 < 12 - g.b2) pipelined = false;
     auto pgrid = [sms](long long tiles) { return (unsigned)(tiles < sms ? tiles : sms); };
-    const size_t smem2 = (size_t)(kTileElems + 512) * 16;
+    const size_t smem2 = (size_t)(2 * kTileElems + 512) * 16;  // two tile buffers + butterfly twiddles
     auto tc_for = [](int b, long long C) {
         long long tc = kTileElems >> b;
         if (tc > C) tc = C;
@@ -1022,13 +1040,13 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         ++launches;
     }
     if (pipelined && g.b1 > 0 && g.b3 >= 7) {
-        const size_t smem = (size_t)(4096 + N3) * 16;
+        const size_t smem = (size_t)(2 * 4096 + N3) * 16;
         if (g.b3 == 9)
-            row_pass2_kernel<9><<<dim3(2 * sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+            row_pass2_kernel<9><<<dim3(sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         else if (g.b3 == 8)
-            row_pass2_kernel<8><<<dim3(2 * sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+            row_pass2_kernel<8><<<dim3(sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         else
-            row_pass2_kernel<7><<<dim3(2 * sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
+            row_pass2_kernel<7><<<dim3(sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         ++launches;
     } else {
         int threads = (int)(N3 / 8) * 2;
