@@ -245,6 +245,26 @@ def traj2diffusion(x, y=None, z=None, stride=1, max_s=1000, timestep=1.0, cell=N
     return d
 
 
+def traj2diffusion_batch(trajectories, stride=1, max_s=1000, timestep=1.0, cell=None, ngpus=None):
+    """traj2diffusion for a list of trajectories, each an (x, y, z) triple (or one array = x three times).
+    Returns (msd[ntraj][max_s], counter[ntraj][max_s], [dict(sum, slope, diffusivity, nframes)]).
+    ngpus=None: the current device; otherwise trajectory t runs on device t mod G (ngpus <= 0: every device)."""
+    trips = [_axes(*t) if isinstance(t, (tuple, list)) else _axes(t) for t in trajectories]
+    nt = len(trips)
+    px, py, pz = ((C.c_void_p * nt)(*[t[a].ctypes.data for t in trips]) for a in range(3))
+    lens = (C.c_int64 * nt)(*[t[0].size for t in trips])
+    out = np.empty((nt, int(max_s)), dtype=np.float64)
+    cnt = np.empty((nt, int(max_s)), dtype=np.int32)
+    res = (MsdResult * nt)()
+    args = [px, py, pz, lens, nt, int(stride), int(max_s), float(timestep), 0.0 if cell is None else float(cell),
+            0 if cell is None else 1, _vp(out), _vp(cnt), res]
+    if ngpus is None:
+        check(_lib.load().acfb200_traj2diffusion_batch(*args))
+    else:
+        check(_lib.load().acfb200_multi_gpu_traj2diffusion_batch(*args, int(ngpus)))
+    return out, cnt, [r.as_dict() for r in res]
+
+
 # ---------------------------------------------------------------------------------------------------
 # device-resident (torch CUDA tensors; torch is plumbing: memory + streams)
 # ---------------------------------------------------------------------------------------------------

@@ -950,37 +950,54 @@ static int check_msd_args(const void* x, const void* y, const void* z, long long
     return 0;
 }
 
-// Displacement sums of the three axes -> msd[max_s], counter[max_s] (device).  Unit stride runs the tiled
+// Displacement sums of ntraj device-resident trajectories -> msd[ntraj][max_s], counter[ntraj][max_s] (device), one
+// launch over all axes of all trajectories.  axes[3*t + a] is coordinate a of trajectory t; when every trajectory
+// passes one array three times (the general reader's y = z = x) each is computed once.  Unit stride runs the tiled
 // displacement kernel (the direct-lag kernel's geometry), larger strides the per-lag strided kernel.
-static int msd_device(Workspace* ws, const double* d_x, const double* d_y, const double* d_z, long long n,
-                      long long stride, long long max_s, double* d_msd, int* d_counter, cudaStream_t st)
+static int msd_batch_device(Workspace* ws, const double* const* axes, const long long* n, int ntraj, long long stride,
+                            long long max_s, double* d_msd, int* d_counter, cudaStream_t st)
 {
-    const bool one_axis = (d_x == d_y && d_y == d_z);
-    const int ns = one_axis ? 1 : 3;
-    SeriesDesc descs[3] = {{d_x, n, n}, {d_y, n, n}, {d_z, n, n}};
+    bool one_axis = true;
+    long long n_max = 1;
+    for (int t = 0; t < ntraj; ++t) {
+        one_axis = one_axis && axes[3 * t] == axes[3 * t + 1] && axes[3 * t + 1] == axes[3 * t + 2];
+        if (n[t] > n_max) n_max = n[t];
+    }
+    const int per = one_axis ? 1 : 3, ns = per * ntraj;
+    std::vector<SeriesDesc> descs(ns);
+    for (int t = 0; t < ntraj; ++t)
+        for (int a = 0; a < per; ++a) descs[per * t + a] = {axes[3 * t + a], n[t], n[t]};
     DirectPlan plan;
     if (stride == 1) {
-        ACF_TRY(plan_direct(n, max_s, ns, ws->sm_count, -1, &plan, true));
+        ACF_TRY(plan_direct(n_max, max_s, ns, ws->sm_count, -1, &plan, true));
         if (plan.mode != 0) {
             set_error("msd: the displacement kernel needs a tiled plan (unset ACFB200_MODE)");
             return ACFB200_ERR_ARG;
         }
     } else {
-        ACF_TRY(plan_msd_strided(n, stride, max_s, ws->sm_count, &plan));
+        ACF_TRY(plan_msd_strided(n_max, stride, max_s, ws->sm_count, &plan));
     }
-    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * 3));
+    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)ns));
     ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, ns) * sizeof(double)));
-    ACF_TRY(ws->out.ensure((size_t)3 * max_s * 8));
-    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs, sizeof(SeriesDesc) * (size_t)ns, cudaMemcpyHostToDevice, st));
+    ACF_TRY(ws->out.ensure((size_t)ns * max_s * 8));
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * (size_t)ns, cudaMemcpyHostToDevice, st));
     if (stride == 1)
         ACF_TRY(launch_direct_msd(plan, ws->desc.as<SeriesDesc>(), ns, max_s, ws->partials.as<double>(), st));
     else
         ACF_TRY(launch_msd_strided(plan, ws->desc.as<SeriesDesc>(), ns, stride, max_s, ws->partials.as<double>(), st));
     ACF_TRY(launch_reduce_partials(plan, ws->desc.as<SeriesDesc>(), ns, max_s, ws->partials.as<double>(),
                                    ws->out.as<double>(), 0, st));
-    ACF_TRY(launch_msd_finalize(ws->out.as<double>(), one_axis ? 0 : max_s, n, stride, max_s, d_msd, d_counter, st));
+    ACF_TRY(launch_msd_finalize(ws->out.as<double>(), ws->desc.as<SeriesDesc>(), per, ntraj, stride, max_s, d_msd,
+                                d_counter, st));
     g_launches += 3;
     return 0;
+}
+
+static int msd_device(Workspace* ws, const double* d_x, const double* d_y, const double* d_z, long long n,
+                      long long stride, long long max_s, double* d_msd, int* d_counter, cudaStream_t st)
+{
+    const double* axes[3] = {d_x, d_y, d_z};
+    return msd_batch_device(ws, axes, &n, 1, stride, max_s, d_msd, d_counter, st);
 }
 
 // Upload three host coordinate arrays (once if they are the same array) into ws->series; d[] receives the device pointers.
@@ -1125,7 +1142,7 @@ int acfb200_msd_slope(const double* msd, int64_t n, double* slope, double* sum)
     ACF_TRY(ws->small.ensure((size_t)n * 8 + 64));
     double* d_msd = ws->small.as<double>() + 2;
     ACF_CUDA_OK(cudaMemcpyAsync(d_msd, msd, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    ACF_TRY(launch_msd_slope(d_msd, n, ws->small.as<double>(), st));
+    ACF_TRY(launch_msd_slope(d_msd, n, 1, ws->small.as<double>(), st));
     g_launches += 1;
     double h[2];
     ACF_CUDA_OK(cudaMemcpyAsync(h, ws->small.p, 16, cudaMemcpyDeviceToHost, st));
@@ -1166,7 +1183,7 @@ int acfb200_traj2diffusion(const double* x, const double* y, const double* z, in
     double* d_msd = d_sl + 2;
     int* d_cnt = reinterpret_cast<int*>(d_msd + max_s);
     ACF_TRY(msd_device(ws, d[0], d[1], d[2], n, stride, max_s, d_msd, d_cnt, st));
-    ACF_TRY(launch_msd_slope(d_msd, max_s, d_sl, st));
+    ACF_TRY(launch_msd_slope(d_msd, max_s, 1, d_sl, st));
     g_launches += 1;
     double h[2];
     if (msd) ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)max_s * 8, cudaMemcpyDeviceToHost, st));
@@ -1183,6 +1200,87 @@ int acfb200_traj2diffusion(const double* x, const double* y, const double* z, in
     return 0;
 }
 
+
+// main() of traj2diffusion for ntraj trajectories in one go (the "many umbrella windows" use of the program): every
+// trajectory is uploaded (and unwrapped, if asked) on the device, ONE displacement launch covers all axes of all
+// trajectories, one launch each finalises, and takes the slopes of, all MSD curves.
+int acfb200_traj2diffusion_batch(const double* const* x, const double* const* y, const double* const* z, const int64_t* n,
+                                 int ntraj, int64_t stride, int64_t max_s, double dt, double cell, int imaging,
+                                 double* msd, int32_t* counter, acfb200_msd_result* result)
+{
+    Lock lk(g_mu);
+    if (!x || !y || !z || !n || ntraj < 1) {
+        set_error("traj2diffusion_batch: null argument or ntraj < 1");
+        return ACFB200_ERR_ARG;
+    }
+    size_t total = 0;
+    bool aliased = !imaging;
+    for (int t = 0; t < ntraj; ++t) {
+        ACF_TRY(check_msd_args(x[t], y[t], z[t], n[t], stride, max_s, "traj2diffusion_batch"));
+        aliased = aliased && x[t] == y[t] && y[t] == z[t];
+    }
+    for (int t = 0; t < ntraj; ++t) total += (aliased ? 1 : 3) * even_up(n[t]);
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    cudaStream_t st = ws->stream;
+    ACF_TRY(ws->series.ensure(total * 8));
+    if (imaging) {
+        long long n_max = 1;
+        for (int t = 0; t < ntraj; ++t) n_max = n[t] > n_max ? n[t] : n_max;
+        ACF_TRY(ws->y.ensure(total * 8));
+        ACF_TRY(ws->vel.ensure(image_workspace_bytes(n_max)));  // reused trajectory after trajectory (stream order)
+    }
+    std::vector<const double*> axes(3 * (size_t)ntraj);
+    std::vector<long long> len(ntraj);
+    size_t off = 0;
+    for (int t = 0; t < ntraj; ++t) {
+        len[t] = n[t];
+        const double* h[3] = {x[t], y[t], z[t]};
+        const size_t pitch = even_up(n[t]);
+        const double* d_in[3];
+        for (int a = 0; a < 3; ++a) {
+            if (aliased && a > 0) {
+                d_in[a] = d_in[0];
+                continue;
+            }
+            double* dst = ws->series.as<double>() + off + a * pitch;
+            ACF_CUDA_OK(cudaMemcpyAsync(dst, h[a], (size_t)n[t] * 8, cudaMemcpyHostToDevice, st));
+            d_in[a] = dst;
+        }
+        if (imaging) {
+            double* d_out[3];
+            for (int a = 0; a < 3; ++a) d_out[a] = ws->y.as<double>() + off + a * pitch;
+            const int launches = launch_image(d_in, d_out, n[t], cell, ws->vel.p, st);
+            if (launches < 0) return ACFB200_ERR_CUDA;
+            g_launches += launches;
+            for (int a = 0; a < 3; ++a) axes[3 * t + a] = d_out[a];
+        } else {
+            for (int a = 0; a < 3; ++a) axes[3 * t + a] = d_in[a];
+        }
+        off += (aliased ? 1 : 3) * pitch;
+    }
+    const size_t curve = (size_t)max_s;
+    ACF_TRY(ws->small.ensure((size_t)ntraj * (curve * 12 + 16) + 64));
+    double* d_sl = ws->small.as<double>();                 // [ntraj][sum, slope]
+    double* d_msd = d_sl + 2 * (size_t)ntraj;               // [ntraj][max_s]
+    int* d_cnt = reinterpret_cast<int*>(d_msd + (size_t)ntraj * curve);
+    ACF_TRY(msd_batch_device(ws, axes.data(), len.data(), ntraj, stride, max_s, d_msd, d_cnt, st));
+    ACF_TRY(launch_msd_slope(d_msd, max_s, ntraj, d_sl, st));
+    g_launches += 1;
+    std::vector<double> h_sl(2 * (size_t)ntraj);
+    if (msd) ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)ntraj * curve * 8, cudaMemcpyDeviceToHost, st));
+    if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)ntraj * curve * 4, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(h_sl.data(), d_sl, h_sl.size() * 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
+    if (result)
+        for (int t = 0; t < ntraj; ++t) {
+            result[t].sum = h_sl[2 * t];
+            result[t].slope = h_sl[2 * t + 1];
+            result[t].diffusivity = h_sl[2 * t + 1] / (dt * (double)stride) / 6.0;  // traj2diffusion.cpp:497, :549
+            result[t].nframes = n[t];
+        }
+    return 0;
+}
 
 // -------------------------------------------------------------------------------------------------
 // multi-GPU entry points: one host thread per device inside this process
@@ -1446,6 +1544,50 @@ int acfb200_multi_gpu_green_kubo(const double* const* comps, int ncomp, int64_t 
 
 // -------------------------------------------------------------------------------------------------
 // measurement
+// Trajectories spread over the devices of this box, trajectory t on device t mod G; no communication.
+int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, const double* const* y, const double* const* z,
+                                           const int64_t* n, int ntraj, int64_t stride, int64_t max_s, double dt,
+                                           double cell, int imaging, double* msd, int32_t* counter,
+                                           acfb200_msd_result* result, int ngpus)
+{
+    if (!x || !y || !z || !n || ntraj < 1) {
+        set_error("multi_gpu_traj2diffusion_batch: null argument or ntraj < 1");
+        return ACFB200_ERR_ARG;
+    }
+    int ndev = usable_devices(ngpus);
+    if (ndev < 1) return ACFB200_ERR_CUDA;
+    if (ndev > ntraj) ndev = ntraj;
+    int home = 0;
+    cudaGetDevice(&home);
+    const int rc = for_each_device(ndev, [&](int d) -> int {
+        std::vector<const double*> px, py, pz;
+        std::vector<int64_t> pn;
+        std::vector<int> idx;
+        for (int t = d; t < ntraj; t += ndev) {
+            px.push_back(x[t]);
+            py.push_back(y[t]);
+            pz.push_back(z[t]);
+            pn.push_back(n[t]);
+            idx.push_back(t);
+        }
+        const size_t cnt = idx.size();
+        std::vector<double> m(cnt * (size_t)max_s);
+        std::vector<int32_t> c(cnt * (size_t)max_s);
+        std::vector<acfb200_msd_result> r(cnt);
+        const int st = acfb200_traj2diffusion_batch(px.data(), py.data(), pz.data(), pn.data(), (int)cnt, stride, max_s, dt,
+                                                    cell, imaging, m.data(), c.data(), r.data());
+        if (st != 0) return st;
+        for (size_t i = 0; i < cnt; ++i) {
+            if (msd) memcpy(msd + (size_t)idx[i] * max_s, m.data() + i * (size_t)max_s, (size_t)max_s * 8);
+            if (counter) memcpy(counter + (size_t)idx[i] * max_s, c.data() + i * (size_t)max_s, (size_t)max_s * 4);
+            if (result) result[idx[i]] = r[i];
+        }
+        return 0;
+    });
+    cudaSetDevice(home);
+    return rc;
+}
+
 // -------------------------------------------------------------------------------------------------
 int acfb200_measure_dfma_peak(double* tflops, double* effective_sm_mhz)
 {

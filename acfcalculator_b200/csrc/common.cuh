@@ -103,12 +103,12 @@ int launch_rescale(double* d_acf, long long ncorr, double target, cudaStream_t s
 int plan_msd_strided(long long n, long long stride, long long ncorr, int sm_count, DirectPlan* plan);
 int launch_msd_strided(const DirectPlan& p, const SeriesDesc* d_desc, int nseries, long long stride, long long ncorr,
                        double* d_partials, cudaStream_t st);
-// msd[j] = (Sx+Sy+Sz)[j] / cnt_j from d_sums (axes axis_pitch doubles apart; 0 = one array for all three);
-// d_counter (nullable) = cnt_j
-int launch_msd_finalize(const double* d_sums, long long axis_pitch, long long n, long long stride, long long ncorr,
-                        double* d_msd, int* d_counter, cudaStream_t st);
-// d_out[0] = sum_{i>=1} msd[i]/i, d_out[1] = d_out[0]/n
-int launch_msd_slope(const double* d_msd, long long n, double* d_out, cudaStream_t st);
+// msd[t][j] = (Sx+Sy+Sz)[j] / cnt_j for ntraj trajectories; trajectory t owns rows [t*axes, (t+1)*axes) of d_sums and
+// desc[t*axes].n frames (axes = 3, or 1 when one array serves all coordinates); d_counter (nullable) = cnt_j
+int launch_msd_finalize(const double* d_sums, const SeriesDesc* d_desc, int axes, int ntraj, long long stride,
+                        long long ncorr, double* d_msd, int* d_counter, cudaStream_t st);
+// per curve c: d_out[2c] = sum_{i>=1} msd_c[i]/i, d_out[2c+1] = that / n
+int launch_msd_slope(const double* d_msd, long long n, int ncurves, double* d_out, cudaStream_t st);
 size_t image_workspace_bytes(long long n);
 int launch_image(const double* const d_in[3], double* const d_out[3], long long n, double L, void* d_work,
                  cudaStream_t st);

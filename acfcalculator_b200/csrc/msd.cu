@@ -79,28 +79,34 @@ int launch_msd_strided(const DirectPlan& p, const SeriesDesc* d_desc, int nserie
 // msd[j] = (Sx[j] + Sy[j] + Sz[j]) / cnt_j,  cnt_j = #{i = 0, stride, ... : i + j < n}
 // cnt_j == 0 (j >= n): the reference divides 0.0 by int 0 -> the x86 default NaN (sign bit set, "-nan").
 // ------------------------------------------------------------------------------------------------
-__global__ void msd_finalize_kernel(const double* __restrict__ sums, long long axis_pitch, long long n, long long stride,
-                                    long long ncorr, double* __restrict__ msd, int* __restrict__ counter)
+// grid (lag blocks, trajectories): trajectory t owns the rows [t*axes, (t+1)*axes) of `sums` (axes = 3, or 1 when
+// one array serves all three coordinates) and has desc[t*axes].n frames.
+__global__ void msd_finalize_kernel(const double* __restrict__ sums, const SeriesDesc* __restrict__ desc, int axes,
+                                    long long stride, long long ncorr, double* __restrict__ msd, int* __restrict__ counter)
 {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncorr) return;
+    const int t = blockIdx.y;
+    const long long n = desc[t * axes].n;
     const long long cnt = j < n ? (n - 1 - j) / stride + 1 : 0;
-    const double s = (sums[j] + sums[axis_pitch + j]) + sums[2 * axis_pitch + j];  // pitch 0: one array serves all axes
-    msd[j] = cnt > 0 ? s / (double)cnt : __longlong_as_double(0xFFF8000000000000ull);
-    if (counter) counter[j] = (int)cnt;
+    const double* row = sums + (size_t)t * axes * ncorr;
+    const long long pitch = axes == 3 ? ncorr : 0;  // pitch 0: one array serves all axes
+    const double s = (row[j] + row[pitch + j]) + row[2 * pitch + j];
+    msd[(size_t)t * ncorr + j] = cnt > 0 ? s / (double)cnt : __longlong_as_double(0xFFF8000000000000ull);
+    if (counter) counter[(size_t)t * ncorr + j] = (int)cnt;
 }
 
-int launch_msd_finalize(const double* d_sums, long long axis_pitch, long long n, long long stride, long long ncorr,
-                        double* d_msd, int* d_counter, cudaStream_t st)
+int launch_msd_finalize(const double* d_sums, const SeriesDesc* d_desc, int axes, int ntraj, long long stride,
+                        long long ncorr, double* d_msd, int* d_counter, cudaStream_t st)
 {
-    msd_finalize_kernel<<<(unsigned)((ncorr + 255) / 256), 256, 0, st>>>(d_sums, axis_pitch, n, stride, ncorr, d_msd,
-                                                                        d_counter);
+    dim3 grid((unsigned)((ncorr + 255) / 256), ntraj);
+    msd_finalize_kernel<<<grid, 256, 0, st>>>(d_sums, d_desc, axes, stride, ncorr, d_msd, d_counter);
     ACF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// slope(): out[0] = sum_{i=1}^{n-1} msd[i]/i, out[1] = out[0]/n.  One CTA; contiguous slices per thread
+// slope(): out[2c] = sum_{i=1}^{n-1} msd_c[i]/i, out[2c+1] = out[2c]/n.  One CTA per curve; contiguous slices per thread
 // folded in thread order (fixed tree => reproducible).
 // ------------------------------------------------------------------------------------------------
 constexpr int kSlopeThreads = 1024;
@@ -108,6 +114,8 @@ constexpr int kSlopeThreads = 1024;
 __global__ void __launch_bounds__(kSlopeThreads)
 msd_slope_kernel(const double* __restrict__ msd, long long n, double* __restrict__ out)
 {
+    msd += (size_t)blockIdx.x * n;  // one CTA per MSD curve
+    out += 2 * blockIdx.x;
     __shared__ double sh[kSlopeThreads];
     const int tid = threadIdx.x;
     const long long terms = n > 1 ? n - 1 : 0;
@@ -132,9 +140,9 @@ msd_slope_kernel(const double* __restrict__ msd, long long n, double* __restrict
     }
 }
 
-int launch_msd_slope(const double* d_msd, long long n, double* d_out, cudaStream_t st)
+int launch_msd_slope(const double* d_msd, long long n, int ncurves, double* d_out, cudaStream_t st)
 {
-    msd_slope_kernel<<<1, kSlopeThreads, 0, st>>>(d_msd, n, d_out);
+    msd_slope_kernel<<<ncurves, kSlopeThreads, 0, st>>>(d_msd, n, d_out);
     ACF_CUDA_OK(cudaGetLastError());
     return 0;
 }

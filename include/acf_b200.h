@@ -193,6 +193,17 @@ ACFB200_API int acfb200_msd_slope(const double* msd, int64_t n, double* slope, d
 ACFB200_API int acfb200_traj2diffusion(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s, double dt,
                                        double cell, int imaging, double* msd, int32_t* counter,
                                        acfb200_msd_result* result);
+/* Many trajectories in one call (the program run over a set of umbrella windows): one displacement launch covers all
+ * axes of all trajectories; msd / counter are [ntraj][max_s] (counter and result may be NULL).  The multi_gpu form puts
+ * trajectory t on device t mod G of this box (ngpus <= 0: all devices); no communication. */
+ACFB200_API int acfb200_traj2diffusion_batch(const double* const* x, const double* const* y, const double* const* z,
+                                             const int64_t* n, int ntraj, int64_t stride, int64_t max_s, double dt,
+                                             double cell, int imaging, double* msd, int32_t* counter,
+                                             acfb200_msd_result* result);
+ACFB200_API int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, const double* const* y,
+                                                       const double* const* z, const int64_t* n, int ntraj, int64_t stride,
+                                                       int64_t max_s, double dt, double cell, int imaging, double* msd,
+                                                       int32_t* counter, acfb200_msd_result* result, int ngpus);
 /* Device-resident forms (stream: a cudaStream_t passed as void*, like the other *_device calls; the out arrays of
  * acfb200_image_device must not alias its inputs).  Passing the same pointer for x, y and z (what the reference's
  * general reader effectively produces, :186-231) is recognised and computed once. */

@@ -72,3 +72,16 @@ def test_green_kubo_and_viscosity_cli(acf, ngpus, tmp_path):
     assert one.returncode == 0 and many.returncode == 0, many.stderr
     assert len(one.stdout.splitlines()) == len(many.stdout.splitlines())
     assert one.stdout.splitlines()[-1].split()[:2] == many.stdout.splitlines()[-1].split()[:2]
+
+
+def test_traj2diffusion_batch_over_devices(acf, ngpus):
+    rng = np.random.default_rng(77)
+    trajs = []
+    for i in range(2 * ngpus + 1):
+        r = 3.0 + np.cumsum(rng.standard_normal((20000 + 1000 * i, 3)) * 0.6, axis=0)
+        w = r - 7.5 * np.floor(r / 7.5)
+        trajs.append(tuple(np.ascontiguousarray(w[:, a]) for a in range(3)))
+    a, ca, ra = acf.traj2diffusion_batch(trajs, stride=1, max_s=500, timestep=2.0, cell=7.5)
+    b, cb, rb = acf.traj2diffusion_batch(trajs, stride=1, max_s=500, timestep=2.0, cell=7.5, ngpus=ngpus)
+    assert np.allclose(a, b, rtol=1e-13, atol=0) and np.array_equal(ca, cb)
+    assert all(abs(x["diffusivity"] - y["diffusivity"]) <= 1e-13 * abs(x["diffusivity"]) for x, y in zip(ra, rb))

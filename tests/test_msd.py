@@ -208,6 +208,37 @@ def test_gpu_traj2diffusion_pipeline(acf, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("stride,cell", [(1, None), (1, 6.25), (4, None), (3, 2.718281828459045)])
+def test_gpu_traj2diffusion_batch(acf, oracle, stride, cell):
+    """Many trajectories of different lengths in one call = each one through the single-trajectory entry point."""
+    lens = [30000, 4999, 120001, 3, 64000, 777]
+    trajs = []
+    for i, n in enumerate(lens):
+        r = walk(n, 900 + i, step=0.7)
+        if cell is not None:
+            r = r - cell * np.floor(r / cell)
+        trajs.append(tuple(np.ascontiguousarray(r[:, a]) for a in range(3)))
+    msd, cnt, res = acf.traj2diffusion_batch(trajs, stride=stride, max_s=600, timestep=2.0, cell=cell)
+    for t, (x, y, z) in enumerate(trajs):
+        if cell is not None:
+            x, y, z = oracle.image(x, y, z, cell)
+        want, wcnt = oracle.msd(x, y, z, stride, 600, threads=0)
+        assert rel_err(msd[t], want) <= REL, t
+        assert np.array_equal(cnt[t], wcnt)
+        d = oracle.msd_diffusivity(want, 2.0, stride)
+        assert (np.isnan(d) and np.isnan(res[t]["diffusivity"])) or abs(res[t]["diffusivity"] - d) <= REL * abs(d)
+        assert res[t]["nframes"] == lens[t]
+        one = acf.traj2diffusion(*trajs[t], stride=stride, max_s=600, timestep=2.0, cell=cell)
+        assert rel_err(one["msd"], want) <= REL
+    # the general reader's y = z = x for every trajectory
+    xs = [t[0] for t in trajs]
+    msd1, cnt1, _ = acf.traj2diffusion_batch(xs, stride=stride, max_s=600)
+    for t, x in enumerate(xs):
+        want, _ = oracle.msd(x, x, x, stride, 600, threads=0)
+        assert rel_err(msd1[t], want) <= REL
+
+
+@pytest.mark.gpu
 def test_gpu_msd_device_entry_points(acf, oracle):
     import torch
     r = walk(100000, 21)
