@@ -439,6 +439,10 @@ int acfb200_describe_plan(int64_t n, int64_t ncorr, int nseries, char* buf, int 
 // -------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // -------------------------------------------------------------------------------------------------
+static bool pipelined_eligible(const int64_t* n, int nseries, long long ncorr);
+static int calc_correlation_pipelined(Workspace* ws, const double* const* y, const int64_t* n, int nseries,
+                                      long long ncorr, double* corr);
+
 int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int nseries, int64_t ncorr,
                                    double* corr)
 {
@@ -450,6 +454,8 @@ int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int
     for (int s = 0; s < nseries; ++s) ACF_TRY(check_common(y[s], n[s], ncorr, "calc_correlation"));
     Workspace* ws;
     ACF_TRY(get_ws(&ws));
+    // a few long series, direct summation: overlap the uploads with the kernels
+    if (pipelined_eligible(n, nseries, ncorr)) return calc_correlation_pipelined(ws, y, n, nseries, ncorr, corr);
     size_t total = 0;
     for (int s = 0; s < nseries; ++s) total += even_up(n[s]);
     ACF_TRY(ws->series.ensure(total * 8));
@@ -468,87 +474,114 @@ int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int
     return 0;
 }
 
-// One long host series, direct summation: the upload is cut into pieces on the copy stream and the lag kernel of
-// piece p (a time block whose halo of ncorr samples belongs to piece p+1, SeriesDesc.i_end < n) starts as soon as the
-// samples it can touch have landed.  Copy p therefore carries piece p plus the halo after it, and the pieces grow
+// Long host series, direct summation: the upload of a series is cut into pieces on the copy stream and the lag kernel
+// of piece p (a time block whose halo of ncorr samples belongs to piece p+1, SeriesDesc.i_end < n) starts as soon as
+// the samples it can touch have landed.  Copy p therefore carries piece p plus the halo after it, and the pieces grow
 // geometrically (1 : 2 : 4 : 8 : rest of n/32 units): the host link is ~4x faster than the kernel consumes samples, so
 // only the first, small piece's transfer is exposed while the later launches are long enough to run at full
 // efficiency.  Every piece has its own plan (same variant and row pitch, its own chunk count); the per-chunk partial
 // sums of all pieces lie back to back and are folded by one reduce launch in fixed order, as for a single launch.
-static int calc_correlation_pipelined(Workspace* ws, const double* y, long long n, long long ncorr, double* corr)
+// Several series go one after the other: the upload of series s+1 runs under the kernels of series s.
+// Everything is only ENQUEUED here (compute stream + copy stream); the caller synchronises and then destroys `events`.
+static bool pipelined_eligible(const int64_t* n, int nseries, long long ncorr)
+{
+    if (g_method != 0 || nseries < 1 || nseries > 16 || ncorr < 1) return false;
+    for (int s = 0; s < nseries; ++s)
+        if (n[s] < (1 << 22) || ncorr * 16 > n[s]) return false;
+    return true;
+}
+
+static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_t* n, int nseries, long long ncorr,
+                             double* d_out, std::vector<cudaEvent_t>& events)
 {
     const int kMaxPieces = 5;
-    long long unit = (n / 32 + 1) & ~1ll;
-    if (unit < 4 * ncorr) unit = (4 * ncorr + 1) & ~1ll;  // a piece much shorter than its halo is all overhead
-    long long bounds[kMaxPieces + 1] = {0};
-    int np = 0;
-    for (long long w = 1; np < kMaxPieces && bounds[np] < n; w *= 2) {
-        long long e = bounds[np] + w * unit;
-        if (np == kMaxPieces - 1 || e + unit / 2 >= n) e = n;
-        bounds[++np] = e;
-    }
     cudaStream_t st = ws->stream;
-    ACF_TRY(ws->series.ensure(even_up(n) * 8));
-    ACF_TRY(ws->out.ensure((size_t)ncorr * 8));
-    double* d = ws->series.as<double>();
-    std::vector<DirectPlan> plans(np);
-    std::vector<size_t> offset(np + 1, 0);
-    long long chunks_total = 0;
-    for (int p = 0; p < np; ++p) {
-        ACF_TRY(plan_direct(bounds[p + 1] - bounds[p], ncorr, 1, ws->sm_count, g_force_variant, &plans[p]));
-        if (plans[p].mode != plans[0].mode || plans[p].mpad != plans[0].mpad) {
-            set_error("pipelined calc_correlation: pieces disagree on the partial-sum layout");
-            return ACFB200_ERR_ARG;
-        }
-        offset[p + 1] = offset[p] + direct_partial_elems(plans[p], 1);
-        chunks_total += plans[p].chunks;
-    }
-    ACF_TRY(ws->partials.ensure(offset[np] * sizeof(double)));
-    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)(np + 1)));
+    size_t total = 0;
+    for (int s = 0; s < nseries; ++s) total += even_up(n[s]);
+    ACF_TRY(ws->series.ensure(total * 8));
+    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)(kMaxPieces + 1)));
     ACF_TRY(ws->queue.ensure(64, true));
-    std::vector<SeriesDesc> descs(np + 1);
-    for (int p = 0; p < np; ++p) {
-        const long long b = bounds[p], e = bounds[p + 1];
-        const long long reach = e + ncorr < n ? e + ncorr : n;  // last sample a pair starting in this piece can touch
-        descs[p] = {d + b, reach - b, e - b};
-    }
-    descs[np] = {d, n, n};  // the whole series, for the divide by (n - k)
-    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * descs.size(), cudaMemcpyHostToDevice, st));
-    std::vector<cudaEvent_t> landed(np, nullptr);
-    int rc = 0;
-    long long copied = 0;
-    for (int p = 0; p < np && rc == 0; ++p) {
-        // copy, then launch: with a pageable source the copy call blocks the host while the previous kernel runs
-        const long long upto = bounds[p + 1] + ncorr < n ? bounds[p + 1] + ncorr : n;
-        cudaError_t e = cudaSuccess;
-        if (upto > copied)
-            e = cudaMemcpyAsync(d + copied, y + copied, (size_t)(upto - copied) * 8, cudaMemcpyHostToDevice, ws->copy_stream);
-        copied = upto > copied ? upto : copied;
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&landed[p], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventRecord(landed[p], ws->copy_stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, landed[p], 0);
-        if (e != cudaSuccess) {
-            set_error("pipelined calc_correlation: upload of piece %d failed: %s", p, cudaGetErrorString(e));
-            rc = ACFB200_ERR_CUDA;
-            break;
+    size_t series_off = 0;
+    for (int s = 0; s < nseries; ++s) {
+        const long long ns = n[s];
+        long long unit = (ns / 32 + 1) & ~1ll;
+        if (unit < 4 * ncorr) unit = (4 * ncorr + 1) & ~1ll;  // a piece much shorter than its halo is all overhead
+        long long bounds[kMaxPieces + 1] = {0};
+        int np = 0;
+        for (long long w = 1; np < kMaxPieces && bounds[np] < ns; w *= 2) {
+            long long e = bounds[np] + w * unit;
+            if (np == kMaxPieces - 1 || e + unit / 2 >= ns) e = ns;
+            bounds[++np] = e;
         }
-        rc = launch_direct(plans[p], ws->desc.as<SeriesDesc>() + p, 1, ncorr, ws->partials.as<double>() + offset[p],
-                           ws->queue.as<unsigned int>(), ws->sm_count, st);
-        g_launches += 1;
-    }
-    if (rc == 0) {
+        double* d = ws->series.as<double>() + series_off;
+        series_off += even_up(ns);
+        std::vector<DirectPlan> plans(np);
+        std::vector<size_t> offset(np + 1, 0);
+        long long chunks_total = 0;
+        for (int p = 0; p < np; ++p) {
+            ACF_TRY(plan_direct(bounds[p + 1] - bounds[p], ncorr, 1, ws->sm_count, g_force_variant, &plans[p]));
+            if (plans[p].mode != plans[0].mode || plans[p].mpad != plans[0].mpad) {
+                set_error("pipelined calc_correlation: pieces disagree on the partial-sum layout");
+                return ACFB200_ERR_ARG;
+            }
+            offset[p + 1] = offset[p] + direct_partial_elems(plans[p], 1);
+            chunks_total += plans[p].chunks;
+        }
+        // grow-only buffer: a reallocation here would pull the rug from under kernels already enqueued
+        if (s == 0) ACF_TRY(ws->partials.ensure((offset[np] + offset[np] / 4) * sizeof(double)));
+        if (offset[np] * sizeof(double) > ws->partials.cap) {
+            ACF_CUDA_OK(cudaStreamSynchronize(st));
+            ACF_TRY(ws->partials.ensure(offset[np] * sizeof(double)));
+        }
+        std::vector<SeriesDesc> descs(np + 1);
+        for (int p = 0; p < np; ++p) {
+            const long long b = bounds[p], e = bounds[p + 1];
+            const long long reach = e + ncorr < ns ? e + ncorr : ns;  // last sample a pair starting in this piece can touch
+            descs[p] = {d + b, reach - b, e - b};
+        }
+        descs[np] = {d, ns, ns};  // the whole series, for the divide by (n - k)
+        // stream-ordered after the previous series' reduce, which was the last reader of this descriptor block
+        ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * descs.size(), cudaMemcpyHostToDevice, st));
+        long long copied = 0;
+        for (int p = 0; p < np; ++p) {
+            // copy, then launch: with a pageable source the copy call blocks the host while the previous kernel runs
+            const long long upto = bounds[p + 1] + ncorr < ns ? bounds[p + 1] + ncorr : ns;
+            if (upto > copied) {
+                ACF_CUDA_OK(cudaMemcpyAsync(d + copied, y[s] + copied, (size_t)(upto - copied) * 8, cudaMemcpyHostToDevice,
+                                            ws->copy_stream));
+                copied = upto;
+            }
+            cudaEvent_t ev = nullptr;
+            ACF_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            events.push_back(ev);
+            ACF_CUDA_OK(cudaEventRecord(ev, ws->copy_stream));
+            ACF_CUDA_OK(cudaStreamWaitEvent(st, ev, 0));
+            ACF_TRY(launch_direct(plans[p], ws->desc.as<SeriesDesc>() + p, 1, ncorr, ws->partials.as<double>() + offset[p],
+                                  ws->queue.as<unsigned int>(), ws->sm_count, st));
+            g_launches += 1;
+        }
         DirectPlan all = plans[0];
         all.chunks = (int)chunks_total;
-        rc = launch_reduce_partials(all, ws->desc.as<SeriesDesc>() + np, 1, ncorr, ws->partials.as<double>(),
-                                    ws->out.as<double>(), 1, st);
+        ACF_TRY(launch_reduce_partials(all, ws->desc.as<SeriesDesc>() + np, 1, ncorr, ws->partials.as<double>(),
+                                       d_out + (size_t)s * ncorr, 1, st));
         g_launches += 1;
     }
+    return 0;
+}
+
+// enqueue + download + synchronise; corr is host [nseries][ncorr]
+static int calc_correlation_pipelined(Workspace* ws, const double* const* y, const int64_t* n, int nseries,
+                                      long long ncorr, double* corr)
+{
+    ACF_TRY(ws->out.ensure((size_t)nseries * ncorr * 8));
+    std::vector<cudaEvent_t> events;
+    int rc = enqueue_pipelined(ws, y, n, nseries, ncorr, ws->out.as<double>(), events);
     cudaError_t e = cudaSuccess;
-    if (rc == 0) e = cudaMemcpyAsync(corr, ws->out.p, (size_t)ncorr * 8, cudaMemcpyDeviceToHost, st);
-    cudaError_t es = cudaStreamSynchronize(st);
+    if (rc == 0)
+        e = cudaMemcpyAsync(corr, ws->out.p, (size_t)nseries * ncorr * 8, cudaMemcpyDeviceToHost, ws->stream);
+    const cudaError_t es = cudaStreamSynchronize(ws->stream);
     cudaStreamSynchronize(ws->copy_stream);
-    for (auto& ev : landed)
-        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : events) cudaEventDestroy(ev);
     if (rc == 0 && (e != cudaSuccess || es != cudaSuccess)) {
         set_error("pipelined calc_correlation failed: %s", cudaGetErrorString(e != cudaSuccess ? e : es));
         rc = ACFB200_ERR_CUDA;
@@ -558,15 +591,6 @@ static int calc_correlation_pipelined(Workspace* ws, const double* y, long long 
 
 int acfb200_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr)
 {
-    {
-        Lock lk(g_mu);
-        // long series, direct summation, lags short enough for 8 pieces: overlap the upload with the kernels
-        if (y && corr && g_method == 0 && n >= (1 << 22) && ncorr >= 1 && ncorr * 16 <= n) {
-            Workspace* ws;
-            ACF_TRY(get_ws(&ws));
-            return calc_correlation_pipelined(ws, y, n, ncorr, corr);
-        }
-    }
     return acfb200_calc_correlation_batch(&y, &n, 1, ncorr, corr);
 }
 
@@ -786,17 +810,30 @@ int acfb200_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t
     ACF_TRY(get_ws(&ws));
     cudaStream_t st = ws->stream;
     const size_t pitch = even_up(n);
-    ACF_TRY(ws->series.ensure(pitch * ncomp * 8));
     ACF_TRY(ws->out.ensure((size_t)ncomp * ncorr * 8));
     ACF_TRY(ws->small.ensure((size_t)16 * ncomp));
-    std::vector<SeriesDesc> descs(ncomp);
-    for (int c = 0; c < ncomp; ++c) {
-        double* d = ws->series.as<double>() + pitch * c;
-        ACF_CUDA_OK(cudaMemcpyAsync(d, comps[c], (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        descs[c] = {d, (long long)n, (long long)n};
-    }
     double* d_o = ws->out.as<double>();
-    ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
+    std::vector<cudaEvent_t> events;
+    std::vector<int64_t> lens(ncomp, n);
+    if (pipelined_eligible(lens.data(), ncomp, ncorr)) {
+        // long components: component c+1 uploads under the kernels of component c
+        const int rc = enqueue_pipelined(ws, comps, lens.data(), ncomp, ncorr, d_o, events);
+        if (rc != 0) {
+            cudaStreamSynchronize(st);
+            cudaStreamSynchronize(ws->copy_stream);
+            for (auto& ev : events) cudaEventDestroy(ev);
+            return rc;
+        }
+    } else {
+        ACF_TRY(ws->series.ensure(pitch * ncomp * 8));
+        std::vector<SeriesDesc> descs(ncomp);
+        for (int c = 0; c < ncomp; ++c) {
+            double* d = ws->series.as<double>() + pitch * c;
+            ACF_CUDA_OK(cudaMemcpyAsync(d, comps[c], (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            descs[c] = {d, (long long)n, (long long)n};
+        }
+        ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
+    }
     double* d_small = ws->small.as<double>();
     for (int c = 0; c < ncomp; ++c) {
         ACF_TRY(launch_integrate_cutoff(d_o + (size_t)c * ncorr, ncorr, dt, 0.0, d_small + 2 * c,
@@ -807,6 +844,7 @@ int acfb200_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t
     if (acf) ACF_CUDA_OK(cudaMemcpyAsync(acf, d_o, (size_t)ncomp * ncorr * 8, cudaMemcpyDeviceToHost, st));
     ACF_CUDA_OK(cudaMemcpyAsync(h_small.data(), d_small, h_small.size() * 8, cudaMemcpyDeviceToHost, st));
     ACF_CUDA_OK(cudaStreamSynchronize(st));
+    for (auto& ev : events) cudaEventDestroy(ev);
     const double kB = 1.38064852E-23;
     for (int c = 0; c < ncomp; ++c) {
         const double I = h_small[2 * c];

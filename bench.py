@@ -304,6 +304,18 @@ def run_native(args):
                                            lambda s_, nt: A.normalise_device(s_, nt, stream=stream))
 
         e2e_step = None
+        if world == 1:
+            # host-buffer call: acfb200_green_kubo uploads the components, correlates, integrates, returns acf + eta
+            import ctypes as C
+            h_acf = torch.empty((comps, m), dtype=torch.float64).pin_memory()
+            h_int = np.empty(comps)
+            h_eta = np.empty(comps)
+            ptrs = (C.c_void_p * comps)(*[h.data_ptr() for h in h_b])
+
+            def e2e_step():
+                A.check(A._lib.load().acfb200_green_kubo(ptrs, comps, n, m, 2.0, 31.0399376148, 298.15,
+                                                         C.c_void_p(h_acf.data_ptr()), C.c_void_p(h_int.ctypes.data),
+                                                         C.c_void_p(h_eta.ctypes.data)))
         h2d, d2h = 8 * (halo_end - lo) * comps, 8 * m * comps
         scaling = "strong"
         total_products = float(comps) * n * m
@@ -345,7 +357,12 @@ def run_native(args):
         def step():
             A.calc_correlation_fft_device(d_x, m, out=d_out, stream=stream)
 
-        e2e_step = None
+        import ctypes as C
+        h_out = torch.empty(m, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            A.check(A._lib.load().acfb200_calc_correlation_fft(C.c_void_p(h_x.data_ptr()), n, m,
+                                                               C.c_void_p(h_out.data_ptr())))
         h2d, d2h = 8 * n, 8 * m
         scaling = "weak"
         total_products = products_rank * world
