@@ -710,10 +710,16 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
     // Window groups: all uploads are queued on the copy stream up front, one event per group; the compute stream
     // starts group g as soon as its windows have landed, so the H2D of group g+1 overlaps the kernels of group g
     // (with pageable host memory the copies degrade to synchronous staging and nothing is lost).
+    // The host link delivers a window ~4x faster than the kernels consume one, so the groups grow 1 : 4 : 16 : rest:
+    // only the first, small group's transfer is exposed and the later launches are large enough to run efficiently.
     const int ngroups = nwindows >= 8 ? 4 : 1;
     std::vector<cudaEvent_t> landed(ngroups);
-    std::vector<int> gbeg(ngroups + 1);
-    for (int g = 0; g <= ngroups; ++g) gbeg[g] = (int)((long long)nwindows * g / ngroups);
+    std::vector<int> gbeg(ngroups + 1, 0);
+    if (ngroups == 4) {
+        const int cum[5] = {0, 1, 5, 21, 32};
+        for (int g = 1; g <= 4; ++g) gbeg[g] = (int)(((long long)nwindows * cum[g] + 31) / 32);
+    }
+    gbeg[ngroups] = nwindows;
     size_t off = 0;
     for (int g = 0; g < ngroups; ++g) {
         for (int w = gbeg[g]; w < gbeg[g + 1]; ++w) {
