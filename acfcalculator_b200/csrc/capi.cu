@@ -1,19 +1,8 @@
 // extern "C" shim: implements include/acf_b200.h on top of the sm_100a kernels.
 // No CPU fallback lives here: every compute entry point needs a CUDA device and says so when it fails.
-#include <dlfcn.h>
-#include <nccl.h>
+// (traj2diffusion entry points: capi_msd.cu; multi-GPU entry points: capi_multi.cu; shared internals: capi_internal.cuh)
 
-#include <atomic>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <string>
-#include <thread>
-#include <vector>
-
-#include "../../include/acf_b200.h"
-#include "common.cuh"
+#include "capi_internal.cuh"
 
 namespace acfb200 {
 
@@ -31,7 +20,7 @@ void set_error(const char* fmt, ...)
 // run concurrently; calls on the same device are serialised like the reference's globals would demand.
 static std::recursive_mutex g_dev_mu[64];
 static std::mutex g_ws_mu;  // guards the workspace table itself
-static std::recursive_mutex& dev_mutex()
+std::recursive_mutex& dev_mutex()
 {
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess) {
@@ -40,87 +29,14 @@ static std::recursive_mutex& dev_mutex()
     }
     return g_dev_mu[d & 63];
 }
-#define g_mu dev_mutex()
-static std::atomic<long long> g_launches{0};
-static int g_force_variant = -1;
-static int g_method = 0;  // 0 direct (default), 1 fft, 2 auto
+std::atomic<long long> g_launches{0};
+int g_force_variant = -1;
+int g_method = 0;
 
-#define ACF_TRY(expr)            \
-    do {                         \
-        int _rc = (expr);        \
-        if (_rc != 0) return _rc; \
-    } while (0)
-
-// Grow-only device buffer.
-struct Buf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes, bool zero = false)
-    {
-        if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + (bytes >> 3) + 256;  // a little slack so slowly growing sizes do not thrash
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
-            cudaGetLastError();
-            return e == cudaErrorMemoryAllocation ? ACFB200_ERR_NOMEM : ACFB200_ERR_CUDA;
-        }
-        cap = want;
-        if (zero) {
-            e = cudaMemset(p, 0, want);
-            if (e != cudaSuccess) {
-                set_error("cudaMemset failed: %s", cudaGetErrorString(e));
-                return ACFB200_ERR_CUDA;
-            }
-        }
-        return 0;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <class T>
-    T* as() const
-    {
-        return reinterpret_cast<T*>(p);
-    }
-};
-
-struct Workspace {
-    int device = -1;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // H2D of the next window group while the current one computes
-    Buf series, y, vel, desc, partials, out, scratch, small, fftwork, queue, wins;
-    void release()
-    {
-        series.release();
-        y.release();
-        vel.release();
-        desc.release();
-        partials.release();
-        out.release();
-        scratch.release();
-        small.release();
-        fftwork.release();
-        queue.release();
-        wins.release();
-        if (stream) cudaStreamDestroy(stream);
-        if (copy_stream) cudaStreamDestroy(copy_stream);
-        stream = nullptr;
-        copy_stream = nullptr;
-        device = -1;
-    }
-};
 
 static std::vector<Workspace*> g_ws;  // one per device, created lazily
 
-static int get_ws(Workspace** out)
+int get_ws(Workspace** out)
 {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -161,10 +77,9 @@ static int get_ws(Workspace** out)
     return 0;
 }
 
-static inline size_t even_up(long long n) { return (size_t)((n + 1) & ~1ll); }
 
 // Direct lag sums of `nseries` device-resident series described by host-side descs.
-static int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long long ncorr, double* d_out,
+int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long long ncorr, double* d_out,
                       int normalise, cudaStream_t st)
 {
     const int ns = (int)descs.size();
@@ -258,7 +173,7 @@ static int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long 
     return 0;
 }
 
-static int check_common(const void* p, long long n, long long ncorr, const char* what)
+int check_common(const void* p, long long n, long long ncorr, const char* what)
 {
     if (!p) {
         set_error("%s: null pointer", what);
@@ -278,7 +193,7 @@ static int check_common(const void* p, long long n, long long ncorr, const char*
 // The main() sequence (ACFcalculator.cpp:712-725,:775) for nw device-resident windows in one go:
 // per window mean / centre+velocity / velocity-mean kernels, then ONE direct-lag launch over the 2*nw
 // centred series, one integral kernel per window.  d_acf/d_vacf (nullable) are device [nw][ncorr].
-static int pipeline_batch_device(Workspace* ws, const double* const* d_series, const int64_t* n, int nw,
+int pipeline_batch_device(Workspace* ws, const double* const* d_series, const int64_t* n, int nw,
                                  long long ncorr, double dt, double cutoff, double* d_acf, double* d_vacf,
                                  acfb200_result* res, cudaStream_t st)
 {
@@ -350,7 +265,6 @@ static int pipeline_batch_device(Workspace* ws, const double* const* d_series, c
 }  // namespace acfb200
 
 using namespace acfb200;
-typedef std::lock_guard<std::recursive_mutex> Lock;
 
 extern "C" {
 
@@ -964,674 +878,8 @@ int acfb200_calc_correlation_fft(const double* y, int64_t n, int64_t ncorr, doub
     return 0;
 }
 
-
-// -------------------------------------------------------------------------------------------------
-// traj2diffusion: mean-square displacement (traj2diffusion.cpp:497-552)
-// -------------------------------------------------------------------------------------------------
-}  // extern "C"
-
-namespace acfb200 {
-
-static int check_msd_args(const void* x, const void* y, const void* z, long long n, long long stride, long long max_s,
-                          const char* what)
-{
-    if (!x || !y || !z) {
-        set_error("%s: null coordinate array", what);
-        return ACFB200_ERR_ARG;
-    }
-    if (n < 1 || max_s < 1) {
-        set_error("%s: need n >= 1 and max_s >= 1 (got n=%lld, max_s=%lld)", what, n, max_s);
-        return ACFB200_ERR_ARG;
-    }
-    if (stride < 1) {  // the reference loops forever on stride 0 (traj2diffusion.cpp:530)
-        set_error("%s: stride must be >= 1 (got %lld)", what, stride);
-        return ACFB200_ERR_ARG;
-    }
-    if (n > 2147483647ll) {  // msd_counter is an int in the reference (:373) and in this ABI
-        set_error("%s: at most 2^31-1 frames (got %lld)", what, n);
-        return ACFB200_ERR_ARG;
-    }
-    return 0;
-}
-
-// Displacement sums of ntraj device-resident trajectories -> msd[ntraj][max_s], counter[ntraj][max_s] (device), one
-// launch over all axes of all trajectories.  axes[3*t + a] is coordinate a of trajectory t; when every trajectory
-// passes one array three times (the general reader's y = z = x) each is computed once.  Unit stride runs the tiled
-// displacement kernel (the direct-lag kernel's geometry), larger strides the per-lag strided kernel.
-static int msd_batch_device(Workspace* ws, const double* const* axes, const long long* n, int ntraj, long long stride,
-                            long long max_s, double* d_msd, int* d_counter, cudaStream_t st)
-{
-    bool one_axis = true;
-    long long n_max = 1;
-    for (int t = 0; t < ntraj; ++t) {
-        one_axis = one_axis && axes[3 * t] == axes[3 * t + 1] && axes[3 * t + 1] == axes[3 * t + 2];
-        if (n[t] > n_max) n_max = n[t];
-    }
-    const int per = one_axis ? 1 : 3, ns = per * ntraj;
-    std::vector<SeriesDesc> descs(ns);
-    for (int t = 0; t < ntraj; ++t)
-        for (int a = 0; a < per; ++a) descs[per * t + a] = {axes[3 * t + a], n[t], n[t]};
-    DirectPlan plan;
-    if (stride == 1) {
-        ACF_TRY(plan_direct(n_max, max_s, ns, ws->sm_count, -1, &plan, true));
-        if (plan.mode != 0) {
-            set_error("msd: the displacement kernel needs a tiled plan (unset ACFB200_MODE)");
-            return ACFB200_ERR_ARG;
-        }
-    } else {
-        ACF_TRY(plan_msd_strided(n_max, stride, max_s, ws->sm_count, &plan));
-    }
-    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)ns));
-    ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, ns) * sizeof(double)));
-    ACF_TRY(ws->out.ensure((size_t)ns * max_s * 8));
-    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * (size_t)ns, cudaMemcpyHostToDevice, st));
-    if (stride == 1)
-        ACF_TRY(launch_direct_msd(plan, ws->desc.as<SeriesDesc>(), ns, max_s, ws->partials.as<double>(), st));
-    else
-        ACF_TRY(launch_msd_strided(plan, ws->desc.as<SeriesDesc>(), ns, stride, max_s, ws->partials.as<double>(), st));
-    ACF_TRY(launch_reduce_partials(plan, ws->desc.as<SeriesDesc>(), ns, max_s, ws->partials.as<double>(),
-                                   ws->out.as<double>(), 0, st));
-    ACF_TRY(launch_msd_finalize(ws->out.as<double>(), ws->desc.as<SeriesDesc>(), per, ntraj, stride, max_s, d_msd,
-                                d_counter, st));
-    g_launches += 3;
-    return 0;
-}
-
-static int msd_device(Workspace* ws, const double* d_x, const double* d_y, const double* d_z, long long n,
-                      long long stride, long long max_s, double* d_msd, int* d_counter, cudaStream_t st)
-{
-    const double* axes[3] = {d_x, d_y, d_z};
-    return msd_batch_device(ws, axes, &n, 1, stride, max_s, d_msd, d_counter, st);
-}
-
-// Upload three host coordinate arrays (once if they are the same array) into ws->series; d[] receives the device pointers.
-static int upload_axes(Workspace* ws, const double* x, const double* y, const double* z, long long n, const double* d[3],
-                       cudaStream_t st)
-{
-    const bool one_axis = (x == y && y == z);
-    const size_t pitch = even_up(n);
-    ACF_TRY(ws->series.ensure((one_axis ? 1 : 3) * pitch * 8));
-    double* base = ws->series.as<double>();
-    const double* h[3] = {x, y, z};
-    for (int a = 0; a < 3; ++a) {
-        if (one_axis && a > 0) {
-            d[a] = base;
-            continue;
-        }
-        ACF_CUDA_OK(cudaMemcpyAsync(base + a * pitch, h[a], (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        d[a] = base + a * pitch;
-    }
-    return 0;
-}
-
-// image() on three device arrays into ws->y; d_out[] receives the unwrapped arrays
-static int image_to_workspace(Workspace* ws, const double* const d_in[3], long long n, double cell, double* d_out[3],
-                              cudaStream_t st)
-{
-    const size_t pitch = even_up(n);
-    ACF_TRY(ws->y.ensure(3 * pitch * 8));
-    ACF_TRY(ws->vel.ensure(image_workspace_bytes(n)));
-    for (int a = 0; a < 3; ++a) d_out[a] = ws->y.as<double>() + a * pitch;
-    const int launches = launch_image(d_in, d_out, n, cell, ws->vel.p, st);
-    if (launches < 0) return ACFB200_ERR_CUDA;
-    g_launches += launches;
-    return 0;
-}
-
-}  // namespace acfb200
-
-extern "C" {
-
-int acfb200_msd_device(const double* d_x, const double* d_y, const double* d_z, int64_t n, int64_t stride, int64_t max_s,
-                       double* d_msd, int32_t* d_counter, void* stream)
-{
-    Lock lk(g_mu);
-    ACF_TRY(check_msd_args(d_x, d_y, d_z, n, stride, max_s, "msd_device"));
-    if (!d_msd) {
-        set_error("msd_device: null output");
-        return ACFB200_ERR_ARG;
-    }
-    Workspace* ws;
-    ACF_TRY(get_ws(&ws));
-    return msd_device(ws, d_x, d_y, d_z, n, stride, max_s, d_msd, d_counter, (cudaStream_t)stream);
-}
-
-int acfb200_image_device(const double* d_x, const double* d_y, const double* d_z, int64_t n, double cell, double* d_xo,
-                         double* d_yo, double* d_zo, void* stream)
-{
-    Lock lk(g_mu);
-    if (!d_x || !d_y || !d_z || !d_xo || !d_yo || !d_zo || n < 1) {
-        set_error("image_device: null argument or n < 1");
-        return ACFB200_ERR_ARG;
-    }
-    if (d_xo == d_x || d_yo == d_y || d_zo == d_z) {
-        set_error("image_device: outputs must not alias the inputs (every frame reads its predecessor)");
-        return ACFB200_ERR_ARG;
-    }
-    Workspace* ws;
-    ACF_TRY(get_ws(&ws));
-    ACF_TRY(ws->vel.ensure(image_workspace_bytes(n)));
-    const double* in[3] = {d_x, d_y, d_z};
-    double* out[3] = {d_xo, d_yo, d_zo};
-    const int launches = launch_image(in, out, n, cell, ws->vel.p, (cudaStream_t)stream);
-    if (launches < 0) return ACFB200_ERR_CUDA;
-    g_launches += launches;
-    return 0;
-}
-
-int acfb200_msd(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s, double* msd,
-                int32_t* counter)
-{
-    Lock lk(g_mu);
-    ACF_TRY(check_msd_args(x, y, z, n, stride, max_s, "msd"));
-    if (!msd) {
-        set_error("msd: null output");
-        return ACFB200_ERR_ARG;
-    }
-    Workspace* ws;
-    ACF_TRY(get_ws(&ws));
-    cudaStream_t st = ws->stream;
-    const double* d[3];
-    ACF_TRY(upload_axes(ws, x, y, z, n, d, st));
-    ACF_TRY(ws->small.ensure((size_t)max_s * 12 + 64));
-    double* d_msd = ws->small.as<double>();
-    int* d_cnt = reinterpret_cast<int*>(d_msd + max_s);
-    ACF_TRY(msd_device(ws, d[0], d[1], d[2], n, stride, max_s, d_msd, d_cnt, st));
-    ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)max_s * 8, cudaMemcpyDeviceToHost, st));
-    if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)max_s * 4, cudaMemcpyDeviceToHost, st));
-    ACF_CUDA_OK(cudaStreamSynchronize(st));
-    return 0;
-}
-
-int acfb200_image(double* x, double* y, double* z, int64_t n, double cell)
-{
-    Lock lk(g_mu);
-    if (!x || !y || !z || n < 1) {
-        set_error("image: null argument or n < 1");
-        return ACFB200_ERR_ARG;
-    }
-    Workspace* ws;
-    ACF_TRY(get_ws(&ws));
-    cudaStream_t st = ws->stream;
-    // three distinct device copies even when the host arrays coincide: every axis is written separately
-    const size_t pitch = even_up(n);
-    ACF_TRY(ws->series.ensure(3 * pitch * 8));
-    double* h[3] = {x, y, z};
-    const double* d_in[3];
-    for (int a = 0; a < 3; ++a) {
-        double* dst = ws->series.as<double>() + a * pitch;
-        ACF_CUDA_OK(cudaMemcpyAsync(dst, h[a], (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        d_in[a] = dst;
-    }
-    double* d_out[3];
-    ACF_TRY(image_to_workspace(ws, d_in, n, cell, d_out, st));
-    for (int a = 0; a < 3; ++a) {
-        if (a > 0 && (h[a] == h[0] || h[a] == h[a - 1])) continue;  // same host array: one copy back is enough
-        ACF_CUDA_OK(cudaMemcpyAsync(h[a], d_out[a], (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    }
-    ACF_CUDA_OK(cudaStreamSynchronize(st));
-    return 0;
-}
-
-int acfb200_msd_slope(const double* msd, int64_t n, double* slope, double* sum)
-{
-    Lock lk(g_mu);
-    if (!msd || n < 1) {
-        set_error("msd_slope: null argument or n < 1");
-        return ACFB200_ERR_ARG;
-    }
-    Workspace* ws;
-    ACF_TRY(get_ws(&ws));
-    cudaStream_t st = ws->stream;
-    ACF_TRY(ws->small.ensure((size_t)n * 8 + 64));
-    double* d_msd = ws->small.as<double>() + 2;
-    ACF_CUDA_OK(cudaMemcpyAsync(d_msd, msd, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    ACF_TRY(launch_msd_slope(d_msd, n, 1, ws->small.as<double>(), st));
-    g_launches += 1;
-    double h[2];
-    ACF_CUDA_OK(cudaMemcpyAsync(h, ws->small.p, 16, cudaMemcpyDeviceToHost, st));
-    ACF_CUDA_OK(cudaStreamSynchronize(st));
-    if (sum) *sum = h[0];
-    if (slope) *slope = h[1];
-    return 0;
-}
-
-int acfb200_traj2diffusion(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s,
-                           double dt, double cell, int imaging, double* msd, int32_t* counter,
-                           acfb200_msd_result* result)
-{
-    Lock lk(g_mu);
-    ACF_TRY(check_msd_args(x, y, z, n, stride, max_s, "traj2diffusion"));
-    Workspace* ws;
-    ACF_TRY(get_ws(&ws));
-    cudaStream_t st = ws->stream;
-    const double* d[3];
-    if (imaging) {
-        const size_t pitch = even_up(n);
-        ACF_TRY(ws->series.ensure(3 * pitch * 8));
-        const double* h[3] = {x, y, z};
-        const double* d_in[3];
-        for (int a = 0; a < 3; ++a) {
-            double* dst = ws->series.as<double>() + a * pitch;
-            ACF_CUDA_OK(cudaMemcpyAsync(dst, h[a], (size_t)n * 8, cudaMemcpyHostToDevice, st));
-            d_in[a] = dst;
-        }
-        double* d_out[3];
-        ACF_TRY(image_to_workspace(ws, d_in, n, cell, d_out, st));
-        for (int a = 0; a < 3; ++a) d[a] = d_out[a];
-    } else {
-        ACF_TRY(upload_axes(ws, x, y, z, n, d, st));
-    }
-    ACF_TRY(ws->small.ensure((size_t)max_s * 12 + 64 + 16));
-    double* d_sl = ws->small.as<double>();  // [sum, slope]
-    double* d_msd = d_sl + 2;
-    int* d_cnt = reinterpret_cast<int*>(d_msd + max_s);
-    ACF_TRY(msd_device(ws, d[0], d[1], d[2], n, stride, max_s, d_msd, d_cnt, st));
-    ACF_TRY(launch_msd_slope(d_msd, max_s, 1, d_sl, st));
-    g_launches += 1;
-    double h[2];
-    if (msd) ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)max_s * 8, cudaMemcpyDeviceToHost, st));
-    if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)max_s * 4, cudaMemcpyDeviceToHost, st));
-    ACF_CUDA_OK(cudaMemcpyAsync(h, d_sl, 16, cudaMemcpyDeviceToHost, st));
-    ACF_CUDA_OK(cudaStreamSynchronize(st));
-    if (result) {
-        result->sum = h[0];
-        result->slope = h[1];
-        const double space_series = dt * (double)stride;      // traj2diffusion.cpp:497 (double * int)
-        result->diffusivity = h[1] / space_series / 6.0;       // :549
-        result->nframes = n;
-    }
-    return 0;
-}
-
-
-// main() of traj2diffusion for ntraj trajectories in one go (the "many umbrella windows" use of the program): every
-// trajectory is uploaded (and unwrapped, if asked) on the device, ONE displacement launch covers all axes of all
-// trajectories, one launch each finalises, and takes the slopes of, all MSD curves.
-int acfb200_traj2diffusion_batch(const double* const* x, const double* const* y, const double* const* z, const int64_t* n,
-                                 int ntraj, int64_t stride, int64_t max_s, double dt, double cell, int imaging,
-                                 double* msd, int32_t* counter, acfb200_msd_result* result)
-{
-    Lock lk(g_mu);
-    if (!x || !y || !z || !n || ntraj < 1) {
-        set_error("traj2diffusion_batch: null argument or ntraj < 1");
-        return ACFB200_ERR_ARG;
-    }
-    size_t total = 0;
-    bool aliased = !imaging;
-    for (int t = 0; t < ntraj; ++t) {
-        ACF_TRY(check_msd_args(x[t], y[t], z[t], n[t], stride, max_s, "traj2diffusion_batch"));
-        aliased = aliased && x[t] == y[t] && y[t] == z[t];
-    }
-    for (int t = 0; t < ntraj; ++t) total += (aliased ? 1 : 3) * even_up(n[t]);
-    Workspace* ws;
-    ACF_TRY(get_ws(&ws));
-    cudaStream_t st = ws->stream;
-    ACF_TRY(ws->series.ensure(total * 8));
-    if (imaging) {
-        long long n_max = 1;
-        for (int t = 0; t < ntraj; ++t) n_max = n[t] > n_max ? n[t] : n_max;
-        ACF_TRY(ws->y.ensure(total * 8));
-        ACF_TRY(ws->vel.ensure(image_workspace_bytes(n_max)));  // reused trajectory after trajectory (stream order)
-    }
-    std::vector<const double*> axes(3 * (size_t)ntraj);
-    std::vector<long long> len(ntraj);
-    size_t off = 0;
-    for (int t = 0; t < ntraj; ++t) {
-        len[t] = n[t];
-        const double* h[3] = {x[t], y[t], z[t]};
-        const size_t pitch = even_up(n[t]);
-        const double* d_in[3];
-        for (int a = 0; a < 3; ++a) {
-            if (aliased && a > 0) {
-                d_in[a] = d_in[0];
-                continue;
-            }
-            double* dst = ws->series.as<double>() + off + a * pitch;
-            ACF_CUDA_OK(cudaMemcpyAsync(dst, h[a], (size_t)n[t] * 8, cudaMemcpyHostToDevice, st));
-            d_in[a] = dst;
-        }
-        if (imaging) {
-            double* d_out[3];
-            for (int a = 0; a < 3; ++a) d_out[a] = ws->y.as<double>() + off + a * pitch;
-            const int launches = launch_image(d_in, d_out, n[t], cell, ws->vel.p, st);
-            if (launches < 0) return ACFB200_ERR_CUDA;
-            g_launches += launches;
-            for (int a = 0; a < 3; ++a) axes[3 * t + a] = d_out[a];
-        } else {
-            for (int a = 0; a < 3; ++a) axes[3 * t + a] = d_in[a];
-        }
-        off += (aliased ? 1 : 3) * pitch;
-    }
-    const size_t curve = (size_t)max_s;
-    ACF_TRY(ws->small.ensure((size_t)ntraj * (curve * 12 + 16) + 64));
-    double* d_sl = ws->small.as<double>();                 // [ntraj][sum, slope]
-    double* d_msd = d_sl + 2 * (size_t)ntraj;               // [ntraj][max_s]
-    int* d_cnt = reinterpret_cast<int*>(d_msd + (size_t)ntraj * curve);
-    ACF_TRY(msd_batch_device(ws, axes.data(), len.data(), ntraj, stride, max_s, d_msd, d_cnt, st));
-    ACF_TRY(launch_msd_slope(d_msd, max_s, ntraj, d_sl, st));
-    g_launches += 1;
-    std::vector<double> h_sl(2 * (size_t)ntraj);
-    if (msd) ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)ntraj * curve * 8, cudaMemcpyDeviceToHost, st));
-    if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)ntraj * curve * 4, cudaMemcpyDeviceToHost, st));
-    ACF_CUDA_OK(cudaMemcpyAsync(h_sl.data(), d_sl, h_sl.size() * 8, cudaMemcpyDeviceToHost, st));
-    ACF_CUDA_OK(cudaStreamSynchronize(st));
-    if (result)
-        for (int t = 0; t < ntraj; ++t) {
-            result[t].sum = h_sl[2 * t];
-            result[t].slope = h_sl[2 * t + 1];
-            result[t].diffusivity = h_sl[2 * t + 1] / (dt * (double)stride) / 6.0;  // traj2diffusion.cpp:497, :549
-            result[t].nframes = n[t];
-        }
-    return 0;
-}
-
-// -------------------------------------------------------------------------------------------------
-// multi-GPU entry points: one host thread per device inside this process
-// -------------------------------------------------------------------------------------------------
-}  // extern "C" (helpers below are C++)
-
-namespace {
-
-// NCCL is resolved at run time (dlopen) so that single-GPU users do not need the library at all.
-struct NcclApi {
-    void* lib = nullptr;
-    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-    std::vector<ncclComm_t> comms;  // communicator clique over devices 0..n-1
-};
-NcclApi g_nccl;
-std::mutex g_nccl_mu;
-
-int nccl_clique(int ndev, NcclApi** out)
-{
-    std::lock_guard<std::mutex> lk(g_nccl_mu);
-    if (!g_nccl.lib) {
-        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-            g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-            if (g_nccl.lib) break;
-        }
-        if (!g_nccl.lib) {
-            set_error("time-block sharding needs NCCL and libnccl.so.2 could not be loaded: %s", dlerror());
-            return ACFB200_ERR_CUDA;
-        }
-        g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))dlsym(g_nccl.lib, "ncclCommInitAll");
-        g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
-        g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
-        g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
-        if (!g_nccl.CommInitAll || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
-            set_error("libnccl.so.2 lacks a required symbol");
-            return ACFB200_ERR_CUDA;
-        }
-    }
-    if ((int)g_nccl.comms.size() != ndev) {
-        for (ncclComm_t c : g_nccl.comms) g_nccl.CommDestroy(c);
-        g_nccl.comms.assign(ndev, nullptr);
-        std::vector<int> devs(ndev);
-        for (int d = 0; d < ndev; ++d) devs[d] = d;
-        const ncclResult_t r = g_nccl.CommInitAll(g_nccl.comms.data(), ndev, devs.data());
-        if (r != ncclSuccess) {
-            set_error("ncclCommInitAll(%d devices) failed: %s", ndev, g_nccl.GetErrorString(r));
-            g_nccl.comms.clear();
-            return ACFB200_ERR_CUDA;
-        }
-    }
-    *out = &g_nccl;
-    return 0;
-}
-
-int usable_devices(int requested)
-{
-    int have = 0;
-    if (cudaGetDeviceCount(&have) != cudaSuccess) {
-        cudaGetLastError();
-        have = 0;
-    }
-    if (requested <= 0 || requested > have) requested = have;
-    return requested;
-}
-
-// Runs fn(device) on one host thread per device; returns the first non-zero status with its message.
-template <class F>
-int for_each_device(int ndev, F fn)
-{
-    std::vector<int> rc(ndev, 0);
-    std::vector<std::string> msg(ndev);
-    std::vector<std::thread> th;
-    for (int d = 0; d < ndev; ++d)
-        th.emplace_back([&, d]() {
-            if (cudaSetDevice(d) != cudaSuccess) {
-                rc[d] = ACFB200_ERR_CUDA;
-                msg[d] = "cudaSetDevice failed";
-                return;
-            }
-            rc[d] = fn(d);
-            if (rc[d] != 0) msg[d] = last_error();
-        });
-    for (auto& t : th) t.join();
-    for (int d = 0; d < ndev; ++d)
-        if (rc[d] != 0) {
-            set_error("device %d: %s", d, msg[d].c_str());
-            return rc[d];
-        }
-    return 0;
-}
-
-}  // namespace
-
-extern "C" {
-
-// calcCorrelation of nseries host series on up to `ngpus` devices of this box:
-//   nseries >= devices : series s on device s mod G, no communication at all;
-//   fewer series       : every series is cut into G time blocks, device g gets block g plus its (ncorr-1)-sample halo,
-//                        computes the raw lag sums of its block, ONE ncclAllReduce(sum, double, nseries*ncorr) over
-//                        NVLink combines them, device 0 divides by (n-k) (ACFcalculator.cpp:139-143 after the sum).
-int acfb200_multi_gpu_calc_correlation(const double* const* y, const int64_t* n, int nseries, int64_t ncorr, double* corr,
-                                       int ngpus)
-{
-    if (!y || !n || !corr || nseries < 1 || ncorr < 1) {
-        set_error("multi_gpu_calc_correlation: null argument, nseries < 1 or ncorr < 1");
-        return ACFB200_ERR_ARG;
-    }
-    const int ndev = usable_devices(ngpus);
-    if (ndev < 1) {
-        set_error("no usable CUDA device; libacf_b200 has no CPU path");
-        return ACFB200_ERR_CUDA;
-    }
-    if (ndev == 1) return acfb200_calc_correlation_batch(y, n, nseries, ncorr, corr);
-    int home = 0;
-    cudaGetDevice(&home);
-    int rc;
-    if (nseries >= ndev) {
-        rc = for_each_device(ndev, [&](int d) -> int {
-            std::vector<const double*> py;
-            std::vector<int64_t> pn;
-            std::vector<int> idx;
-            for (int s = d; s < nseries; s += ndev) {
-                py.push_back(y[s]);
-                pn.push_back(n[s]);
-                idx.push_back(s);
-            }
-            std::vector<double> out(py.size() * (size_t)ncorr);
-            const int r = acfb200_calc_correlation_batch(py.data(), pn.data(), (int)py.size(), ncorr, out.data());
-            if (r != 0) return r;
-            for (size_t i = 0; i < idx.size(); ++i)
-                memcpy(corr + (size_t)idx[i] * ncorr, out.data() + i * (size_t)ncorr, (size_t)ncorr * 8);
-            return 0;
-        });
-    } else {
-        for (int s = 0; s < nseries; ++s)
-            if (n[s] < 1) {
-                set_error("series %d is empty", s);
-                return ACFB200_ERR_ARG;
-            }
-        NcclApi* nccl = nullptr;
-        ACF_TRY(nccl_clique(ndev, &nccl));
-        rc = for_each_device(ndev, [&](int d) -> int {
-            Lock lk(g_mu);
-            Workspace* ws;
-            ACF_TRY(get_ws(&ws));
-            cudaStream_t st = ws->stream;
-            // block + halo of every series, back to back
-            std::vector<SeriesDesc> descs(nseries);
-            size_t total = 0;
-            std::vector<long long> lo(nseries), len(nseries);
-            for (int s = 0; s < nseries; ++s) {
-                const long long b = n[s] * d / ndev, e = n[s] * (d + 1) / ndev;
-                long long reach = e + ncorr - 1;
-                if (reach > n[s]) reach = n[s];
-                lo[s] = b;
-                len[s] = reach - b;
-                total += even_up(len[s] > 0 ? len[s] : 1);
-            }
-            ACF_TRY(ws->series.ensure(total * 8));
-            ACF_TRY(ws->out.ensure((size_t)nseries * ncorr * 8));
-            size_t off = 0;
-            for (int s = 0; s < nseries; ++s) {
-                double* dst = ws->series.as<double>() + off;
-                const long long e = n[s] * (d + 1) / ndev;
-                if (len[s] > 0)
-                    ACF_CUDA_OK(cudaMemcpyAsync(dst, y[s] + lo[s], (size_t)len[s] * 8, cudaMemcpyHostToDevice, st));
-                descs[s] = {dst, len[s] > 0 ? len[s] : 0, e - lo[s]};
-                off += even_up(len[s] > 0 ? len[s] : 1);
-            }
-            double* d_sums = ws->out.as<double>();
-            ACF_TRY(run_direct(ws, descs, ncorr, d_sums, 0, st));
-            const ncclResult_t r = nccl->AllReduce(d_sums, d_sums, (size_t)nseries * ncorr, ncclDouble, ncclSum,
-                                                   nccl->comms[d], st);
-            if (r != ncclSuccess) {
-                set_error("ncclAllReduce failed: %s", nccl->GetErrorString(r));
-                return ACFB200_ERR_CUDA;
-            }
-            if (d == 0) {
-                for (int s = 0; s < nseries; ++s) {
-                    ACF_TRY(launch_normalise(d_sums + (size_t)s * ncorr, n[s], ncorr, d_sums + (size_t)s * ncorr, st));
-                    g_launches += 1;
-                }
-                ACF_CUDA_OK(cudaMemcpyAsync(corr, d_sums, (size_t)nseries * ncorr * 8, cudaMemcpyDeviceToHost, st));
-            }
-            ACF_CUDA_OK(cudaStreamSynchronize(st));
-            return 0;
-        });
-    }
-    cudaSetDevice(home);
-    return rc;
-}
-
-// setup.sh-style windows on up to `ngpus` devices: window w on device w mod G, full pipeline per window, no
-// communication (acf/vacf [nwindows][ncorr], result [nwindows], as acfb200_acf_pipeline_batch).
-int acfb200_multi_gpu_pipeline_batch(const double* const* series, const int64_t* n, int nwindows, int64_t ncorr, double dt,
-                                     double cutoff, double* acf, double* vacf, acfb200_result* result, int ngpus)
-{
-    if (!series || !n || nwindows < 1) {
-        set_error("multi_gpu_pipeline_batch: null argument or nwindows < 1");
-        return ACFB200_ERR_ARG;
-    }
-    int ndev = usable_devices(ngpus);
-    if (ndev > nwindows) ndev = nwindows;
-    if (ndev < 1) {
-        set_error("no usable CUDA device; libacf_b200 has no CPU path");
-        return ACFB200_ERR_CUDA;
-    }
-    if (ndev == 1) return acfb200_acf_pipeline_batch(series, n, nwindows, ncorr, dt, cutoff, acf, vacf, result);
-    int home = 0;
-    cudaGetDevice(&home);
-    const int rc = for_each_device(ndev, [&](int d) -> int {
-        std::vector<const double*> ps;
-        std::vector<int64_t> pn;
-        std::vector<int> idx;
-        for (int w = d; w < nwindows; w += ndev) {
-            ps.push_back(series[w]);
-            pn.push_back(n[w]);
-            idx.push_back(w);
-        }
-        const size_t cnt = ps.size();
-        std::vector<double> a(cnt * (size_t)ncorr), v(cnt * (size_t)ncorr);
-        std::vector<acfb200_result> r(cnt);
-        const int st = acfb200_acf_pipeline_batch(ps.data(), pn.data(), (int)cnt, ncorr, dt, cutoff, a.data(), v.data(),
-                                                  r.data());
-        if (st != 0) return st;
-        for (size_t i = 0; i < cnt; ++i) {
-            if (acf) memcpy(acf + (size_t)idx[i] * ncorr, a.data() + i * (size_t)ncorr, (size_t)ncorr * 8);
-            if (vacf) memcpy(vacf + (size_t)idx[i] * ncorr, v.data() + i * (size_t)ncorr, (size_t)ncorr * 8);
-            if (result) result[idx[i]] = r[i];
-        }
-        return 0;
-    });
-    cudaSetDevice(home);
-    return rc;
-}
-
-// viscosity.cpp:197-215 on up to `ngpus` devices (components sharded, or time blocks + all-reduce when there are
-// fewer components than devices); integrals and eta as acfb200_green_kubo.
-int acfb200_multi_gpu_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t ncorr, double dt,
-                                 double box_length, double temperature, double* acf, double* integrals, double* eta,
-                                 int ngpus)
-{
-    if (!comps || ncomp < 1 || !acf) {
-        set_error("multi_gpu_green_kubo: null argument or ncomp < 1");
-        return ACFB200_ERR_ARG;
-    }
-    std::vector<int64_t> lens(ncomp, n);
-    ACF_TRY(acfb200_multi_gpu_calc_correlation(comps, lens.data(), ncomp, ncorr, acf, ngpus));
-    const double kB = 1.38064852E-23;
-    for (int c = 0; c < ncomp; ++c) {
-        double I = 0.0;
-        ACF_TRY(acfb200_integrate_corr(acf + (size_t)c * ncorr, ncorr, dt, &I));
-        if (integrals) integrals[c] = I;
-        if (eta) eta[c] = box_length * box_length * box_length / (kB * temperature) * I * 1E-30 * 1E-15 * 1E10;
-    }
-    return 0;
-}
-
 // -------------------------------------------------------------------------------------------------
 // measurement
-// Trajectories spread over the devices of this box, trajectory t on device t mod G; no communication.
-int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, const double* const* y, const double* const* z,
-                                           const int64_t* n, int ntraj, int64_t stride, int64_t max_s, double dt,
-                                           double cell, int imaging, double* msd, int32_t* counter,
-                                           acfb200_msd_result* result, int ngpus)
-{
-    if (!x || !y || !z || !n || ntraj < 1) {
-        set_error("multi_gpu_traj2diffusion_batch: null argument or ntraj < 1");
-        return ACFB200_ERR_ARG;
-    }
-    int ndev = usable_devices(ngpus);
-    if (ndev < 1) return ACFB200_ERR_CUDA;
-    if (ndev > ntraj) ndev = ntraj;
-    int home = 0;
-    cudaGetDevice(&home);
-    const int rc = for_each_device(ndev, [&](int d) -> int {
-        std::vector<const double*> px, py, pz;
-        std::vector<int64_t> pn;
-        std::vector<int> idx;
-        for (int t = d; t < ntraj; t += ndev) {
-            px.push_back(x[t]);
-            py.push_back(y[t]);
-            pz.push_back(z[t]);
-            pn.push_back(n[t]);
-            idx.push_back(t);
-        }
-        const size_t cnt = idx.size();
-        std::vector<double> m(cnt * (size_t)max_s);
-        std::vector<int32_t> c(cnt * (size_t)max_s);
-        std::vector<acfb200_msd_result> r(cnt);
-        const int st = acfb200_traj2diffusion_batch(px.data(), py.data(), pz.data(), pn.data(), (int)cnt, stride, max_s, dt,
-                                                    cell, imaging, m.data(), c.data(), r.data());
-        if (st != 0) return st;
-        for (size_t i = 0; i < cnt; ++i) {
-            if (msd) memcpy(msd + (size_t)idx[i] * max_s, m.data() + i * (size_t)max_s, (size_t)max_s * 8);
-            if (counter) memcpy(counter + (size_t)idx[i] * max_s, c.data() + i * (size_t)max_s, (size_t)max_s * 4);
-            if (result) result[idx[i]] = r[i];
-        }
-        return 0;
-    });
-    cudaSetDevice(home);
-    return rc;
-}
-
 // -------------------------------------------------------------------------------------------------
 int acfb200_measure_dfma_peak(double* tflops, double* effective_sm_mhz)
 {

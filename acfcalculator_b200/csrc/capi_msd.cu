@@ -1,0 +1,366 @@
+// C ABI of the traj2diffusion path (include/acf_b200.h): MSD, imaging, slope, the batched and device-resident forms.
+#include "capi_internal.cuh"
+
+using namespace acfb200;
+
+// -------------------------------------------------------------------------------------------------
+// traj2diffusion: mean-square displacement (traj2diffusion.cpp:497-552)
+// -------------------------------------------------------------------------------------------------
+
+namespace acfb200 {
+
+static int check_msd_args(const void* x, const void* y, const void* z, long long n, long long stride, long long max_s,
+                          const char* what)
+{
+    if (!x || !y || !z) {
+        set_error("%s: null coordinate array", what);
+        return ACFB200_ERR_ARG;
+    }
+    if (n < 1 || max_s < 1) {
+        set_error("%s: need n >= 1 and max_s >= 1 (got n=%lld, max_s=%lld)", what, n, max_s);
+        return ACFB200_ERR_ARG;
+    }
+    if (stride < 1) {  // the reference loops forever on stride 0 (traj2diffusion.cpp:530)
+        set_error("%s: stride must be >= 1 (got %lld)", what, stride);
+        return ACFB200_ERR_ARG;
+    }
+    if (n > 2147483647ll) {  // msd_counter is an int in the reference (:373) and in this ABI
+        set_error("%s: at most 2^31-1 frames (got %lld)", what, n);
+        return ACFB200_ERR_ARG;
+    }
+    return 0;
+}
+
+// Displacement sums of ntraj device-resident trajectories -> msd[ntraj][max_s], counter[ntraj][max_s] (device), one
+// launch over all axes of all trajectories.  axes[3*t + a] is coordinate a of trajectory t; when every trajectory
+// passes one array three times (the general reader's y = z = x) each is computed once.  Unit stride runs the tiled
+// displacement kernel (the direct-lag kernel's geometry), larger strides the per-lag strided kernel.
+static int msd_batch_device(Workspace* ws, const double* const* axes, const long long* n, int ntraj, long long stride,
+                            long long max_s, double* d_msd, int* d_counter, cudaStream_t st)
+{
+    bool one_axis = true;
+    long long n_max = 1;
+    for (int t = 0; t < ntraj; ++t) {
+        one_axis = one_axis && axes[3 * t] == axes[3 * t + 1] && axes[3 * t + 1] == axes[3 * t + 2];
+        if (n[t] > n_max) n_max = n[t];
+    }
+    const int per = one_axis ? 1 : 3, ns = per * ntraj;
+    std::vector<SeriesDesc> descs(ns);
+    for (int t = 0; t < ntraj; ++t)
+        for (int a = 0; a < per; ++a) descs[per * t + a] = {axes[3 * t + a], n[t], n[t]};
+    DirectPlan plan;
+    if (stride == 1) {
+        ACF_TRY(plan_direct(n_max, max_s, ns, ws->sm_count, -1, &plan, true));
+        if (plan.mode != 0) {
+            set_error("msd: the displacement kernel needs a tiled plan (unset ACFB200_MODE)");
+            return ACFB200_ERR_ARG;
+        }
+    } else {
+        ACF_TRY(plan_msd_strided(n_max, stride, max_s, ws->sm_count, &plan));
+    }
+    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)ns));
+    ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, ns) * sizeof(double)));
+    ACF_TRY(ws->out.ensure((size_t)ns * max_s * 8));
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * (size_t)ns, cudaMemcpyHostToDevice, st));
+    if (stride == 1)
+        ACF_TRY(launch_direct_msd(plan, ws->desc.as<SeriesDesc>(), ns, max_s, ws->partials.as<double>(), st));
+    else
+        ACF_TRY(launch_msd_strided(plan, ws->desc.as<SeriesDesc>(), ns, stride, max_s, ws->partials.as<double>(), st));
+    ACF_TRY(launch_reduce_partials(plan, ws->desc.as<SeriesDesc>(), ns, max_s, ws->partials.as<double>(),
+                                   ws->out.as<double>(), 0, st));
+    ACF_TRY(launch_msd_finalize(ws->out.as<double>(), ws->desc.as<SeriesDesc>(), per, ntraj, stride, max_s, d_msd,
+                                d_counter, st));
+    g_launches += 3;
+    return 0;
+}
+
+static int msd_device(Workspace* ws, const double* d_x, const double* d_y, const double* d_z, long long n,
+                      long long stride, long long max_s, double* d_msd, int* d_counter, cudaStream_t st)
+{
+    const double* axes[3] = {d_x, d_y, d_z};
+    return msd_batch_device(ws, axes, &n, 1, stride, max_s, d_msd, d_counter, st);
+}
+
+// Upload three host coordinate arrays (once if they are the same array) into ws->series; d[] receives the device pointers.
+static int upload_axes(Workspace* ws, const double* x, const double* y, const double* z, long long n, const double* d[3],
+                       cudaStream_t st)
+{
+    const bool one_axis = (x == y && y == z);
+    const size_t pitch = even_up(n);
+    ACF_TRY(ws->series.ensure((one_axis ? 1 : 3) * pitch * 8));
+    double* base = ws->series.as<double>();
+    const double* h[3] = {x, y, z};
+    for (int a = 0; a < 3; ++a) {
+        if (one_axis && a > 0) {
+            d[a] = base;
+            continue;
+        }
+        ACF_CUDA_OK(cudaMemcpyAsync(base + a * pitch, h[a], (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        d[a] = base + a * pitch;
+    }
+    return 0;
+}
+
+// image() on three device arrays into ws->y; d_out[] receives the unwrapped arrays
+static int image_to_workspace(Workspace* ws, const double* const d_in[3], long long n, double cell, double* d_out[3],
+                              cudaStream_t st)
+{
+    const size_t pitch = even_up(n);
+    ACF_TRY(ws->y.ensure(3 * pitch * 8));
+    ACF_TRY(ws->vel.ensure(image_workspace_bytes(n)));
+    for (int a = 0; a < 3; ++a) d_out[a] = ws->y.as<double>() + a * pitch;
+    const int launches = launch_image(d_in, d_out, n, cell, ws->vel.p, st);
+    if (launches < 0) return ACFB200_ERR_CUDA;
+    g_launches += launches;
+    return 0;
+}
+
+}  // namespace acfb200
+
+extern "C" {
+
+int acfb200_msd_device(const double* d_x, const double* d_y, const double* d_z, int64_t n, int64_t stride, int64_t max_s,
+                       double* d_msd, int32_t* d_counter, void* stream)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_msd_args(d_x, d_y, d_z, n, stride, max_s, "msd_device"));
+    if (!d_msd) {
+        set_error("msd_device: null output");
+        return ACFB200_ERR_ARG;
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    return msd_device(ws, d_x, d_y, d_z, n, stride, max_s, d_msd, d_counter, (cudaStream_t)stream);
+}
+
+int acfb200_image_device(const double* d_x, const double* d_y, const double* d_z, int64_t n, double cell, double* d_xo,
+                         double* d_yo, double* d_zo, void* stream)
+{
+    Lock lk(g_mu);
+    if (!d_x || !d_y || !d_z || !d_xo || !d_yo || !d_zo || n < 1) {
+        set_error("image_device: null argument or n < 1");
+        return ACFB200_ERR_ARG;
+    }
+    if (d_xo == d_x || d_yo == d_y || d_zo == d_z) {
+        set_error("image_device: outputs must not alias the inputs (every frame reads its predecessor)");
+        return ACFB200_ERR_ARG;
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    ACF_TRY(ws->vel.ensure(image_workspace_bytes(n)));
+    const double* in[3] = {d_x, d_y, d_z};
+    double* out[3] = {d_xo, d_yo, d_zo};
+    const int launches = launch_image(in, out, n, cell, ws->vel.p, (cudaStream_t)stream);
+    if (launches < 0) return ACFB200_ERR_CUDA;
+    g_launches += launches;
+    return 0;
+}
+
+int acfb200_msd(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s, double* msd,
+                int32_t* counter)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_msd_args(x, y, z, n, stride, max_s, "msd"));
+    if (!msd) {
+        set_error("msd: null output");
+        return ACFB200_ERR_ARG;
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    cudaStream_t st = ws->stream;
+    const double* d[3];
+    ACF_TRY(upload_axes(ws, x, y, z, n, d, st));
+    ACF_TRY(ws->small.ensure((size_t)max_s * 12 + 64));
+    double* d_msd = ws->small.as<double>();
+    int* d_cnt = reinterpret_cast<int*>(d_msd + max_s);
+    ACF_TRY(msd_device(ws, d[0], d[1], d[2], n, stride, max_s, d_msd, d_cnt, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)max_s * 8, cudaMemcpyDeviceToHost, st));
+    if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)max_s * 4, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int acfb200_image(double* x, double* y, double* z, int64_t n, double cell)
+{
+    Lock lk(g_mu);
+    if (!x || !y || !z || n < 1) {
+        set_error("image: null argument or n < 1");
+        return ACFB200_ERR_ARG;
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    cudaStream_t st = ws->stream;
+    // three distinct device copies even when the host arrays coincide: every axis is written separately
+    const size_t pitch = even_up(n);
+    ACF_TRY(ws->series.ensure(3 * pitch * 8));
+    double* h[3] = {x, y, z};
+    const double* d_in[3];
+    for (int a = 0; a < 3; ++a) {
+        double* dst = ws->series.as<double>() + a * pitch;
+        ACF_CUDA_OK(cudaMemcpyAsync(dst, h[a], (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        d_in[a] = dst;
+    }
+    double* d_out[3];
+    ACF_TRY(image_to_workspace(ws, d_in, n, cell, d_out, st));
+    for (int a = 0; a < 3; ++a) {
+        if (a > 0 && (h[a] == h[0] || h[a] == h[a - 1])) continue;  // same host array: one copy back is enough
+        ACF_CUDA_OK(cudaMemcpyAsync(h[a], d_out[a], (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int acfb200_msd_slope(const double* msd, int64_t n, double* slope, double* sum)
+{
+    Lock lk(g_mu);
+    if (!msd || n < 1) {
+        set_error("msd_slope: null argument or n < 1");
+        return ACFB200_ERR_ARG;
+    }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    cudaStream_t st = ws->stream;
+    ACF_TRY(ws->small.ensure((size_t)n * 8 + 64));
+    double* d_msd = ws->small.as<double>() + 2;
+    ACF_CUDA_OK(cudaMemcpyAsync(d_msd, msd, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    ACF_TRY(launch_msd_slope(d_msd, n, 1, ws->small.as<double>(), st));
+    g_launches += 1;
+    double h[2];
+    ACF_CUDA_OK(cudaMemcpyAsync(h, ws->small.p, 16, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
+    if (sum) *sum = h[0];
+    if (slope) *slope = h[1];
+    return 0;
+}
+
+int acfb200_traj2diffusion(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s,
+                           double dt, double cell, int imaging, double* msd, int32_t* counter,
+                           acfb200_msd_result* result)
+{
+    Lock lk(g_mu);
+    ACF_TRY(check_msd_args(x, y, z, n, stride, max_s, "traj2diffusion"));
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    cudaStream_t st = ws->stream;
+    const double* d[3];
+    if (imaging) {
+        const size_t pitch = even_up(n);
+        ACF_TRY(ws->series.ensure(3 * pitch * 8));
+        const double* h[3] = {x, y, z};
+        const double* d_in[3];
+        for (int a = 0; a < 3; ++a) {
+            double* dst = ws->series.as<double>() + a * pitch;
+            ACF_CUDA_OK(cudaMemcpyAsync(dst, h[a], (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            d_in[a] = dst;
+        }
+        double* d_out[3];
+        ACF_TRY(image_to_workspace(ws, d_in, n, cell, d_out, st));
+        for (int a = 0; a < 3; ++a) d[a] = d_out[a];
+    } else {
+        ACF_TRY(upload_axes(ws, x, y, z, n, d, st));
+    }
+    ACF_TRY(ws->small.ensure((size_t)max_s * 12 + 64 + 16));
+    double* d_sl = ws->small.as<double>();  // [sum, slope]
+    double* d_msd = d_sl + 2;
+    int* d_cnt = reinterpret_cast<int*>(d_msd + max_s);
+    ACF_TRY(msd_device(ws, d[0], d[1], d[2], n, stride, max_s, d_msd, d_cnt, st));
+    ACF_TRY(launch_msd_slope(d_msd, max_s, 1, d_sl, st));
+    g_launches += 1;
+    double h[2];
+    if (msd) ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)max_s * 8, cudaMemcpyDeviceToHost, st));
+    if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)max_s * 4, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(h, d_sl, 16, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
+    if (result) {
+        result->sum = h[0];
+        result->slope = h[1];
+        const double space_series = dt * (double)stride;      // traj2diffusion.cpp:497 (double * int)
+        result->diffusivity = h[1] / space_series / 6.0;       // :549
+        result->nframes = n;
+    }
+    return 0;
+}
+
+
+// main() of traj2diffusion for ntraj trajectories in one go (the "many umbrella windows" use of the program): every
+// trajectory is uploaded (and unwrapped, if asked) on the device, ONE displacement launch covers all axes of all
+// trajectories, one launch each finalises, and takes the slopes of, all MSD curves.
+int acfb200_traj2diffusion_batch(const double* const* x, const double* const* y, const double* const* z, const int64_t* n,
+                                 int ntraj, int64_t stride, int64_t max_s, double dt, double cell, int imaging,
+                                 double* msd, int32_t* counter, acfb200_msd_result* result)
+{
+    Lock lk(g_mu);
+    if (!x || !y || !z || !n || ntraj < 1) {
+        set_error("traj2diffusion_batch: null argument or ntraj < 1");
+        return ACFB200_ERR_ARG;
+    }
+    size_t total = 0;
+    bool aliased = !imaging;
+    for (int t = 0; t < ntraj; ++t) {
+        ACF_TRY(check_msd_args(x[t], y[t], z[t], n[t], stride, max_s, "traj2diffusion_batch"));
+        aliased = aliased && x[t] == y[t] && y[t] == z[t];
+    }
+    for (int t = 0; t < ntraj; ++t) total += (aliased ? 1 : 3) * even_up(n[t]);
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    cudaStream_t st = ws->stream;
+    ACF_TRY(ws->series.ensure(total * 8));
+    if (imaging) {
+        long long n_max = 1;
+        for (int t = 0; t < ntraj; ++t) n_max = n[t] > n_max ? n[t] : n_max;
+        ACF_TRY(ws->y.ensure(total * 8));
+        ACF_TRY(ws->vel.ensure(image_workspace_bytes(n_max)));  // reused trajectory after trajectory (stream order)
+    }
+    std::vector<const double*> axes(3 * (size_t)ntraj);
+    std::vector<long long> len(ntraj);
+    size_t off = 0;
+    for (int t = 0; t < ntraj; ++t) {
+        len[t] = n[t];
+        const double* h[3] = {x[t], y[t], z[t]};
+        const size_t pitch = even_up(n[t]);
+        const double* d_in[3];
+        for (int a = 0; a < 3; ++a) {
+            if (aliased && a > 0) {
+                d_in[a] = d_in[0];
+                continue;
+            }
+            double* dst = ws->series.as<double>() + off + a * pitch;
+            ACF_CUDA_OK(cudaMemcpyAsync(dst, h[a], (size_t)n[t] * 8, cudaMemcpyHostToDevice, st));
+            d_in[a] = dst;
+        }
+        if (imaging) {
+            double* d_out[3];
+            for (int a = 0; a < 3; ++a) d_out[a] = ws->y.as<double>() + off + a * pitch;
+            const int launches = launch_image(d_in, d_out, n[t], cell, ws->vel.p, st);
+            if (launches < 0) return ACFB200_ERR_CUDA;
+            g_launches += launches;
+            for (int a = 0; a < 3; ++a) axes[3 * t + a] = d_out[a];
+        } else {
+            for (int a = 0; a < 3; ++a) axes[3 * t + a] = d_in[a];
+        }
+        off += (aliased ? 1 : 3) * pitch;
+    }
+    const size_t curve = (size_t)max_s;
+    ACF_TRY(ws->small.ensure((size_t)ntraj * (curve * 12 + 16) + 64));
+    double* d_sl = ws->small.as<double>();                 // [ntraj][sum, slope]
+    double* d_msd = d_sl + 2 * (size_t)ntraj;               // [ntraj][max_s]
+    int* d_cnt = reinterpret_cast<int*>(d_msd + (size_t)ntraj * curve);
+    ACF_TRY(msd_batch_device(ws, axes.data(), len.data(), ntraj, stride, max_s, d_msd, d_cnt, st));
+    ACF_TRY(launch_msd_slope(d_msd, max_s, ntraj, d_sl, st));
+    g_launches += 1;
+    std::vector<double> h_sl(2 * (size_t)ntraj);
+    if (msd) ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)ntraj * curve * 8, cudaMemcpyDeviceToHost, st));
+    if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)ntraj * curve * 4, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(h_sl.data(), d_sl, h_sl.size() * 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
+    if (result)
+        for (int t = 0; t < ntraj; ++t) {
+            result[t].sum = h_sl[2 * t];
+            result[t].slope = h_sl[2 * t + 1];
+            result[t].diffusivity = h_sl[2 * t + 1] / (dt * (double)stride) / 6.0;  // traj2diffusion.cpp:497, :549
+            result[t].nframes = n[t];
+        }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// C ABI, multi-GPU entry points (include/acf_b200.h): one host thread per device inside this process; series /
+// windows / trajectories shard with no communication, long series are cut into time blocks whose lag sums are
+// combined with one ncclAllReduce (NCCL resolved with dlopen so single-GPU users do not need it).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <thread>
+
+#include "capi_internal.cuh"
+
+using namespace acfb200;
+
+// -------------------------------------------------------------------------------------------------
+// multi-GPU entry points: one host thread per device inside this process
+// -------------------------------------------------------------------------------------------------
+
+namespace {
+
+// NCCL is resolved at run time (dlopen) so that single-GPU users do not need the library at all.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::vector<ncclComm_t> comms;  // communicator clique over devices 0..n-1
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int nccl_clique(int ndev, NcclApi** out)
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (!g_nccl.lib) {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.lib) break;
+        }
+        if (!g_nccl.lib) {
+            set_error("time-block sharding needs NCCL and libnccl.so.2 could not be loaded: %s", dlerror());
+            return ACFB200_ERR_CUDA;
+        }
+        g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))dlsym(g_nccl.lib, "ncclCommInitAll");
+        g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+        g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+        g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+        if (!g_nccl.CommInitAll || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
+            set_error("libnccl.so.2 lacks a required symbol");
+            return ACFB200_ERR_CUDA;
+        }
+    }
+    if ((int)g_nccl.comms.size() != ndev) {
+        for (ncclComm_t c : g_nccl.comms) g_nccl.CommDestroy(c);
+        g_nccl.comms.assign(ndev, nullptr);
+        std::vector<int> devs(ndev);
+        for (int d = 0; d < ndev; ++d) devs[d] = d;
+        const ncclResult_t r = g_nccl.CommInitAll(g_nccl.comms.data(), ndev, devs.data());
+        if (r != ncclSuccess) {
+            set_error("ncclCommInitAll(%d devices) failed: %s", ndev, g_nccl.GetErrorString(r));
+            g_nccl.comms.clear();
+            return ACFB200_ERR_CUDA;
+        }
+    }
+    *out = &g_nccl;
+    return 0;
+}
+
+int usable_devices(int requested)
+{
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess) {
+        cudaGetLastError();
+        have = 0;
+    }
+    if (requested <= 0 || requested > have) requested = have;
+    return requested;
+}
+
+// Runs fn(device) on one host thread per device; returns the first non-zero status with its message.
+template <class F>
+int for_each_device(int ndev, F fn)
+{
+    std::vector<int> rc(ndev, 0);
+    std::vector<std::string> msg(ndev);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; ++d)
+        th.emplace_back([&, d]() {
+            if (cudaSetDevice(d) != cudaSuccess) {
+                rc[d] = ACFB200_ERR_CUDA;
+                msg[d] = "cudaSetDevice failed";
+                return;
+            }
+            rc[d] = fn(d);
+            if (rc[d] != 0) msg[d] = last_error();
+        });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < ndev; ++d)
+        if (rc[d] != 0) {
+            set_error("device %d: %s", d, msg[d].c_str());
+            return rc[d];
+        }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// calcCorrelation of nseries host series on up to `ngpus` devices of this box:
+//   nseries >= devices : series s on device s mod G, no communication at all;
+//   fewer series       : every series is cut into G time blocks, device g gets block g plus its (ncorr-1)-sample halo,
+//                        computes the raw lag sums of its block, ONE ncclAllReduce(sum, double, nseries*ncorr) over
+//                        NVLink combines them, device 0 divides by (n-k) (ACFcalculator.cpp:139-143 after the sum).
+int acfb200_multi_gpu_calc_correlation(const double* const* y, const int64_t* n, int nseries, int64_t ncorr, double* corr,
+                                       int ngpus)
+{
+    if (!y || !n || !corr || nseries < 1 || ncorr < 1) {
+        set_error("multi_gpu_calc_correlation: null argument, nseries < 1 or ncorr < 1");
+        return ACFB200_ERR_ARG;
+    }
+    const int ndev = usable_devices(ngpus);
+    if (ndev < 1) {
+        set_error("no usable CUDA device; libacf_b200 has no CPU path");
+        return ACFB200_ERR_CUDA;
+    }
+    if (ndev == 1) return acfb200_calc_correlation_batch(y, n, nseries, ncorr, corr);
+    int home = 0;
+    cudaGetDevice(&home);
+    int rc;
+    if (nseries >= ndev) {
+        rc = for_each_device(ndev, [&](int d) -> int {
+            std::vector<const double*> py;
+            std::vector<int64_t> pn;
+            std::vector<int> idx;
+            for (int s = d; s < nseries; s += ndev) {
+                py.push_back(y[s]);
+                pn.push_back(n[s]);
+                idx.push_back(s);
+            }
+            std::vector<double> out(py.size() * (size_t)ncorr);
+            const int r = acfb200_calc_correlation_batch(py.data(), pn.data(), (int)py.size(), ncorr, out.data());
+            if (r != 0) return r;
+            for (size_t i = 0; i < idx.size(); ++i)
+                memcpy(corr + (size_t)idx[i] * ncorr, out.data() + i * (size_t)ncorr, (size_t)ncorr * 8);
+            return 0;
+        });
+    } else {
+        for (int s = 0; s < nseries; ++s)
+            if (n[s] < 1) {
+                set_error("series %d is empty", s);
+                return ACFB200_ERR_ARG;
+            }
+        NcclApi* nccl = nullptr;
+        ACF_TRY(nccl_clique(ndev, &nccl));
+        rc = for_each_device(ndev, [&](int d) -> int {
+            Lock lk(g_mu);
+            Workspace* ws;
+            ACF_TRY(get_ws(&ws));
+            cudaStream_t st = ws->stream;
+            // block + halo of every series, back to back
+            std::vector<SeriesDesc> descs(nseries);
+            size_t total = 0;
+            std::vector<long long> lo(nseries), len(nseries);
+            for (int s = 0; s < nseries; ++s) {
+                const long long b = n[s] * d / ndev, e = n[s] * (d + 1) / ndev;
+                long long reach = e + ncorr - 1;
+                if (reach > n[s]) reach = n[s];
+                lo[s] = b;
+                len[s] = reach - b;
+                total += even_up(len[s] > 0 ? len[s] : 1);
+            }
+            ACF_TRY(ws->series.ensure(total * 8));
+            ACF_TRY(ws->out.ensure((size_t)nseries * ncorr * 8));
+            size_t off = 0;
+            for (int s = 0; s < nseries; ++s) {
+                double* dst = ws->series.as<double>() + off;
+                const long long e = n[s] * (d + 1) / ndev;
+                if (len[s] > 0)
+                    ACF_CUDA_OK(cudaMemcpyAsync(dst, y[s] + lo[s], (size_t)len[s] * 8, cudaMemcpyHostToDevice, st));
+                descs[s] = {dst, len[s] > 0 ? len[s] : 0, e - lo[s]};
+                off += even_up(len[s] > 0 ? len[s] : 1);
+            }
+            double* d_sums = ws->out.as<double>();
+            ACF_TRY(run_direct(ws, descs, ncorr, d_sums, 0, st));
+            const ncclResult_t r = nccl->AllReduce(d_sums, d_sums, (size_t)nseries * ncorr, ncclDouble, ncclSum,
+                                                   nccl->comms[d], st);
+            if (r != ncclSuccess) {
+                set_error("ncclAllReduce failed: %s", nccl->GetErrorString(r));
+                return ACFB200_ERR_CUDA;
+            }
+            if (d == 0) {
+                for (int s = 0; s < nseries; ++s) {
+                    ACF_TRY(launch_normalise(d_sums + (size_t)s * ncorr, n[s], ncorr, d_sums + (size_t)s * ncorr, st));
+                    g_launches += 1;
+                }
+                ACF_CUDA_OK(cudaMemcpyAsync(corr, d_sums, (size_t)nseries * ncorr * 8, cudaMemcpyDeviceToHost, st));
+            }
+            ACF_CUDA_OK(cudaStreamSynchronize(st));
+            return 0;
+        });
+    }
+    cudaSetDevice(home);
+    return rc;
+}
+
+// setup.sh-style windows on up to `ngpus` devices: window w on device w mod G, full pipeline per window, no
+// communication (acf/vacf [nwindows][ncorr], result [nwindows], as acfb200_acf_pipeline_batch).
+int acfb200_multi_gpu_pipeline_batch(const double* const* series, const int64_t* n, int nwindows, int64_t ncorr, double dt,
+                                     double cutoff, double* acf, double* vacf, acfb200_result* result, int ngpus)
+{
+    if (!series || !n || nwindows < 1) {
+        set_error("multi_gpu_pipeline_batch: null argument or nwindows < 1");
+        return ACFB200_ERR_ARG;
+    }
+    int ndev = usable_devices(ngpus);
+    if (ndev > nwindows) ndev = nwindows;
+    if (ndev < 1) {
+        set_error("no usable CUDA device; libacf_b200 has no CPU path");
+        return ACFB200_ERR_CUDA;
+    }
+    if (ndev == 1) return acfb200_acf_pipeline_batch(series, n, nwindows, ncorr, dt, cutoff, acf, vacf, result);
+    int home = 0;
+    cudaGetDevice(&home);
+    const int rc = for_each_device(ndev, [&](int d) -> int {
+        std::vector<const double*> ps;
+        std::vector<int64_t> pn;
+        std::vector<int> idx;
+        for (int w = d; w < nwindows; w += ndev) {
+            ps.push_back(series[w]);
+            pn.push_back(n[w]);
+            idx.push_back(w);
+        }
+        const size_t cnt = ps.size();
+        std::vector<double> a(cnt * (size_t)ncorr), v(cnt * (size_t)ncorr);
+        std::vector<acfb200_result> r(cnt);
+        const int st = acfb200_acf_pipeline_batch(ps.data(), pn.data(), (int)cnt, ncorr, dt, cutoff, a.data(), v.data(),
+                                                  r.data());
+        if (st != 0) return st;
+        for (size_t i = 0; i < cnt; ++i) {
+            if (acf) memcpy(acf + (size_t)idx[i] * ncorr, a.data() + i * (size_t)ncorr, (size_t)ncorr * 8);
+            if (vacf) memcpy(vacf + (size_t)idx[i] * ncorr, v.data() + i * (size_t)ncorr, (size_t)ncorr * 8);
+            if (result) result[idx[i]] = r[i];
+        }
+        return 0;
+    });
+    cudaSetDevice(home);
+    return rc;
+}
+
+// viscosity.cpp:197-215 on up to `ngpus` devices (components sharded, or time blocks + all-reduce when there are
+// fewer components than devices); integrals and eta as acfb200_green_kubo.
+int acfb200_multi_gpu_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t ncorr, double dt,
+                                 double box_length, double temperature, double* acf, double* integrals, double* eta,
+                                 int ngpus)
+{
+    if (!comps || ncomp < 1 || !acf) {
+        set_error("multi_gpu_green_kubo: null argument or ncomp < 1");
+        return ACFB200_ERR_ARG;
+    }
+    std::vector<int64_t> lens(ncomp, n);
+    ACF_TRY(acfb200_multi_gpu_calc_correlation(comps, lens.data(), ncomp, ncorr, acf, ngpus));
+    const double kB = 1.38064852E-23;
+    for (int c = 0; c < ncomp; ++c) {
+        double I = 0.0;
+        ACF_TRY(acfb200_integrate_corr(acf + (size_t)c * ncorr, ncorr, dt, &I));
+        if (integrals) integrals[c] = I;
+        if (eta) eta[c] = box_length * box_length * box_length / (kB * temperature) * I * 1E-30 * 1E-15 * 1E10;
+    }
+    return 0;
+}
+
+// Trajectories spread over the devices of this box, trajectory t on device t mod G; no communication.
+int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, const double* const* y, const double* const* z,
+                                           const int64_t* n, int ntraj, int64_t stride, int64_t max_s, double dt,
+                                           double cell, int imaging, double* msd, int32_t* counter,
+                                           acfb200_msd_result* result, int ngpus)
+{
+    if (!x || !y || !z || !n || ntraj < 1) {
+        set_error("multi_gpu_traj2diffusion_batch: null argument or ntraj < 1");
+        return ACFB200_ERR_ARG;
+    }
+    int ndev = usable_devices(ngpus);
+    if (ndev < 1) return ACFB200_ERR_CUDA;
+    if (ndev > ntraj) ndev = ntraj;
+    int home = 0;
+    cudaGetDevice(&home);
+    const int rc = for_each_device(ndev, [&](int d) -> int {
+        std::vector<const double*> px, py, pz;
+        std::vector<int64_t> pn;
+        std::vector<int> idx;
+        for (int t = d; t < ntraj; t += ndev) {
+            px.push_back(x[t]);
+            py.push_back(y[t]);
+            pz.push_back(z[t]);
+            pn.push_back(n[t]);
+            idx.push_back(t);
+        }
+        const size_t cnt = idx.size();
+        std::vector<double> m(cnt * (size_t)max_s);
+        std::vector<int32_t> c(cnt * (size_t)max_s);
+        std::vector<acfb200_msd_result> r(cnt);
+        const int st = acfb200_traj2diffusion_batch(px.data(), py.data(), pz.data(), pn.data(), (int)cnt, stride, max_s, dt,
+                                                    cell, imaging, m.data(), c.data(), r.data());
+        if (st != 0) return st;
+        for (size_t i = 0; i < cnt; ++i) {
+            if (msd) memcpy(msd + (size_t)idx[i] * max_s, m.data() + i * (size_t)max_s, (size_t)max_s * 8);
+            if (counter) memcpy(counter + (size_t)idx[i] * max_s, c.data() + i * (size_t)max_s, (size_t)max_s * 4);
+            if (result) result[idx[i]] = r[i];
+        }
+        return 0;
+    });
+    cudaSetDevice(home);
+    return rc;
+}
+
+}  // extern "C"
