@@ -104,8 +104,8 @@ int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long long nc
                 eligible = false;
                 break;
             }
-            t_direct += (double)d.n * (double)ncorr / 1.5e13;            // measured direct-lag rate (lag-products/s)
-            t_fft += (8.0 * d.n + 64.0 * (double)L) / 3.5e12 + 4.0e-5;  // measured FFT-path HBM rate + launches
+            t_direct += (double)d.n * (double)ncorr / 1.6e13;            // measured direct-lag rate (lag-products/s)
+            t_fft += (8.0 * d.n + 64.0 * (double)L) / 4.2e12 + 4.0e-5;  // measured FFT-path HBM rate + launches
         }
         if (eligible && (g_method == 1 || t_fft < t_direct)) {
             // Batches: series of one length whose addresses form an arithmetic progression go out as one set of
