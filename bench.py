@@ -435,8 +435,8 @@ def run_native(args):
             "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf,
             # DRAM bytes of one direct_lag_kernel launch from the committed ncu capture of this command
-            # (profiles/r1d_direct_lag_ncu_raw.csv: 80.69 MB read + 11.15 MB written); irrelevant to an FP64-bound kernel
-            "traffic": 91.83e6 if (args.workload == "ou" and n == 10**7 and m == 10**4) else None,
+            # (profiles/r1e_direct_lag_ncu_raw.csv: 80.25 MB read + 16.01 MB written); irrelevant to an FP64-bound kernel
+            "traffic": 96.26e6 if (args.workload == "ou" and n == 10**7 and m == 10**4) else None,
             "peak_source": "DFMA-chain micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
             "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS, "nominal_peak": FP64_NOMINAL_TFLOPS,
             "kernel": "direct_lag_kernel (step time includes the ~us reduce_partials epilogue)",
