@@ -4,8 +4,9 @@
 // (/root/reference/ACFcalculator.cpp:125-137, viscosity.cpp:50-62); the divide by (n-k)
 // (ACFcalculator.cpp:139-143) is the reduce_partials / normalise epilogue below.
 //
-// Bound: the FP64 pipe (64 DFMA/clk/SM).  HBM is irrelevant (8 B loaded per 2*ncorr flops), so the
-// design problem is feeding DFMAs from shared memory at < 1 LDS per ~9 DFMAs:
+// Bound: the FP64 pipe (64 DFMA/clk/SM).  HBM is irrelevant (8 B loaded per 2*ncorr flops); the design
+// problem is feeding DFMAs with as few register writes as possible -- a full-rate DFMA stream saturates
+// the register-file write port, so every loaded double costs it cycles:
 //   * a CTA stages two contiguous pieces of x with TMA bulk copies (cp.async.bulk, one elected
 //     thread, mbarrier completion): the tile x[it, it+TI) and the shifted piece
 //     x[it+K0, it+K0+TI+lag_span) -- the "tile + maxcorr-wide halo".
@@ -312,7 +313,7 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
         return 1;
     }
 
-    // ---- streaming kernel: default; a forced variant index >= kNumVariants selects one explicitly -------
+    // ---- streaming kernel (direct_stream.cu): only when a variant index >= kNumVariants or ACFB200_MODE=1 asks for it
     // mode 0 (tiled CTAs) is the default: measured faster than the streaming form
     const int mode = env_int("ACFB200_MODE", fv >= kNumVariants ? 1 : 0);
     if (mode == 1) {
