@@ -48,6 +48,7 @@ SIGNATURES = {
     "acfb200_set_device": (C.c_int, [C.c_int]),
     "acfb200_launch_count": (_I64, []),
     "acfb200_release": (C.c_int, []),
+    "acfb200_warmup": (C.c_int, []),
     "acfb200_calc_correlation": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p]),
     "acfb200_calc_correlation_batch": (C.c_int, [_PP, _PI64, C.c_int, _I64, C.c_void_p]),
     "acfb200_variance": (C.c_int, [C.c_void_p, _I64, _P]),

@@ -293,6 +293,15 @@ int acfb200_set_device(int device)
 
 int64_t acfb200_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int acfb200_warmup(void)
+{
+    Lock lk(g_mu);
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    ACF_CUDA_OK(cudaStreamSynchronize(ws->stream));
+    return 0;
+}
+
 int acfb200_release(void)
 {
     std::lock_guard<std::mutex> table_lock(g_ws_mu);

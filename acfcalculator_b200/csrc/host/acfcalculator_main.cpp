@@ -16,6 +16,7 @@
 
 #include "../../../include/acf_b200.h"
 #include "fast_readers.hpp"
+#include "gpu_warmup.hpp"
 #include "gle.hpp"
 #include "options.hpp"
 #include "readers.hpp"
@@ -119,6 +120,7 @@ int main(int argc, char* argv[])
         return 1;
     }
 
+    GpuWarmup warm;  // the CUDA context comes up while the file is parsed
     std::vector<double> series;
     int num_samples = 0;
     char* fname_c = const_cast<char*>(fname.c_str());
@@ -151,6 +153,7 @@ int main(int argc, char* argv[])
     // ---- hot path on the GPU: mean, velocity, acf, vacf, var, varVel (ACFcalculator.cpp:712-725) ----
     std::vector<double> acf(ncorr > 0 ? ncorr : 0), vacf(ncorr > 0 ? ncorr : 0);
     acfb200_result res;
+    warm.wait();
     if (acfb200_acf_pipeline(series.data(), num_samples, ncorr, timestep, cutoff, acf.data(), vacf.data(), &res) !=
         ACFB200_OK)
         return gpu_failure("autocorrelation pipeline failed");

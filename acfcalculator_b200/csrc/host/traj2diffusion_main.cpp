@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../../include/acf_b200.h"
+#include "gpu_warmup.hpp"
 #include "options.hpp"
 #include "t2d_readers.hpp"
 
@@ -72,6 +73,7 @@ int main(int argc, char* argv[])
         return 1;
     }
 
+    GpuWarmup warm;  // the CUDA context comes up while the trajectory is parsed
     const Trajectory traj = namd ? read_traj_namd(traj_fname.c_str()) : read_traj_general(traj_fname.c_str());
     const int nframes = traj.frames();
     std::cout << "#" << nframes << std::endl;
@@ -88,6 +90,7 @@ int main(int argc, char* argv[])
         const double* x = traj.x.data();
         const double* y = traj.xyz_identical ? x : traj.y.data();
         const double* z = traj.xyz_identical ? x : traj.z.data();
+        warm.wait();
         const int rc = acfb200_traj2diffusion(x, y, z, nframes, stride, max_s, dt, L, imaging ? 1 : 0, msd.data(), nullptr,
                                               &res);
         if (rc != ACFB200_OK) {

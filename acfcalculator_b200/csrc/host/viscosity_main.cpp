@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../../include/acf_b200.h"
+#include "gpu_warmup.hpp"
 #include "readers.hpp"
 
 int main(int argc, char* argv[])
@@ -45,6 +46,7 @@ int main(int argc, char* argv[])
             return 1;
         }
     }
+    acfhost::GpuWarmup warm;  // the CUDA context comes up while the log is parsed
     int num_samples = 0;
     const std::vector<std::vector<double> > comps = acfhost::read_pressure_namd(fname, num_samples, quirk);
 
@@ -57,6 +59,7 @@ int main(int argc, char* argv[])
     }
     const int nc = (int)ptrs.size();
     std::vector<double> acf((size_t)nc * ncorr), integrals(nc), eta(nc);
+    warm.wait();
     const int rc = gpus == 1 ? acfb200_green_kubo(ptrs.data(), nc, num_samples, ncorr, timestep, box_length, temperature,
                                                   acf.data(), integrals.data(), eta.data())
                              : acfb200_multi_gpu_green_kubo(ptrs.data(), nc, num_samples, ncorr, timestep, box_length,

@@ -45,6 +45,9 @@ ACFB200_API int acfb200_device_count(int* count);
 ACFB200_API int acfb200_set_device(int device);
 /* kernels launched by this library since load (bench.py's "gpu_launches"). */
 ACFB200_API int64_t acfb200_launch_count(void);
+/* Create the CUDA context and the library's streams for the current device now instead of inside the first compute
+ * call (1-2 s on a multi-GPU box).  The front-ends call it from a helper thread while they parse their input. */
+ACFB200_API int acfb200_warmup(void);
 /* Release cached device/pinned workspaces. */
 ACFB200_API int acfb200_release(void);
 

@@ -44,6 +44,7 @@ int acfb200_traj2diffusion(const double* x, const double* y, const double* z, in
     return 0;
 }
 int acfb200_set_method(int) { return 0; }
+int acfb200_warmup(void) { return 0; }
 
 int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double dt, double cutoff, double* acf,
                          double* vacf, acfb200_result* r)
