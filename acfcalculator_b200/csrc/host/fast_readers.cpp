@@ -7,6 +7,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
 
 namespace acfhost {
@@ -20,13 +21,87 @@ struct Piece {
     bool ok = true;
 };
 
-// strtod on a NUL-terminated copy of [p, p+len): what atof(std::string(...).c_str()) evaluates
+// Decimal text -> double without strtod for the common case (Clinger's fast path): when the digit string is an
+// integer m <= 2^53 and the decimal exponent satisfies |e| <= 22, both m and 10^|e| are exact doubles and the single
+// IEEE multiplication or division rounds correctly -- the same bits strtod returns.  Anything else (more than 19
+// digits, large exponents, hex floats, inf/nan, no digits) reports failure and the caller uses strtod.
+// Consumes the longest prefix strtod would: [ws][sign]digits[.digits][(e|E)[sign]digits].
+inline bool fast_decimal(const char* p, size_t len, double* value, size_t* used)
+{
+    static const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                      1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    size_t i = 0;
+    while (i < len && (p[i] == ' ' || (p[i] >= '\t' && p[i] <= '\r'))) ++i;  // isspace in the C locale
+    bool neg = false;
+    if (i < len && (p[i] == '-' || p[i] == '+')) neg = p[i++] == '-';
+    unsigned long long m = 0;
+    int digits = 0, frac = 0;
+    bool any = false;
+    while (i < len && p[i] >= '0' && p[i] <= '9') {
+        if (m != 0 || p[i] != '0') ++digits;
+        if (digits > 19) return false;
+        m = m * 10 + (unsigned)(p[i] - '0');
+        ++i;
+        any = true;
+    }
+    if (i < len && p[i] == '.') {
+        size_t j = i + 1;
+        while (j < len && p[j] >= '0' && p[j] <= '9') {
+            if (m != 0 || p[j] != '0') ++digits;
+            if (digits > 19) return false;
+            m = m * 10 + (unsigned)(p[j] - '0');
+            ++frac;
+            ++j;
+            any = true;
+        }
+        if (any) i = j;  // "." alone is not a number
+    }
+    if (!any) return false;  // inf, nan, hex, empty: let strtod decide
+    int e10 = 0;
+    if (i < len && (p[i] == 'e' || p[i] == 'E')) {
+        size_t j = i + 1;
+        bool eneg = false;
+        if (j < len && (p[j] == '-' || p[j] == '+')) eneg = p[j++] == '-';
+        if (j < len && p[j] >= '0' && p[j] <= '9') {
+            int e = 0;
+            while (j < len && p[j] >= '0' && p[j] <= '9') {
+                if (e < 10000) e = e * 10 + (p[j] - '0');
+                ++j;
+            }
+            e10 = eneg ? -e : e;
+            i = j;
+        }
+    }
+    if (i < len && (p[i] == 'x' || p[i] == 'X')) return false;  // "0x..." is a hex float for strtod
+    e10 -= frac;
+    if (m > (1ull << 53) || e10 < -22 || e10 > 22) return false;
+    double v = (double)m;
+    v = e10 < 0 ? v / kPow10[-e10] : v * kPow10[e10];
+    *value = neg ? -v : v;
+    *used = i;
+    return true;
+}
+
+// what atof(std::string(p, len).c_str()) evaluates: the fast path above, else strtod on a NUL-terminated copy
 inline double parse_prefix(const char* p, size_t len, bool* converted, size_t* used)
 {
-    char buf[128];
-    if (len >= sizeof(buf)) len = sizeof(buf) - 1;
-    memcpy(buf, p, len);
-    buf[len] = '\0';
+    double fv;
+    size_t fu;
+    if (fast_decimal(p, len, &fv, &fu)) {
+        if (converted) *converted = true;
+        if (used) *used = fu;
+        return fv;
+    }
+    char small[128];
+    std::string big;  // a token can be hundreds of digits long ("%f" of 1e300)
+    char* buf = small;
+    if (len >= sizeof(small)) {
+        big.assign(p, len);
+        buf = &big[0];
+    } else {
+        memcpy(small, p, len);
+        small[len] = '\0';
+    }
     char* endp = nullptr;
     const double v = strtod(buf, &endp);
     if (converted) *converted = endp != buf;
@@ -76,7 +151,7 @@ bool parse_line(const char* l, size_t len, FastFormat fmt, int field, double p_f
         }
         case FAST_GROMACS: {
             if (l[0] == '#' || l[0] == '@') return true;
-            if (field < 1 || len >= 127) return false;
+            if (field < 1) return false;
             size_t pos = 0;
             double v = 0.0;
             for (int i = 1; i <= field; ++i) {
@@ -85,6 +160,9 @@ bool parse_line(const char* l, size_t len, FastFormat fmt, int field, double p_f
                 v = parse_prefix(l + pos, len - pos, &conv, &used);
                 if (!conv) return false;  // fewer columns than `field`: stale-value quirk, faithful reader
                 pos += used;
+                // sscanf("%lf") and strtod agree on a number that ends at white space; where they can differ
+                // (a dangling exponent such as "1e", "0x", "infi") the faithful reader decides
+                if (pos < len && !(l[pos] == ' ' || (l[pos] >= '\t' && l[pos] <= '\r'))) return false;
             }
             pc.values.push_back(v * 10.0);
             return true;

@@ -1,0 +1,52 @@
+// Test harness (CPU only): reads one file with the mapped multi-threaded reader and with the faithful line-by-line
+// reader and compares the two series bit for bit.  usage: reader_bits <namd|charmm|gromacs|general> <field> <p> <file>
+// prints "same <n>" / "differ at <i>" / "fast declined"; exit 0 / 1 / 2.  Timings go to stderr.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../acfcalculator_b200/csrc/host/fast_readers.hpp"
+#include "../../acfcalculator_b200/csrc/host/readers.hpp"
+
+int main(int argc, char** argv)
+{
+    if (argc != 5) return 3;
+    const std::string type = argv[1];
+    const int field = atoi(argv[2]);
+    const double p = atof(argv[3]);
+    const char* fname = argv[4];
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    acfhost::FastFormat fmt = type == "namd"      ? acfhost::FAST_NAMD
+                              : type == "charmm"  ? acfhost::FAST_CHARMM
+                              : type == "gromacs" ? acfhost::FAST_GROMACS
+                                                  : acfhost::FAST_GENERAL;
+    std::vector<double> fast;
+    auto t0 = now();
+    const bool ok = acfhost::fast_read_series(fname, fmt, field, p, fast);
+    auto t1 = now();
+    int n = 0;
+    std::vector<double> slow = type == "namd"      ? acfhost::read_series_namd(fname, n, field)
+                               : type == "charmm"  ? acfhost::read_series_charmm(fname, n)
+                               : type == "gromacs" ? acfhost::read_series_gromacs(fname, n, field)
+                                                   : acfhost::read_series_general(fname, n, field, p);
+    auto t2 = now();
+    fprintf(stderr, "fast %.3f s, line-by-line %.3f s\n", std::chrono::duration<double>(t1 - t0).count(),
+            std::chrono::duration<double>(t2 - t1).count());
+    if (!ok) {
+        printf("fast declined\n");
+        return 2;
+    }
+    if (fast.size() != slow.size()) {
+        printf("differ in length %zu %zu\n", fast.size(), slow.size());
+        return 1;
+    }
+    for (size_t i = 0; i < fast.size(); ++i)
+        if (memcmp(&fast[i], &slow[i], sizeof(double)) != 0) {
+            printf("differ at %zu: %.17g %.17g\n", i, fast[i], slow[i]);
+            return 1;
+        }
+    printf("same %zu\n", fast.size());
+    return 0;
+}
