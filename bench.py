@@ -129,48 +129,83 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU code on a bounded sample
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_rate(workload, steps, warmup, sample_products=1.0e10):
+def _host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def _timed_concurrent(fns, steps, warmup):
+    """Runs the callables of `fns` concurrently (one OS thread each; ctypes drops the GIL inside the C call),
+    `warmup` untimed rounds and `steps` timed rounds.  Returns seconds per round (all callables finished)."""
+    import threading
+
+    def round_():
+        if len(fns) == 1:
+            fns[0]()
+            return
+        th = [threading.Thread(target=f) for f in fns]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    for _ in range(warmup):
+        round_()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        round_()
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
+def cpu_reference_rate(workload, steps, warmup, sample_products=1.0e10, cores=1):
     """Times calcCorrelation from oracle/_ref (kind 'reference', the unmodified ACFcalculator.cpp:113-146
-    body compiled -O3) -- or, if that was not built, the oracle port -- on a time-slice of the workload's
-    series.  Serial: the reference's only correct configuration (its OpenMP pragma races)."""
+    body compiled -O3) -- or, if that was not built, the oracle port -- on time-slices of the workload's
+    series.  One call is serial: the reference's only correct configuration (its OpenMP pragma races).
+    With cores > 1 that many unmodified serial calls run side by side, each on its own slice of `sample_products`
+    lag-products (the time-block decomposition of section 8e), so the box's host cores are all busy and every
+    result is still the reference's; the rate is the aggregate."""
     from oracle import oracle as O
     w = WORKLOADS[workload]
     m = min(w["m"], 20000) if workload != "fft" else 20000
     sample_products = float(os.environ.get("ACFB200_BENCH_CPU_PRODUCTS", sample_products))  # tests shrink the sample
+    cores = max(1, int(cores))
+    how = "1 serial call" if cores == 1 else "%d serial calls side by side, one slice each" % cores
     if workload == "msd":
-        # the reference's own MSD loop (traj2diffusion.cpp:530-541, oracle/_ref/libref_msd_fast.so), 1 core
+        # the reference's own MSD loop (traj2diffusion.cpp:530-541, oracle/_ref/libref_msd_fast.so)
         ns = int(min(w["n"], max(4 * m, sample_products / 4 / m)))
-        xyz = np.ascontiguousarray(np.stack(walk_xyz(ns, 1), axis=1))
+        base = np.ascontiguousarray(np.stack(walk_xyz(ns + 64 * (cores - 1), 1), axis=1))
+        xyzs = [base[64 * c:64 * c + ns] for c in range(cores)]  # shifted views of one walk
         if O.ref_available("libref_msd_fast.so"):
-            kind, fn = "reference", (lambda: O.ref_msd(xyz, 1, m, "libref_msd_fast.so"))
+            kind = "reference"
+            O.ref_lib("libref_msd_fast.so")
+            fns = [(lambda a=a: O.ref_msd(a, 1, m, "libref_msd_fast.so")) for a in xyzs]
         else:
-            cols = [np.ascontiguousarray(xyz[:, a]) for a in range(3)]
-            kind, fn = "port", (lambda: O.msd(cols[0], cols[1], cols[2], 1, m))
-        for _ in range(warmup):
-            fn()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
-        dt = (time.perf_counter() - t0) / steps
-        return dict(value=ns * m / dt, unit=w["unit"], cores=1, kind=kind, ms_per_step=dt * 1e3,
-                    sample="MSD loop on the first %d frames, stride 1, max %d (%.1e frame-lag pairs per step)" % (
-                        ns, m, ns * m))
+            kind = "port"
+            O.lib()
+            cols = [[np.ascontiguousarray(a[:, k]) for k in range(3)] for a in xyzs]
+            fns = [(lambda c=c: O.msd(c[0], c[1], c[2], 1, m)) for c in cols]
+        dt = _timed_concurrent(fns, steps, warmup)
+        return dict(value=cores * ns * m / dt, unit=w["unit"], cores=cores, kind=kind, ms_per_step=dt * 1e3,
+                    sample="MSD loop on %d frames, stride 1, max %d (%.1e frame-lag pairs per call); %s" % (
+                        ns, m, ns * m, how))
     ns = int(min(w["n"], max(4 * m, sample_products / m)))
-    x = ou_series(ns, 200.0, mu=0.0, seed=1)
+    base = ou_series(ns + 64 * (cores - 1), 200.0, mu=0.0, seed=1)
+    xs = [base[64 * c:64 * c + ns] for c in range(cores)]  # shifted views of one series (read-only)
     if O.ref_available("libref_acf_fast.so"):
-        kind, fn = "reference", (lambda: O.ref_calc_correlation(x, m, "libref_acf_fast.so"))
+        kind = "reference"
+        O.ref_lib("libref_acf_fast.so")
+        fns = [(lambda x=x: O.ref_calc_correlation(x, m, "libref_acf_fast.so")) for x in xs]
     else:
-        kind, fn = "port", (lambda: O.calc_correlation(x, m, threads=1))
-    for _ in range(warmup):
-        fn()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        fn()
-    dt = (time.perf_counter() - t0) / steps
-    rate = ns * m / dt
-    sample = "calcCorrelation on the first %d samples of the series, maxcorr=%d (%.1e lag-products per step)" % (
-        ns, m, ns * m)
-    return dict(value=rate, unit=UNIT, cores=1, kind=kind, sample=sample, ms_per_step=dt * 1e3)
+        kind = "port"
+        O.lib()
+        fns = [(lambda x=x: O.calc_correlation(x, m, threads=1)) for x in xs]
+    dt = _timed_concurrent(fns, steps, warmup)
+    rate = cores * ns * m / dt
+    sample = "calcCorrelation on %d samples of the series, maxcorr=%d (%.1e lag-products per call); %s" % (
+        ns, m, ns * m, how)
+    return dict(value=rate, unit=UNIT, cores=cores, kind=kind, sample=sample, ms_per_step=dt * 1e3)
 
 
 def cpu_allcores_rate(workload, sample_products=4.0e10):
@@ -192,7 +227,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_rate(args.workload, args.steps, args.warmup)
+    # every host core busy with the unmodified serial reference (its own OpenMP build races and is not used)
+    r = cpu_reference_rate(args.workload, args.steps, args.warmup, cores=_host_cores())
+    one = cpu_reference_rate(args.workload, 1, 0, cores=1) if r["cores"] > 1 else r
     w = WORKLOADS[args.workload]
     METRIC, UNIT = metric_of(args.workload)
     line = {
@@ -200,7 +237,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak" if args.workload in ("ou", "fft", "msd") else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": w["desc"], "sample": r["sample"]},
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": dict({k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                             one_core_value=one["value"]),
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -463,7 +501,10 @@ def run_native(args):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        cpu = cpu_reference_rate(args.workload, 1, 0, sample_products=5.0e10)  # ~10 s of one host core
+        # ~10 s with every host core running the serial reference on its own slice; one core alone beside it
+        cpu = cpu_reference_rate(args.workload, 1, 0, sample_products=5.0e10, cores=_host_cores())
+        if cpu["cores"] > 1:
+            cpu["one_core_value"] = cpu_reference_rate(args.workload, 1, 0, sample_products=1.0e10)["value"]
         cpu.pop("ms_per_step", None)
     # informational: the same step with acfb200_set_method("auto") (the cost model sends config 2 through the
     # Wiener-Khinchin path); NOT the headline, which is the direct-lag kernel BASELINE.json names
