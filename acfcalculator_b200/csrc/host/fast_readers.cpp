@@ -5,6 +5,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <cerrno>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -214,9 +215,10 @@ void parse_piece(Piece* pc, FastFormat fmt, int field, double p_factor)
     }
 }
 
-}  // namespace
-
-bool fast_read_series(const char* fname, FastFormat fmt, int field, double p_factor, std::vector<double>& out)
+// Maps `fname`, cuts it into per-thread pieces at line boundaries (>= 1 MB each, at most 32) and runs work(t) for every
+// piece on its own thread.  false: the file could not be opened / mapped or is empty.
+template <class PieceT, class Work>
+bool for_each_piece(const char* fname, std::vector<PieceT>& pieces, Work work)
 {
     const int fd = open(fname, O_RDONLY);
     if (fd < 0) return false;
@@ -235,7 +237,7 @@ bool fast_read_series(const char* fname, FastFormat fmt, int field, double p_fac
     if (hw > 32) hw = 32;
     size_t nth = size / (1u << 20) + 1;  // at least 1 MB per thread
     if (nth > hw) nth = hw;
-    std::vector<Piece> pieces(nth);
+    pieces.assign(nth, PieceT());
     const char* cur = base;
     for (size_t t = 0; t < nth; ++t) {
         const char* stop = (t + 1 == nth) ? base + size : base + size * (t + 1) / nth;
@@ -249,10 +251,61 @@ bool fast_read_series(const char* fname, FastFormat fmt, int field, double p_fac
         cur = stop;
     }
     std::vector<std::thread> threads;
-    for (size_t t = 1; t < nth; ++t) threads.emplace_back(parse_piece, &pieces[t], fmt, field, p_factor);
-    parse_piece(&pieces[0], fmt, field, p_factor);
+    for (size_t t = 1; t < nth; ++t) threads.emplace_back(work, &pieces[t]);
+    work(&pieces[0]);
     for (auto& th : threads) th.join();
     munmap(map, size);
+    return true;
+}
+
+// ---- NAMD log, "PRESSURE:" lines (viscosity.cpp:117-169) --------------------------------------------------------
+struct PressurePiece {
+    const char* begin;
+    const char* end;
+    std::vector<double> values;  // 9 per accepted line
+    bool ok = true;
+};
+
+inline bool is_space(char ch) { return ch == ' ' || (ch >= '\t' && ch <= '\r'); }
+
+void parse_pressure_piece(PressurePiece* pc)
+{
+    const char* p = pc->begin;
+    pc->values.reserve((size_t)(pc->end - pc->begin) / 40 + 16);
+    while (p < pc->end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(pc->end - p));
+        const char* e = nl ? nl : pc->end;
+        if (e - p >= 9 && memcmp(p, "PRESSURE:", 9) == 0) {  // line.compare(0, 9, "PRESSURE:") == 0   (:138)
+            const char* q = p;
+            for (int tok = 0; tok < 11; ++tok) {  // operator>> : skip white space, take the run of non-blanks
+                while (q < e && is_space(*q)) ++q;
+                if (q == e) {  // fewer than 11 tokens: the reference converts a stale string -- faithful reader
+                    pc->ok = false;
+                    return;
+                }
+                const char* t0 = q;
+                while (q < e && !is_space(*q)) ++q;
+                if (tok < 2) continue;  // "PRESSURE:" and the time step   (:143-145)
+                bool conv = false;
+                errno = 0;
+                const double v = parse_prefix(t0, (size_t)(q - t0), &conv, nullptr);  // std::stod = strtod of a prefix
+                if (!conv || errno == ERANGE) {  // std::stod throws here and the reference dies: faithful reader
+                    pc->ok = false;
+                    return;
+                }
+                pc->values.push_back(v);
+            }
+        }
+        p = nl ? nl + 1 : pc->end;
+    }
+}
+
+}  // namespace
+
+bool fast_read_series(const char* fname, FastFormat fmt, int field, double p_factor, std::vector<double>& out)
+{
+    std::vector<Piece> pieces;
+    if (!for_each_piece(fname, pieces, [=](Piece* pc) { parse_piece(pc, fmt, field, p_factor); })) return false;
     size_t total = 0;
     for (const auto& pc : pieces) {
         if (!pc.ok) return false;
@@ -261,6 +314,31 @@ bool fast_read_series(const char* fname, FastFormat fmt, int field, double p_fac
     out.clear();
     out.reserve(total);
     for (const auto& pc : pieces) out.insert(out.end(), pc.values.begin(), pc.values.end());
+    return true;
+}
+
+bool fast_read_pressure(const char* fname, std::vector<std::vector<double> >& comps, int& num_samples,
+                        bool reference_quirk)
+{
+    std::vector<PressurePiece> pieces;
+    if (!for_each_piece(fname, pieces, [](PressurePiece* pc) { parse_pressure_piece(pc); })) return false;
+    size_t lines = 0;
+    for (const auto& pc : pieces) {
+        if (!pc.ok) return false;
+        lines += pc.values.size() / 9;
+    }
+    // viscosity.cpp:120 starts every component with ten zeros and :162-164 copies the first numSamples entries only
+    const size_t lead = reference_quirk ? 10 : 0;
+    comps.assign(9, std::vector<double>());
+    for (int i = 0; i < 9; ++i) {
+        std::vector<double>& c = comps[i];
+        c.reserve(lines + lead);
+        c.assign(lead, 0.0);
+        for (const auto& pc : pieces)
+            for (size_t r = 0; r + 8 < pc.values.size(); r += 9) c.push_back(pc.values[r + i]);
+        c.resize(lines);
+    }
+    num_samples = (int)lines;
     return true;
 }
 

@@ -15,4 +15,10 @@ enum FastFormat { FAST_NAMD, FAST_CHARMM, FAST_GROMACS, FAST_GENERAL };
 // true: `out` holds the whole series.  false: nothing usable was produced, use the faithful reader.
 bool fast_read_series(const char* fname, FastFormat fmt, int field, double p_factor, std::vector<double>& out);
 
+// The NAMD-log reader of viscosity.cpp:117-169 (nine pressure-tensor components per "PRESSURE:" line), same contract:
+// false when any such line has fewer than eleven tokens or a value std::stod would reject -- the faithful reader
+// (read_pressure_namd in readers.cpp) then reproduces what the reference does with it.
+bool fast_read_pressure(const char* fname, std::vector<std::vector<double> >& comps, int& num_samples,
+                        bool reference_quirk);
+
 }  // namespace acfhost

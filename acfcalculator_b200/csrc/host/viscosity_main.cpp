@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../../include/acf_b200.h"
+#include "fast_readers.hpp"
 #include "gpu_warmup.hpp"
 #include "readers.hpp"
 
@@ -48,7 +49,14 @@ int main(int argc, char* argv[])
     }
     acfhost::GpuWarmup warm;  // the CUDA context comes up while the log is parsed
     int num_samples = 0;
-    const std::vector<std::vector<double> > comps = acfhost::read_pressure_namd(fname, num_samples, quirk);
+    // mapped, multi-threaded reader for logs the reference reads without incident; anything unusual falls back to the
+    // line-by-line reader (ACFB200_FAST_READER=0 disables it, ACFB200_READER_DEBUG=1 says which ran)
+    std::vector<std::vector<double> > comps;
+    const char* fr = getenv("ACFB200_FAST_READER");
+    bool fast_done = false;
+    if (!(fr && fr[0] == '0')) fast_done = acfhost::fast_read_pressure(fname, comps, num_samples, quirk);
+    if (getenv("ACFB200_READER_DEBUG")) std::cerr << "#reader: " << (fast_done ? "fast" : "line-by-line") << std::endl;
+    if (!fast_done) comps = acfhost::read_pressure_namd(fname, num_samples, quirk);
 
     std::vector<const double*> ptrs;
     std::vector<int> which;

@@ -1,5 +1,5 @@
 // Test harness (CPU only): reads one file with the mapped multi-threaded reader and with the faithful line-by-line
-// reader and compares the two series bit for bit.  usage: reader_bits <namd|charmm|gromacs|general> <field> <p> <file>
+// reader and compares the two series bit for bit.  usage: reader_bits <namd|charmm|gromacs|general|pressure|pressure_exact> <field> <p> <file>
 // prints "same <n>" / "differ at <i>" / "fast declined"; exit 0 / 1 / 2.  Timings go to stderr.
 #include <chrono>
 #include <cstdio>
@@ -18,6 +18,38 @@ int main(int argc, char** argv)
     const double p = atof(argv[3]);
     const char* fname = argv[4];
     auto now = [] { return std::chrono::steady_clock::now(); };
+    if (type == "pressure" || type == "pressure_exact") {  // NAMD log reader of the viscosity front-end
+        const bool quirk = type == "pressure";
+        std::vector<std::vector<double> > fastc;
+        int nf = 0, ns = 0;
+        auto t0 = now();
+        const bool ok = acfhost::fast_read_pressure(fname, fastc, nf, quirk);
+        auto t1 = now();
+        if (!ok) {
+            printf("fast declined\n");
+            return 2;
+        }
+        const std::vector<std::vector<double> > slowc = acfhost::read_pressure_namd(fname, ns, quirk);
+        auto t2 = now();
+        fprintf(stderr, "fast %.3f s, line-by-line %.3f s\n", std::chrono::duration<double>(t1 - t0).count(),
+                std::chrono::duration<double>(t2 - t1).count());
+        if (nf != ns || fastc.size() != slowc.size()) {
+            printf("differ in length %d %d\n", nf, ns);
+            return 1;
+        }
+        for (size_t c = 0; c < fastc.size(); ++c) {
+            if (fastc[c].size() != slowc[c].size()) {
+                printf("differ in length of component %zu\n", c);
+                return 1;
+            }
+            if (!fastc[c].empty() && memcmp(fastc[c].data(), slowc[c].data(), fastc[c].size() * sizeof(double)) != 0) {
+                printf("differ in component %zu\n", c);
+                return 1;
+            }
+        }
+        printf("same %d\n", nf);
+        return 0;
+    }
     acfhost::FastFormat fmt = type == "namd"      ? acfhost::FAST_NAMD
                               : type == "charmm"  ? acfhost::FAST_CHARMM
                               : type == "gromacs" ? acfhost::FAST_GROMACS

@@ -119,9 +119,12 @@ def test_viscosity_frontend_with_oracle_backend(oracle_frontends, tmp_path):
     pres = np.load(os.path.join(GOLDEN, "cli_pressure.npz"))["pressure"]
     log = str(tmp_path / "namd.log")
     write_pressure_log(log, pres)
-    p = subprocess.run([oracle_frontends["viscosity"], log], capture_output=True, text=True)
-    assert p.returncode == CASES["viscosity_log"]["returncode"]
-    assert p.stdout == CASES["viscosity_log"]["stdout"]
+    for mode, which in (("1", "fast"), ("0", "line-by-line")):  # mapped reader and the faithful one: same bytes
+        env = dict(os.environ, ACFB200_FAST_READER=mode, ACFB200_READER_DEBUG="1")
+        p = subprocess.run([oracle_frontends["viscosity"], log], capture_output=True, text=True, env=env)
+        assert p.returncode == CASES["viscosity_log"]["returncode"]
+        assert p.stdout == CASES["viscosity_log"]["stdout"]
+        assert [l for l in p.stderr.splitlines() if l.startswith("#reader:")] == ["#reader: " + which]
 
 
 FAST_READER_CASES = {  # case -> does the mapped reader handle it (True) or defer to the line-by-line one (False)

@@ -106,3 +106,34 @@ def test_mapped_reader_odd_number_spellings(reader_bits, tmp_path):
             f.write("@ odd\n0.0\t1.5\n0.002\t%s\n0.004\t2.5\n" % l)
         p = subprocess.run([reader_bits, "gromacs", "2", "1.0", path], capture_output=True, text=True)
         assert p.returncode in (0, 2), (l, p.stdout + p.stderr)
+
+
+@pytest.mark.parametrize("mode", ["pressure", "pressure_exact"])
+def test_mapped_pressure_reader_bits_equal_line_reader_bits(reader_bits, mode, tmp_path):
+    """NAMD log reader of the viscosity front-end (viscosity.cpp:117-169): nine components per PRESSURE: line."""
+    n = 40000
+    v = _values(9 * n, 3).reshape(n, 9)
+    v = np.where(np.abs(v) < 1e-290, 0.0, v)  # std::stod throws on subnormal results; that case is tested below
+    fsel = np.random.default_rng(9).integers(0, len(FORMATS), (n, 9))
+    path = str(tmp_path / "namd.log")
+    with open(path, "w") as f:
+        f.write("Info: synthetic log\n")
+        for i in range(n):
+            f.write("ENERGY: %d 0 0 0\nPRESSURE: %d " % (i, i))
+            f.write(" ".join(_text(v[i, k], i, fsel[i, k]) for k in range(9)))
+            f.write("\r\n" if i % 5 == 0 else "\n")
+            f.write("GPRESSURE: %d 1 2 3 4 5 6 7 8 9\nPRESSAVG: %d 1 2 3 4 5 6 7 8 9\n" % (i, i))
+    p = subprocess.run([reader_bits, mode, "1", "1.0", path], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.strip() == "same %d" % n
+
+
+@pytest.mark.parametrize("bad", ["PRESSURE: 7 1 2 3 4 5 6 7 8", "PRESSURE: 7 1 2 3 x 5 6 7 8 9",
+                                 "PRESSURE: 7 1 2 3 1e-320 5 6 7 8 9", "PRESSURE: 7 1 2 3 1e999 5 6 7 8 9"])
+def test_mapped_pressure_reader_steps_aside(reader_bits, bad, tmp_path):
+    """Short lines (the reference converts a stale token) and values std::stod rejects go to the faithful reader."""
+    path = str(tmp_path / "bad.log")
+    with open(path, "w") as f:
+        f.write("PRESSURE: 6 1 2 3 4 5 6 7 8 9\n" + bad + "\nPRESSURE: 8 1 2 3 4 5 6 7 8 9\n")
+    p = subprocess.run([reader_bits, "pressure", "1", "1.0", path], capture_output=True, text=True)
+    assert p.returncode == 2 and p.stdout.strip() == "fast declined"
