@@ -300,6 +300,59 @@ void parse_pressure_piece(PressurePiece* pc)
     }
 }
 
+// ---- traj2diffusion trajectories (traj2diffusion.cpp:59-121 fixed columns, :145-260 general) -------------------
+struct TrajPiece {
+    const char* begin;
+    const char* end;
+    std::vector<double> values;  // namd: x, y, z per frame; general: x per frame
+    bool ok = true;
+};
+
+// isNumeric(), traj2diffusion.cpp:123-143
+inline bool t2d_numeric(char ch)
+{
+    return (ch >= '0' && ch <= '9') || ch == '-' || ch == '+' || ch == '.' || ch == 'e' || ch == 'E';
+}
+
+void parse_traj_piece(TrajPiece* pc, bool namd)
+{
+    const char* p = pc->begin;
+    pc->values.reserve((size_t)(pc->end - pc->begin) / (namd ? 28 : 40) + 16);
+    while (p < pc->end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(pc->end - p));
+        const char* e = nl ? nl : pc->end;
+        const size_t len = (size_t)(e - p);
+        if (namd) {
+            if (len == 0 || (p[0] != '#' && len < 61)) {  // blank line: the reference throws; short line: it stops
+                pc->ok = false;
+                return;
+            }
+            if (p[0] != '#') {
+                const size_t off[3] = {15, 37, 61};
+                for (int a = 0; a < 3; ++a) {
+                    size_t w = len - off[a];
+                    if (w > 23) w = 23;
+                    pc->values.push_back(parse_prefix(p + off[a], w, nullptr, nullptr));
+                }
+            }
+        } else {
+            const char first = len ? p[0] : '\0';
+            if (t2d_numeric(first) || first == ' ') {
+                size_t start = 0, end;
+                while (start < len && !t2d_numeric(p[start])) ++start;  // time-step column
+                end = start;
+                while (end < len && t2d_numeric(p[end])) ++end;
+                start = end;
+                while (start < len && !t2d_numeric(p[start])) ++start;  // x (y and z are copies of it upstream)
+                end = start;
+                while (end < len && t2d_numeric(p[end])) ++end;
+                pc->values.push_back(parse_prefix(p + start, end - start, nullptr, nullptr));
+            }
+        }
+        p = nl ? nl + 1 : pc->end;
+    }
+}
+
 }  // namespace
 
 bool fast_read_series(const char* fname, FastFormat fmt, int field, double p_factor, std::vector<double>& out)
@@ -339,6 +392,36 @@ bool fast_read_pressure(const char* fname, std::vector<std::vector<double> >& co
         c.resize(lines);
     }
     num_samples = (int)lines;
+    return true;
+}
+
+bool fast_read_traj(const char* fname, bool namd, std::vector<double>& x, std::vector<double>& y,
+                    std::vector<double>& z)
+{
+    std::vector<TrajPiece> pieces;
+    if (!for_each_piece(fname, pieces, [namd](TrajPiece* pc) { parse_traj_piece(pc, namd); })) return false;
+    size_t total = 0;
+    for (const auto& pc : pieces) {
+        if (!pc.ok) return false;
+        total += pc.values.size();
+    }
+    x.clear();
+    y.clear();
+    z.clear();
+    if (!namd) {
+        x.reserve(total);
+        for (const auto& pc : pieces) x.insert(x.end(), pc.values.begin(), pc.values.end());
+        return true;
+    }
+    x.reserve(total / 3);
+    y.reserve(total / 3);
+    z.reserve(total / 3);
+    for (const auto& pc : pieces)
+        for (size_t r = 0; r + 2 < pc.values.size(); r += 3) {
+            x.push_back(pc.values[r]);
+            y.push_back(pc.values[r + 1]);
+            z.push_back(pc.values[r + 2]);
+        }
     return true;
 }
 

@@ -21,4 +21,9 @@ bool fast_read_series(const char* fname, FastFormat fmt, int field, double p_fac
 bool fast_read_pressure(const char* fname, std::vector<std::vector<double> >& comps, int& num_samples,
                         bool reference_quirk);
 
+// The trajectory readers of traj2diffusion.cpp (:59-121 fixed columns when `namd`, else :145-260 where only x is
+// filled and y, z are copies of it).  false on a blank or short fixed-column line (the reference throws / stops).
+bool fast_read_traj(const char* fname, bool namd, std::vector<double>& x, std::vector<double>& y,
+                    std::vector<double>& z);
+
 }  // namespace acfhost

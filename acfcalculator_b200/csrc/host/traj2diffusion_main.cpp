@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../../include/acf_b200.h"
+#include "fast_readers.hpp"
 #include "gpu_warmup.hpp"
 #include "options.hpp"
 #include "t2d_readers.hpp"
@@ -74,7 +75,17 @@ int main(int argc, char* argv[])
     }
 
     GpuWarmup warm;  // the CUDA context comes up while the trajectory is parsed
-    const Trajectory traj = namd ? read_traj_namd(traj_fname.c_str()) : read_traj_general(traj_fname.c_str());
+    // mapped, multi-threaded reader for files the reference reads without incident; anything unusual falls back to the
+    // line-by-line readers (ACFB200_FAST_READER=0 disables it, ACFB200_READER_DEBUG=1 says which ran)
+    Trajectory traj;
+    const char* fr = getenv("ACFB200_FAST_READER");
+    bool fast_done = false;
+    if (!(fr && fr[0] == '0')) {
+        fast_done = fast_read_traj(traj_fname.c_str(), namd, traj.x, traj.y, traj.z);
+        if (fast_done) traj.xyz_identical = !namd;
+    }
+    if (getenv("ACFB200_READER_DEBUG")) std::cerr << "#reader: " << (fast_done ? "fast" : "line-by-line") << std::endl;
+    if (!fast_done) traj = namd ? read_traj_namd(traj_fname.c_str()) : read_traj_general(traj_fname.c_str());
     const int nframes = traj.frames();
     std::cout << "#" << nframes << std::endl;
     if (max_s < 0) throw std::bad_alloc();  // new double[negative] (:514)

@@ -1,5 +1,5 @@
 // Test harness (CPU only): reads one file with the mapped multi-threaded reader and with the faithful line-by-line
-// reader and compares the two series bit for bit.  usage: reader_bits <namd|charmm|gromacs|general|pressure|pressure_exact> <field> <p> <file>
+// reader and compares the two series bit for bit.  usage: reader_bits <namd|charmm|gromacs|general|pressure|pressure_exact|traj_namd|traj_general> <field> <p> <file>
 // prints "same <n>" / "differ at <i>" / "fast declined"; exit 0 / 1 / 2.  Timings go to stderr.
 #include <chrono>
 #include <cstdio>
@@ -9,6 +9,7 @@
 
 #include "../../acfcalculator_b200/csrc/host/fast_readers.hpp"
 #include "../../acfcalculator_b200/csrc/host/readers.hpp"
+#include "../../acfcalculator_b200/csrc/host/t2d_readers.hpp"
 
 int main(int argc, char** argv)
 {
@@ -18,6 +19,30 @@ int main(int argc, char** argv)
     const double p = atof(argv[3]);
     const char* fname = argv[4];
     auto now = [] { return std::chrono::steady_clock::now(); };
+    if (type == "traj_namd" || type == "traj_general") {  // trajectory readers of the traj2diffusion front-end
+        const bool namd = type == "traj_namd";
+        std::vector<double> x, y, z;
+        auto t0 = now();
+        const bool ok = acfhost::fast_read_traj(fname, namd, x, y, z);
+        auto t1 = now();
+        if (!ok) {
+            printf("fast declined\n");
+            return 2;
+        }
+        const acfhost::Trajectory tr = namd ? acfhost::read_traj_namd(fname) : acfhost::read_traj_general(fname);
+        auto t2 = now();
+        fprintf(stderr, "fast %.3f s, line-by-line %.3f s\n", std::chrono::duration<double>(t1 - t0).count(),
+                std::chrono::duration<double>(t2 - t1).count());
+        auto same = [](const std::vector<double>& a, const std::vector<double>& b) {
+            return a.size() == b.size() && (a.empty() || memcmp(a.data(), b.data(), a.size() * sizeof(double)) == 0);
+        };
+        if (!same(x, tr.x) || (namd && (!same(y, tr.y) || !same(z, tr.z)))) {
+            printf("differ\n");
+            return 1;
+        }
+        printf("same %zu\n", x.size());
+        return 0;
+    }
     if (type == "pressure" || type == "pressure_exact") {  // NAMD log reader of the viscosity front-end
         const bool quirk = type == "pressure";
         std::vector<std::vector<double> > fastc;

@@ -203,15 +203,16 @@ def test_factor_alias_equals_p_factor(oracle_frontends, tmp_path):
 
 
 # ---- traj2diffusion (reference: oracle/_ref/traj2diffusion_ref, see tests/golden/make_t2d_golden.py) ------------
-def run_t2d(exe, name, tmp_path):
+def run_t2d(exe, name, tmp_path, fast_reader="1"):
     c = T2D[name]
+    env = dict(os.environ, ACFB200_FAST_READER=fast_reader)
     if name.startswith("opt_"):
-        p = subprocess.run([exe] + c["args"], capture_output=True, text=True, cwd=str(tmp_path))
+        p = subprocess.run([exe] + c["args"], capture_output=True, text=True, cwd=str(tmp_path), env=env)
         return p, None
     inp = str(tmp_path / (name + ".traj"))
     if c["format"] != "none":
         write_traj(inp, T2D_TRAJ[c["traj"]], c["format"])
-    return subprocess.run([exe, "-t", inp] + c["args"], capture_output=True, text=True, cwd=str(tmp_path)), inp
+    return subprocess.run([exe, "-t", inp] + c["args"], capture_output=True, text=True, cwd=str(tmp_path), env=env), inp
 
 
 def check_t2d(p, inp, name, rel):
@@ -223,9 +224,10 @@ def check_t2d(p, inp, name, rel):
         assert head == want["stderr_head"], (name, head)
 
 
+@pytest.mark.parametrize("fast_reader", ["1", "0"])  # mapped readers (default) and the line-by-line ones
 @pytest.mark.parametrize("name", T2D_CASES)
-def test_traj2diffusion_frontend_with_oracle_backend_is_byte_identical(oracle_frontends, name, tmp_path):
-    p, inp = run_t2d(oracle_frontends["traj2diffusion"], name, tmp_path)
+def test_traj2diffusion_frontend_with_oracle_backend_is_byte_identical(oracle_frontends, name, fast_reader, tmp_path):
+    p, inp = run_t2d(oracle_frontends["traj2diffusion"], name, tmp_path, fast_reader)
     check_t2d(p, inp, name, rel=0)
 
 

@@ -22,7 +22,7 @@ def reader_bits():
     os.makedirs(BUILD, exist_ok=True)
     exe = os.path.join(BUILD, "reader_bits")
     srcs = [os.path.join(ROOT, "tests", "host", "reader_bits.cpp"), os.path.join(HOST, "readers.cpp"),
-            os.path.join(HOST, "fast_readers.cpp")]
+            os.path.join(HOST, "fast_readers.cpp"), os.path.join(HOST, "t2d_readers.cpp")]
     if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.run([cxx, "-O2", "-std=c++14", "-o", exe] + srcs + ["-pthread"], check=True)
@@ -137,3 +137,33 @@ def test_mapped_pressure_reader_steps_aside(reader_bits, bad, tmp_path):
         f.write("PRESSURE: 6 1 2 3 4 5 6 7 8 9\n" + bad + "\nPRESSURE: 8 1 2 3 4 5 6 7 8 9\n")
     p = subprocess.run([reader_bits, "pressure", "1", "1.0", path], capture_output=True, text=True)
     assert p.returncode == 2 and p.stdout.strip() == "fast declined"
+
+
+@pytest.mark.parametrize("fmt", ["traj_namd", "traj_general"])
+def test_mapped_trajectory_reader_bits_equal_line_reader_bits(reader_bits, fmt, tmp_path):
+    """traj2diffusion readers (traj2diffusion.cpp:59-121 fixed columns, :145-260 general)."""
+    n = 60000
+    v = _values(3 * n, 21).reshape(n, 3)
+    path = str(tmp_path / "traj.dat")
+    with open(path, "w") as f:
+        f.write("# step x y z\n")
+        for i in range(n):
+            if fmt == "traj_namd":
+                f.write("%15d%22.14e%23.14e %23.14e\n" % (10 * i, v[i, 0], v[i, 1], v[i, 2]))
+            elif i % 3 == 0:
+                f.write(" %10d % .14e % .14e % .14e\n" % (i, v[i, 0], v[i, 1], v[i, 2]))
+            else:
+                f.write("%d %.10f %.6g %s\n" % (i, v[i, 0] if abs(v[i, 0]) < 1e20 else 1.5, v[i, 1], "x"))
+    p = subprocess.run([reader_bits, fmt, "1", "1.0", path], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.strip() == "same %d" % n
+
+
+def test_mapped_trajectory_reader_steps_aside(reader_bits, tmp_path):
+    for k, bad in enumerate(["", "%15d%22.14e" % (20, 1.0)]):  # blank line (the reference throws), short line (it stops)
+        path = str(tmp_path / ("bad%d.traj" % k))
+        with open(path, "w") as f:
+            f.write("# step\n%15d%22.14e%23.14e %23.14e\n%s\n%15d%22.14e%23.14e %23.14e\n" % (
+                10, 1.0, 2.0, 3.0, bad, 30, 1.0, 2.0, 3.0))
+        p = subprocess.run([reader_bits, "traj_namd", "1", "1.0", path], capture_output=True, text=True)
+        assert p.returncode == 2 and p.stdout.strip() == "fast declined"
