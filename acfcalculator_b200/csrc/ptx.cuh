@@ -57,4 +57,29 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- Ampere-style asynchronous 16-byte copies (SASS LDGSTS) completing on an mbarrier ---------------------------
+// copies 16 bytes global -> shared; the first `src_bytes` (0, 8 or 16) come from memory, the rest is zero-filled
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src_gmem, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+// the mbarrier receives one arrival (already counted in its init value: .noinc) once every cp.async this thread has
+// issued so far has landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// barrier among `count` threads (a multiple of 32) that all name the same id (1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 }  // namespace acfb200
