@@ -209,7 +209,10 @@ def cpu_reference_rate(workload, steps, warmup, sample_products=1.0e10, cores=1)
 
 
 def cpu_allcores_rate(workload, sample_products=4.0e10):
-    """Race-free lag-parallel OpenMP restatement (bit-identical to the serial reference) on all host cores."""
+    """The other CPU figures SURVEY section 8d lists, all on the same kind of sample (ACF workloads only):
+    the race-free lag-parallel OpenMP restatement (bit-identical to the serial reference) on all host cores, the
+    reference compiled as its CMakeLists.txt does (no -O flag) on one core, and the reference's own OpenMP build on all
+    cores -- TIME ONLY, its pragma at ACFcalculator.cpp:125 races and the numbers it returns are wrong."""
     from oracle import oracle as O
     w = WORKLOADS[workload]
     m = min(w["m"], 20000)
@@ -219,8 +222,19 @@ def cpu_allcores_rate(workload, sample_products=4.0e10):
     t0 = time.perf_counter()
     O.calc_correlation(x, m, threads=0)
     dt = time.perf_counter() - t0
-    return dict(value=ns * m / dt, unit=UNIT, cores=O.max_threads(), kind="port",
-                sample="lag-parallel OpenMP oracle on %d samples, maxcorr=%d" % (ns, m))
+    out = dict(value=ns * m / dt, unit=UNIT, cores=O.max_threads(), kind="port",
+               sample="lag-parallel OpenMP oracle on %d samples, maxcorr=%d" % (ns, m))
+    if O.ref_available("libref_acf_O0.so"):
+        xs = x[: max(4 * m, ns // 20)]
+        t0 = time.perf_counter()
+        O.ref_calc_correlation(xs, m, "libref_acf_O0.so")
+        out["reference_as_distributed_O0_one_core"] = xs.size * m / (time.perf_counter() - t0)
+    if O.ref_available("libref_acf_omp.so"):
+        O.ref_calc_correlation(x[: ns // 8], m, "libref_acf_omp.so")
+        t0 = time.perf_counter()
+        O.ref_calc_correlation(x, m, "libref_acf_omp.so")
+        out["reference_openmp_racy_time_only"] = ns * m / (time.perf_counter() - t0)
+    return out
 
 
 def run_reference(args):
@@ -553,7 +567,7 @@ def main():
     ap.add_argument("--m", type=float, default=0)
     ap.add_argument("--windows", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--allcores", action="store_true", help="also time the OpenMP oracle on all cores")
+    ap.add_argument("--allcores", action="store_true", help="also time the other CPU builds of SURVEY 8d (lag-parallel port, -O0, racy OpenMP)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
