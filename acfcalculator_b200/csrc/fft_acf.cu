@@ -523,7 +523,7 @@ col_pass3_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
 {
     constexpr int DIR = (MODE <= 1) ? -1 : +1;
     constexpr int B = 9, NB8 = 64, LTC = 3;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* bufs = reinterpret_cast<double2*>(smem_raw);
     double2* tw = bufs + kC3Stages * kTileElems;   // tw[(u-1)*64 + g] = W_512^{g*u}   (pass 1)
     double2* tw2 = tw + 7 * NB8;                   // tw2[(u-1)*8 + p] = W_512^{8*p*u} (middle pass)
