@@ -336,7 +336,9 @@ std::vector<double> running_mean5(const std::vector<double>& y)
 
 }  // namespace
 
-GleResult run_gle_stage(const GleInput& in)
+GleResult run_gle_stage(const GleInput& in) { return run_gle_stage(in, std::cout); }
+
+GleResult run_gle_stage(const GleInput& in, std::ostream& log)
 {
     const double* vacf = in.vacf;
     const int ncorr = in.ncorr;
@@ -377,9 +379,9 @@ GleResult run_gle_stage(const GleInput& in)
     double s2 = root2.first;
     while (denom(s2) > den_tol) s2 -= kSIncrement;
     const std::pair<double, double> ds_min = minimise_brent(ds_of, s1, s2, bits);
-    std::cout << "#s1 " << s1 << std::endl;
-    std::cout << "#s2 " << s2 << std::endl;
-    std::cout << "#Ds_min " << ds_min.second << std::endl;
+    log << "#s1 " << s1 << std::endl;
+    log << "#s2 " << s2 << std::endl;
+    log << "#Ds_min " << ds_min.second << std::endl;
     out.s1 = s1;
     out.s2 = s2;
     out.ds_min = ds_min.second;

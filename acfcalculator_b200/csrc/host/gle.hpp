@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <functional>
+#include <iosfwd>
 #include <utility>
 #include <vector>
 
@@ -36,5 +37,7 @@ std::pair<double, double> solve_toms748(const std::function<double(double)>& f, 
 // The whole stage (ACFcalculator.cpp:778-899).  Prints "#s1", "#s2", "#Ds_min" to stdout at the same point
 // as the reference and throws what the reference throws (std::domain_error / std::out_of_range).
 GleResult run_gle_stage(const GleInput& in);
+// same, with the three "#..." lines going to `log` (batch mode collects the lines of each job)
+GleResult run_gle_stage(const GleInput& in, std::ostream& log);
 
 }  // namespace acfhost

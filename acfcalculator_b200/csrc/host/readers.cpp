@@ -73,6 +73,14 @@ std::vector<double> read_series_gromacs(const char* fname, int& num_samples, int
 
 // boost::char_separator<char>{" ", "\t"} with the default drop_empty_tokens policy: blanks separate and
 // vanish, every tab separates and is itself returned as a one-character token (ACFcalculator.cpp:385,:391).
+static bool g_faults_throw = false;
+void set_reader_faults_throw(bool on) { g_faults_throw = on; }
+static void reader_fault(const char* what)
+{
+    if (g_faults_throw) throw ReaderFault{what};
+    raise(SIGSEGV);
+}
+
 static void split_general(const std::string& line, std::vector<std::string>& out)
 {
     out.clear();
@@ -106,9 +114,9 @@ std::vector<double> read_series_general(const char* fname, int& num_samples, int
     num_samples = 0;
     while (std::getline(in, line)) {
         split_general(line, tok);
-        if (tok.empty()) raise(SIGSEGV);
+        if (tok.empty()) reader_fault("blank line");
         if (!std::regex_match(tok[0], numeric)) continue;
-        if (field < 0 || (size_t)field >= tok.size()) raise(SIGSEGV);
+        if (field < 0 || (size_t)field >= tok.size()) reader_fault("field beyond the last token");
         series.push_back(atof(tok[field].c_str()) * p_factor);
         ++num_samples;
     }

@@ -8,6 +8,14 @@
 
 namespace acfhost {
 
+// The general reader reproduces the reference's crashes on a blank line / a field beyond the last token with
+// raise(SIGSEGV) (exit 139).  A program that reads many files in one process (ACFcalculator --batch) switches to
+// throwing ReaderFault instead, so that one bad file does not take the other jobs with it.
+struct ReaderFault {
+    const char* what;
+};
+void set_reader_faults_throw(bool on);
+
 std::vector<double> read_series_namd(const char* fname, int& num_samples, int field);
 std::vector<double> read_series_charmm(const char* fname, int& num_samples);
 std::vector<double> read_series_gromacs(const char* fname, int& num_samples, int field);

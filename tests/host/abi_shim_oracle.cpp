@@ -63,6 +63,20 @@ int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double 
     return 0;
 }
 
+int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, int nwindows, int64_t ncorr, double dt,
+                               double cutoff, double* acf, double* vacf, acfb200_result* result)
+{
+    for (int w = 0; w < nwindows; ++w)
+        acfb200_acf_pipeline(series[w], n[w], ncorr, dt, cutoff, acf + (size_t)w * ncorr, vacf + (size_t)w * ncorr,
+                             result + w);
+    return 0;
+}
+int acfb200_multi_gpu_pipeline_batch(const double* const* series, const int64_t* n, int nwindows, int64_t ncorr,
+                                     double dt, double cutoff, double* acf, double* vacf, acfb200_result* result, int)
+{
+    return acfb200_acf_pipeline_batch(series, n, nwindows, ncorr, dt, cutoff, acf, vacf, result);
+}
+
 int acfb200_spring_rescale(double* acf, double* vacf, int64_t ncorr, double k, double mass, double temperature,
                            double* var, double* var_vel)
 {

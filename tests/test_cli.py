@@ -127,6 +127,90 @@ def test_viscosity_frontend_with_oracle_backend(oracle_frontends, tmp_path):
         assert [l for l in p.stderr.splitlines() if l.startswith("#reader:")] == ["#reader: " + which]
 
 
+def _batch_expectation(name):
+    """Exit status a run has inside a batch: the shipped binary's, with signals mapped to 128 + signal."""
+    rc = CASES[name]["returncode"]
+    return 128 - rc if rc < 0 else rc
+
+
+def run_batch(exe, names, tmp_path, extra=()):
+    lines, files = ["# one ACFcalculator run per line", ""], {}
+    for k, name in enumerate(names):
+        c = CASES[name]
+        inp = str(tmp_path / (name + ".in"))
+        write_input(inp, SERIES[c["series"]], c["format"])
+        acf_f, out_f = str(tmp_path / (name + ".acf")), str(tmp_path / (name + ".out"))
+        files[name] = (acf_f, out_f)
+        prefix = "./ACFcalculator " if k % 2 else ""  # lines pasted from setup.sh carry the program name
+        lines.append(prefix + " ".join(["-i", inp, "-a", acf_f, "-o", out_f] + c["args"]))
+    listing = str(tmp_path / "runs.txt")
+    open(listing, "w").write("\n".join(lines) + "\n")
+    p = subprocess.run([exe, "--batch", listing] + list(extra), capture_output=True, text=True, cwd=str(tmp_path))
+    # split stdout into the per-run sections
+    sections, cur = {}, None
+    for l in p.stdout.splitlines(keepends=True):
+        m = re.match(r"#batch run (\d+): ", l)
+        if m:
+            cur = int(m.group(1))
+            sections[cur] = ""
+        elif re.match(r"#batch run \d+ ended with status", l):
+            sections[cur] += l
+        else:
+            sections[cur] += l
+    return p, sections, files
+
+
+def check_batch(p, sections, files, names, rel):
+    first_bad = 0
+    for k, name in enumerate(names):
+        want = CASES[name]
+        status = _batch_expectation(name)
+        acf_f, out_f = files[name]
+        text = sections[k].replace(out_f, "<OUT>")
+        tail = "#batch run %d ended with status %d\n" % (k, status)
+        if status:
+            assert text.endswith(tail), (name, text[-200:])
+            text = text[: -len(tail)]
+            first_bad = first_bad or status
+        assert same_text(text, want["stdout"], rel), (name, text, want["stdout"])
+        for key, f in (("acf_file", acf_f), ("out_file", out_f)):
+            if want[key] is None:
+                assert not os.path.exists(f), (name, key)
+            else:
+                assert os.path.exists(f) and same_text(open(f).read(), want[key], rel), (name, key)
+    assert p.returncode == first_bad
+
+
+def test_batch_mode_with_oracle_backend_reproduces_every_single_run(oracle_frontends, tmp_path):
+    """ACFcalculator --batch FILE: every recorded case as one line of one batch.  Each run's stdout section, ACF file
+    and .out file are byte-identical to the shipped binary's single run; runs the reference aborts or crashes on are
+    reported with that status (134 / 139) and do not stop the others; the exit status is the first failure's."""
+    p, sections, files = run_batch(oracle_frontends["ACFcalculator"], ACF_CASES, tmp_path)
+    assert len(sections) == len(ACF_CASES)
+    check_batch(p, sections, files, ACF_CASES, rel=0)
+
+
+def test_batch_mode_all_good_runs_exit_zero_and_gpus_flag(oracle_frontends, tmp_path):
+    names = [n for n in ACF_CASES if CASES[n]["returncode"] == 0]
+    p, sections, files = run_batch(oracle_frontends["ACFcalculator"], names, tmp_path, extra=["--gpus", "2"])
+    assert p.returncode == 0 and p.stderr == ""
+    check_batch(p, sections, files, names, rel=0)
+
+
+def test_batch_mode_argument_errors(oracle_frontends, tmp_path):
+    exe = oracle_frontends["ACFcalculator"]
+    p = subprocess.run([exe, "--batch", str(tmp_path / "missing.txt")], capture_output=True, text=True)
+    assert p.returncode == 1 and "cannot read the batch file" in p.stderr
+    p = subprocess.run([exe, "--batch", "x", "-m", "5"], capture_output=True, text=True)
+    assert p.returncode == 1 and "takes no other arguments" in p.stderr
+    listing = str(tmp_path / "bad.txt")
+    open(listing, "w").write("-i a -a b\n-i a -a b -o c -m abc\n")
+    p = subprocess.run([exe, "--batch", listing], capture_output=True, text=True)
+    assert p.returncode == 1
+    assert "#batch run 0: the option '--output' is required but missing" in p.stderr
+    assert "#batch run 1: the argument ('abc') for option '--maxcorr' is invalid" in p.stderr
+
+
 FAST_READER_CASES = {  # case -> does the mapped reader handle it (True) or defer to the line-by-line one (False)
     "general_langevin1": True, "general_tabs_field2": True, "gromacs_field2": True, "namd_field1": True, "charmm": True,
     "general_pfactor": True, "gromacs_field_beyond_columns": False, "namd_field0_empty": False,
@@ -259,6 +343,15 @@ def test_gpu_frontend_matches_reference_binary(name, tmp_path):
     everything else (line grid, lag indices, exit status, which files exist) exactly."""
     got = run_case(os.path.join(GPU_BIN, "ACFcalculator"), name, tmp_path)
     check_case(got, name, rel=2e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_batch_mode_matches_reference_binary_run_by_run(tmp_path):
+    """All recorded cases as ONE --batch invocation of the shipped front-end (one CUDA context, the windows grouped into
+    acfb200_acf_pipeline_batch calls): every run's section, files and status as in the single runs."""
+    p, sections, files = run_batch(os.path.join(GPU_BIN, "ACFcalculator"), ACF_CASES, tmp_path)
+    assert len(sections) == len(ACF_CASES)
+    check_batch(p, sections, files, ACF_CASES, rel=2e-6)
 
 
 @pytest.mark.gpu
