@@ -442,10 +442,11 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
     const long long groups = (long long)nseries * p.lag_tiles;
     // Time chunks per (series, lag tile): the grid is groups*chunks CTAs of equal work, scheduled `slots` at a time.
     // Pick the count that minimises  waves/(groups*chunks)  -- the time of a grid that runs in whole waves -- times
-    // two measured corrections: a CTA's fixed cost (its first TMA round trip and the epilogue) is worth ~0.65 tile,
-    // and the last wave drains unevenly (~15 % of one wave).  Examples on 148 SMs x 8 CTAs: one series, 15 lag
-    // tiles -> 315 chunks (4 waves); 128 series x 15 lag tiles -> 8 chunks (12.97 waves, where 4 chunks would
-    // leave the seventh wave half empty).
+    // two measured corrections: a CTA's fixed cost (its first TMA round trip and the epilogue) is worth ~1.2 tiles,
+    // and the last wave drains unevenly (~15 % of one wave).  Examples on 148 SMs x 8 CTAs: one series of 1e7 samples,
+    // 15 lag tiles -> 315 chunks (4 waves: 6.29 ms, where 394 chunks = 5 waves take 6.39 ms and 236 = 3 waves 6.33 ms);
+    // 1e8 samples -> 631 chunks (8 waves, 61.9 ms; 16 waves 62.1 ms); 128 series x 15 lag tiles -> 8 chunks (12.97
+    // waves, where 4 chunks would leave the seventh wave half empty).
     long long chunks = 1;
     {
         const int max_waves = env_int("ACFB200_MAX_WAVES", 16);
@@ -456,7 +457,7 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
         for (long long c = 1; c <= (cmax < 1 ? 1 : cmax); ++c) {
             const long long ctas = groups * c;
             const long long waves = (ctas + slots - 1) / slots;
-            const double cost = (double)waves / (double)ctas * (1.0 + 0.65 * (double)c / (double)n_tiles) *
+            const double cost = (double)waves / (double)ctas * (1.0 + 1.2 * (double)c / (double)n_tiles) *
                                 (1.0 + 0.15 / (double)waves);
             if (cost < best_cost * (1.0 - 1e-9)) {
                 best_cost = cost;
