@@ -400,9 +400,10 @@ int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int
 // Long host series, direct summation: the upload of a series is cut into pieces on the copy stream and the lag kernel
 // of piece p (a time block whose halo of ncorr samples belongs to piece p+1, SeriesDesc.i_end < n) starts as soon as
 // the samples it can touch have landed.  Copy p therefore carries piece p plus the halo after it, and the pieces grow
-// geometrically (1 : 2 : 4 : 8 : rest of n/32 units): the host link is ~4x faster than the kernel consumes samples, so
-// only the first, small piece's transfer is exposed while the later launches are long enough to run at full
-// efficiency.  Every piece has its own plan (same variant and row pitch, its own chunk count); the per-chunk partial
+// geometrically (1 : 4 : 16 of n/21 units): at maxcorr = 1e4 the host link is ~4x faster than the kernel consumes
+// samples, so only the first, small piece's transfer is exposed, and every extra piece costs about one CTA wave of
+// fixed cost (~80 us), which is why there are three pieces and not five (1 : 2 : 4 : 8 : 17 measured 6.77 ms end to
+// end at N = 1e7 against 6.29 ms on the device).  Every piece has its own plan (same variant and row pitch, its own chunk count); the per-chunk partial
 // sums of all pieces lie back to back and are folded by one reduce launch in fixed order, as for a single launch.
 // Several series go one after the other: the upload of series s+1 runs under the kernels of series s.
 // Everything is only ENQUEUED here (compute stream + copy stream); the caller synchronises and then destroys `events`.
@@ -427,11 +428,11 @@ static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_
     size_t series_off = 0;
     for (int s = 0; s < nseries; ++s) {
         const long long ns = n[s];
-        long long unit = (ns / 32 + 1) & ~1ll;
+        long long unit = (ns / 21 + 1) & ~1ll;
         if (unit < 4 * ncorr) unit = (4 * ncorr + 1) & ~1ll;  // a piece much shorter than its halo is all overhead
         long long bounds[kMaxPieces + 1] = {0};
         int np = 0;
-        for (long long w = 1; np < kMaxPieces && bounds[np] < ns; w *= 2) {
+        for (long long w = 1; np < kMaxPieces && bounds[np] < ns; w *= 4) {
             long long e = bounds[np] + w * unit;
             if (np == kMaxPieces - 1 || e + unit / 2 >= ns) e = ns;
             bounds[++np] = e;
