@@ -85,3 +85,25 @@ def test_traj2diffusion_batch_over_devices(acf, ngpus):
     b, cb, rb = acf.traj2diffusion_batch(trajs, stride=1, max_s=500, timestep=2.0, cell=7.5, ngpus=ngpus)
     assert np.allclose(a, b, rtol=1e-13, atol=0) and np.array_equal(ca, cb)
     assert all(abs(x["diffusivity"] - y["diffusivity"]) <= 1e-13 * abs(x["diffusivity"]) for x, y in zip(ra, rb))
+
+
+def test_batch_front_end_on_several_gpus(ngpus, tmp_path):
+    """ACFcalculator --batch FILE --gpus G (the setup.sh loop in one process): window w on device w mod G; every window's
+    ACF file is the same text as from the one-GPU batch (6 printed digits) and all runs end with status 0."""
+    from cli_inputs import write_input
+    exe = os.path.join(ROOT, "acfcalculator_b200", "bin", "ACFcalculator")
+    outs = {}
+    for g in (1, ngpus):
+        lines = []
+        for w in range(2 * ngpus + 1):
+            inp = str(tmp_path / ("w%d.in" % w))
+            write_input(inp, ou_series(30000 + 7 * w, 15.0 + w, seed=900 + w), "general")
+            lines.append("-i %s -t general -f 1 -s 1 -m 400 -a %s -o %s" % (
+                inp, tmp_path / ("g%d_w%d.acf" % (g, w)), tmp_path / ("g%d_w%d.out" % (g, w))))
+        listing = str(tmp_path / ("runs_g%d.txt" % g))
+        open(listing, "w").write("\n".join(lines) + "\n")
+        p = subprocess.run([exe, "--batch", listing, "--gpus", str(g)], capture_output=True, text=True)
+        assert "autocorrelation pipeline failed" not in p.stderr, p.stderr
+        outs[g] = [open(str(tmp_path / ("g%d_w%d.acf" % (g, w)))).read() for w in range(2 * ngpus + 1)]
+        assert p.stdout.count("#batch run ") >= 2 * ngpus + 1
+    assert outs[1] == outs[ngpus]
