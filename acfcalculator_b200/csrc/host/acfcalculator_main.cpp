@@ -200,7 +200,7 @@ int finish_job(Job& j, std::ostream& out, std::ostream& err)
 
     {
         std::ofstream acf_file(j.acf_fname.c_str());
-        for (int i = 0; i < ncorr; ++i) acf_file << i << " " << j.acf[i] << " " << j.vacf[i] << std::endl;
+        for (int i = 0; i < ncorr; ++i) acf_file << i << " " << j.acf[i] << " " << j.vacf[i] << '\n';  // same bytes as endl
         acf_file.close();
     }
 

@@ -81,7 +81,8 @@ int main(int argc, char* argv[])
         std::cout << "#" << integrals[c] << std::endl;
         std::cout << "#eta " << which[c] << " " << eta[c] << std::endl;
         all.push_back(eta[c]);
-        for (int j = 0; j < ncorr; ++j) std::cout << j << " " << acf[(size_t)c * ncorr + j] << std::endl;
+        // same bytes as the reference's per-line std::endl, without a write() per lag
+        for (int j = 0; j < ncorr; ++j) std::cout << j << " " << acf[(size_t)c * ncorr + j] << '\n';
         std::cout << std::endl;
     }
     // mean and population standard deviation over the components (:217-222)
