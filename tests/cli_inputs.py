@@ -11,6 +11,29 @@ def write_input(path, series, fmt):
                 if fmt == "general_blank" and i == 10:
                     f.write("\n")
                 f.write("%11d % .14e\n" % (i, v))
+        elif fmt == "general_crlf":  # a file that went through a DOS editor: every line ends in \r\n
+            f.write("# step solute1\r\n")
+            for i, v in enumerate(series):
+                f.write("%11d % .14e\r\n" % (i, v))
+        elif fmt == "general_odd_first_tokens":
+            # the line filter is a regex on the FIRST token (ACFcalculator.cpp:384,:400): [-]?[0-9]*\.?[0-9]+ ; a step
+            # column written as 1e+03, +7 or 12,5 makes the reference skip the line
+            f.write("# step solute1\n")
+            for i, v in enumerate(series):
+                if i % 7 == 3:
+                    f.write("%.3e % .14e\n" % (i, v))
+                elif i % 7 == 5:
+                    f.write("+%d % .14e\n" % (i, v))
+                elif i % 11 == 6:
+                    f.write("%d,5 % .14e\n" % (i, v))
+                elif i % 13 == 2:
+                    f.write("-%d.25 % .14e\n" % (i, v))  # a negative, fractional first token passes
+                else:
+                    f.write("%11d % .14e\n" % (i, v))
+        elif fmt == "general_commas":  # documentation.md:72 promises comma separation; the tokenizer does not do it
+            f.write("# step,solute1\n")
+            for i, v in enumerate(series):
+                f.write("%d,%.14e\n" % (i, v))
         elif fmt == "general_tab":
             f.write("# time\tvalue\n")
             for i, v in enumerate(series):
@@ -24,6 +47,11 @@ def write_input(path, series, fmt):
             for i, v in enumerate(series):
                 # 11-char step, 4 blanks, then 21-char fields separated by 2 blanks: value k starts at 23*(k-1)+15
                 f.write("%11d    %21.14e  %21.14e\n" % (i, v, -v))
+        elif fmt == "namd_short_line":  # a truncated line: the reference stops reading there and keeps what it has
+            f.write("# step         solute1               solute2\n")
+            for i, v in enumerate(series):
+                line = "%11d    %21.14e  %21.14e" % (i, v, -v)
+                f.write((line[:12] if i == (3 * len(series)) // 5 else line) + "\n")
         elif fmt in ("charmm", "charmm_blank"):
             f.write("# charmm time series\n")
             for i, v in enumerate(series):

@@ -46,6 +46,11 @@ CASES = [
     ("maxcorr_beyond_n", "short", "general", ["-t", "general", "-f", "1", "-s", "1", "-m", "60"]),
     ("blank_line_general", "short", "general_blank", ["-t", "general", "-f", "1", "-m", "20"]),
     ("blank_line_charmm", "short", "charmm_blank", ["-t", "charmm", "-m", "20"]),
+    ("general_crlf", "lv3", "general_crlf", ["-t", "general", "-f", "1", "-s", "1", "-m", "500"]),
+    ("general_odd_first_tokens", "lv1", "general_odd_first_tokens", ["-t", "general", "-f", "1", "-s", "1", "-m", "500"]),
+    ("general_commas", "short", "general_commas", ["-t", "general", "-f", "1", "-s", "1", "-m", "20"]),
+    ("namd_short_line", "lv1", "namd_short_line", ["-t", "namd", "-f", "1", "-s", "1", "-m", "500"]),
+    ("namd_short_line_field2", "lv1", "namd_short_line", ["-t", "namd", "-f", "2", "-s", "1", "-m", "500"]),
 ]
 
 

@@ -215,6 +215,8 @@ FAST_READER_CASES = {  # case -> does the mapped reader handle it (True) or defe
     "general_langevin1": True, "general_tabs_field2": True, "gromacs_field2": True, "namd_field1": True, "charmm": True,
     "general_pfactor": True, "gromacs_field_beyond_columns": False, "namd_field0_empty": False,
     "blank_line_general": False, "blank_line_charmm": False, "general_tabs_field1_zero": True,
+    "general_crlf": True, "general_odd_first_tokens": True, "general_commas": True, "namd_short_line": False,
+    "namd_short_line_field2": False,
 }
 
 
