@@ -102,3 +102,28 @@ def write_traj(path, xyz, fmt):
                 f.write("%15d%22.14e%23.14e %23.14e\n" % (10 * i, r[0], r[1], r[2]))
         else:
             raise ValueError(fmt)
+
+
+def write_pressure_log_variant(path, pressure, variant):
+    """The same log with one of the irregularities the reference's reader (viscosity.cpp:117-169) meets in the wild:
+    short_line  one PRESSURE: line cut after 5 of its 9 values (the reference converts a stale token for the rest);
+    bad_value   a value std::stod rejects (the reference dies in std::terminate, status 134);
+    no_pressure no PRESSURE: line at all (zero samples: every lag is 0/0 or 0/negative);
+    few_lines   5 samples against maxcorr 1000."""
+    write_pressure_log(path, pressure)
+    lines = open(path).read().split("\n")
+    idx = [i for i, l in enumerate(lines) if l.startswith("PRESSURE:")]
+    if variant == "short_line":
+        lines[idx[500]] = " ".join(lines[idx[500]].split()[:7])
+    elif variant == "bad_value":
+        t = lines[idx[500]].split()
+        t[5] = "abc"
+        lines[idx[500]] = " ".join(t)
+    elif variant == "no_pressure":
+        lines = [l for l in lines if not l.startswith("PRESSURE:")]
+    elif variant == "few_lines":
+        keep = set(idx[:5])
+        lines = [l for i, l in enumerate(lines) if not l.startswith("PRESSURE:") or i in keep]
+    else:
+        raise ValueError(variant)
+    open(path, "w").write("\n".join(lines))

@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT_DIR = os.path.join(ROOT, "tests", "golden")
 from oracle import oracle as O  # noqa: E402
-from cli_inputs import write_input, write_pressure_log  # noqa: E402
+from cli_inputs import write_input, write_pressure_log, write_pressure_log_variant  # noqa: E402
 sys.path.insert(0, OUT_DIR)
 from make_golden import langevin  # noqa: E402
 
@@ -54,6 +54,9 @@ CASES = [
 ]
 
 
+VISCOSITY_VARIANTS = ["short_line", "bad_value", "no_pressure", "few_lines"]
+
+
 def main():
     O.build()
     series = {"lv1": langevin(20000, 1), "lv2": langevin(20000, 2), "lv3": langevin(20000, 3),
@@ -86,6 +89,13 @@ def main():
         out["viscosity_log"] = {"returncode": p.returncode, "stdout": p.stdout}
         print("viscosity rc=%d, %d stdout lines, last: %s" % (p.returncode, len(p.stdout.splitlines()),
                                                              p.stdout.splitlines()[-1]))
+        # irregular logs: only status, stderr head and a digest of stdout are kept for the long outputs
+        for variant in VISCOSITY_VARIANTS:
+            write_pressure_log_variant(log, pres[:1200], variant)
+            p = subprocess.run([O.ref_path("viscosity_ref"), log], capture_output=True, text=True)
+            out["viscosity_" + variant] = {"returncode": p.returncode, "stdout": p.stdout,
+                                           "stderr_head": p.stderr.splitlines()[:1]}
+            print("viscosity %-12s rc=%d, %d stdout lines" % (variant, p.returncode, len(p.stdout.splitlines())))
     json.dump(out, open(os.path.join(OUT, "cli_cases.json"), "w"), indent=0)
 
 

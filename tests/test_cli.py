@@ -12,14 +12,15 @@ import subprocess
 import numpy as np
 import pytest
 
-from cli_inputs import write_input, write_pressure_log, write_traj
+from cli_inputs import write_input, write_pressure_log, write_pressure_log_variant, write_traj
 from conftest import GOLDEN, ROOT
 
 HOST = os.path.join(ROOT, "acfcalculator_b200", "csrc", "host")
 BUILD = os.path.join(ROOT, "tests", "_build")
 CASES = json.load(open(os.path.join(GOLDEN, "cli_cases.json")))
 SERIES = np.load(os.path.join(GOLDEN, "cli_series.npz"))
-ACF_CASES = [k for k in CASES if k != "viscosity_log"]
+ACF_CASES = [k for k in CASES if not k.startswith("viscosity_")]
+VISCOSITY_VARIANTS = [k[len("viscosity_"):] for k in CASES if k.startswith("viscosity_") and k != "viscosity_log"]
 T2D = json.load(open(os.path.join(GOLDEN, "t2d_cases.json")))
 T2D_TRAJ = np.load(os.path.join(GOLDEN, "t2d_traj.npz"))
 T2D_CASES = [k for k in T2D if not k.startswith("opt_")]
@@ -211,6 +212,26 @@ def test_batch_mode_argument_errors(oracle_frontends, tmp_path):
     assert "#batch run 1: the argument ('abc') for option '--maxcorr' is invalid" in p.stderr
 
 
+@pytest.mark.parametrize("variant", VISCOSITY_VARIANTS)
+@pytest.mark.parametrize("fast_reader", ["1", "0"])
+def test_viscosity_frontend_on_irregular_logs(oracle_frontends, variant, fast_reader, tmp_path):
+    """Short PRESSURE: line (stale-token quirk), a value std::stod rejects (abort), no samples at all, fewer samples
+    than maxcorr: stdout and exit status of the reference program, with either reader."""
+    pres = np.load(os.path.join(GOLDEN, "cli_pressure.npz"))["pressure"][:1200]
+    log = str(tmp_path / "namd.log")
+    write_pressure_log_variant(log, pres, variant)
+    want = CASES["viscosity_" + variant]
+    env = dict(os.environ, ACFB200_FAST_READER=fast_reader, ACFB200_READER_DEBUG="1")
+    p = subprocess.run([oracle_frontends["viscosity"], log], capture_output=True, text=True, env=env)
+    assert p.returncode == want["returncode"]
+    assert p.stdout == want["stdout"]
+    which = [l for l in p.stderr.splitlines() if l.startswith("#reader:")]
+    declines = variant in ("short_line", "bad_value")  # the mapped reader leaves these to the line-by-line one
+    assert which == ["#reader: " + ("fast" if fast_reader == "1" and not declines else "line-by-line")]
+    if want["returncode"] < 0:
+        assert [l for l in p.stderr.splitlines() if not l.startswith("#reader:")][:1] == want["stderr_head"]
+
+
 FAST_READER_CASES = {  # case -> does the mapped reader handle it (True) or defer to the line-by-line one (False)
     "general_langevin1": True, "general_tabs_field2": True, "gromacs_field2": True, "namd_field1": True, "charmm": True,
     "general_pfactor": True, "gromacs_field_beyond_columns": False, "namd_field0_empty": False,
@@ -364,6 +385,18 @@ def test_gpu_viscosity_matches_reference_program(tmp_path):
     p = subprocess.run([os.path.join(GPU_BIN, "viscosity"), log], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert same_text(p.stdout, CASES["viscosity_log"]["stdout"], 2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", VISCOSITY_VARIANTS)
+def test_gpu_viscosity_on_irregular_logs(variant, tmp_path):
+    pres = np.load(os.path.join(GOLDEN, "cli_pressure.npz"))["pressure"][:1200]
+    log = str(tmp_path / "namd.log")
+    write_pressure_log_variant(log, pres, variant)
+    want = CASES["viscosity_" + variant]
+    p = subprocess.run([os.path.join(GPU_BIN, "viscosity"), log], capture_output=True, text=True)
+    assert p.returncode == want["returncode"], p.stderr[-300:]
+    assert same_text(p.stdout, want["stdout"], 2e-6)
 
 
 @pytest.mark.gpu
