@@ -51,6 +51,9 @@ CASES = [
     ("general_commas", "short", "general_commas", ["-t", "general", "-f", "1", "-s", "1", "-m", "20"]),
     ("namd_short_line", "lv1", "namd_short_line", ["-t", "namd", "-f", "1", "-s", "1", "-m", "500"]),
     ("namd_short_line_field2", "lv1", "namd_short_line", ["-t", "namd", "-f", "2", "-s", "1", "-m", "500"]),
+    # three and four samples: one or two remain after the velocity series (n - 2), every later lag is 0/0 or 0/negative
+    ("tiny_three_samples", "tiny3", "general", ["-t", "general", "-f", "1", "-m", "5"]),
+    ("tiny_four_samples", "tiny4", "general", ["-t", "general", "-f", "1", "-m", "5"]),
 ]
 
 
@@ -61,6 +64,8 @@ def main():
     O.build()
     series = {"lv1": langevin(20000, 1), "lv2": langevin(20000, 2), "lv3": langevin(20000, 3),
               "short": langevin(50, 5)}
+    series["tiny3"] = series["short"][:3].copy()
+    series["tiny4"] = series["short"][:4].copy()
     np.savez_compressed(os.path.join(OUT, "cli_series.npz"), **series)
     ref = O.ref_path("ACFcalculator_ref")
     out = {}
