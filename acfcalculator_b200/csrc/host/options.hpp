@@ -44,7 +44,7 @@ public:
     std::string help_text() const;
 
 private:
-    const OptionSpec* find_long(const std::string& name, bool allow_prefix) const;
+    const OptionSpec* find_long(const std::string& name, bool allow_prefix, const std::string& token) const;
     const OptionSpec* find_short(char c) const;
     std::vector<OptionSpec> specs_;
     std::map<std::string, std::string> values_;

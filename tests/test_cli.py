@@ -274,6 +274,29 @@ OPTION_ERRORS = [
     (["-i", "x", "-a", "y", "-o", "z", "-m", "5", "--maxcorr", "6"], "option '--maxcorr' cannot be specified more than once"),
     (["-i", "x", "-a", "y", "-o", "z", "--bogus=1"], "unrecognised option '--bogus=1'"),
     (["-i", "x", "-a", "y", "-o", "z", "-q"], "unrecognised option '-q'"),
+    # recorded from the shipped binary while fuzzing the option parser against it (8000 random command lines, no
+    # difference left in exit status, first stderr line or stdout):
+    (["-x1"], "unrecognised option '-x1'"),                     # the whole token is named
+    (["-1.5e-3"], "unrecognised option '-1.5e-3'"),
+    (["-h1"], "unrecognised option '-h1'"),                     # -h then the unknown -1
+    (["-habc", "--acf", "n"], "option '--acf' cannot be specified more than once"),   # sticky: -h, then -a "bc"
+    (["--ma=3"], "option '--ma=3' is ambiguous and matches '--mass', and '--maxcorr'"),
+    (["--t", "1"], "option '--t' is ambiguous and matches '--temperature', '--timestep', and '--type'"),
+    (["--f=0x10"], "the argument ('0x10') for option '--field' is invalid"),   # the alias --factor does not shadow --f
+    (["--fac", "2"], "unrecognised option '--fac'"),
+    (["--help=1"], "option '--help' does not take any arguments"),
+    (["--help="], "the argument for option '--help' should follow immediately after the equal sign"),
+    (["--o="], "the argument for option '--o' should follow immediately after the equal sign"),
+    (["--t="], "the argument for option '--t' should follow immediately after the equal sign"),
+    (["-f", "--inp="], "the argument for option '--field' should follow immediately after the equal sign"),
+    (["-c", "-m"], "the required argument for option '--cutoff' is missing"),   # "-m" is an option, not a value ...
+    (["-c", "--maxcorr"], "the argument ('--maxcorr') for option '--cutoff' is invalid"),   # ... "--maxcorr" is a value
+    (["-s", ""], "the argument for option '--timestep' is invalid"),
+    (["-h", "-h"], "option '--help' cannot be specified more than once"),
+    (["-s", "1e400"], "the argument ('1e400') for option '--timestep' is invalid"),   # overflow; inf, nan, 1e-400 pass
+    (["-s", "5 "], "the argument ('5 ') for option '--timestep' is invalid"),
+    (["-m", "2147483648"], "the argument ('2147483648') for option '--maxcorr' is invalid"),
+    (["-s", "inf", "-c", "nan", "-k", "1e-400", "-m", "-2147483648", "-c5"], "option '--cutoff' cannot be specified more than once"),
 ]
 
 
