@@ -16,6 +16,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <new>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -167,6 +168,8 @@ int read_job(Job& j, std::ostream& err)
         err << "Error: Time series could not be read from file." << std::endl;
         return 1;
     }
+    // one sample: velocity_series() asks for new double[n - 2] = new double[-1] (:233) and the reference dies there
+    if (j.series.size() == 1) throw std::bad_array_new_length();
     return 0;
 }
 
