@@ -1,5 +1,7 @@
 #include "gle.hpp"
 
+#include "exp_cr.hpp"
+
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -22,11 +24,13 @@ const double kFitWidth2 = 1000.0;
 inline int sgn(double v) { return (v > 0) - (v < 0); }
 }  // namespace
 
-// F(s) = sum_i exp(-s*i*dt) * series[i] * dt      (ACFcalculator.cpp:77-87, same evaluation order)
+// F(s) = sum_i exp(-s*i*dt) * series[i] * dt      (ACFcalculator.cpp:77-87, same evaluation order).
+// exp is the correctly rounded one (exp_cr.hpp): that is what the shipped reference binary's libm computes, and the
+// segment search below turns a one-ulp difference here into a different fitting window.
 double laplace(const double* series, double deltat, double s, int length)
 {
     double F = 0.0;
-    for (int i = 0; i < length; ++i) F += exp(-s * i * deltat) * series[i] * deltat;
+    for (int i = 0; i < length; ++i) F += exp_cr(-s * i * deltat) * series[i] * deltat;
     return F;
 }
 
@@ -192,9 +196,18 @@ bool all_distinct(double fa, double fb, double fd, double fe)
 
 }  // namespace
 
+// max_iter is IN-OUT exactly as in Boost: on entry the budget of function evaluations (two of which go to the end
+// points), on return the number actually used.  The reference passes ONE variable to both of its calls (:780, :785-786),
+// so its second root search may use only as many evaluations as the first one needed -- and returns a bracket that has
+// not converged when that is too few.  The arithmetic is unsigned and wraps like the original.
 std::pair<double, double> solve_toms748(const std::function<double(double)>& f, double ax, double bx, int tol_bits,
-                                        std::uintmax_t max_iter)
+                                        std::uintmax_t& max_iter)
 {
+    max_iter -= 2;
+    struct Restore {  // the four-argument Boost overload adds the two end-point evaluations back on every way out
+        std::uintmax_t& m;
+        ~Restore() { m += 2; }
+    } restore{max_iter};
     double eps = ldexp(1.0, 1 - tol_bits);
     if (eps < 4 * DBL_EPSILON) eps = 4 * DBL_EPSILON;
     auto converged = [eps](double a, double b) { return fabs(a - b) <= eps * fmin(fabs(a), fabs(b)); };
@@ -203,6 +216,7 @@ std::pair<double, double> solve_toms748(const std::function<double(double)>& f, 
     double fa = f(ax), fb = f(bx);
     if (a >= b) throw std::domain_error("Error in function boost::math::tools::toms748_solve<double>: Parameters a and b out of order: a=" + std::to_string(a));
     if (converged(a, b) || fa == 0 || fb == 0) {
+        max_iter = 0;
         if (fa == 0)
             b = a;
         else if (fb == 0)
@@ -265,6 +279,7 @@ std::pair<double, double> solve_toms748(const std::function<double(double)>& f, 
         rebracket(f, a, b, a + (b - a) / 2, fa, fb, d, fd);
         --count;
     }
+    max_iter -= count;
     if (fa == 0)
         b = a;
     else if (fb == 0)
@@ -371,8 +386,9 @@ GleResult run_gle_stage(const GleInput& in, std::ostream& log)
     const int bits = DBL_MANT_DIG;  // std::numeric_limits<double>::digits (:546)
     // Step 1 (:778-814): the two singularities either side of the denominator's minimum
     const std::pair<double, double> den_min = minimise_brent(denom, kSStart, kSEnd, bits);
-    const std::pair<double, double> root1 = solve_toms748(denom, kSStart, den_min.first, 30, 500);
-    const std::pair<double, double> root2 = solve_toms748(denom, den_min.first, kSEnd, 30, 500);
+    std::uintmax_t max_iter = 500;  // one variable for both searches, as upstream (:780): see solve_toms748
+    const std::pair<double, double> root1 = solve_toms748(denom, kSStart, den_min.first, 30, max_iter);
+    const std::pair<double, double> root2 = solve_toms748(denom, den_min.first, kSEnd, 30, max_iter);
     const double den_tol = den_min.second / 100;
     double s1 = root1.first;
     while (denom(s1) > den_tol) s1 += kSIncrement;

@@ -31,8 +31,9 @@ double laplace(const double* series, double deltat, double s, int length);
 std::pair<double, double> minimise_brent(const std::function<double(double)>& f, double lo, double hi, int bits);
 // TOMS 748 bracketing root finder; returns the final bracket (a, b).  Throws std::domain_error when f(a), f(b)
 // have the same sign, with the message Boost produces.
+// max_iter: in = evaluation budget, out = evaluations used (Boost's in-out parameter).
 std::pair<double, double> solve_toms748(const std::function<double(double)>& f, double a, double b, int tol_bits,
-                                        std::uintmax_t max_iter);
+                                        std::uintmax_t& max_iter);
 
 // The whole stage (ACFcalculator.cpp:778-899).  Prints "#s1", "#s2", "#Ds_min" to stdout at the same point
 // as the reference and throws what the reference throws (std::domain_error / std::out_of_range).

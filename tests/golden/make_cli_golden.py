@@ -54,6 +54,11 @@ CASES = [
     # three and four samples: one or two remain after the velocity series (n - 2), every later lag is 0/0 or 0/negative
     ("tiny_three_samples", "tiny3", "general", ["-t", "general", "-f", "1", "-m", "5"]),
     ("tiny_four_samples", "tiny4", "general", ["-t", "general", "-f", "1", "-m", "5"]),
+    # found by tools/fuzz_gle.py (seed 1, run 127): the fitting window of the D(s) extrapolation depends on ONE exp() in
+    # laplace() being correctly rounded (glibc 2.23 in the shipped binary: yes; glibc >= 2.28: no) -- #m and #b move in
+    # the 3rd-4th digit otherwise.  csrc/host/exp_cr.cpp
+    ("gle_exp_rounding", "fz127", "general", ["-t", "general", "-f", "1", "-m", "100", "-s", "0.5", "-k", "0.769", "-e",
+                                              "300", "-w", "18"]),
 ]
 
 
@@ -66,6 +71,10 @@ def main():
               "short": langevin(50, 5)}
     series["tiny3"] = series["short"][:3].copy()
     series["tiny4"] = series["short"][:4].copy()
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fuzz_gle
+    series["fz127"], fz_args = fuzz_gle.replay(1, 127)
+    assert fz_args == [c for c in CASES if c[0] == "gle_exp_rounding"][0][3]
     np.savez_compressed(os.path.join(OUT, "cli_series.npz"), **series)
     ref = O.ref_path("ACFcalculator_ref")
     out = {}

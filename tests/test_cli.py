@@ -36,7 +36,7 @@ def oracle_frontends(oracle):
     """ACFcalculator / viscosity front-ends linked against the oracle shim (CPU only)."""
     os.makedirs(BUILD, exist_ok=True)
     shim = os.path.join(ROOT, "tests", "host", "abi_shim_oracle.cpp")
-    common = [os.path.join(HOST, f) for f in ("options.cpp", "readers.cpp", "fast_readers.cpp", "gle.cpp")]
+    common = [os.path.join(HOST, f) for f in ("options.cpp", "readers.cpp", "fast_readers.cpp", "gle.cpp", "exp_cr.cpp")]
     link = ["-pthread", "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"),
             "-fopenmp"]
     exe = {}
@@ -379,10 +379,14 @@ def test_traj2diffusion_refuses_nonpositive_stride(oracle_frontends, tmp_path):
 
 # ---- GPU: the shipped binaries end to end -----------------------------------------------------------------
 GPU_BIN = os.path.join(ROOT, "acfcalculator_b200", "bin")
+# gle_exp_rounding sits, by construction, where one ulp in one exp() moves the fitting window of the host-side D(s)
+# extrapolation: it pins the host arithmetic (oracle-backed tests above, bit-identical C(k)); with the GPU sums'
+# ~1e-15 reordering differences in vacf which side of that boundary a run lands on is not a property of the hot path.
+GPU_ACF_CASES = [k for k in ACF_CASES if k != "gle_exp_rounding"]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ACF_CASES)
+@pytest.mark.parametrize("name", GPU_ACF_CASES)
 def test_gpu_frontend_matches_reference_binary(name, tmp_path):
     """6 significant digits are printed; the GPU sums differ from the serial ones at ~1e-15, so a printed
     digit may differ by one unit in the last place in rare cases: numbers are compared to 2e-6 relative,
@@ -395,9 +399,9 @@ def test_gpu_frontend_matches_reference_binary(name, tmp_path):
 def test_gpu_batch_mode_matches_reference_binary_run_by_run(tmp_path):
     """All recorded cases as ONE --batch invocation of the shipped front-end (one CUDA context, the windows grouped into
     acfb200_acf_pipeline_batch calls): every run's section, files and status as in the single runs."""
-    p, sections, files = run_batch(os.path.join(GPU_BIN, "ACFcalculator"), ACF_CASES, tmp_path)
-    assert len(sections) == len(ACF_CASES)
-    check_batch(p, sections, files, ACF_CASES, rel=2e-6)
+    p, sections, files = run_batch(os.path.join(GPU_BIN, "ACFcalculator"), GPU_ACF_CASES, tmp_path)
+    assert len(sections) == len(GPU_ACF_CASES)
+    check_batch(p, sections, files, GPU_ACF_CASES, rel=2e-6)
 
 
 @pytest.mark.gpu
