@@ -74,6 +74,7 @@ struct Job {
     std::vector<double> acf, vacf;
     acfb200_result res;
     int status = 0;  // exit status of this run so far (0 = still going)
+    int gle_threads = 0;  // host threads the GLE stage may use (0 = all; batch mode shares them between the runs)
 };
 
 // Option handling of main() (:554-686) with its stdout lines; returns the exit status the reference would end with
@@ -214,7 +215,7 @@ int finish_job(Job& j, std::ostream& out, std::ostream& err)
         return gpu_failure("cutoff integral failed", err);
     std::ofstream out_file(j.output_fname.c_str(), std::ofstream::out);  // created before the stage that may abort
 
-    GleInput gin = {j.vacf.data(), ncorr, var, var_vel, j.timestep};
+    GleInput gin = {j.vacf.data(), ncorr, var, var_vel, j.timestep, j.gle_threads};
     const GleResult g = run_gle_stage(gin, out);  // throws like the reference when the roots are not bracketed
 
     out_file << "#m= " << g.m << std::endl;
@@ -348,6 +349,8 @@ int run_batch(const std::string& list_fname, int gpus)
     };
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 1;
+    // fewer runs than host threads: each run's GLE stage spreads its D(s) sampling over its share of them
+    for (size_t i = 0; i < njobs; ++i) jobs[i].gle_threads = hw > njobs ? (int)(hw / njobs) : 1;
     if (hw > njobs) hw = (unsigned)njobs;
     std::vector<std::thread> pool;
     for (unsigned t = 1; t < hw; ++t) pool.emplace_back(worker);

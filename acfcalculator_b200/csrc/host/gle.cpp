@@ -9,6 +9,7 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 namespace acfhost {
 
@@ -368,18 +369,43 @@ GleResult run_gle_stage(const GleInput& in, std::ostream& log)
         const double lv = laplace(vacf, dt, s, ncorr);
         return -(lv * var * var_vel) / (lv * (s * var + var_vel / s) - var * var_vel);
     };
-    // D(s) sampled from s to s_max, positive values only (:514-530)
+    // D(s) sampled from s to s_max, positive values only (:514-530).  The abscissae come from the reference's own
+    // recurrence s = s + s_delta; the evaluations are independent of each other, so they are spread over host threads
+    // (each value is computed exactly as in the serial loop, the results are collected in order: same bits).
     auto sample_ds = [&](double s, double s_max, double s_delta, std::vector<double>& sv, std::vector<double>& dv) {
+        std::vector<double> grid;
         while (s <= s_max) {
-            const double lv = laplace(vacf, dt, s, ncorr);
-            const double den = lv * (s * var + var_vel / s) - var * var_vel;
-            const double val = -(lv * var * var_vel) / den;
-            if (val > 0.0) {
-                sv.push_back(s);
-                dv.push_back(val);
-            }
+            grid.push_back(s);
             s = s + s_delta;
         }
+        std::vector<double> val(grid.size());
+        auto evaluate = [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const double lv = laplace(vacf, dt, grid[i], ncorr);
+                const double den = lv * (grid[i] * var + var_vel / grid[i]) - var * var_vel;
+                val[i] = -(lv * var * var_vel) / den;
+            }
+        };
+        size_t nthreads = in.threads > 0 ? (size_t)in.threads : std::thread::hardware_concurrency();
+        const double work = (double)grid.size() * (double)ncorr;  // exp() evaluations
+        if (nthreads > grid.size() / 8) nthreads = grid.size() / 8;
+        if (nthreads < 2 || work < 2e5) {
+            evaluate(0, grid.size());
+        } else {
+            std::vector<std::thread> pool;
+            const size_t per = (grid.size() + nthreads - 1) / nthreads;
+            for (size_t t = 1; t < nthreads; ++t) {
+                const size_t lo = t * per, hi = lo + per < grid.size() ? lo + per : grid.size();
+                if (lo < hi) pool.emplace_back(evaluate, lo, hi);
+            }
+            evaluate(0, per < grid.size() ? per : grid.size());
+            for (auto& th : pool) th.join();
+        }
+        for (size_t i = 0; i < grid.size(); ++i)
+            if (val[i] > 0.0) {
+                sv.push_back(grid[i]);
+                dv.push_back(val[i]);
+            }
     };
 
     GleResult out;

@@ -4,7 +4,8 @@
 // toms748_solve; Boost is absent here, so minimise_brent() and solve_toms748() below restate those two
 // published algorithms (Brent 1973; Alefeld, Potra & Shi, ACM TOMS 21 (1995) 327, algorithm 748) with the
 // same control constants the reference passes (bits = 53 -> 26 effective, eps_tolerance(30), 500 iterations).
-// Not accelerated: O(maxcorr) exp() per evaluation, ~1e4 evaluations.
+// O(maxcorr) correctly rounded exp() per evaluation (exp_cr.hpp), ~3e3 evaluations; the two D(s) sampling sweeps
+// (2/3 of them) are spread over host threads.
 #pragma once
 #include <cstdint>
 #include <functional>
@@ -18,6 +19,7 @@ struct GleInput {
     const double* vacf;
     int ncorr;
     double var, var_vel, timestep;
+    int threads;  // host threads for the D(s) sampling (<= 0: all hardware threads); the result does not depend on it
 };
 
 struct GleResult {

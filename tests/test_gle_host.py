@@ -45,6 +45,7 @@ def test_exp_cr_is_correctly_rounded_against_mpmath(gle_unit):
     mp.mp.prec = 300
     rng = np.random.default_rng(7)
     xs = np.concatenate([rng.uniform(-745.2, 709.7, 4000), rng.uniform(-40, 0, 6000), rng.uniform(-1e-3, 1e-3, 1000),
+                         rng.uniform(-745.3, -707.9, 4000), rng.uniform(-708.45, -708.35, 1000),  # subnormal results
                          -rng.uniform(1e-6, 1, 3000) * rng.integers(0, 1000, 3000) * rng.choice([0.5, 1, 2], 3000),
                          [0.0, -0.0, 1.0, -1.0, 2.0 ** -54, -2.0 ** -54, 1.5 * 2.0 ** -54, 1e-300, -1e-300,
                           709.782712893384, 709.7827128933841, -708.3964185322641, -708.5, -744.9, -745.13321910194111,
@@ -65,7 +66,7 @@ def test_exp_cr_is_correctly_rounded_against_mpmath(gle_unit):
 
 def test_exp_cr_fast_path_equals_binary128_path(gle_unit):
     rng = np.random.default_rng(8)
-    xs = np.concatenate([rng.uniform(-760, 720, 100000), rng.uniform(-30, 0, 200000)])
+    xs = np.concatenate([rng.uniform(-760, 720, 100000), rng.uniform(-30, 0, 200000), rng.uniform(-746, -707, 100000)])
     fast, slow = run_exp(gle_unit, xs)
     assert fast == slow
 
