@@ -2,7 +2,9 @@
 // make by calling the CPU oracle (oracle/acf_oracle.c).  Linked ONLY into tests/_build/*_oracle, the
 // CPU-side builds of the front-ends used by tests/test_cli.py to check options, readers, the GLE stage and
 // the output formats against the reference binary's recorded output without a GPU.  Never shipped.
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -52,6 +54,22 @@ int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double 
     std::vector<double> s(series, series + n);
     oracle_pipeline_result o;
     oracle_acf_pipeline(s.data(), n, ncorr, dt, cutoff, acf, vacf, &o, 1);
+    // ACF_SHIM_PERTURB=<seed>: emulate the GPU's summation-order differences (observed: up to 3e-15 * C(0)) so the CPU
+    // suite can check that the tolerances the GPU tests use for the GLE lines hold under them (tests/test_cli.py)
+    if (const char* ps = getenv("ACF_SHIM_PERTURB")) {
+        unsigned long long st = strtoull(ps, nullptr, 10) * 6364136223846793005ULL + 1442695040888963407ULL;
+        auto u = [&st]() {
+            st = st * 6364136223846793005ULL + 1442695040888963407ULL;
+            return ((double)(st >> 11) / 9007199254740992.0) * 2 - 1;
+        };
+        const double a0 = acf[0], v0 = vacf[0];
+        for (int64_t k = 0; k < ncorr; ++k) {
+            if (std::isfinite(acf[k]) && acf[k] != 0.0) acf[k] += u() * 2e-15 * a0;
+            if (std::isfinite(vacf[k]) && vacf[k] != 0.0) vacf[k] += u() * 2e-15 * v0;
+        }
+        o.var = acf[0];
+        o.var_vel = vacf[0];
+    }
     r->avg = o.avg;
     r->var = o.var;
     r->var_vel = o.var_vel;
