@@ -8,7 +8,7 @@ no GPU is involved.  Command lines that use this repo's extensions (-r/--factor,
 import os
 import subprocess, random, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ref = os.path.join(ROOT, 'oracle', '_ref', 'ACFcalculator_ref'); ours = os.path.join(ROOT, 'tests', '_build', 'ACFcalculator_oracle')
+ref = os.path.join(ROOT, 'oracle', '_ref', 'ACFcalculator_ref'); ours = os.environ.get('FUZZ_OURS', os.path.join(ROOT, 'tests', '_build', 'ACFcalculator_oracle'))
 random.seed(int(sys.argv[1]) if len(sys.argv)>1 else 1)
 longs=["input","type","cutoff","acf","output","timestep","maxcorr","field","p_factor","spring","mass","temperature","help","bogus"]
 shorts=list("itcaosmfpkweh")+["x","z","1"]

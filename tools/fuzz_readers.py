@@ -13,7 +13,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "ACFcalculator_ref")
-OURS = os.path.join(ROOT, "tests", "_build", "ACFcalculator_oracle")
+OURS = os.environ.get("FUZZ_OURS", os.path.join(ROOT, "tests", "_build", "ACFcalculator_oracle"))  # e.g. a sanitizer build
 
 NUMS = ["%.6f", "%.14e", "% .14e", "%.3g", "%d", "%+.4f", "%.10g", "%.1f"]
 # not in the list: "nan" / "inf" samples -- they turn every lag into a NaN whose SIGN depends on the operand order the

@@ -16,7 +16,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "traj2diffusion_ref")
-OURS = os.path.join(ROOT, "tests", "_build", "traj2diffusion_oracle")
+OURS = os.environ.get("FUZZ_OURS", os.path.join(ROOT, "tests", "_build", "traj2diffusion_oracle"))  # e.g. a sanitizer build
 
 ODD = ["1e", "e5", "-", "+", ".", "1.5abc", "abc", "1,5", "0x1p3", "--3", "1e400", "+7", "1.2.3", "", "1d5", "E", "e"]
 

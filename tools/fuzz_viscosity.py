@@ -13,7 +13,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "viscosity_ref")
-OURS = os.path.join(ROOT, "tests", "_build", "viscosity_oracle")
+OURS = os.environ.get("FUZZ_OURS", os.path.join(ROOT, "tests", "_build", "viscosity_oracle"))  # e.g. a sanitizer build
 
 NUMS = ["%.6f", "%.4f", "%.14e", "%.3g", "%d", "%+.4f", "%.10g"]
 # accepted by std::stod: hex floats, trailing junk, leading '+', "1." ; rejected (std::terminate): words, "", lone signs
