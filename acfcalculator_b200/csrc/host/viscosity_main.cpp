@@ -3,7 +3,11 @@
 // off-diagonal components (i % 4 != 0), maxcorr 1000, 2 fs, box length and temperature as hard-coded there,
 // and the same stdout grammar.  The correlations and integrals run on the GPU through libacf_b200.so.
 //
-//   viscosity <namd.log> [--maxcorr M] [--timestep fs] [--box A] [--temperature K] [--exact-reader] [--gpus G]
+//   viscosity <namd.log> [--maxcorr M] [--timestep fs] [--box A] [--temperature K] [--components LIST]
+//             [--exact-reader] [--gpus G]
+// --components: comma-separated tensor entries, by index 0..8 (row-major, as the log lists them) or name (xy, xz, yx,
+// yz, zx, zy, xx, yy, zz); default: the six off-diagonal ones the reference loops over.  "xy,xz,yz" halves the work
+// for a symmetric tensor.
 // The optional switches are extensions; without them the output is the reference's.
 #include <cmath>
 #include <cstdlib>
@@ -26,6 +30,9 @@ int main(int argc, char* argv[])
     double temperature = 298.15;        // :188
     bool quirk = true;
     int gpus = 1;  // --gpus G: spread the components (or time blocks of them) over G devices of this box
+    std::vector<int> which;
+    for (int i = 0; i < 9; ++i)
+        if (i % 4 != 0) which.push_back(i);  // off-diagonal components only (:200)
     if (argc < 2) return 1;
     const char* fname = argv[1];
     for (int i = 2; i < argc; ++i) {
@@ -42,6 +49,24 @@ int main(int argc, char* argv[])
             temperature = atof(argv[++i]);
         else if (i + 1 < argc && a == "--gpus")
             gpus = atoi(argv[++i]);
+        else if (i + 1 < argc && a == "--components") {
+            static const char* const names[9] = {"xx", "xy", "xz", "yx", "yy", "yz", "zx", "zy", "zz"};
+            which.clear();
+            std::string list = argv[++i];
+            for (size_t pos = 0; pos <= list.size();) {
+                const size_t end = list.find(',', pos) == std::string::npos ? list.size() : list.find(',', pos);
+                const std::string tok = list.substr(pos, end - pos);
+                int idx = -1;
+                for (int k = 0; k < 9; ++k)
+                    if (tok == names[k] || (tok.size() == 1 && tok[0] == '0' + k)) idx = k;
+                if (idx < 0) {
+                    std::cerr << "viscosity: --components takes entries 0..8 or xx..zz, got '" << tok << "'" << std::endl;
+                    return 1;
+                }
+                which.push_back(idx);
+                pos = end + 1;
+            }
+        }
         else {
             std::cerr << "viscosity: unknown argument " << a << std::endl;
             return 1;
@@ -59,12 +84,7 @@ int main(int argc, char* argv[])
     if (!fast_done) comps = acfhost::read_pressure_namd(fname, num_samples, quirk);
 
     std::vector<const double*> ptrs;
-    std::vector<int> which;
-    for (int i = 0; i < 9; ++i) {
-        if (i % 4 == 0) continue;  // off-diagonal components only (:200)
-        ptrs.push_back(comps[i].data());
-        which.push_back(i);
-    }
+    for (int i : which) ptrs.push_back(comps[i].data());
     const int nc = (int)ptrs.size();
     std::vector<double> acf((size_t)nc * ncorr), integrals(nc), eta(nc);
     int rc = ACFB200_OK;

@@ -145,6 +145,27 @@ def test_viscosity_frontend_with_oracle_backend(oracle_frontends, tmp_path):
         assert [l for l in p.stderr.splitlines() if l.startswith("#reader:")] == ["#reader: " + which]
 
 
+def test_viscosity_component_selection(oracle_frontends, tmp_path):
+    """--components (extension): the selected tensor entries give exactly the sections the default run
+    prints for them, in the order asked for; mean and deviation are taken over the selection (viscosity.cpp:217-222)."""
+    pres = np.load(os.path.join(GOLDEN, "cli_pressure.npz"))["pressure"]
+    log = str(tmp_path / "namd.log")
+    write_pressure_log(log, pres)
+    sections = CASES["viscosity_log"]["stdout"].split("\n\n")  # six "#I / #eta i ... / rows" blocks, then "#eta = ..."
+    by_index = {int(sec.split("\n")[1].split()[1]): sec for sec in sections[:6]}
+    for spec, idx in (("xy,xz,yz", [1, 2, 5]), ("7,1", [7, 1]), ("zx", [6])):
+        p = subprocess.run([oracle_frontends["viscosity"], log, "--components", spec], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        got = p.stdout.split("\n\n")
+        assert got[:-1] == [by_index[i] for i in idx]
+        etas = np.array([float(by_index[i].split("\n")[1].split()[2]) for i in idx])
+        mean, dev = (float(v) for v in got[-1].split()[2:4])
+        assert mean == pytest.approx(etas.mean(), rel=2e-5)  # etas are read back from 6 printed digits
+        assert dev == pytest.approx(np.sqrt(max((etas ** 2).mean() - etas.mean() ** 2, 0.0)), rel=1e-3, abs=1e-5 * abs(mean))
+    p = subprocess.run([oracle_frontends["viscosity"], log, "--components", "xy,ab"], capture_output=True, text=True)
+    assert p.returncode == 1 and "--components" in p.stderr
+
+
 def _batch_expectation(name):
     """Exit status a run has inside a batch: the shipped binary's, with signals mapped to 128 + signal."""
     rc = CASES[name]["returncode"]
