@@ -394,6 +394,35 @@ int main(int argc, char* argv[])
         }
     }
 
+    // ACFB200_COLLECT=FILE: record this invocation as one line of FILE instead of running it, so that an existing
+    // setup.sh-style script (one process per window) can be replayed as ONE --batch run without editing it:
+    //     ACFB200_COLLECT=runs.txt ./setup.sh && ACFcalculator --batch runs.txt
+    // The option check is the reference's, so a wrong command line fails here exactly as it would have.
+    if (const char* collect = getenv("ACFB200_COLLECT")) {
+        Job probe;
+        std::ostringstream sink;
+        const int prc = parse_job(argc, argv, probe, sink, std::cerr);
+        if (prc != 0) {
+            std::cout << sink.str();  // --help: the usage text
+            return prc;
+        }
+        std::string line;
+        for (int a = 1; a < argc; ++a) {
+            if (argv[a][0] == 0 || strpbrk(argv[a], " \t\r\n") != nullptr) {
+                std::cerr << "ACFcalculator: ACFB200_COLLECT cannot record an empty argument or one with blanks ("
+                          << argv[a] << "): batch files have no quoting" << std::endl;
+                return 1;
+            }
+            line += (a > 1 ? " " : "") + std::string(argv[a]);
+        }
+        std::ofstream list(collect, std::ofstream::app);
+        if (!list || !(list << line << '\n')) {
+            std::cerr << "ACFcalculator: cannot append to " << collect << std::endl;
+            return 1;
+        }
+        return 0;
+    }
+
     Job j;
     int rc = parse_job(argc, argv, j, std::cout, std::cerr);
     if (rc != 0) return rc;

@@ -236,6 +236,42 @@ def test_batch_mode_all_good_runs_exit_zero_and_gpus_flag(oracle_frontends, tmp_
     check_batch(p, sections, files, names, rel=0)
 
 
+def test_collect_mode_turns_a_setup_sh_loop_into_a_batch_file(oracle_frontends, tmp_path):
+    """ACFB200_COLLECT=FILE: every invocation is recorded instead of run (after the reference's own option check), and
+    the recorded file replayed with --batch gives each run's files and stdout section."""
+    exe = oracle_frontends["ACFcalculator"]
+    names = ["general_langevin3_m500", "gromacs_field2", "charmm", "general_langevin2_aborts"]
+    listing = str(tmp_path / "runs.txt")
+    env = dict(os.environ, ACFB200_COLLECT=listing)
+    files = {}
+    for name in names:  # what a setup.sh loop does, one process per window
+        c = CASES[name]
+        inp = str(tmp_path / (name + ".in"))
+        write_input(inp, SERIES[c["series"]], c["format"])
+        files[name] = (str(tmp_path / (name + ".acf")), str(tmp_path / (name + ".out")))
+        p = subprocess.run([exe, "-i", inp, "-a", files[name][0], "-o", files[name][1]] + c["args"], capture_output=True,
+                           text=True, env=env)
+        assert (p.returncode, p.stdout, p.stderr) == (0, "", "")
+        assert not os.path.exists(files[name][0])  # nothing ran
+    assert len(open(listing).read().splitlines()) == len(names)
+    # a wrong command line fails at collect time as it would have failed when run; nothing is recorded for it
+    bad = subprocess.run([exe, "-i", "x", "-a", "y"], capture_output=True, text=True, env=env)
+    assert bad.returncode == 1 and "the option '--output' is required but missing" in bad.stderr
+    blank = subprocess.run([exe, "-i", "a b", "-a", "y", "-o", "z"], capture_output=True, text=True, env=env)
+    assert blank.returncode == 1 and "no quoting" in blank.stderr
+    assert len(open(listing).read().splitlines()) == len(names)
+    p = subprocess.run([exe, "--batch", listing], capture_output=True, text=True, cwd=str(tmp_path))
+    sections, cur = {}, None
+    for l in p.stdout.splitlines(keepends=True):
+        m = re.match(r"#batch run (\d+): ", l)
+        if m:
+            cur = int(m.group(1))
+            sections[cur] = ""
+        else:
+            sections[cur] += l
+    check_batch(p, sections, files, names, rel=0)
+
+
 def test_batch_mode_argument_errors(oracle_frontends, tmp_path):
     exe = oracle_frontends["ACFcalculator"]
     p = subprocess.run([exe, "--batch", str(tmp_path / "missing.txt")], capture_output=True, text=True)
