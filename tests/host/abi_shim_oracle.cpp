@@ -45,6 +45,25 @@ int acfb200_traj2diffusion(const double* x, const double* y, const double* z, in
     r->nframes = n;
     return 0;
 }
+int acfb200_traj2diffusion_batch(const double* const* x, const double* const* y, const double* const* z, const int64_t* n,
+                                 int ntraj, int64_t stride, int64_t max_s, double dt, double cell, int imaging, double* msd,
+                                 int32_t* counter, acfb200_msd_result* result)
+{
+    for (int t = 0; t < ntraj; ++t) {
+        acfb200_msd_result r;
+        acfb200_traj2diffusion(x[t], y[t], z[t], n[t], stride, max_s, dt, cell, imaging, msd + (size_t)t * max_s,
+                               counter ? counter + (size_t)t * max_s : nullptr, &r);
+        if (result) result[t] = r;
+    }
+    return 0;
+}
+int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, const double* const* y, const double* const* z,
+                                           const int64_t* n, int ntraj, int64_t stride, int64_t max_s, double dt,
+                                           double cell, int imaging, double* msd, int32_t* counter,
+                                           acfb200_msd_result* result, int)
+{
+    return acfb200_traj2diffusion_batch(x, y, z, n, ntraj, stride, max_s, dt, cell, imaging, msd, counter, result);
+}
 int acfb200_set_method(int) { return 0; }
 int acfb200_warmup(void) { return 0; }
 

@@ -435,6 +435,75 @@ def test_traj2diffusion_frontend_with_oracle_backend_is_byte_identical(oracle_fr
     check_t2d(p, inp, name, rel=0)
 
 
+def run_t2d_batch(exe, names, tmp_path, extra=()):
+    """All runs as one `traj2diffusion --batch` invocation; every second run redirects its stdout with "> file"."""
+    lines, outfiles = ["# one traj2diffusion run per line", ""], {}
+    for k, name in enumerate(names):
+        c = T2D[name]
+        inp = str(tmp_path / (name + ".traj"))
+        if c["format"] != "none":
+            write_traj(inp, T2D_TRAJ[c["traj"]], c["format"])
+        words = (["./traj2diffusion"] if k % 3 == 1 else []) + ["-t", inp] + c["args"]
+        if k % 2 == 0:
+            outfiles[name] = str(tmp_path / (name + ".msd"))
+            words += [">", outfiles[name]] if k % 4 == 0 else [">" + outfiles[name]]
+        lines.append(" ".join(words))
+    listing = str(tmp_path / "runs.txt")
+    open(listing, "w").write("\n".join(lines) + "\n")
+    p = subprocess.run([exe, "--batch", listing] + list(extra), capture_output=True, text=True, cwd=str(tmp_path))
+    sections, cur = {}, None
+    for l in p.stdout.splitlines(keepends=True):
+        m = re.match(r"#batch run (\d+): ", l)
+        if m:
+            cur = int(m.group(1))
+            sections[cur] = ""
+        else:
+            sections[cur] += l
+    return p, sections, outfiles
+
+
+def check_t2d_batch(p, sections, outfiles, names, rel):
+    first_bad = 0
+    for k, name in enumerate(names):
+        want = T2D[name]
+        status = 128 - want["returncode"] if want["returncode"] < 0 else want["returncode"]
+        text = sections[k]
+        tail = "#batch run %d ended with status %d\n" % (k, status)
+        if status:
+            assert text.endswith(tail), (name, text[-200:])
+            text = text[: -len(tail)]
+            first_bad = first_bad or status
+        if name in outfiles:  # the run's stdout went to its file; nothing but the header (and status) in the section
+            assert text == "", (name, text[:200])
+            text = open(outfiles[name]).read()
+        assert same_text(text, want["stdout"], rel), (name, text[-300:], want["stdout"][-300:])
+    assert p.returncode == first_bad
+
+
+def test_traj2diffusion_batch_mode_reproduces_every_single_run(oracle_frontends, tmp_path):
+    """traj2diffusion --batch (extension): one process for a set of trajectories; each run's stdout -- to its "> file" or
+    to its section -- is byte for byte that of the single run, aborting runs are contained (status 134)."""
+    p, sections, outfiles = run_t2d_batch(oracle_frontends["traj2diffusion"], T2D_CASES, tmp_path)
+    assert len(sections) == len(T2D_CASES)
+    check_t2d_batch(p, sections, outfiles, T2D_CASES, rel=0)
+    # --gpus is accepted (same results through the multi-GPU entry point); anything else next to --batch is refused
+    good = [n for n in T2D_CASES if T2D[n]["returncode"] == 0]
+    p, sections, outfiles = run_t2d_batch(oracle_frontends["traj2diffusion"], good, tmp_path, extra=["--gpus", "2"])
+    check_t2d_batch(p, sections, outfiles, good, rel=0)
+    assert p.returncode == 0
+    exe = oracle_frontends["traj2diffusion"]
+    bad = subprocess.run([exe, "--batch", str(tmp_path / "runs.txt"), "-m", "5"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "takes no other arguments" in bad.stderr
+    missing = subprocess.run([exe, "--batch", str(tmp_path / "nope.txt")], capture_output=True, text=True)
+    assert missing.returncode == 1 and "cannot read the batch file" in missing.stderr
+    # option errors stay inside their run
+    listing = str(tmp_path / "opts.txt")
+    open(listing, "w").write("-t x --bogus 1\n-t %s -m 3\n" % str(tmp_path / "general_default.traj"))
+    p = subprocess.run([exe, "--batch", listing], capture_output=True, text=True)
+    assert p.returncode == 1 and "#batch run 0 ended with status 1" in p.stdout and "#D " in p.stdout
+    assert "unrecognised option '--bogus'" in p.stderr
+
+
 @pytest.mark.parametrize("name", T2D_OPT)
 def test_traj2diffusion_option_handling(oracle_frontends, name, tmp_path):
     """Help layout, the required-option message, unknown options and bad values.  The recorded text comes from
