@@ -64,6 +64,11 @@ int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, const double*
 {
     return acfb200_traj2diffusion_batch(x, y, z, n, ntraj, stride, max_s, dt, cell, imaging, msd, counter, result);
 }
+int acfb200_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr)
+{
+    oracle_calc_correlation(y, n, ncorr, corr);
+    return 0;
+}
 int acfb200_set_method(int) { return 0; }
 int acfb200_warmup(void) { return 0; }
 
