@@ -46,6 +46,8 @@ def test_exp_cr_is_correctly_rounded_against_mpmath(gle_unit):
     rng = np.random.default_rng(7)
     xs = np.concatenate([rng.uniform(-745.2, 709.7, 4000), rng.uniform(-40, 0, 6000), rng.uniform(-1e-3, 1e-3, 1000),
                          rng.uniform(-745.3, -707.9, 4000), rng.uniform(-708.45, -708.35, 1000),  # subnormal results
+                         np.floor(rng.uniform(-95000, 90000, 1000)) * 0.0054152123481245727,  # next to multiples of ln2/128
+                         np.ldexp(rng.uniform(1, 2, 1000), rng.integers(-80, 10, 1000)) * rng.choice([-1.0, 1.0], 1000),
                          -rng.uniform(1e-6, 1, 3000) * rng.integers(0, 1000, 3000) * rng.choice([0.5, 1, 2], 3000),
                          [0.0, -0.0, 1.0, -1.0, 2.0 ** -54, -2.0 ** -54, 1.5 * 2.0 ** -54, 1e-300, -1e-300,
                           709.782712893384, 709.7827128933841, -708.3964185322641, -708.5, -744.9, -745.13321910194111,
@@ -66,7 +68,12 @@ def test_exp_cr_is_correctly_rounded_against_mpmath(gle_unit):
 
 def test_exp_cr_fast_path_equals_binary128_path(gle_unit):
     rng = np.random.default_rng(8)
-    xs = np.concatenate([rng.uniform(-760, 720, 100000), rng.uniform(-30, 0, 200000), rng.uniform(-746, -707, 100000)])
+    step = 0.0054152123481245727  # ln2/128: arguments next to its multiples cancel heavily in the range reduction
+    near = np.floor(rng.uniform(-95000, 90000, 100000)) * step
+    near = (near.view(np.int64) + rng.integers(-3, 4, near.size)).view(np.float64)
+    logu = np.ldexp(rng.uniform(1, 2, 100000), rng.integers(-80, 10, 100000)) * rng.choice([-1.0, 1.0], 100000)
+    xs = np.concatenate([rng.uniform(-760, 720, 100000), rng.uniform(-30, 0, 200000), rng.uniform(-746, -707, 100000),
+                         near, logu])
     fast, slow = run_exp(gle_unit, xs)
     assert fast == slow
 
