@@ -64,6 +64,28 @@ int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, const double*
 {
     return acfb200_traj2diffusion_batch(x, y, z, n, ntraj, stride, max_s, dt, cell, imaging, msd, counter, result);
 }
+int acfb200_msd(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s, double* msd,
+                int32_t* counter)
+{
+    std::vector<int32_t> cnt(max_s);
+    oracle_msd(x, y, z, n, stride, max_s, msd, counter ? counter : cnt.data());
+    return 0;
+}
+int acfb200_image(double* x, double* y, double* z, int64_t n, double cell)
+{
+    oracle_image_axis(x, n, cell);
+    oracle_image_axis(y, n, cell);
+    oracle_image_axis(z, n, cell);
+    return 0;
+}
+int acfb200_msd_slope(const double* msd, int64_t n, double* slope, double* sum)
+{
+    double s = 0.0;
+    const double v = oracle_msd_slope(msd, n, &s);
+    if (slope) *slope = v;
+    if (sum) *sum = s;
+    return 0;
+}
 int acfb200_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr)
 {
     oracle_calc_correlation(y, n, ncorr, corr);

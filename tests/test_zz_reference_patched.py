@@ -5,6 +5,9 @@ output code compiled from /root/reference/viscosity.cpp where it lies -- with no
 CPU: the same cut linked against the oracle shim reproduces the unmodified program byte for byte (the patch mechanics),
 and the GPU-linked build refuses to run without a device.  GPU: oracle/_ref/viscosity_patched (built by oracle/Makefile
 in the build container, travels to the GPU box) against the recorded output of the unmodified program.
+The same for traj2diffusion.cpp: image() (:275-340), slope() (:342-355) and the MSD accumulation loop of main()
+(:530-541) answered by the library (oracle/patch/traj2diffusion_acfb200.cpp); options (via oracle/boost_stub), readers,
+the divide-and-print loop and the D lines are the reference's own code.
 (The file name keeps these tests at the end of the run.)"""
 import os
 import subprocess
@@ -15,9 +18,11 @@ import pytest
 
 from cli_inputs import write_pressure_log
 from conftest import GOLDEN, ROOT
-from test_cli import CASES, same_text
+from test_cli import CASES, T2D, T2D_CASES, check_t2d, run_t2d, same_text
 
 REF_SRC = "/root/reference/viscosity.cpp"
+REF_T2D_SRC = "/root/reference/traj2diffusion.cpp"
+PATCHED_T2D = os.path.join(ROOT, "oracle", "_ref", "traj2diffusion_patched")
 PATCHED = os.path.join(ROOT, "oracle", "_ref", "viscosity_patched")
 PATCH_DIR = os.path.join(ROOT, "oracle", "patch")
 
@@ -65,3 +70,39 @@ def test_gpu_patched_reference_matches_the_unmodified_program(tmp_path):
     p = subprocess.run([PATCHED, _log(tmp_path)], capture_output=True, text=True)
     assert p.returncode == CASES["viscosity_log"]["returncode"], p.stderr[-300:]
     assert same_text(p.stdout, CASES["viscosity_log"]["stdout"], 2e-6)
+
+
+# ---- traj2diffusion ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def t2d_patched_oracle(oracle, tmp_path_factory):
+    if not os.path.exists(REF_T2D_SRC):
+        pytest.skip("needs the reference tree (build container only)")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = str(tmp_path_factory.mktemp("t2d_patched") / "traj2diffusion_patched_oracle")
+    with tempfile.TemporaryDirectory() as t:  # the cut never enters the repo
+        cut = os.path.join(t, "t2d_cut.cpp")
+        lines = open(REF_T2D_SRC).read().split("\n")
+        assert lines[274].startswith("void image(") and lines[341].startswith("double slope(") and lines[353] == "}"
+        assert "for(i=0;i<nframes;i+=stride)" in lines[529] and lines[539].strip() == "}"
+        call = "  acfb200_patch_msd(crd, nframes, stride, max_s, msd, msd_counter);"
+        open(cut, "w").write("\n".join(lines[:274] + lines[340:341] + lines[354:529] + [call] + lines[540:]))
+        subprocess.run([cxx, "-O2", "-ffp-contract=off", "-w", "-include", os.path.join(PATCH_DIR, "traj2diffusion_decl.hpp"),
+                        "-I", os.path.join(ROOT, "oracle", "boost_stub"), "-I", os.path.join(ROOT, "include"), "-o", exe, cut,
+                        os.path.join(PATCH_DIR, "traj2diffusion_acfb200.cpp"),
+                        os.path.join(ROOT, "tests", "host", "abi_shim_oracle.cpp"), "-L" + os.path.join(ROOT, "oracle"),
+                        "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("name", T2D_CASES)
+def test_patched_traj2diffusion_on_the_oracle_shim_is_byte_identical(t2d_patched_oracle, name, tmp_path):
+    p, inp = run_t2d(t2d_patched_oracle, name, tmp_path)
+    check_t2d(p, inp, name, rel=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(PATCHED_T2D), reason="oracle/_ref/traj2diffusion_patched not built")
+@pytest.mark.parametrize("name", T2D_CASES)
+def test_gpu_patched_traj2diffusion_matches_the_unmodified_program(name, tmp_path):
+    p, inp = run_t2d(PATCHED_T2D, name, tmp_path)
+    check_t2d(p, inp, name, rel=2e-6)
