@@ -23,6 +23,9 @@ void oracle_spring_rescale(double* acf, double* vacf, int64_t ncorr, double k_sp
 double oracle_integrate_corr_cutoff(const double* acf, int64_t ncorr, double dt, double cutoff, int64_t* brk);
 double oracle_integrate_corr(const double* acf, int64_t ncorr, double dt);
 void oracle_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr);
+double oracle_variance(const double* y, int64_t n);
+double oracle_calc_subtract_average(double* y, int64_t n);
+double oracle_velocity_series(const double* y, int64_t n, double dt, double* vel);
 double oracle_viscosity_eta(double box_length, double temperature, double integral);
 
 void oracle_msd(const double* x, const double* y, const double* z, int64_t n, int64_t stride, int64_t max_s, double* msd,
@@ -84,6 +87,22 @@ int acfb200_msd_slope(const double* msd, int64_t n, double* slope, double* sum)
     const double v = oracle_msd_slope(msd, n, &s);
     if (slope) *slope = v;
     if (sum) *sum = s;
+    return 0;
+}
+int acfb200_variance(const double* y, int64_t n, double* var)
+{
+    *var = oracle_variance(y, n);
+    return 0;
+}
+int acfb200_calc_subtract_average(double* y, int64_t n, double* avg)
+{
+    const double a = oracle_calc_subtract_average(y, n);
+    if (avg) *avg = a;
+    return 0;
+}
+int acfb200_velocity_series(const double* y, int64_t n, double dt, double* vel)
+{
+    oracle_velocity_series(y, n, dt, vel);
     return 0;
 }
 int acfb200_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr)
