@@ -24,7 +24,8 @@ import pytest
 
 from cli_inputs import write_pressure_log
 from conftest import GOLDEN, ROOT
-from test_cli import ACF_CASES, CASES, GPU_ACF_CASES, T2D, T2D_CASES, check_case, check_t2d, run_case, run_t2d, same_text
+from test_cli import (ACF_CASES, CASES, GPU_ACF_CASES, GPU_BIN, T2D, T2D_CASES, check_case, check_t2d, check_t2d_batch,
+                      run_case, run_t2d, run_t2d_batch, same_text)
 
 REF_SRC = "/root/reference/viscosity.cpp"
 REF_T2D_SRC = "/root/reference/traj2diffusion.cpp"
@@ -171,3 +172,22 @@ def test_gpu_patched_acfcalculator_matches_the_shipped_binary(name, tmp_path):
     """Five separate host-buffer calls per run (mean, velocity, two correlations, two variances, the integral), as the
     reference's main() makes them; numbers to the print precision, GLE lines to the tolerances of tests/test_cli.py."""
     check_case(run_case(PATCHED_ACF, name, tmp_path), name, rel=2e-6)
+
+
+# ---- front-end extensions added after the last GPU session of round 1 (CPU-tested in tests/test_cli.py) ---------------
+@pytest.mark.gpu
+def test_gpu_traj2diffusion_batch_mode_matches_the_single_runs(tmp_path):
+    p, sections, outfiles = run_t2d_batch(os.path.join(GPU_BIN, "traj2diffusion"), T2D_CASES, tmp_path)
+    assert len(sections) == len(T2D_CASES)
+    check_t2d_batch(p, sections, outfiles, T2D_CASES, rel=2e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_viscosity_component_selection(tmp_path):
+    log = _log(tmp_path)
+    exe = os.path.join(GPU_BIN, "viscosity")
+    full = subprocess.run([exe, log], capture_output=True, text=True)
+    part = subprocess.run([exe, log, "--components", "xy,xz,yz"], capture_output=True, text=True)
+    assert full.returncode == 0 and part.returncode == 0, part.stderr
+    by_index = {int(sec.split("\n")[1].split()[1]): sec for sec in full.stdout.split("\n\n")[:6]}
+    assert part.stdout.split("\n\n")[:-1] == [by_index[i] for i in (1, 2, 5)]
