@@ -66,6 +66,8 @@ def main():
     ap.add_argument("--sizes", default="20000,1000000,10000000")
     ap.add_argument("--maxcorr", type=int, default=1000)
     ap.add_argument("--skip-reference-above", type=float, default=2e7)
+    ap.add_argument("--patched", action="store_true",
+                    help="also time oracle/_ref/ACFcalculator_patched (the reference source calling libacf_b200.so)")
     args = ap.parse_args()
     ref = os.path.join(ROOT, "oracle", "_ref", "ACFcalculator_ref")
     ours = os.path.join(ROOT, "acfcalculator_b200", "bin", "ACFcalculator")
@@ -86,6 +88,19 @@ def main():
                            d_acf_line_ours=[l for l in a2["out"].splitlines() if l.startswith("#D (ACF)")],
                            d_acf_line_reference=[l for l in b["out"].splitlines() if l.startswith("#D (ACF)")],
                            speedup=round(b["seconds"] / a2["seconds"], 2))
+            # the reference SOURCE built here with -O2 against oracle/boost_stub (the shipped binary is an unoptimised
+            # GCC 5.4 build): the fairer CPU figure, and -- with --patched -- the same source running on libacf_b200.so
+            stubbed = os.path.join(ROOT, "oracle", "_ref", "ACFcalculator_stubbed")
+            if os.path.exists(stubbed) and n <= args.skip_reference_above:
+                c = run(stubbed, inp, "stubbed", d, args.maxcorr)
+                rec.update(reference_O2_s=round(c["seconds"], 3), reference_O2_acf_identical=c["acf"] == a2["acf"],
+                           speedup_vs_O2=round(c["seconds"] / a2["seconds"], 2))
+            patched = os.path.join(ROOT, "oracle", "_ref", "ACFcalculator_patched")
+            if args.patched and os.path.exists(patched):
+                run(patched, inp, "patched", d, args.maxcorr)
+                e = run(patched, inp, "patched2", d, args.maxcorr)
+                rec.update(patched_reference_s=round(e["seconds"], 3), patched_rc=e["returncode"],
+                           patched_acf_identical=e["acf"] == a2["acf"])
             print(json.dumps(rec), flush=True)
 
 

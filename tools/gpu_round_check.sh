@@ -18,7 +18,7 @@ for w in windows viscosity fft msd; do
     python bench.py --workload $w > $OUT/${TAG}_$w.json 2> $OUT/${TAG}_$w.err; echo "bench $w rc=$?"
 done
 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_reference.json 2> $OUT/${TAG}_reference.err
-python tools/cli_compare.py > $OUT/${TAG}_cli.jsonl 2> $OUT/${TAG}_cli.err
+python tools/cli_compare.py --patched > $OUT/${TAG}_cli.jsonl 2> $OUT/${TAG}_cli.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_bench_ou.csv \
     python bench.py --steps 2 --warmup 1 > $OUT/${TAG}_ncu.log 2>&1
 for f in ou ou_n1e8 windows viscosity fft msd; do
