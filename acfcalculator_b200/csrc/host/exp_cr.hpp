@@ -8,11 +8,15 @@
 // correctly rounded exp has exactly one right answer per argument, so providing our own makes the GLE stage
 // independent of the libm it is built against and equal to the shipped binary (tools/fuzz_gle.py).
 #pragma once
+#include <cstddef>
 
 namespace acfhost {
 
 // exp(x) rounded to nearest-even, for every double x (overflow -> inf, underflow -> subnormals / 0, NaN -> NaN).
 double exp_cr(double x);
+
+// y[i] = exp_cr(x[i]), i < n -- bit for bit; four lanes at a time (AVX2) where the CPU allows.
+void exp_cr_array(const double* x, double* y, std::size_t n);
 
 // The slow path alone (binary128 arithmetic): exposed for the tests, which check the fast path against it.
 double exp_cr_slow(double x);

@@ -31,7 +31,14 @@ inline int sgn(double v) { return (v > 0) - (v < 0); }
 double laplace(const double* series, double deltat, double s, int length)
 {
     double F = 0.0;
-    for (int i = 0; i < length; ++i) F += exp_cr(-s * i * deltat) * series[i] * deltat;
+    const int kBlock = 256;  // arguments and exponentials of a block at a time (exp_cr_array: four lanes where it can)
+    double arg[kBlock], e[kBlock];
+    for (int i0 = 0; i0 < length; i0 += kBlock) {
+        const int m = length - i0 < kBlock ? length - i0 : kBlock;
+        for (int j = 0; j < m; ++j) arg[j] = -s * (i0 + j) * deltat;
+        exp_cr_array(arg, e, (size_t)m);
+        for (int j = 0; j < m; ++j) F += e[j] * series[i0 + j] * deltat;
+    }
     return F;
 }
 

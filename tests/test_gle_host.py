@@ -33,6 +33,7 @@ def run_exp(exe, xs):
     p = subprocess.run([exe, "exp"], input=text, capture_output=True, text=True, check=True)
     rows = [line.split() for line in p.stdout.splitlines()]
     assert len(rows) == len(xs)
+    assert [r[2] for r in rows] == [r[0] for r in rows]  # the array form (AVX2 lanes) is bit for bit the scalar one
     return [int(r[0], 16) for r in rows], [int(r[1], 16) for r in rows]
 
 
