@@ -108,6 +108,16 @@ int acfb200_velocity_series(const double* y, int64_t n, double dt, double* vel)
 int acfb200_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* corr)
 {
     oracle_calc_correlation(y, n, ncorr, corr);
+    if (const char* ps = getenv("ACF_SHIM_PERTURB")) {  // as in acfb200_acf_pipeline below; a new pattern per call
+        static unsigned long long calls = 0;
+        unsigned long long st = (strtoull(ps, nullptr, 10) + 1000 * ++calls) * 6364136223846793005ULL + 1442695040888963407ULL;
+        const double c0 = corr[0];
+        for (int64_t k = 0; k < ncorr; ++k) {
+            st = st * 6364136223846793005ULL + 1442695040888963407ULL;
+            const double u = ((double)(st >> 11) / 9007199254740992.0) * 2 - 1;
+            if (std::isfinite(corr[k]) && corr[k] != 0.0) corr[k] += u * 2e-15 * c0;
+        }
+    }
     return 0;
 }
 int acfb200_set_method(int) { return 0; }
