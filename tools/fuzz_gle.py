@@ -5,7 +5,7 @@ random Langevin-like series, maxcorr and time steps; stdout, exit status, ACF fi
 The front-end under test is the oracle-backed build (tests/_build/ACFcalculator_oracle), whose C(k) is bit-identical to
 the reference's, so every difference found here belongs to the GLE stage.
 
-    python tools/fuzz_gle.py [seed] [runs]"""
+    python tools/fuzz_gle.py [seed] [runs] [big]"""
 import os
 import subprocess
 import sys
@@ -44,9 +44,16 @@ def run(exe, args, d):
     return p.returncode, p.stdout, out[0], out[1]
 
 
-def draw_case(rng):
-    """One fuzz case: (series, option list after -i/-a/-o).  The order of the draws is part of the recipe."""
+def draw_case(rng, big=False):
+    """One fuzz case: (series, option list after -i/-a/-o).  The order of the draws is part of the recipe.
+    big: maxcorr 2000-5000 and time steps up to 4 fs, so that most of every Laplace sum lies where exp() underflows
+    through the subnormal range to zero."""
     x = series(rng)
+    if big:
+        while len(x) < 10000:
+            x = series(rng)
+        m = min(int(rng.choice([2000, 3000, 5000])), len(x) // 3)
+        return x, ["-t", "general", "-f", "1", "-m", str(m), "-s", str(rng.choice([1, 2, 4]))]
     m = int(rng.choice([20, 100, 300, 1000]))
     m = min(m, len(x) // 3)
     args = ["-t", "general", "-f", "1", "-m", str(m), "-s", str(rng.choice([1, 2, 0.5]))]
@@ -68,12 +75,13 @@ def replay(seed, run_index):
 def main():
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     runs = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    big = len(sys.argv) > 3 and sys.argv[3] == "big"
     rng = np.random.default_rng(seed)
     bad = completed = 0
     with tempfile.TemporaryDirectory() as d:
         inp = os.path.join(d, "in.dat")
         for it in range(runs):
-            x, opts = draw_case(rng)
+            x, opts = draw_case(rng, big)
             with open(inp, "w") as f:
                 f.write("# step x\n" + "".join("%d % .14e\n" % (i, v) for i, v in enumerate(x)))
             args = ["-i", inp, "-a", "o.acf", "-o", "o.out"] + opts
