@@ -88,6 +88,9 @@ SIGNATURES = {
                                                C.c_void_p, C.c_void_p, C.POINTER(MsdResult)]),
     "acfb200_multi_gpu_traj2diffusion_batch": (C.c_int, [_PP, _PP, _PP, _PI64, C.c_int, _I64, _I64, C.c_double, C.c_double,
                                                          C.c_int, C.c_void_p, C.c_void_p, C.POINTER(MsdResult), C.c_int]),
+    "acfb200_multi_gpu_traj2diffusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, _I64, _I64, C.c_double,
+                                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(MsdResult),
+                                                   C.c_int]),
     "acfb200_msd_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, _I64, _I64, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
     "acfb200_image_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, C.c_double, C.c_void_p, C.c_void_p,

@@ -245,6 +245,22 @@ def traj2diffusion(x, y=None, z=None, stride=1, max_s=1000, timestep=1.0, cell=N
     return d
 
 
+def multi_gpu_traj2diffusion(x, y=None, z=None, stride=1, max_s=1000, timestep=1.0, cell=None, ngpus=0):
+    """traj2diffusion() for ONE long trajectory cut into time blocks over `ngpus` devices (<= 0: all): block + halo per
+    device, one all-reduce of the displacement sums, finalised on device 0.  Same dict as traj2diffusion()."""
+    x, y, z = _axes(x, y, z)
+    out = np.empty(int(max_s), dtype=np.float64)
+    cnt = np.empty(int(max_s), dtype=np.int32)
+    res = MsdResult()
+    check(_lib.load().acfb200_multi_gpu_traj2diffusion(_vp(x), _vp(y), _vp(z), x.size, int(stride), int(max_s),
+                                                       float(timestep), 0.0 if cell is None else float(cell),
+                                                       0 if cell is None else 1, _vp(out), _vp(cnt), C.byref(res),
+                                                       int(ngpus)))
+    d = res.as_dict()
+    d.update(msd=out, counter=cnt)
+    return d
+
+
 def traj2diffusion_batch(trajectories, stride=1, max_s=1000, timestep=1.0, cell=None, ngpus=None):
     """traj2diffusion for a list of trajectories, each an (x, y, z) triple (or one array = x three times).
     Returns (msd[ntraj][max_s], counter[ntraj][max_s], [dict(sum, slope, diffusivity, nframes)]).

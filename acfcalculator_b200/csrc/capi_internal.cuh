@@ -104,6 +104,13 @@ int check_common(const void* p, long long n, long long ncorr, const char* what);
 int pipeline_batch_device(Workspace* ws, const double* const* d_series, const int64_t* n, int nw, long long ncorr,
                           double dt, double cutoff, double* d_acf, double* d_vacf, acfb200_result* res, cudaStream_t st);
 
+// traj2diffusion internals shared with the multi-GPU driver (capi_msd.cu)
+int check_msd_args(const void* x, const void* y, const void* z, long long n, long long stride, long long max_s,
+                   const char* what);
+int msd_block_sums(Workspace* ws, const std::vector<SeriesDesc>& descs, long long stride, long long max_s, cudaStream_t st);
+int msd_finalize_sums(Workspace* ws, int axes, const long long* n_total, int ntraj, long long stride, long long max_s,
+                      double* d_msd, int* d_counter, cudaStream_t st);
+
 }  // namespace acfb200
 
 typedef std::lock_guard<std::recursive_mutex> Lock;

@@ -9,8 +9,8 @@ using namespace acfb200;
 
 namespace acfb200 {
 
-static int check_msd_args(const void* x, const void* y, const void* z, long long n, long long stride, long long max_s,
-                          const char* what)
+int check_msd_args(const void* x, const void* y, const void* z, long long n, long long stride, long long max_s,
+                   const char* what)
 {
     if (!x || !y || !z) {
         set_error("%s: null coordinate array", what);
@@ -28,6 +28,60 @@ static int check_msd_args(const void* x, const void* y, const void* z, long long
         set_error("%s: at most 2^31-1 frames (got %lld)", what, n);
         return ACFB200_ERR_ARG;
     }
+    return 0;
+}
+
+// (The two functions below serve the multi-GPU time-block driver in capi_multi.cu; msd_batch_device further down is the
+// single-device path, whose launches they mirror.)
+// Raw displacement sums  S[j] = sum_{origins i in the block, i + j < n} (x[i+j] - x[i])^2  of the series described by
+// `descs` (x = block start, n = block + halo length, i_end = block length; whole series: i_end == n), one launch
+// for all of them, left in ws->out as [nseries][max_s].  Unit stride runs the tiled displacement kernel (the
+// direct-lag kernel's geometry), larger strides the per-lag strided kernel (block starts must then be multiples of
+// the stride so that the origins of all blocks are those of the whole series).
+int msd_block_sums(Workspace* ws, const std::vector<SeriesDesc>& descs, long long stride, long long max_s, cudaStream_t st)
+{
+    const int ns = (int)descs.size();
+    long long i_end_max = 1;
+    for (const auto& d : descs)
+        if (d.i_end > i_end_max) i_end_max = d.i_end;
+    DirectPlan plan;
+    if (stride == 1) {
+        ACF_TRY(plan_direct(i_end_max, max_s, ns, ws->sm_count, -1, &plan, true));
+        if (plan.mode != 0) {
+            set_error("msd: the displacement kernel needs a tiled plan (unset ACFB200_MODE)");
+            return ACFB200_ERR_ARG;
+        }
+    } else {
+        ACF_TRY(plan_msd_strided(i_end_max, stride, max_s, ws->sm_count, &plan));
+    }
+    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)ns));
+    ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, ns) * sizeof(double)));
+    ACF_TRY(ws->out.ensure((size_t)ns * max_s * 8));
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * (size_t)ns, cudaMemcpyHostToDevice, st));
+    if (stride == 1)
+        ACF_TRY(launch_direct_msd(plan, ws->desc.as<SeriesDesc>(), ns, max_s, ws->partials.as<double>(), st));
+    else
+        ACF_TRY(launch_msd_strided(plan, ws->desc.as<SeriesDesc>(), ns, stride, max_s, ws->partials.as<double>(), st));
+    ACF_TRY(launch_reduce_partials(plan, ws->desc.as<SeriesDesc>(), ns, max_s, ws->partials.as<double>(),
+                                   ws->out.as<double>(), 0, st));
+    g_launches += 2;
+    return 0;
+}
+
+// ws->out [ntraj * axes][max_s] raw sums -> msd / counter: the three axes added, divided by the origin count of a
+// trajectory of n_total[t] frames (traj2diffusion.cpp:545).  Reuses ws->desc for the frame counts (stream-ordered after
+// the kernels that read the block descriptors).
+int msd_finalize_sums(Workspace* ws, int axes, const long long* n_total, int ntraj, long long stride, long long max_s,
+                      double* d_msd, int* d_counter, cudaStream_t st)
+{
+    std::vector<SeriesDesc> full((size_t)ntraj * axes);
+    for (int t = 0; t < ntraj; ++t)
+        for (int a = 0; a < axes; ++a) full[(size_t)t * axes + a] = {nullptr, n_total[t], n_total[t]};
+    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * full.size()));
+    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, full.data(), sizeof(SeriesDesc) * full.size(), cudaMemcpyHostToDevice, st));
+    ACF_TRY(launch_msd_finalize(ws->out.as<double>(), ws->desc.as<SeriesDesc>(), axes, ntraj, stride, max_s, d_msd,
+                                d_counter, st));
+    g_launches += 1;
     return 0;
 }
 

@@ -313,4 +313,98 @@ int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, const double*
     return rc;
 }
 
+// ONE long trajectory on up to `ngpus` devices (the time-block case): device g takes the origins
+// of block g (block starts are multiples of the origin stride) plus a halo of max_s - 1 frames, computes the raw
+// displacement sums of its block per axis, ONE ncclAllReduce(sum) of axes*max_s doubles combines them, device 0 divides by
+// the origin counts of the whole trajectory, takes the slope and D.  Imaging (a sequential scan over the whole
+// trajectory, HBM-bound) runs on device 0 first.  Same outputs as acfb200_traj2diffusion; sums are grouped differently,
+// so the values agree to rounding (~1e-15 relative), not bit for bit.
+int acfb200_multi_gpu_traj2diffusion(const double* x, const double* y, const double* z, int64_t n, int64_t stride,
+                                     int64_t max_s, double dt, double cell, int imaging, double* msd, int32_t* counter,
+                                     acfb200_msd_result* result, int ngpus)
+{
+    ACF_TRY(check_msd_args(x, y, z, n, stride, max_s, "multi_gpu_traj2diffusion"));
+    int ndev = usable_devices(ngpus);
+    if (ndev < 1) {
+        set_error("no usable CUDA device; libacf_b200 has no CPU path");
+        return ACFB200_ERR_CUDA;
+    }
+    // a block much shorter than its halo is all overhead
+    while (ndev > 1 && n / ndev < 4 * max_s) --ndev;
+    if (ndev == 1) return acfb200_traj2diffusion(x, y, z, n, stride, max_s, dt, cell, imaging, msd, counter, result);
+    int home = 0;
+    cudaGetDevice(&home);
+    // unwrap once, on device 0, into host copies every device then reads its block from
+    std::vector<double> unwrapped[3];
+    const double* src[3] = {x, y, z};
+    if (imaging) {
+        for (int a = 0; a < 3; ++a) unwrapped[a].assign(src[a], src[a] + n);
+        cudaSetDevice(0);
+        const int rc = acfb200_image(unwrapped[0].data(), unwrapped[1].data(), unwrapped[2].data(), n, cell);
+        cudaSetDevice(home);
+        if (rc != 0) return rc;
+        for (int a = 0; a < 3; ++a) src[a] = unwrapped[a].data();
+    }
+    const bool one_axis = src[0] == src[1] && src[1] == src[2];
+    const int per = one_axis ? 1 : 3;
+    NcclApi* nccl = nullptr;
+    ACF_TRY(nccl_clique(ndev, &nccl));
+    const int rc = for_each_device(ndev, [&](int d) -> int {
+        Lock lk(g_mu);
+        Workspace* ws;
+        ACF_TRY(get_ws(&ws));
+        cudaStream_t st = ws->stream;
+        // origins of block d: [b, e), both multiples of the stride (the last block ends at n)
+        auto cut = [&](int g) {
+            if (g >= ndev) return (long long)n;
+            const long long raw = (long long)n * g / ndev;
+            return raw / (long long)stride * (long long)stride;
+        };
+        const long long b = cut(d), e = cut(d + 1);
+        long long reach = e + max_s - 1;
+        if (reach > n) reach = n;
+        const long long len = reach - b;
+        const size_t pitch = even_up(len > 0 ? len : 1);
+        ACF_TRY(ws->series.ensure((size_t)per * pitch * 8));
+        std::vector<SeriesDesc> descs(per);
+        for (int a = 0; a < per; ++a) {
+            double* dst = ws->series.as<double>() + (size_t)a * pitch;
+            if (len > 0) ACF_CUDA_OK(cudaMemcpyAsync(dst, src[a] + b, (size_t)len * 8, cudaMemcpyHostToDevice, st));
+            descs[a] = {dst, len > 0 ? len : 0, e - b};
+        }
+        ACF_TRY(msd_block_sums(ws, descs, stride, max_s, st));
+        double* d_sums = ws->out.as<double>();
+        const ncclResult_t r = nccl->AllReduce(d_sums, d_sums, (size_t)per * max_s, ncclDouble, ncclSum, nccl->comms[d], st);
+        if (r != ncclSuccess) {
+            set_error("ncclAllReduce failed: %s", nccl->GetErrorString(r));
+            return ACFB200_ERR_CUDA;
+        }
+        if (d == 0) {
+            ACF_TRY(ws->small.ensure((size_t)max_s * 12 + 64 + 16));
+            double* d_sl = ws->small.as<double>();  // [sum, slope]
+            double* d_msd = d_sl + 2;
+            int* d_cnt = reinterpret_cast<int*>(d_msd + max_s);
+            const long long n_total = n;
+            ACF_TRY(msd_finalize_sums(ws, per, &n_total, 1, stride, max_s, d_msd, d_cnt, st));
+            ACF_TRY(launch_msd_slope(d_msd, max_s, 1, d_sl, st));
+            g_launches += 1;
+            double h[2];
+            if (msd) ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)max_s * 8, cudaMemcpyDeviceToHost, st));
+            if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)max_s * 4, cudaMemcpyDeviceToHost, st));
+            ACF_CUDA_OK(cudaMemcpyAsync(h, d_sl, 16, cudaMemcpyDeviceToHost, st));
+            ACF_CUDA_OK(cudaStreamSynchronize(st));
+            if (result) {
+                result->sum = h[0];
+                result->slope = h[1];
+                result->diffusivity = h[1] / (dt * (double)stride) / 6.0;  // traj2diffusion.cpp:497, :549
+                result->nframes = n;
+            }
+        }
+        ACF_CUDA_OK(cudaStreamSynchronize(st));
+        return 0;
+    });
+    cudaSetDevice(home);
+    return rc;
+}
+
 }  // extern "C"

@@ -207,6 +207,13 @@ ACFB200_API int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, c
                                                        const double* const* z, const int64_t* n, int ntraj, int64_t stride,
                                                        int64_t max_s, double dt, double cell, int imaging, double* msd,
                                                        int32_t* counter, acfb200_msd_result* result, int ngpus);
+/* ONE long trajectory cut into time blocks over the devices of this box (block g plus a halo of max_s - 1 frames on
+ * device g, raw displacement sums per block, one ncclAllReduce of 3*max_s doubles, divide / slope / D on device 0;
+ * imaging, a sequential scan, runs on device 0 first).  Same contract as acfb200_traj2diffusion; values agree with it
+ * to rounding.  Falls back to one device when the trajectory is short against max_s. */
+ACFB200_API int acfb200_multi_gpu_traj2diffusion(const double* x, const double* y, const double* z, int64_t n, int64_t stride,
+                                                 int64_t max_s, double dt, double cell, int imaging, double* msd,
+                                                 int32_t* counter, acfb200_msd_result* result, int ngpus);
 /* Device-resident forms (stream: a cudaStream_t passed as void*, like the other *_device calls; the out arrays of
  * acfb200_image_device must not alias its inputs).  Passing the same pointer for x, y and z (what the reference's
  * general reader effectively produces, :186-231) is recognised and computed once. */

@@ -107,3 +107,28 @@ def test_batch_front_end_on_several_gpus(ngpus, tmp_path):
         outs[g] = [open(str(tmp_path / ("g%d_w%d.acf" % (g, w)))).read() for w in range(2 * ngpus + 1)]
         assert p.stdout.count("#batch run ") >= 2 * ngpus + 1
     assert outs[1] == outs[ngpus]
+
+
+def test_one_trajectory_in_time_blocks(acf, ngpus):
+    """traj2diffusion for ONE long trajectory split over the devices (block + halo each, one all-reduce of the
+    displacement sums): MSD, counters, slope sum and D as from one device, to rounding; unit and larger origin strides,
+    with and without imaging, and the one-array form of the general reader."""
+    rng = np.random.default_rng(77)
+    n = 600_001
+    r = 3.0 + np.cumsum(rng.standard_normal((n, 3)) * 0.4, axis=0)
+    cell = 11.5
+    w = [np.ascontiguousarray((r - cell * np.floor(r / cell))[:, a]) for a in range(3)]
+    u = [np.ascontiguousarray(r[:, a]) for a in range(3)]
+    for axes, kw in ((u, dict(stride=1, max_s=700)), (u, dict(stride=7, max_s=500)), (w, dict(stride=1, max_s=300, cell=cell)),
+                     ((u[0],), dict(stride=3, max_s=400))):
+        one = acf.traj2diffusion(*axes, timestep=2.0, **kw)
+        many = acf.multi_gpu_traj2diffusion(*axes, timestep=2.0, ngpus=ngpus, **kw)
+        assert np.array_equal(one["counter"], many["counter"])
+        assert many["msd"][0] == 0.0
+        assert np.max(np.abs(many["msd"][1:] - one["msd"][1:]) / one["msd"][1:]) <= 1e-12
+        assert abs(many["diffusivity"] - one["diffusivity"]) <= 1e-12 * abs(one["diffusivity"])
+        assert abs(many["sum"] - one["sum"]) <= 1e-12 * abs(one["sum"]) and many["nframes"] == n
+    # a trajectory too short for its halo runs on one device: identical bits
+    short = [a[:2000] for a in u]
+    assert np.array_equal(acf.multi_gpu_traj2diffusion(*short, max_s=900, ngpus=ngpus)["msd"],
+                          acf.traj2diffusion(*short, max_s=900)["msd"])
