@@ -79,6 +79,7 @@ SIGNATURES = {
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "acfb200_calc_correlation_fft": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p]),
     "acfb200_calc_correlation_fft_device": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p, C.c_void_p]),
+    "acfb200_fft_plan": (C.c_int, [_I64, _I64, _PI64, C.POINTER(C.c_int)]),
     "acfb200_msd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, _I64, _I64, C.c_void_p, C.c_void_p]),
     "acfb200_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, C.c_double]),
     "acfb200_msd_slope": (C.c_int, [C.c_void_p, _I64, _P, _P]),

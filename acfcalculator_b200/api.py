@@ -97,6 +97,14 @@ def calcCorrelationFFT(y, nCorr):
     return corr
 
 
+def fft_plan(n, nCorr):
+    """(L, factors) of the Wiener-Khinchin transform for (n, nCorr): padded real length and number of factors of L/2."""
+    L = C.c_int64(0)
+    f = C.c_int(0)
+    check(_lib.load().acfb200_fft_plan(int(n), int(nCorr), C.byref(L), C.byref(f)))
+    return L.value, f.value
+
+
 def variance(y, nSamples=None):
     """sum(y^2)/n.  ACFcalculator.cpp:203-210."""
     y = _f64(y)
@@ -462,6 +470,8 @@ def multi_gpu_green_kubo(components, nCorr, timestep, box_length=31.0399376148, 
     arrs = [_f64(c) for c in components]
     nc = len(arrs)
     n = arrs[0].size
+    if any(a.size != n for a in arrs):
+        raise ValueError("all components must have the same length")
     ptrs = (C.c_void_p * nc)(*[a.ctypes.data for a in arrs])
     acf = np.empty((nc, int(nCorr)), dtype=np.float64)
     integ = np.empty(nc, dtype=np.float64)

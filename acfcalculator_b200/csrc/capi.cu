@@ -304,6 +304,7 @@ int acfb200_warmup(void)
 
 int acfb200_release(void)
 {
+    nccl_release();
     std::lock_guard<std::mutex> table_lock(g_ws_mu);
     int cur = 0;
     cudaGetDevice(&cur);
@@ -866,6 +867,16 @@ int acfb200_calc_correlation_fft_device(const double* d_y, int64_t n, int64_t nc
     int launches = launch_fft_acf(d_y, n, ncorr, d_corr, 1, ws->fftwork.p, ws->fftwork.cap, (cudaStream_t)stream);
     if (launches < 0) return -launches;
     g_launches += launches;
+    return 0;
+}
+
+int acfb200_fft_plan(int64_t n, int64_t ncorr, int64_t* L, int* factors)
+{
+    long long l = 0;
+    int f = 0;
+    if (fft_acf_plan(n, ncorr, &l, &f) != 0) return ACFB200_ERR_ARG;
+    if (L) *L = l;
+    if (factors) *factors = f;
     return 0;
 }
 

@@ -46,7 +46,11 @@ struct Buf {
         }
         cap = want;
         if (zero) {
+            // cudaMemset on device memory is asynchronous to the host and ordered on the legacy stream only; the
+            // consumers (tickets, work-queue counters) run on non-blocking streams, so wait for it here -- this is the
+            // allocation path, taken once per buffer growth
             e = cudaMemset(p, 0, want);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
             if (e != cudaSuccess) {
                 set_error("cudaMemset failed: %s", cudaGetErrorString(e));
                 return ACFB200_ERR_CUDA;
@@ -103,6 +107,8 @@ int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long long nc
 int check_common(const void* p, long long n, long long ncorr, const char* what);
 int pipeline_batch_device(Workspace* ws, const double* const* d_series, const int64_t* n, int nw, long long ncorr,
                           double dt, double cutoff, double* d_acf, double* d_vacf, acfb200_result* res, cudaStream_t st);
+
+void nccl_release();  // capi_multi.cu: destroys the cached NCCL communicator clique (acfb200_release)
 
 // traj2diffusion internals shared with the multi-GPU driver (capi_msd.cu)
 int check_msd_args(const void* x, const void* y, const void* z, long long n, long long stride, long long max_s,

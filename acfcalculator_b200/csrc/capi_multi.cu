@@ -4,6 +4,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <condition_variable>
+#include <exception>
 #include <thread>
 
 #include "capi_internal.cuh"
@@ -21,16 +23,21 @@ struct NcclApi {
     void* lib = nullptr;
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::vector<ncclComm_t> comms;  // communicator clique over devices 0..n-1
 };
 NcclApi g_nccl;
+// ONE process-wide lock around every section that touches the communicator clique: (re)initialisation, the whole
+// time-block call from the first per-device thread to the last join, and the teardown in acfb200_release.  Two host
+// threads entering time-block calls at once would otherwise cross-match collectives of different sizes, or destroy
+// communicators that are in use when they ask for different device counts.
 std::mutex g_nccl_mu;
 
+// Caller holds g_nccl_mu.
 int nccl_clique(int ndev, NcclApi** out)
 {
-    std::lock_guard<std::mutex> lk(g_nccl_mu);
     if (!g_nccl.lib) {
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
             g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
@@ -42,9 +49,11 @@ int nccl_clique(int ndev, NcclApi** out)
         }
         g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))dlsym(g_nccl.lib, "ncclCommInitAll");
         g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+        g_nccl.CommAbort = (decltype(g_nccl.CommAbort))dlsym(g_nccl.lib, "ncclCommAbort");
         g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
         g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
-        if (!g_nccl.CommInitAll || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
+        if (!g_nccl.CommInitAll || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.CommAbort ||
+            !g_nccl.GetErrorString) {
             set_error("libnccl.so.2 lacks a required symbol");
             return ACFB200_ERR_CUDA;
         }
@@ -76,7 +85,25 @@ int usable_devices(int requested)
     return requested;
 }
 
-// Runs fn(device) on one host thread per device; returns the first non-zero status with its message.
+// Runs fn(device) on one host thread per device; returns the first non-zero status with its message.  Nothing may
+// propagate out of a thread body (an exception there would end the process in std::terminate, across the C ABI).
+template <class F>
+int guarded(F fn, int d)
+{
+    try {
+        return fn(d);
+    } catch (const std::bad_alloc&) {
+        set_error("host allocation failed in the worker thread of device %d", d);
+        return ACFB200_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        set_error("exception in the worker thread of device %d: %s", d, e.what());
+        return ACFB200_ERR_ARG;
+    } catch (...) {
+        set_error("unknown exception in the worker thread of device %d", d);
+        return ACFB200_ERR_ARG;
+    }
+}
+
 template <class F>
 int for_each_device(int ndev, F fn)
 {
@@ -90,7 +117,7 @@ int for_each_device(int ndev, F fn)
                 msg[d] = "cudaSetDevice failed";
                 return;
             }
-            rc[d] = fn(d);
+            rc[d] = guarded(fn, d);
             if (rc[d] != 0) msg[d] = last_error();
         });
     for (auto& t : th) t.join();
@@ -102,7 +129,96 @@ int for_each_device(int ndev, F fn)
     return 0;
 }
 
+// Time-block calls: every device thread first runs prepare(d) -- everything that can fail on its own (workspace,
+// allocations, uploads, the lag kernels) -- then ALL threads meet at a host rendezvous and agree on one status.  Only
+// if every device is ready does anyone enqueue the collective in exchange(d); a device that failed early therefore
+// cannot leave its peers waiting in an all-reduce that will never be matched.  The per-device lock is held from
+// prepare to the end of exchange.  If the collective itself fails on one device, that thread aborts every
+// communicator of the clique (which unblocks the peers) and the clique is rebuilt on the next call.
+struct Rendezvous {
+    std::mutex m;
+    std::condition_variable cv;
+    int expected, arrived = 0;
+    bool failed = false;
+    explicit Rendezvous(int n) : expected(n) {}
+    // returns true when every participant arrived without a failure
+    bool arrive(bool ok)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        if (!ok) failed = true;
+        if (++arrived == expected)
+            cv.notify_all();
+        else
+            cv.wait(lk, [&] { return arrived == expected; });
+        return !failed;
+    }
+};
+
+template <class P, class X>
+int for_each_device_exchange(int ndev, P prepare, X exchange)
+{
+    std::vector<int> rc(ndev, 0);
+    std::vector<std::string> msg(ndev);
+    std::vector<std::thread> th;
+    Rendezvous ready(ndev);
+    for (int d = 0; d < ndev; ++d)
+        th.emplace_back([&, d]() {
+            bool have_device = cudaSetDevice(d) == cudaSuccess;
+            if (!have_device) {
+                rc[d] = ACFB200_ERR_CUDA;
+                msg[d] = "cudaSetDevice failed";
+                ready.arrive(false);
+                return;
+            }
+            Lock lk(g_mu);  // this device's lock, prepare through exchange
+            rc[d] = guarded(prepare, d);
+            if (rc[d] != 0) msg[d] = last_error();
+            if (!ready.arrive(rc[d] == 0)) {
+                if (rc[d] == 0) {  // a peer failed: drain what this device enqueued and leave without the collective
+                    Workspace* ws = nullptr;
+                    if (get_ws(&ws) == 0) cudaStreamSynchronize(ws->stream);
+                }
+                return;
+            }
+            rc[d] = guarded(exchange, d);
+            if (rc[d] != 0) msg[d] = last_error();
+        });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < ndev; ++d)
+        if (rc[d] != 0) {
+            set_error("device %d: %s", d, msg[d].c_str());
+            return rc[d];
+        }
+    return 0;
+}
+
+// Caller holds g_nccl_mu.  A failed collective leaves the clique unusable: abort every communicator so that peers
+// blocked in the kernel return, and forget the clique (the next call builds a fresh one).
+std::atomic<bool> g_nccl_broken{false};
+void nccl_abort_clique()  // from the device thread whose collective failed; the vector itself is left alone (peers index it)
+{
+    if (g_nccl_broken.exchange(true)) return;
+    for (ncclComm_t c : g_nccl.comms)
+        if (c) g_nccl.CommAbort(c);
+}
+void nccl_forget_if_broken()  // after the join, still under g_nccl_mu
+{
+    if (g_nccl_broken.exchange(false)) g_nccl.comms.clear();
+}
+
 }  // namespace
+
+namespace acfb200 {
+// acfb200_release: the communicators go with the workspaces (not while a time-block call is in flight: same lock)
+void nccl_release()
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (!g_nccl.lib) return;
+    for (ncclComm_t c : g_nccl.comms)
+        if (c) g_nccl.CommDestroy(c);
+    g_nccl.comms.clear();
+}
+}  // namespace acfb200
 
 extern "C" {
 
@@ -150,54 +266,68 @@ int acfb200_multi_gpu_calc_correlation(const double* const* y, const int64_t* n,
                 set_error("series %d is empty", s);
                 return ACFB200_ERR_ARG;
             }
+        std::lock_guard<std::mutex> nccl_section(g_nccl_mu);
         NcclApi* nccl = nullptr;
         ACF_TRY(nccl_clique(ndev, &nccl));
-        rc = for_each_device(ndev, [&](int d) -> int {
-            Lock lk(g_mu);
-            Workspace* ws;
-            ACF_TRY(get_ws(&ws));
-            cudaStream_t st = ws->stream;
-            // block + halo of every series, back to back
-            std::vector<SeriesDesc> descs(nseries);
-            size_t total = 0;
-            std::vector<long long> lo(nseries), len(nseries);
-            for (int s = 0; s < nseries; ++s) {
-                const long long b = n[s] * d / ndev, e = n[s] * (d + 1) / ndev;
-                long long reach = e + ncorr - 1;
-                if (reach > n[s]) reach = n[s];
-                lo[s] = b;
-                len[s] = reach - b;
-                total += even_up(len[s] > 0 ? len[s] : 1);
-            }
-            ACF_TRY(ws->series.ensure(total * 8));
-            ACF_TRY(ws->out.ensure((size_t)nseries * ncorr * 8));
-            size_t off = 0;
-            for (int s = 0; s < nseries; ++s) {
-                double* dst = ws->series.as<double>() + off;
-                const long long e = n[s] * (d + 1) / ndev;
-                if (len[s] > 0)
-                    ACF_CUDA_OK(cudaMemcpyAsync(dst, y[s] + lo[s], (size_t)len[s] * 8, cudaMemcpyHostToDevice, st));
-                descs[s] = {dst, len[s] > 0 ? len[s] : 0, e - lo[s]};
-                off += even_up(len[s] > 0 ? len[s] : 1);
-            }
-            double* d_sums = ws->out.as<double>();
-            ACF_TRY(run_direct(ws, descs, ncorr, d_sums, 0, st));
-            const ncclResult_t r = nccl->AllReduce(d_sums, d_sums, (size_t)nseries * ncorr, ncclDouble, ncclSum,
-                                                   nccl->comms[d], st);
-            if (r != ncclSuccess) {
-                set_error("ncclAllReduce failed: %s", nccl->GetErrorString(r));
-                return ACFB200_ERR_CUDA;
-            }
-            if (d == 0) {
+        std::vector<double*> sums(ndev, nullptr);
+        rc = for_each_device_exchange(
+            ndev,
+            // prepare: block + halo of every series, back to back, and the raw lag sums of the block
+            [&](int d) -> int {
+                Workspace* ws;
+                ACF_TRY(get_ws(&ws));
+                cudaStream_t st = ws->stream;
+                std::vector<SeriesDesc> descs(nseries);
+                size_t total = 0;
+                std::vector<long long> lo(nseries), len(nseries);
                 for (int s = 0; s < nseries; ++s) {
-                    ACF_TRY(launch_normalise(d_sums + (size_t)s * ncorr, n[s], ncorr, d_sums + (size_t)s * ncorr, st));
-                    g_launches += 1;
+                    const long long b = n[s] * d / ndev, e = n[s] * (d + 1) / ndev;
+                    long long reach = e + ncorr - 1;
+                    if (reach > n[s]) reach = n[s];
+                    lo[s] = b;
+                    len[s] = reach - b;
+                    total += even_up(len[s] > 0 ? len[s] : 1);
                 }
-                ACF_CUDA_OK(cudaMemcpyAsync(corr, d_sums, (size_t)nseries * ncorr * 8, cudaMemcpyDeviceToHost, st));
-            }
-            ACF_CUDA_OK(cudaStreamSynchronize(st));
-            return 0;
-        });
+                ACF_TRY(ws->series.ensure(total * 8));
+                ACF_TRY(ws->out.ensure((size_t)nseries * ncorr * 8));
+                size_t off = 0;
+                for (int s = 0; s < nseries; ++s) {
+                    double* dst = ws->series.as<double>() + off;
+                    const long long e = n[s] * (d + 1) / ndev;
+                    if (len[s] > 0)
+                        ACF_CUDA_OK(cudaMemcpyAsync(dst, y[s] + lo[s], (size_t)len[s] * 8, cudaMemcpyHostToDevice, st));
+                    descs[s] = {dst, len[s] > 0 ? len[s] : 0, e - lo[s]};
+                    off += even_up(len[s] > 0 ? len[s] : 1);
+                }
+                sums[d] = ws->out.as<double>();
+                ACF_TRY(run_direct(ws, descs, ncorr, sums[d], 0, st));
+                return 0;
+            },
+            // exchange: ONE all-reduce of the lag sums, the divide after the sum on device 0
+            [&](int d) -> int {
+                Workspace* ws;
+                ACF_TRY(get_ws(&ws));
+                cudaStream_t st = ws->stream;
+                double* d_sums = sums[d];
+                const ncclResult_t r = nccl->AllReduce(d_sums, d_sums, (size_t)nseries * ncorr, ncclDouble, ncclSum,
+                                                       nccl->comms[d], st);
+                if (r != ncclSuccess) {
+                    set_error("ncclAllReduce failed: %s", nccl->GetErrorString(r));
+                    nccl_abort_clique();
+                    return ACFB200_ERR_CUDA;
+                }
+                g_launches += 1;
+                if (d == 0) {
+                    for (int s = 0; s < nseries; ++s) {
+                        ACF_TRY(launch_normalise(d_sums + (size_t)s * ncorr, n[s], ncorr, d_sums + (size_t)s * ncorr, st));
+                        g_launches += 1;
+                    }
+                    ACF_CUDA_OK(cudaMemcpyAsync(corr, d_sums, (size_t)nseries * ncorr * 8, cudaMemcpyDeviceToHost, st));
+                }
+                ACF_CUDA_OK(cudaStreamSynchronize(st));
+                return 0;
+            });
+        nccl_forget_if_broken();
     }
     cudaSetDevice(home);
     return rc;
@@ -208,8 +338,8 @@ int acfb200_multi_gpu_calc_correlation(const double* const* y, const int64_t* n,
 int acfb200_multi_gpu_pipeline_batch(const double* const* series, const int64_t* n, int nwindows, int64_t ncorr, double dt,
                                      double cutoff, double* acf, double* vacf, acfb200_result* result, int ngpus)
 {
-    if (!series || !n || nwindows < 1) {
-        set_error("multi_gpu_pipeline_batch: null argument or nwindows < 1");
+    if (!series || !n || nwindows < 1 || ncorr < 1) {
+        set_error("multi_gpu_pipeline_batch: null argument, nwindows < 1 or ncorr < 1");
         return ACFB200_ERR_ARG;
     }
     int ndev = usable_devices(ngpus);
@@ -279,8 +409,12 @@ int acfb200_multi_gpu_traj2diffusion_batch(const double* const* x, const double*
         set_error("multi_gpu_traj2diffusion_batch: null argument or ntraj < 1");
         return ACFB200_ERR_ARG;
     }
+    for (int t = 0; t < ntraj; ++t) ACF_TRY(check_msd_args(x[t], y[t], z[t], n[t], stride, max_s, "multi_gpu_traj2diffusion_batch"));
     int ndev = usable_devices(ngpus);
-    if (ndev < 1) return ACFB200_ERR_CUDA;
+    if (ndev < 1) {
+        set_error("no usable CUDA device; libacf_b200 has no CPU path");
+        return ACFB200_ERR_CUDA;
+    }
     if (ndev > ntraj) ndev = ntraj;
     int home = 0;
     cudaGetDevice(&home);
@@ -347,62 +481,75 @@ int acfb200_multi_gpu_traj2diffusion(const double* x, const double* y, const dou
     }
     const bool one_axis = src[0] == src[1] && src[1] == src[2];
     const int per = one_axis ? 1 : 3;
+    std::lock_guard<std::mutex> nccl_section(g_nccl_mu);
     NcclApi* nccl = nullptr;
     ACF_TRY(nccl_clique(ndev, &nccl));
-    const int rc = for_each_device(ndev, [&](int d) -> int {
-        Lock lk(g_mu);
-        Workspace* ws;
-        ACF_TRY(get_ws(&ws));
-        cudaStream_t st = ws->stream;
-        // origins of block d: [b, e), both multiples of the stride (the last block ends at n)
-        auto cut = [&](int g) {
-            if (g >= ndev) return (long long)n;
-            const long long raw = (long long)n * g / ndev;
-            return raw / (long long)stride * (long long)stride;
-        };
-        const long long b = cut(d), e = cut(d + 1);
-        long long reach = e + max_s - 1;
-        if (reach > n) reach = n;
-        const long long len = reach - b;
-        const size_t pitch = even_up(len > 0 ? len : 1);
-        ACF_TRY(ws->series.ensure((size_t)per * pitch * 8));
-        std::vector<SeriesDesc> descs(per);
-        for (int a = 0; a < per; ++a) {
-            double* dst = ws->series.as<double>() + (size_t)a * pitch;
-            if (len > 0) ACF_CUDA_OK(cudaMemcpyAsync(dst, src[a] + b, (size_t)len * 8, cudaMemcpyHostToDevice, st));
-            descs[a] = {dst, len > 0 ? len : 0, e - b};
-        }
-        ACF_TRY(msd_block_sums(ws, descs, stride, max_s, st));
-        double* d_sums = ws->out.as<double>();
-        const ncclResult_t r = nccl->AllReduce(d_sums, d_sums, (size_t)per * max_s, ncclDouble, ncclSum, nccl->comms[d], st);
-        if (r != ncclSuccess) {
-            set_error("ncclAllReduce failed: %s", nccl->GetErrorString(r));
-            return ACFB200_ERR_CUDA;
-        }
-        if (d == 0) {
-            ACF_TRY(ws->small.ensure((size_t)max_s * 12 + 64 + 16));
-            double* d_sl = ws->small.as<double>();  // [sum, slope]
-            double* d_msd = d_sl + 2;
-            int* d_cnt = reinterpret_cast<int*>(d_msd + max_s);
-            const long long n_total = n;
-            ACF_TRY(msd_finalize_sums(ws, per, &n_total, 1, stride, max_s, d_msd, d_cnt, st));
-            ACF_TRY(launch_msd_slope(d_msd, max_s, 1, d_sl, st));
-            g_launches += 1;
-            double h[2];
-            if (msd) ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)max_s * 8, cudaMemcpyDeviceToHost, st));
-            if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)max_s * 4, cudaMemcpyDeviceToHost, st));
-            ACF_CUDA_OK(cudaMemcpyAsync(h, d_sl, 16, cudaMemcpyDeviceToHost, st));
-            ACF_CUDA_OK(cudaStreamSynchronize(st));
-            if (result) {
-                result->sum = h[0];
-                result->slope = h[1];
-                result->diffusivity = h[1] / (dt * (double)stride) / 6.0;  // traj2diffusion.cpp:497, :549
-                result->nframes = n;
+    const int rc = for_each_device_exchange(
+        ndev,
+        // prepare: origins of block d are [b, e), both multiples of the stride (the last block ends at n)
+        [&](int d) -> int {
+            Workspace* ws;
+            ACF_TRY(get_ws(&ws));
+            cudaStream_t st = ws->stream;
+            auto cut = [&](int g) {
+                if (g >= ndev) return (long long)n;
+                const long long raw = (long long)n * g / ndev;
+                return raw / (long long)stride * (long long)stride;
+            };
+            const long long b = cut(d), e = cut(d + 1);
+            long long reach = e + max_s - 1;
+            if (reach > n) reach = n;
+            const long long len = reach - b;
+            const size_t pitch = even_up(len > 0 ? len : 1);
+            ACF_TRY(ws->series.ensure((size_t)per * pitch * 8));
+            if (d == 0) ACF_TRY(ws->small.ensure((size_t)max_s * 12 + 64 + 16));
+            std::vector<SeriesDesc> descs(per);
+            for (int a = 0; a < per; ++a) {
+                double* dst = ws->series.as<double>() + (size_t)a * pitch;
+                if (len > 0) ACF_CUDA_OK(cudaMemcpyAsync(dst, src[a] + b, (size_t)len * 8, cudaMemcpyHostToDevice, st));
+                descs[a] = {dst, len > 0 ? len : 0, e - b};
             }
-        }
-        ACF_CUDA_OK(cudaStreamSynchronize(st));
-        return 0;
-    });
+            ACF_TRY(msd_block_sums(ws, descs, stride, max_s, st));
+            return 0;
+        },
+        // exchange: ONE all-reduce of the displacement sums; counts, MSD, slope and D on device 0
+        [&](int d) -> int {
+            Workspace* ws;
+            ACF_TRY(get_ws(&ws));
+            cudaStream_t st = ws->stream;
+            double* d_sums = ws->out.as<double>();
+            const ncclResult_t r =
+                nccl->AllReduce(d_sums, d_sums, (size_t)per * max_s, ncclDouble, ncclSum, nccl->comms[d], st);
+            if (r != ncclSuccess) {
+                set_error("ncclAllReduce failed: %s", nccl->GetErrorString(r));
+                nccl_abort_clique();
+                return ACFB200_ERR_CUDA;
+            }
+            g_launches += 1;
+            if (d == 0) {
+                double* d_sl = ws->small.as<double>();  // [sum, slope]
+                double* d_msd = d_sl + 2;
+                int* d_cnt = reinterpret_cast<int*>(d_msd + max_s);
+                const long long n_total = n;
+                ACF_TRY(msd_finalize_sums(ws, per, &n_total, 1, stride, max_s, d_msd, d_cnt, st));
+                ACF_TRY(launch_msd_slope(d_msd, max_s, 1, d_sl, st));
+                g_launches += 1;
+                double h[2];
+                if (msd) ACF_CUDA_OK(cudaMemcpyAsync(msd, d_msd, (size_t)max_s * 8, cudaMemcpyDeviceToHost, st));
+                if (counter) ACF_CUDA_OK(cudaMemcpyAsync(counter, d_cnt, (size_t)max_s * 4, cudaMemcpyDeviceToHost, st));
+                ACF_CUDA_OK(cudaMemcpyAsync(h, d_sl, 16, cudaMemcpyDeviceToHost, st));
+                ACF_CUDA_OK(cudaStreamSynchronize(st));
+                if (result) {
+                    result->sum = h[0];
+                    result->slope = h[1];
+                    result->diffusivity = h[1] / (dt * (double)stride) / 6.0;  // traj2diffusion.cpp:497, :549
+                    result->nframes = n;
+                }
+            }
+            ACF_CUDA_OK(cudaStreamSynchronize(st));
+            return 0;
+        });
+    nccl_forget_if_broken();
     cudaSetDevice(home);
     return rc;
 }

@@ -122,6 +122,7 @@ int measure_dfma_probe(int probe, double* tflops);
 int fft_acf_workspace_bytes(long long n, long long ncorr, size_t* bytes, long long* L);
 int launch_fft_acf(const double* d_x, long long n, long long ncorr, double* d_out, int normalise,
                    void* d_work, size_t work_bytes, cudaStream_t st);
+int fft_acf_plan(long long n, long long ncorr, long long* L, int* factors);
 int fft_acf_workspace_bytes_batch(long long n, long long ncorr, int nbatch, size_t* bytes, long long* L);
 int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int nbatch, long long ncorr, double* d_out,
                          long long out_stride, int normalise, void* d_work, size_t work_bytes, cudaStream_t st);

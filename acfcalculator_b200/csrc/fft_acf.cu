@@ -1163,6 +1163,15 @@ static int make_geom(long long n, long long ncorr, FftGeom* g)
     return 0;
 }
 
+int fft_acf_plan(long long n, long long ncorr, long long* L, int* factors)
+{
+    FftGeom g;
+    if (make_geom(n, ncorr, &g)) return 1;
+    if (L) *L = g.L;
+    if (factors) *factors = (g.b1 > 0 ? 1 : 0) + (g.b2 > 0 ? 1 : 0) + 1;
+    return 0;
+}
+
 int fft_acf_workspace_bytes(long long n, long long ncorr, size_t* bytes, long long* L)
 {
     return fft_acf_workspace_bytes_batch(n, ncorr, 1, bytes, L);

@@ -113,7 +113,11 @@ int read_run(Run& r, std::ostream& out, std::ostream& err)
     if (!fast_done) r.traj = r.namd ? read_traj_namd(r.traj_fname.c_str()) : read_traj_general(r.traj_fname.c_str());
     r.nframes = r.traj.frames();
     out << "#" << r.nframes << std::endl;
-    if (r.max_s < 0) throw std::bad_alloc();  // new double[negative] (:514)
+    if (r.max_s < 0) {
+        // new double[negative] throws std::bad_array_new_length, which the reference's catch(std::bad_alloc&) takes (:515-524)
+        err << "Error: Could not allocate memory." << std::endl;
+        return 1;
+    }
     if (r.stride < 1) {
         // the reference never leaves its origin loop for stride <= 0 (:530); refuse instead of hanging
         err << "Error: stride must be a positive number of frames." << std::endl;

@@ -169,6 +169,10 @@ ACFB200_API int acfb200_multi_gpu_green_kubo(const double* const* comps, int nco
  * acfb200_calc_correlation[_device]; results agree with the direct sum to ~1e-13*corr[0]. */
 ACFB200_API int acfb200_calc_correlation_fft(const double* y, int64_t n, int64_t ncorr, double* corr);
 ACFB200_API int acfb200_calc_correlation_fft_device(const double* d_y, int64_t n, int64_t ncorr, double* d_corr, void* stream);
+/* The transform this path would run for (n, ncorr): *L = padded real length (the smallest 2^a or 3*2^a that holds
+ * n + ncorr - 1), *factors = number of sweeps-defining factors of L/2 (1..3).  Needs no device.  Algorithmic HBM bytes of
+ * one call: 8n + 8ncorr + 8L * 2 * (2*factors - 2). */
+ACFB200_API int acfb200_fft_plan(int64_t n, int64_t ncorr, int64_t* L, int* factors);
 
 /* ---- traj2diffusion: mean-square displacement (traj2diffusion.cpp) --------------------------------
  * Coordinates are three separate arrays (the reference holds crd[frame][0..2], :59-121, :145-260).

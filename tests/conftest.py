@@ -42,6 +42,11 @@ def acf():
     """The product package.  Importing it loads libacf_b200.so and fails loudly if it is not built."""
     import acfcalculator_b200 as A
     A._lib.load()
+    # ACFB200_TEST_METHOD=auto|fft runs the whole suite with acfb200_set_method (the opt-in Wiener-Khinchin routing);
+    # the default is the reference's direct summation
+    method = os.environ.get("ACFB200_TEST_METHOD")
+    if method:
+        A.set_method(method)
     return A
 
 

@@ -56,6 +56,8 @@ CASES = [
     ("max_beyond_frames", "short", "general", ["-m", "60"]),
     ("missing_file_namd", "short", "none", ["-f", "namd", "-m", "4"]),
     ("missing_file_general", "short", "none", ["-m", "1"]),
+    # new double[negative] -> bad_array_new_length, caught by the reference's catch(std::bad_alloc&) (:515-524): exit 1
+    ("negative_max", "short", "general", ["--max=-5"]),
 ]
 
 
