@@ -29,8 +29,10 @@ constexpr int kTileElems = 4096;  // complex doubles per column-pass tile (64 KB
 constexpr int kColThreads = 512;
 
 struct FftGeom {
-    int b1, b2, b3;   // log2 of the factors; 0 = factor absent
-    int q;            // log2(Nc)
+    int b1, b2, b3;   // log2 of the factors; 0 = factor absent.  three: N1 = 3 * 2^b1 (b1 == 7, N1 = 384)
+    int three;        // L = 3 * 2^a: the first axis carries the factor 3 (radix 8 x 8 x 6), the others are powers of two
+    int n1;           // N1 (1 when absent)
+    int q;            // log2(Nc) (power-of-two transforms only)
     long long Nc, L;
     long long n, ncorr;
     long long x_stride, out_stride;  // batch: series b starts at x + b*x_stride, its lags go to out + b*out_stride
@@ -115,6 +117,39 @@ __device__ __forceinline__ void dft2(double2* v)
     const double2 a = cadd(v[0], v[1]), b = csub(v[0], v[1]);
     v[0] = a;
     v[1] = b;
+}
+
+// 3-point DFT in place: w = exp(DIR * 2 pi i / 3) = (-1/2, DIR * sqrt(3)/2)
+template <int DIR>
+__device__ __forceinline__ void dft3(double2& a, double2& b, double2& c)
+{
+    constexpr double hs3 = 0.86602540378443864676;  // sqrt(3)/2
+    const double2 t = cadd(b, c);
+    const double2 m = make_double2(a.x - 0.5 * t.x, a.y - 0.5 * t.y);
+    const double2 d = make_double2(hs3 * (b.x - c.x), hs3 * (b.y - c.y));
+    const double2 id = mul_i<DIR>(d);  // DIR * i * (sqrt(3)/2) (b - c)
+    a = cadd(a, t);
+    b = cadd(m, id);
+    c = csub(m, id);
+}
+// 6-point DFT, outputs in natural order: X[k] = E[k mod 3] + W6^k O[k mod 3] with E, O the 3-point DFTs of the even
+// and odd inputs, W6 = exp(DIR * i pi / 3)
+template <int DIR>
+__device__ __forceinline__ void dft6(double2* v)
+{
+    constexpr double hs3 = 0.86602540378443864676;
+    double2 e0 = v[0], e1 = v[2], e2 = v[4], o0 = v[1], o1 = v[3], o2 = v[5];
+    dft3<DIR>(e0, e1, e2);
+    dft3<DIR>(o0, o1, o2);
+    // W6^1 = (1/2, DIR*sqrt(3)/2), W6^2 = (-1/2, DIR*sqrt(3)/2)
+    const double2 p1 = make_double2(0.5 * o1.x - (DIR * hs3) * o1.y, 0.5 * o1.y + (DIR * hs3) * o1.x);
+    const double2 p2 = make_double2(-0.5 * o2.x - (DIR * hs3) * o2.y, -0.5 * o2.y + (DIR * hs3) * o2.x);
+    v[0] = cadd(e0, o0);
+    v[3] = csub(e0, o0);
+    v[1] = cadd(e1, p1);
+    v[4] = csub(e1, p1);
+    v[2] = cadd(e2, p2);
+    v[5] = csub(e2, p2);
 }
 
 // One Stockham pass of radix R = 2^LR over a length-NB axis held in shared memory.
@@ -295,15 +330,21 @@ col_pass_kernel(double2* __restrict__ data, const double* __restrict__ x, double
 //   * the 8 inputs a thread needs for radix pass 1 of the NEXT tile are loaded from HBM into registers before the
 //     current tile is computed; radix pass 1 runs on registers and the last radix pass stores straight to HBM
 //     (inter-step twiddle / normalisation fused), so only the middle hand-offs go through shared memory.
-template <int MODE, int B>
+template <int MODE, int B, bool THREE = false>
 __global__ void __launch_bounds__(kColThreads, 1)
 col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, double* __restrict__ out, FftGeom G,
                  int logC, int A, const double2* __restrict__ lo, const double2* __restrict__ hi)
 {
+    // THREE: NB = 3 * 2^B = 384 rows (B == 7), radix 8 x 8 x 6; tiles of 384 x 8.  The radix-8 passes occupy 48 groups x
+    // 8 columns = 384 of the 512 threads, the radix-6 pass 64 groups x 8 columns = all of them.
     constexpr int DIR = (MODE <= 1) ? -1 : +1;
-    constexpr int NB = 1 << B;
-    constexpr int LTC = 12 - B, TC = 1 << LTC;     // tile = NB rows x TC columns = 4096 elements
+    constexpr int NB = THREE ? (3 << B) : (1 << B);
+    constexpr int LTC = THREE ? 3 : 12 - B, TC = 1 << LTC;   // tile = NB rows x TC columns (4096 elements; 3072 for 384)
     constexpr int NB8 = NB >> 3;                   // radix-8 groups per column (>= 1)
+    constexpr int P1_THREADS = NB8 * TC;           // threads with a role in the radix-8 passes
+    constexpr bool HAS_MID = NB > 64;              // three radix passes (8, 8, NB/64) instead of two (8, NB/8)
+    static_assert(!THREE || B == 7, "the factor-3 axis is 384 = 8 * 8 * 6");
+    static_assert(P1_THREADS <= kColThreads, "one radix-8 group per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // two tile buffers: every radix pass reads one and writes the other (or alternates per tile when there is no middle
     // pass), so a pass needs one barrier -- after its writes -- instead of a second one guarding the in-place overwrite
@@ -311,7 +352,8 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     double2* s1 = s0 + NB * TC;
     double2* tw = s1 + NB * TC;                    // W_NB^m (conjugated for the inverse), m < NB
     const int tid = threadIdx.x;
-    const int g = tid >> LTC, c = tid & (TC - 1);  // pass-1 role: group g of column c; NB8 * TC == 512 threads
+    const int g = tid >> LTC, c = tid & (TC - 1);  // pass-1 role: group g of column c
+    const bool p1 = !THREE || tid < P1_THREADS;
     const unsigned int tiles_c_log = logC - LTC;
     unsigned int tiles = (unsigned int)A << tiles_c_log;
     if (MODE == 3) {
@@ -328,7 +370,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     // the last pass of a Stockham transform has p = 0: no twiddles
     double2* tw2 = tw + 7 * NB8;
     {
-        const unsigned int wstep = (unsigned int)(G.L >> B);   // W_NB = W_L^wstep
+        const unsigned int wstep = (unsigned int)(G.L / NB);   // W_NB = W_L^wstep
         for (int m = tid; m < 7 * NB8 + 7 * (NB8 / 8); m += kColThreads) {
             unsigned int e;
             if (m < 7 * NB8)
@@ -340,7 +382,10 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             tw[m] = DIR > 0 ? cconj(w) : w;
         }
     }
-    const unsigned int nc_mask = (unsigned int)(G.Nc - 1);
+    // every inter-step twiddle exponent below is a product of digits of one index and stays below Nc by construction;
+    // the mask only documents that for power-of-two Nc
+    const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);
+    const unsigned int n1 = (unsigned int)G.n1;
 
     auto load_tile = [&](unsigned int tile, double2 (&v)[8]) {
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & ((1u << tiles_c_log) - 1)) << LTC;
@@ -356,7 +401,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
                 v[t] = z;
             }
         } else {
-            const double2* base = bdata + (((size_t)a << B) << logC) + c0 + c;
+            const double2* base = bdata + (((size_t)a * NB) << logC) + c0 + c;
 #pragma unroll
             for (int t = 0; t < 8; ++t) v[t] = base[(size_t)(g + t * NB8) << logC];
         }
@@ -395,8 +440,8 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             e0 = base * cc;
             de = stride * cc;
         } else if (MODE == 1) {
-            e0 = (base << G.b1) * cc;
-            de = (stride << G.b1) * cc;
+            e0 = (base * n1) * cc;
+            de = (stride * n1) * cc;
         } else {
             e0 = ((base << logC) + cc) * a;
             de = (stride << logC) * a;
@@ -407,7 +452,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             t = cconj(t);
             d = cconj(d);
         }
-        double2* dst = bdata + (((size_t)a << B) << logC) + cc;
+        double2* dst = bdata + (((size_t)a * NB) << logC) + cc;
         for (int u = 0; u < R; ++u) {
             dst[(size_t)(base + stride * u) << logC] = cmul(r[u], t);
             t = cmul(t, d);
@@ -416,70 +461,77 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
 
     double2 nxt[8];
     unsigned int tile = blockIdx.x;
-    if (tile < tiles) load_tile(tile, nxt);
+    if (tile < tiles && p1) load_tile(tile, nxt);
     __syncthreads();  // twiddle table ready
     unsigned int parity = 0;
     for (; tile < tiles; tile += gridDim.x, parity ^= 1) {
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & ((1u << tiles_c_log) - 1)) << LTC;
-        double2 v[8];
+        double2* sa = HAS_MID ? s0 : (parity ? s1 : s0);
+        if (p1) {
+            double2 v[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = nxt[t];
-        if (tile + gridDim.x < tiles) load_tile(tile + gridDim.x, nxt);   // in flight during the math below
+            for (int t = 0; t < 8; ++t) v[t] = nxt[t];
+            if (tile + gridDim.x < tiles) load_tile(tile + gridDim.x, nxt);   // in flight during the math below
 
-        // ---- radix pass 1 (Stockham stride 1, p = g) on registers
-        dft8<DIR>(v);
-        if (g != 0) {
+            // ---- radix pass 1 (Stockham stride 1, p = g) on registers
+            dft8<DIR>(v);
+            if (g != 0) {
 #pragma unroll
-            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], tw[(u - 1) * NB8 + g]);
-        }
-        if (B == 3) {
-            store_group(a, c0 + c, 0, 1, 8, v);
-            continue;
-        }
-        // with a middle pass: pass 1 -> s0, middle s0 -> s1, last reads s1.  Without: the buffers alternate per tile.
-        double2* sa = (B > 6) ? s0 : (parity ? s1 : s0);
+                for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], tw[(u - 1) * NB8 + g]);
+            }
+            if (NB == 8) {
+                store_group(a, c0 + c, 0, 1, 8, v);
+                continue;
+            }
+            // with a middle pass: pass 1 -> s0, middle s0 -> s1, last reads s1.  Without: the buffers alternate per tile.
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sa[((8 * g + u) << LTC) + c] = v[u];
+            for (int u = 0; u < 8; ++u) sa[((8 * g + u) << LTC) + c] = v[u];
+        }
         __syncthreads();
 
         // ---- middle radix-8 pass (stride 8) through shared memory, only for NB >= 128
-        if (B > 6) {
-            double2 r[8];
+        if (HAS_MID) {
+            if (p1) {
+                double2 r[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) r[t] = s0[((g + t * NB8) << LTC) + c];
-            dft8<DIR>(r);
-            const int qq = g & 7, ps = g - qq;
-            if (ps != 0) {
+                for (int t = 0; t < 8; ++t) r[t] = s0[((g + t * NB8) << LTC) + c];
+                dft8<DIR>(r);
+                const int qq = g & 7, ps = g - qq;
+                if (ps != 0) {
 #pragma unroll
-                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], tw2[(u - 1) * (NB8 / 8) + (g >> 3)]);
+                    for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], tw2[(u - 1) * (NB8 / 8) + (g >> 3)]);
+                }
+                const int base = qq + ps * 8;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s1[((base + 8 * u) << LTC) + c] = r[u];
             }
-            const int base = qq + ps * 8;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s1[((base + 8 * u) << LTC) + c] = r[u];
             __syncthreads();
             sa = s1;
         }
 
         // ---- last pass: shared memory -> registers -> HBM
         {
-            constexpr int LEFT = (B > 6) ? B - 6 : B - 3;   // log2 of the last radix: 1, 2 or 3
-            constexpr int STRIDE = (B > 6) ? 64 : 8;
-            constexpr int R = 1 << LEFT, GPT = 8 / R;
+            constexpr int STRIDE = HAS_MID ? 64 : 8;
+            constexpr int R = NB / STRIDE;                   // last radix: 2, 4 or 8; 6 for NB = 384
             constexpr int GROUPS = NB / R;                   // per column
+            constexpr int GPT = (GROUPS * TC) / kColThreads; // groups per thread
+            static_assert(GROUPS * TC == GPT * kColThreads && GPT >= 1, "the last pass keeps every thread busy");
+            static_assert(GROUPS <= STRIDE, "last Stockham pass: p == 0, no twiddles");
 #pragma unroll
             for (int it = 0; it < GPT; ++it) {
-                const int w = tid + it * kColThreads;        // GROUPS * TC == GPT * 512
+                const int w = tid + it * kColThreads;
                 const int gg = w >> LTC, cc = w & (TC - 1);
                 double2 r[8];
 #pragma unroll
                 for (int t = 0; t < R; ++t) r[t] = sa[((gg + t * GROUPS) << LTC) + cc];
-                if (LEFT == 3)
+                if (R == 8)
                     dft8<DIR>(r);
-                else if (LEFT == 2)
+                else if (R == 6)
+                    dft6<DIR>(r);
+                else if (R == 4)
                     dft4<DIR>(r);
                 else
                     dft2(r);
-                static_assert(GROUPS <= STRIDE, "last Stockham pass: p == 0, no twiddles");
                 store_group(a, c0 + cc, gg, STRIDE, R, r);
             }
         }
@@ -738,6 +790,8 @@ static col2_fn col2_select(int mode, int b)
 {
     return mode == 0 ? col2_for<0>(b) : mode == 1 ? col2_for<1>(b) : mode == 2 ? col2_for<2>(b) : col2_for<3>(b);
 }
+// the factor-3 axis is always axis 1: forward step 1 (mode 0) and inverse step 1' (mode 3)
+static col2_fn col2_three(int mode) { return mode == 0 ? col_pass2_kernel<0, 7, true> : col_pass2_kernel<3, 7, true>; }
 
 // ---- fused row pass: forward step 3, |X|^2 pair operation with the mirror row, inverse step 3' ------------
 // Rows are indexed by (k1, k2); a row holds k3 = 0..N3-1 contiguously.  The mirror of spectrum index k is Nc-k:
@@ -870,7 +924,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     double2* twf = s + 2 * 4096;                      // W_N3^m
     const int tid = threadIdx.x;
     const int rs = tid >> LG8, g = tid & (G8 - 1);    // row slot, radix group
-    const unsigned int N1 = 1u << G.b1, N2 = 1u << G.b2;
+    const unsigned int N1 = (unsigned int)G.n1, N2 = 1u << G.b2;   // N1 may be 384 = 3 * 2^7 (even either way)
     // pair list: k1 = 0 -> k2 in [0, N2/2];  0 < k1 < N1/2 -> every k2;  k1 = N1/2 -> k2 in [0, max(N2/2,1))
     const unsigned int cnt0 = N2 / 2 + 1, cntm = (N1 / 2 - 1) * N2, cnth = N2 >= 2 ? N2 / 2 : 1;
     const unsigned int npairs = cnt0 + cntm + cnth;
@@ -889,8 +943,8 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             twf[m] = tw_L(lo, hi, (unsigned long long)e * wstep);
         }
     }
-    const unsigned int nc_mask = (unsigned int)(G.Nc - 1);
-    const int shift12 = G.b1 + G.b2;
+    const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);  // exponents stay below Nc anyway
+    const unsigned int n12 = N1 << G.b2;              // N1 * N2: spectrum index k = k1 + N1*k2 + N1*N2*k3
 
     // digits (k1, k2) of the row held by slot `rs` of tile `tile`; false past the end of the list
     auto slot_row = [&](unsigned int tile, unsigned int& r1, unsigned int& r2, bool& origin) -> bool {
@@ -1013,8 +1067,8 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
 
         // ================= |X|^2 pair operation for this thread's 8 spectrum points (reads X) =================
         // W_L^k for k = kbase + N1*N2*(g + t*N3/8): successive t differ by W_L^{Nc/8} = exp(-i pi/8), a constant
-        const unsigned int kbase = r1 + (r2 << G.b1);
-        double2 W = tw_L(lo, hi, (unsigned long long)(kbase + ((unsigned int)g << shift12)));
+        const unsigned int kbase = r1 + r2 * N1;
+        double2 W = tw_L(lo, hi, (unsigned long long)(kbase + (unsigned int)g * n12));
         const double2 rot = make_double2(0.92387953251128675613, -0.38268343236508977173);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -1059,7 +1113,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         }
         {   // last inverse pass (reads X) -> post twiddle conj(W_Nc^{j3 * f}) -> HBM
             constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
-            const unsigned int f = (G.b2 > 0) ? (r2 << G.b1) : r1;
+            const unsigned int f = (G.b2 > 0) ? (r2 * N1) : r1;
             double2* dst = bdata + ((size_t)((r1 << G.b2) + r2) << B3);
 #pragma unroll
             for (int it = 0; it < GPT; ++it) {
@@ -1124,6 +1178,16 @@ __global__ void fft_pack_kernel(const double* __restrict__ x, double2* __restric
 }
 
 // ---- host side --------------------------------------------------------------------------------------
+static bool three_allowed()
+{
+    const char* e3 = getenv("ACFB200_FFT_THREE");       // "0": powers of two only (the round-1 plans)
+    const char* ep = getenv("ACFB200_FFT_PIPELINED");   // the factor-3 axis exists in the pipelined kernels only
+    return !(e3 && e3[0] == '0') && !(ep && ep[0] == '0');
+}
+
+// L = the smallest of 2^a and 3*2^a that holds n + ncorr - 1 (the circular correlation then has no wrap for k < ncorr).
+// 3*2^a saves a quarter of every sweep whenever n + ncorr - 1 falls in (2^(a+1), 3*2^a]; config 5 (n = 2^27, ncorr = 2^26)
+// needs exactly 3*2^26 - 1 points.  Nc = L/2 = N1*N2*N3; with the factor 3: N1 = 384 (radix 8 x 8 x 6), N2*N3 = 2^(a-8).
 static int make_geom(long long n, long long ncorr, FftGeom* g)
 {
     if (n < 1 || ncorr < 1) {
@@ -1140,13 +1204,32 @@ static int make_geom(long long n, long long ncorr, FftGeom* g)
                   lq);
         return 1;
     }
-    g->q = q;
-    g->L = 1ll << lq;
-    g->Nc = 1ll << q;
     g->n = n;
     g->ncorr = ncorr;
     g->x_stride = n;
     g->out_stride = ncorr;
+    g->three = 0;
+    // 3 * 2^(lq-2) lies between 2^(lq-1) (< need) and 2^lq
+    const int a3 = lq - 2, rest = a3 - 8;  // rest = log2(N2 * N3)
+    if (a3 >= 8 && 3ll << a3 >= need && three_allowed() && ((rest >= 7 && rest <= 9) || (rest >= 12 && rest <= 18))) {
+        g->three = 1;
+        g->q = 0;
+        g->L = 3ll << a3;
+        g->Nc = g->L / 2;
+        g->b1 = 7;
+        g->n1 = 384;
+        if (rest <= 9) {
+            g->b2 = 0;
+            g->b3 = rest;
+        } else {
+            g->b3 = 9;
+            g->b2 = rest - 9;   // 3..9: a pipelined column pass of its own
+        }
+        return 0;
+    }
+    g->q = q;
+    g->L = 1ll << lq;
+    g->Nc = 1ll << q;
     if (q <= 9) {
         g->b1 = 0;
         g->b2 = 0;
@@ -1160,6 +1243,7 @@ static int make_geom(long long n, long long ncorr, FftGeom* g)
         g->b2 = (q - 9 - 3 >= 9) ? 9 : q - 9 - 3;
         g->b1 = q - 9 - g->b2;
     }
+    g->n1 = 1 << g->b1;
     return 0;
 }
 
@@ -1243,21 +1327,27 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
             for (int bb = 3; bb <= 9; ++bb)
                 cudaFuncSetAttribute(col2_select(mode, bb), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (2 * kTileElems + 512) * 16);
+        cudaFuncSetAttribute(col2_three(0), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
+        cudaFuncSetAttribute(col2_three(3), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
         cudaFuncSetAttribute(col_pass3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes);
         cudaFuncSetAttribute(col_pass3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes);
         cudaFuncSetAttribute(col_pass3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes);
         cudaFuncSetAttribute(col_pass3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes);
         if (dev < 64) attr_done[dev] = true;
     }
-    const long long N1 = 1ll << g.b1, N2 = 1ll << g.b2, N3 = 1ll << g.b3;
+    const long long N1 = g.n1, N2 = 1ll << g.b2, N3 = 1ll << g.b3;
     const char* env = getenv("ACFB200_FFT_PIPELINED");
     bool pipelined = !(env && env[0] == '0');
     // the pipelined kernels use fixed 4096-element tiles: every pass must offer at least one full tile width
-    if (g.b1 > 0 && g.b2 + g.b3 < 12 - g.b1) pipelined = false;
+    if (g.b1 > 0 && !g.three && g.b2 + g.b3 < 12 - g.b1) pipelined = false;
     if (g.b2 > 0 && g.b3 < 12 - g.b2) pipelined = false;
+    if (g.three && (!pipelined || g.b3 < 7)) {
+        set_error("fft_acf: internal error, a factor-3 plan needs the pipelined kernels (b2=%d b3=%d)", g.b2, g.b3);
+        return -1;
+    }
     // 512-point column passes: the warp-private kernels (col_pass3_kernel), opt-in while they are being measured
     const char* env3 = getenv("ACFB200_FFT_COL3");
-    const bool col3 = pipelined && env3 && env3[0] == '1';
+    const bool col3 = pipelined && env3 && env3[0] == '1' && !g.three;  // (its twiddles assume N1 = 2^b1)
     auto pgrid = [sms](long long tiles) { return (unsigned)(tiles < sms ? tiles : sms); };
     const size_t smem2 = (size_t)(2 * kTileElems + 512) * 16;  // two tile buffers + butterfly twiddles
     auto tc_for = [](int b, long long C) {
@@ -1268,7 +1358,10 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     if (g.b1 > 0) {
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
-        if (col3 && g.b1 == 9)
+        if (g.three)
+            col2_three(0)<<<dim3(pgrid(C >> 3), nb, 1), kColThreads, smem2, st>>>(data, d_x, nullptr, g, g.b2 + g.b3, 1, lo,
+                                                                                   hi);
+        else if (col3 && g.b1 == 9)
             col_pass3_kernel<0><<<dim3(pgrid(C >> 3), nb, 1), kC3Threads, kC3SmemBytes, st>>>(
                 data, d_x, nullptr, g, g.b2 + g.b3, 1, lo, hi);
         else if (pipelined)
@@ -1327,7 +1420,10 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     if (g.b1 > 0) {
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
-        if (col3 && g.b1 == 9)
+        if (g.three)
+            col2_three(3)<<<dim3(pgrid(C >> 3), nb, 1), kColThreads, smem2, st>>>(data, nullptr, d_out, g, g.b2 + g.b3, 1,
+                                                                                   lo, hi);
+        else if (col3 && g.b1 == 9)
             col_pass3_kernel<3><<<dim3(pgrid(C >> 3), nb, 1), kC3Threads, kC3SmemBytes, st>>>(
                 data, nullptr, d_out, g, g.b2 + g.b3, 1, lo, hi);
         else if (pipelined)

@@ -73,6 +73,26 @@ def test_planner_geometry_tiled(acf, n, m, s):
         assert p["useful_lag_frac"] > 0.97
 
 
+def test_fft_plan_lengths(acf):
+    """acfb200_fft_plan (no device needed): L is the smallest of 2^a and 3*2^a that holds n + maxcorr - 1, where the
+    factor-3 kernels apply; it never wraps a wanted lag."""
+    assert acf.fft_plan(2**27, 2**26) == (3 << 26, 3)          # config 5: n + maxcorr - 1 = 3*2^26 - 1
+    assert acf.fft_plan(10**7, 10**4) == (3 << 22, 3)          # config 2 through the auto method
+    assert acf.fft_plan(100000, 50000) == (3 << 16, 2)
+    assert acf.fft_plan(4999, 1000) == (8192, 2)               # too short for the 384-point axis
+    assert acf.fft_plan(2**20, 2**19) == (1 << 21, 3)          # 3*2^19 would need a 4-point middle axis: power of two
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        n = int(rng.integers(1, 2**27))
+        m = int(rng.integers(1, n + 5))
+        if n + m - 1 > 2**28:
+            continue
+        L, f = acf.fft_plan(n, m)
+        assert L >= n + m - 1 and 1 <= f <= 3
+        assert L & (L - 1) == 0 or (L % 3 == 0 and (L // 3) & (L // 3 - 1) == 0)
+        assert L < 2 * max(n + m - 1, 16)
+
+
 def test_no_cpu_fallback(acf):
     """Without a usable GPU every compute entry point must fail loudly, never compute on the host."""
     import torch

@@ -110,7 +110,7 @@ def test_green_kubo_and_viscosity_cli(acf, oracle, ngpus, tmp_path):
     sel1 = subprocess.run([exe, log, "--components", "1,2,5"], capture_output=True, text=True)
     assert sel.returncode == 0 and sel1.returncode == 0, sel.stderr
     assert [l.split()[:1] for l in sel.stdout.splitlines()] == [l.split()[:1] for l in sel1.stdout.splitlines()]
-    assert sum(l.startswith("#eta ") for l in sel.stdout.splitlines()) == 3
+    assert sum(l.startswith("#eta ") and not l.startswith("#eta =") for l in sel.stdout.splitlines()) == 3
 
 
 def test_traj2diffusion_batch_over_devices(acf, oracle, ngpus, tmp_path):

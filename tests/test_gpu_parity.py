@@ -237,7 +237,10 @@ def test_errors_are_reported_not_swallowed(acf):
 
 # ---- K2: zero-padded Wiener-Khinchin path --------------------------------------------------------------
 @pytest.mark.parametrize("n,m", [(7, 3), (100, 100), (500, 13), (513, 512), (1500, 500), (3000, 1000), (5001, 1000),
-                                 (40000, 30000), (100000, 99999), (262144, 1), (300000, 262144)])
+                                 (40000, 30000), (100000, 99999), (262144, 1), (300000, 262144),
+                                 # L = 3 * 2^a plans (first axis 384 = 8 x 8 x 6): two factors with 128/256/512-point rows,
+                                 # three factors with an 8- and a 32-point middle axis, ragged n
+                                 (70000, 20000), (100000, 50000), (300001, 80000), (2_500_001, 600_000), (10**7, 10**4)])
 def test_fft_path_matches_oracle(acf, oracle, n, m):
     """One-, two- and three-factor transform plans against the direct-sum oracle."""
     x = ou_series(n, 30.0, mu=0.25, seed=n + 3 * m)
@@ -411,6 +414,16 @@ def test_full_size_config5_fft(acf, oracle):
     assert rel_to_c0(got[lags], ref, ref[0]) <= TOL
     assert _close(got[0], float(np.dot(x, x)) / n, 1e-12)
     assert np.all(np.isfinite(got))
+    # the plan is L = 3 * 2^26 (n + maxcorr - 1 fits exactly); the power-of-two plan L = 2^28 must give the same lags to
+    # rounding (different transform length => different rounding, not different numbers)
+    assert acf.fft_plan(n, m) == (3 << 26, 3)
+    os.environ["ACFB200_FFT_THREE"] = "0"
+    try:
+        assert acf.fft_plan(n, m) == (1 << 28, 3)
+        pow2 = acf.calcCorrelationFFT(x, m)
+    finally:
+        os.environ.pop("ACFB200_FFT_THREE", None)
+    assert rel_to_c0(pow2, got, got[0]) <= 1e-12
     # the warp-private 512-point column passes (col_pass3_kernel, opt-in) do the same arithmetic in another order of
     # execution: every lag must come out bit for bit the same
     os.environ["ACFB200_FFT_COL3"] = "1"
