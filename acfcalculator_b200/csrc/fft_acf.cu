@@ -459,19 +459,16 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
         }
     };
 
-    double2 nxt[8];
-    unsigned int tile = blockIdx.x;
-    if (tile < tiles && p1) load_tile(tile, nxt);
-    __syncthreads();  // twiddle table ready
-    unsigned int parity = 0;
-    for (; tile < tiles; tile += gridDim.x, parity ^= 1) {
+    // One tile: `v` holds this thread's eight pass-1 inputs (loaded one tile ago), `nx` receives those of the CTA's next
+    // tile.  The tile loop below is unrolled by two with the register sets swapping roles.  (ncu, round 2: with a single
+    // loop-carried set the compiler loads into scratch registers and copies them into the carried set right after radix
+    // pass 1 -- 32 moves that wait for the loads, so the prefetch covered one radix pass instead of a whole tile: 18 % of
+    // all stall samples of the 384-row forward pass sat on the first of those moves.)
+    auto do_tile = [&](unsigned int tile, double2 (&v)[8], double2 (&nx)[8], const unsigned int parity) {
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & ((1u << tiles_c_log) - 1)) << LTC;
         double2* sa = HAS_MID ? s0 : (parity ? s1 : s0);
         if (p1) {
-            double2 v[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = nxt[t];
-            if (tile + gridDim.x < tiles) load_tile(tile + gridDim.x, nxt);   // in flight during the math below
+            if (tile + gridDim.x < tiles) load_tile(tile + gridDim.x, nx);   // in flight during the whole tile
 
             // ---- radix pass 1 (Stockham stride 1, p = g) on registers
             dft8<DIR>(v);
@@ -481,7 +478,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             }
             if (NB == 8) {
                 store_group(a, c0 + c, 0, 1, 8, v);
-                continue;
+                return;
             }
             // with a middle pass: pass 1 -> s0, middle s0 -> s1, last reads s1.  Without: the buffers alternate per tile.
 #pragma unroll
@@ -536,240 +533,19 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             }
         }
         // no barrier here: the next tile's pass 1 writes the buffer that was last READ two barriers ago
-    }
-}
-
-// ---- column pass, warp-private form (NB = 512 only) ----------------------------------------------------------
-// Same transform, modes and arithmetic as col_pass2_kernel<MODE, 9> (the results are bit-identical), different
-// execution structure.  ncu on col_pass2 (profiles/r1e_fft_kernels_ncu_raw.csv): all four column passes take ~0.8 ms
-// whatever their traffic (2.7-4.2 GB), top stalls `barrier` and `mio_throttle` -- 16 warps marching through load /
-// butterfly / exchange / store phases in lock step leave HBM, the FP64 pipe and the shared-memory pipe idle in turn.
-// Here nothing is CTA-wide:
-//   * 512 x 8 tiles (128-byte row segments) live in a ring of three 64 KB buffers, filled with 16-byte cp.async copies
-//     (LDGSTS; zero fill does the padding of MODE 0) that complete on one mbarrier per buffer;
-//   * the sixteen warps form two groups of eight; group k % 2 owns tile k, and inside it a WARP owns a COLUMN: 16 values
-//     per lane, three radix-8 passes on registers with the two exchanges going through the warp's own column of the
-//     tile buffer in place (__syncwarp only);
-//   * the group meets once per tile (named barrier, 256 threads) so that the finished tile leaves as coalesced 128-byte
-//     row segments; every thread then refills exactly the 16-byte units it has just read with tile k + 3 -- which the
-//     OTHER group will transform -- so handing a buffer on needs no second barrier.
-// Bank conflicts: the eight 16-byte chunks of row r sit at chunk position c ^ (r & 7), and intermediate position p of a
-// column is kept in row rho(p) = p with its low three bits advanced by (p >> 3); every access of the three passes then
-// touches eight different bank groups per quarter warp.
-// MEASURED (B200, config 5, profiles/r1f_fft_col_pass3_ncu_raw.csv): bit-identical lags, barrier stalls gone (0.4-0.9
-// warps per issue against 2.3-2.9), but 4.89 ms per step against 4.40 ms: a warp that owns a column must transpose the
-// tile through shared memory on the way in AND on the way out, 8 shared-memory operations per element instead of 4,
-// and the LSU data pipe sits at 75-83 % of its wavefront peak (shared 58-64 %, the inter-step twiddle gathers and the
-// global side of the copies the rest).  Kept as an opt-in variant (ACFB200_FFT_COL3=1), parity-tested.
-constexpr int kC3Stages = 3;
-constexpr int kC3Threads = 512;
-constexpr size_t kC3SmemBytes = (size_t)(kC3Stages * kTileElems + 7 * 64 + 7 * 8) * 16 + kC3Stages * 8;
-
-__device__ __forceinline__ int c3_rho(int p) { return (p & ~7) | ((p + (p >> 3)) & 7); }
-__device__ __forceinline__ int c3_unit(int r, int c) { return (r << 3) | ((c ^ r) & 7); }
-
-template <int MODE>
-__global__ void __launch_bounds__(kC3Threads, 1)
-col_pass3_kernel(double2* __restrict__ data, const double* __restrict__ x, double* __restrict__ out, FftGeom G,
-                 int logC, int A, const double2* __restrict__ lo, const double2* __restrict__ hi)
-{
-    constexpr int DIR = (MODE <= 1) ? -1 : +1;
-    constexpr int B = 9, NB8 = 64, LTC = 3;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* bufs = reinterpret_cast<double2*>(smem_raw);
-    double2* tw = bufs + kC3Stages * kTileElems;   // tw[(u-1)*64 + g] = W_512^{g*u}   (pass 1)
-    double2* tw2 = tw + 7 * NB8;                   // tw2[(u-1)*8 + p] = W_512^{8*p*u} (middle pass)
-    uint64_t* full = reinterpret_cast<uint64_t*>(tw2 + 7 * 8);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned int tiles_c_log = logC - LTC;
-    unsigned int tiles = (unsigned int)A << tiles_c_log;
-    if (MODE == 3) {
-        const long long need = (G.ncorr + 1) / 2;  // complex outputs j < need
-        if (need < (1ll << logC)) tiles = (unsigned int)((need + 7) >> LTC);
-    }
-    const long long batch = blockIdx.y;
-    double2* bdata = data + batch * G.Nc;
-    const double* xs = (MODE == 0) ? x + batch * G.x_stride : nullptr;
-    {
-        const unsigned int wstep = (unsigned int)(G.L >> B);   // W_512 = W_L^wstep
-        for (int m = tid; m < 7 * NB8 + 7 * 8; m += kC3Threads) {
-            unsigned int e;
-            if (m < 7 * NB8)
-                e = (unsigned int)(m % NB8) * (unsigned int)(m / NB8 + 1);
-            else
-                e = 8u * (unsigned int)((m - 7 * NB8) % 8) * (unsigned int)((m - 7 * NB8) / 8 + 1);
-            const double2 w = tw_L(lo, hi, (unsigned long long)e * wstep);
-            tw[m] = DIR > 0 ? cconj(w) : w;
-        }
-        if (tid == 0) {
-            // one arrival per thread of the filling group, each once all of its copies have landed
-            for (int s = 0; s < kC3Stages; ++s) mbar_init(&full[s], 256);
-        }
-    }
-    __syncthreads();
-    const unsigned int c_mask = (1u << tiles_c_log) - 1;
-    const int grp = warp >> 3, c = warp & 7, tg = tid & 255;
-    const unsigned int nc_mask = (unsigned int)(G.Nc - 1);
-
-    // This thread's share of tile number kt of this CTA: the sixteen 16-byte units idx = tg + 256*i, into buffer kt % 3.
-    auto fill = [&](unsigned int kt) {
-        const unsigned int tile = blockIdx.x + kt * gridDim.x;
-        if (tile >= tiles) return;
-        const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << LTC;
-        double2* buf = bufs + (kt % kC3Stages) * kTileElems;
-        const int chunk = tg & 7, r0 = tg >> 3;
-        if (MODE == 0) {
-            // complex point j = (row << logC) + c0 + chunk is the sample pair 2j, 2j+1; beyond n: zeros
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int row = 32 * i + r0;
-                const long long j = ((long long)row << logC) + c0 + chunk;
-                const long long rem = G.n - 2 * j;
-                const unsigned int bytes = rem >= 2 ? 16u : (rem == 1 ? 8u : 0u);
-                cp_async16_zfill(buf + c3_unit(row, chunk), rem > 0 ? xs + 2 * j : xs, bytes);
-            }
-        } else {
-            const double2* base = bdata + (((size_t)a << B) << logC) + c0 + chunk;
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int row = 32 * i + r0;
-                cp_async16(buf + c3_unit(row, chunk), base + ((size_t)row << logC));
-            }
-        }
-        cp_async_mbar_arrive_noinc(&full[kt % kC3Stages]);
     };
-    // tile kt is filled by group (kt + 1) % 2: from kt = 3 on that is the group which emptied the buffer (tile kt - 3)
-    if (grp == 1) {
-        fill(0);
-        fill(2);
-    } else {
-        fill(1);
-    }
 
-    unsigned int k = grp;
-    for (unsigned int tile = blockIdx.x + grp * gridDim.x; tile < tiles; tile += 2 * gridDim.x, k += 2) {
-        const unsigned int b = k % kC3Stages, use = k / kC3Stages;
-        const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << LTC;
-        double2* buf = bufs + b * kTileElems;
-        mbar_wait(&full[b], use & 1);
-        double2 v[2][8];
-        // ---- radix pass 1 (Stockham stride 1, p = g): rows as loaded -> permuted rows
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[h][t] = buf[c3_unit(lane + 32 * h + 64 * t, c)];
-        __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int g = lane + 32 * h;
-            dft8<DIR>(v[h]);
-            if (g != 0) {
-#pragma unroll
-                for (int u = 1; u < 8; ++u) v[h][u] = cmul(v[h][u], tw[(u - 1) * NB8 + g]);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) buf[c3_unit(c3_rho(8 * g + u), c)] = v[h][u];
-        }
-        __syncwarp();
-        // ---- middle radix-8 pass (stride 8)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[h][t] = buf[c3_unit(c3_rho(lane + 32 * h + 64 * t), c)];
-        __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int g = lane + 32 * h;
-            dft8<DIR>(v[h]);
-            const int qq = g & 7, ps = g - qq;
-            if (ps != 0) {
-#pragma unroll
-                for (int u = 1; u < 8; ++u) v[h][u] = cmul(v[h][u], tw2[(u - 1) * 8 + (g >> 3)]);
-            }
-            const int base = qq + ps * 8;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) buf[c3_unit(c3_rho(base + 8 * u), c)] = v[h][u];
-        }
-        __syncwarp();
-        // ---- last radix-8 pass (stride 64, no butterfly twiddles): permuted rows -> rows in output order, with the
-        //      inter-step twiddle of the mode (exponents in arithmetic progression, as in col_pass2_kernel)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[h][t] = buf[c3_unit(c3_rho(lane + 32 * h + 64 * t), c)];
-        __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const unsigned int gg = lane + 32 * h, cc = c0 + c;
-            dft8<DIR>(v[h]);
-            if (MODE != 3) {
-                unsigned int e0, de;  // exponents of W_Nc; every product stays below 2^28
-                if (MODE == 0) {
-                    e0 = gg * cc;
-                    de = 64u * cc;
-                } else if (MODE == 1) {
-                    e0 = (gg << G.b1) * cc;
-                    de = (64u << G.b1) * cc;
-                } else {
-                    e0 = ((gg << logC) + cc) * a;
-                    de = (64u << logC) * a;
-                }
-                double2 t = tw_L(lo, hi, 2ull * (e0 & nc_mask));  // W_Nc = W_L^2
-                double2 d = tw_L(lo, hi, 2ull * (de & nc_mask));
-                if (DIR > 0) {
-                    t = cconj(t);
-                    d = cconj(d);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    v[h][u] = cmul(v[h][u], t);
-                    t = cmul(t, d);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) buf[c3_unit(gg + 64 * u, c)] = v[h][u];
-        }
-        named_bar_sync(1 + grp, 256);
-        // ---- the tile leaves as 128-byte row segments: 8 consecutive threads = one row
-        {
-            const int chunk = tg & 7, r0 = tg >> 3;
-            if (MODE == 3) {
-                double* o = out + batch * G.out_stride;
-                const double inv_nc = 1.0 / (double)G.Nc;
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int row = 32 * i + r0;
-                    const double2 r = buf[c3_unit(row, chunk)];
-                    const long long j = ((long long)row << logC) + c0 + chunk;
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const long long kk = 2 * j + hh;
-                        if (kk < G.ncorr) {
-                            const long long m = G.n - kk;
-                            double val = (hh ? r.y : r.x) * inv_nc;
-                            if (m > 0)
-                                val = val / (double)m;
-                            else if (m == 0)
-                                val = __longlong_as_double(0xFFF8000000000000ull);  // reference: 0/0
-                            else
-                                val = -0.0;                                          // reference: 0/negative
-                            o[kk] = val;
-                        }
-                    }
-                }
-            } else {
-                double2* dst = bdata + (((size_t)a << B) << logC) + c0 + chunk;
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int row = 32 * i + r0;
-                    dst[(size_t)row << logC] = buf[c3_unit(row, chunk)];
-                }
-            }
-        }
-        // the units this thread has just read are the ones it fills again (same idx -> same unit): no barrier needed
-        fill(k + kC3Stages);
+    double2 ra[8], rb[8];
+    unsigned int tile = blockIdx.x;
+    if (tile < tiles && p1) load_tile(tile, ra);
+    __syncthreads();  // twiddle table ready
+    while (tile < tiles) {
+        do_tile(tile, ra, rb, 0);
+        tile += gridDim.x;
+        if (tile >= tiles) break;
+        do_tile(tile, rb, ra, 1);
+        tile += gridDim.x;
     }
-    cp_async_wait_all();
 }
 
 typedef void (*col2_fn)(double2*, const double*, double*, FftGeom, int, int, const double2*, const double2*);
@@ -1329,10 +1105,6 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
                                      (2 * kTileElems + 512) * 16);
         cudaFuncSetAttribute(col2_three(0), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
         cudaFuncSetAttribute(col2_three(3), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
-        cudaFuncSetAttribute(col_pass3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes);
-        cudaFuncSetAttribute(col_pass3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes);
-        cudaFuncSetAttribute(col_pass3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes);
-        cudaFuncSetAttribute(col_pass3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes);
         if (dev < 64) attr_done[dev] = true;
     }
     const long long N1 = g.n1, N2 = 1ll << g.b2, N3 = 1ll << g.b3;
@@ -1345,9 +1117,6 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         set_error("fft_acf: internal error, a factor-3 plan needs the pipelined kernels (b2=%d b3=%d)", g.b2, g.b3);
         return -1;
     }
-    // 512-point column passes: the warp-private kernels (col_pass3_kernel), opt-in while they are being measured
-    const char* env3 = getenv("ACFB200_FFT_COL3");
-    const bool col3 = pipelined && env3 && env3[0] == '1' && !g.three;  // (its twiddles assume N1 = 2^b1)
     auto pgrid = [sms](long long tiles) { return (unsigned)(tiles < sms ? tiles : sms); };
     const size_t smem2 = (size_t)(2 * kTileElems + 512) * 16;  // two tile buffers + butterfly twiddles
     auto tc_for = [](int b, long long C) {
@@ -1361,9 +1130,6 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         if (g.three)
             col2_three(0)<<<dim3(pgrid(C >> 3), nb, 1), kColThreads, smem2, st>>>(data, d_x, nullptr, g, g.b2 + g.b3, 1, lo,
                                                                                    hi);
-        else if (col3 && g.b1 == 9)
-            col_pass3_kernel<0><<<dim3(pgrid(C >> 3), nb, 1), kC3Threads, kC3SmemBytes, st>>>(
-                data, d_x, nullptr, g, g.b2 + g.b3, 1, lo, hi);
         else if (pipelined)
             col2_select(0, g.b1)<<<dim3(pgrid(C >> (12 - g.b1)), nb, 1), kColThreads, smem2, st>>>(
                 data, d_x, nullptr, g, g.b2 + g.b3, 1, lo, hi);
@@ -1377,10 +1143,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     }
     if (g.b2 > 0) {
         const int TC = tc_for(g.b2, N3);
-        if (col3 && g.b2 == 9)
-            col_pass3_kernel<1><<<dim3(pgrid((N3 >> 3) * N1), nb, 1), kC3Threads, kC3SmemBytes, st>>>(
-                data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
-        else if (pipelined)
+        if (pipelined)
             col2_select(1, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), nb, 1), kColThreads, smem2, st>>>(
                 data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
         else
@@ -1406,10 +1169,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     }
     if (g.b2 > 0) {
         const int TC = tc_for(g.b2, N3);
-        if (col3 && g.b2 == 9)
-            col_pass3_kernel<2><<<dim3(pgrid((N3 >> 3) * N1), nb, 1), kC3Threads, kC3SmemBytes, st>>>(
-                data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
-        else if (pipelined)
+        if (pipelined)
             col2_select(2, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), nb, 1), kColThreads, smem2, st>>>(
                 data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
         else
@@ -1423,9 +1183,6 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         if (g.three)
             col2_three(3)<<<dim3(pgrid(C >> 3), nb, 1), kColThreads, smem2, st>>>(data, nullptr, d_out, g, g.b2 + g.b3, 1,
                                                                                    lo, hi);
-        else if (col3 && g.b1 == 9)
-            col_pass3_kernel<3><<<dim3(pgrid(C >> 3), nb, 1), kC3Threads, kC3SmemBytes, st>>>(
-                data, nullptr, d_out, g, g.b2 + g.b3, 1, lo, hi);
         else if (pipelined)
             col2_select(3, g.b1)<<<dim3(pgrid(C >> (12 - g.b1)), nb, 1), kColThreads, smem2, st>>>(
                 data, nullptr, d_out, g, g.b2 + g.b3, 1, lo, hi);

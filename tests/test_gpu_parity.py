@@ -424,29 +424,6 @@ def test_full_size_config5_fft(acf, oracle):
     finally:
         os.environ.pop("ACFB200_FFT_THREE", None)
     assert rel_to_c0(pow2, got, got[0]) <= 1e-12
-    # the warp-private 512-point column passes (col_pass3_kernel, opt-in) do the same arithmetic in another order of
-    # execution: every lag must come out bit for bit the same
-    os.environ["ACFB200_FFT_COL3"] = "1"
-    try:
-        alt = acf.calcCorrelationFFT(x, m)
-    finally:
-        os.environ.pop("ACFB200_FFT_COL3", None)
-    assert np.array_equal(alt.view(np.int64), got.view(np.int64))
-
-
-def test_fft_warp_private_column_passes_are_bit_identical(acf):
-    """Same check on shapes where only the middle column passes are 512 points long, with ragged n and maxcorr, and on
-    a stacked batch."""
-    rng = np.random.default_rng(3)
-    for n, m in ((3_000_001, 1_048_000), ((1 << 22) - 5, 7), (2_500_000, 1_500_000)):
-        x = rng.standard_normal(n) + 0.25
-        ref = acf.calcCorrelationFFT(x, m)
-        os.environ["ACFB200_FFT_COL3"] = "1"
-        try:
-            alt = acf.calcCorrelationFFT(x, m)
-        finally:
-            os.environ.pop("ACFB200_FFT_COL3", None)
-        assert np.array_equal(alt.view(np.int64), ref.view(np.int64)), (n, m)
 
 
 def test_fft_small_batches_use_the_simple_kernels(acf):

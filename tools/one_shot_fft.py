@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs the Wiener-Khinchin path a few times on random data (for ncu captures): python tools/one_shot_fft.py LOG2N [reps]
-(n = 2^LOG2N, maxcorr = n/2; ACFB200_FFT_COL3=1 selects the warp-private column passes)"""
+(n = 2^LOG2N, maxcorr = n/2; ACFB200_FFT_THREE=0 selects the power-of-two plan)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
