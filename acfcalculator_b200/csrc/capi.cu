@@ -65,6 +65,7 @@ int get_ws(Workspace** out)
         }
         w->sm_count = prop.multiProcessorCount;
         e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
             set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
@@ -193,9 +194,24 @@ int check_common(const void* p, long long n, long long ncorr, const char* what)
 // The main() sequence (ACFcalculator.cpp:712-725,:775) for nw device-resident windows in one go:
 // per window mean / centre+velocity / velocity-mean kernels, then ONE direct-lag launch over the 2*nw
 // centred series, one integral kernel per window.  d_acf/d_vacf (nullable) are device [nw][ncorr].
-int pipeline_batch_device(Workspace* ws, const double* const* d_series, const int64_t* n, int nw,
-                                 long long ncorr, double dt, double cutoff, double* d_acf, double* d_vacf,
-                                 acfb200_result* res, cudaStream_t st)
+// Everything is only ENQUEUED on `st`; the per-window scalars travel to `stage` (page-locked host memory, nullable)
+// with asynchronous copies, to be turned into acfb200_result by pipeline_batch_collect once the stream has reached them.
+struct PipelineStage {
+    double* small;  // [nw][2]  integral, cutoff bin (as bits)
+    double* means;  // [nw][4]  sum, mean, vel_sum, vel_mean
+    double* c0;     // [nw][2]  acf[0], vacf[0]
+    static size_t doubles(int nw) { return (size_t)8 * nw; }
+    void carve(double* base, int nw)
+    {
+        small = base;
+        means = base + 2 * (size_t)nw;
+        c0 = base + 6 * (size_t)nw;
+    }
+};
+
+static int pipeline_batch_enqueue(Workspace* ws, const double* const* d_series, const int64_t* n, int nw, long long ncorr,
+                                  double dt, double cutoff, double* d_acf, double* d_vacf, const PipelineStage* stage,
+                                  cudaStream_t st)
 {
     size_t total = 0;
     for (int w = 0; w < nw; ++w) {
@@ -239,25 +255,45 @@ int pipeline_batch_device(Workspace* ws, const double* const* d_series, const in
     if (d_vacf)
         ACF_CUDA_OK(cudaMemcpy2DAsync(d_vacf, ncorr * 8, d_o + ncorr, 2 * ncorr * 8, ncorr * 8, nw,
                                       cudaMemcpyDeviceToDevice, st));
+    if (stage) {
+        ACF_CUDA_OK(cudaMemcpyAsync(stage->small, d_small, (size_t)2 * nw * 8, cudaMemcpyDeviceToHost, st));
+        ACF_CUDA_OK(cudaMemcpy2DAsync(stage->means, 32, sc, sizeof(ReduceScratch), 32, nw, cudaMemcpyDeviceToHost, st));
+        ACF_CUDA_OK(cudaMemcpy2DAsync(stage->c0, 8, d_o, ncorr * 8, 8, 2 * (size_t)nw, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
+// After the stream has passed the staging copies: the scalars of ACFcalculator.cpp:724-725,:775,:905 per window.
+static void pipeline_batch_collect(const PipelineStage& stage, const int64_t* n, int nw, acfb200_result* res)
+{
+    for (int w = 0; w < nw; ++w) {
+        acfb200_result& r = res[w];
+        r.avg = stage.means[4 * w + 1];
+        r.vel_avg = stage.means[4 * w + 3];
+        r.var = stage.c0[2 * w];          // == variance(timeSeries, n-2): same terms as lag 0 (:724)
+        r.var_vel = stage.c0[2 * w + 1];
+        r.acf_int = stage.small[2 * w];
+        long long brk;
+        memcpy(&brk, &stage.small[2 * w + 1], 8);
+        r.cutoff_index = brk;
+        r.n_used = n[w] - 2;
+        r.diffusivity = r.var * r.var / r.acf_int * 0.1;  // ACFcalculator.cpp:905
+    }
+}
+
+int pipeline_batch_device(Workspace* ws, const double* const* d_series, const int64_t* n, int nw,
+                                 long long ncorr, double dt, double cutoff, double* d_acf, double* d_vacf,
+                                 acfb200_result* res, cudaStream_t st)
+{
+    PipelineStage stage;
     if (res) {
-        std::vector<double> h_small(2 * (size_t)nw), h_means(4 * (size_t)nw), h_c0(2 * (size_t)nw);
-        ACF_CUDA_OK(cudaMemcpyAsync(h_small.data(), d_small, h_small.size() * 8, cudaMemcpyDeviceToHost, st));
-        ACF_CUDA_OK(cudaMemcpy2DAsync(h_means.data(), 32, sc, sizeof(ReduceScratch), 32, nw, cudaMemcpyDeviceToHost, st));
-        ACF_CUDA_OK(cudaMemcpy2DAsync(h_c0.data(), 8, d_o, ncorr * 8, 8, 2 * (size_t)nw, cudaMemcpyDeviceToHost, st));
-        ACF_CUDA_OK(cudaStreamSynchronize(st));
-        for (int w = 0; w < nw; ++w) {
-            acfb200_result& r = res[w];
-            r.avg = h_means[4 * w + 1];
-            r.vel_avg = h_means[4 * w + 3];
-            r.var = h_c0[2 * w];          // == variance(timeSeries, n-2): same terms as lag 0 (:724)
-            r.var_vel = h_c0[2 * w + 1];
-            r.acf_int = h_small[2 * w];
-            long long brk;
-            memcpy(&brk, &h_small[2 * w + 1], 8);
-            r.cutoff_index = brk;
-            r.n_used = n[w] - 2;
-            r.diffusivity = r.var * r.var / r.acf_int * 0.1;  // ACFcalculator.cpp:905
-        }
+        ACF_TRY(ws->pinned.ensure(PipelineStage::doubles(nw) * 8));
+        stage.carve(ws->pinned.as<double>(), nw);
+    }
+    ACF_TRY(pipeline_batch_enqueue(ws, d_series, n, nw, ncorr, dt, cutoff, d_acf, d_vacf, res ? &stage : nullptr, st));
+    if (res) {
+        ACF_CUDA_OK(cudaStreamSynchronize(st));   // the one synchronisation of the call: host scalars are its contract
+        pipeline_batch_collect(stage, n, nw, res);
     }
     return 0;
 }
@@ -419,21 +455,26 @@ static bool pipelined_eligible(const int64_t* n, int nseries, long long ncorr)
 static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_t* n, int nseries, long long ncorr,
                              double* d_out, std::vector<cudaEvent_t>& events)
 {
-    const int kMaxPieces = 5;
+    const int kMaxPieces = 6;
     cudaStream_t st = ws->stream;
     size_t total = 0;
     for (int s = 0; s < nseries; ++s) total += even_up(n[s]);
     ACF_TRY(ws->series.ensure(total * 8));
     ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)(kMaxPieces + 1)));
     ACF_TRY(ws->queue.ensure(64, true));
+    auto new_event = [&](cudaEvent_t* ev) -> cudaError_t {
+        cudaError_t e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) events.push_back(*ev);
+        return e;
+    };
     size_t series_off = 0;
     for (int s = 0; s < nseries; ++s) {
         const long long ns = n[s];
-        long long unit = (ns / 21 + 1) & ~1ll;
+        long long unit = (ns / 31 + 1) & ~1ll;
         if (unit < 4 * ncorr) unit = (4 * ncorr + 1) & ~1ll;  // a piece much shorter than its halo is all overhead
         long long bounds[kMaxPieces + 1] = {0};
         int np = 0;
-        for (long long w = 1; np < kMaxPieces && bounds[np] < ns; w *= 4) {
+        for (long long w = 1; np < kMaxPieces && bounds[np] < ns; w *= 2) {
             long long e = bounds[np] + w * unit;
             if (np == kMaxPieces - 1 || e + unit / 2 >= ns) e = ns;
             bounds[++np] = e;
@@ -456,6 +497,7 @@ static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_
         if (s == 0) ACF_TRY(ws->partials.ensure((offset[np] + offset[np] / 4) * sizeof(double)));
         if (offset[np] * sizeof(double) > ws->partials.cap) {
             ACF_CUDA_OK(cudaStreamSynchronize(st));
+            ACF_CUDA_OK(cudaStreamSynchronize(ws->stream2));
             ACF_TRY(ws->partials.ensure(offset[np] * sizeof(double)));
         }
         std::vector<SeriesDesc> descs(np + 1);
@@ -467,6 +509,17 @@ static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_
         descs[np] = {d, ns, ns};  // the whole series, for the divide by (n - k)
         // stream-ordered after the previous series' reduce, which was the last reader of this descriptor block
         ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * descs.size(), cudaMemcpyHostToDevice, st));
+        // The pieces are independent launches (disjoint partial sums): they alternate between two compute streams so
+        // that piece p+1 fills the SMs as piece p's last wave drains -- in one stream every piece boundary costs a
+        // partly empty wave, which is what limited round 1 to three pieces.  (The per-warp streaming variant shares one
+        // work-queue counter between launches and stays on one stream.)
+        const bool two_streams = plans[0].mode == 0;
+        cudaEvent_t desc_ready = nullptr;
+        if (two_streams) {
+            ACF_CUDA_OK(new_event(&desc_ready));
+            ACF_CUDA_OK(cudaEventRecord(desc_ready, st));
+            ACF_CUDA_OK(cudaStreamWaitEvent(ws->stream2, desc_ready, 0));
+        }
         long long copied = 0;
         for (int p = 0; p < np; ++p) {
             // copy, then launch: with a pageable source the copy call blocks the host while the previous kernel runs
@@ -476,14 +529,20 @@ static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_
                                             ws->copy_stream));
                 copied = upto;
             }
+            cudaStream_t sp = (two_streams && (p & 1)) ? ws->stream2 : st;
             cudaEvent_t ev = nullptr;
-            ACF_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            events.push_back(ev);
+            ACF_CUDA_OK(new_event(&ev));
             ACF_CUDA_OK(cudaEventRecord(ev, ws->copy_stream));
-            ACF_CUDA_OK(cudaStreamWaitEvent(st, ev, 0));
+            ACF_CUDA_OK(cudaStreamWaitEvent(sp, ev, 0));
             ACF_TRY(launch_direct(plans[p], ws->desc.as<SeriesDesc>() + p, 1, ncorr, ws->partials.as<double>() + offset[p],
-                                  ws->queue.as<unsigned int>(), ws->sm_count, st));
+                                  ws->queue.as<unsigned int>(), ws->sm_count, sp));
             g_launches += 1;
+        }
+        if (two_streams && np > 1) {
+            cudaEvent_t joined = nullptr;
+            ACF_CUDA_OK(new_event(&joined));
+            ACF_CUDA_OK(cudaEventRecord(joined, ws->stream2));
+            ACF_CUDA_OK(cudaStreamWaitEvent(st, joined, 0));
         }
         DirectPlan all = plans[0];
         all.chunks = (int)chunks_total;
@@ -635,52 +694,130 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
     // Window groups: all uploads are queued on the copy stream up front, one event per group; the compute stream
     // starts group g as soon as its windows have landed, so the H2D of group g+1 overlaps the kernels of group g
     // (with pageable host memory the copies degrade to synchronous staging and nothing is lost).
-    // The host link delivers a window ~4x faster than the kernels consume one, so the groups grow 1 : 4 : 16 : rest:
-    // only the first, small group's transfer is exposed and the later launches are large enough to run efficiently.
-    const int ngroups = nwindows >= 8 ? 4 : 1;
-    std::vector<cudaEvent_t> landed(ngroups);
+    // The groups grow 1 : 2 : 4 : 8 : 16 -- every upload hides under the previous group's kernels as long as the host
+    // link delivers windows at least twice as fast as the kernels consume them (alone on the box it is ~4x; with eight
+    // processes pulling from one NUMA node it drops towards 2x, which is what the round-1 1 : 4 : 16 split stalled on).
+    // Nothing below waits for the device until everything is enqueued: results (lags and scalars) are copied to
+    // page-locked staging memory asynchronously, then the host walks the groups' completion events and moves each
+    // group's results to the caller's arrays while the later groups are still computing.
+    const int ngroups = nwindows >= 8 ? 5 : 1;
+    std::vector<cudaEvent_t> landed(ngroups, nullptr), done(ngroups, nullptr);
     std::vector<int> gbeg(ngroups + 1, 0);
-    if (ngroups == 4) {
-        const int cum[5] = {0, 1, 5, 21, 32};
-        for (int g = 1; g <= 4; ++g) gbeg[g] = (int)(((long long)nwindows * cum[g] + 31) / 32);
+    if (ngroups == 5) {
+        const int cum[6] = {0, 1, 3, 7, 15, 31};
+        for (int g = 1; g <= 5; ++g) gbeg[g] = (int)(((long long)nwindows * cum[g] + 30) / 31);
     }
     gbeg[ngroups] = nwindows;
+    const bool want_lags = acf || vacf;
+    const size_t lag_doubles = want_lags ? (size_t)2 * nwindows * ncorr : 0;
+    const bool staged = lag_doubles * 8 <= ((size_t)1 << 30);   // beyond 1 GiB: copy straight to the caller (blocking)
+    int rc = ws->pinned.ensure((PipelineStage::doubles(nwindows) + (staged ? lag_doubles : 0)) * 8);
+    if (rc != 0) return rc;
+    double* h_scal = ws->pinned.as<double>();
+    double* h_lags = h_scal + PipelineStage::doubles(nwindows);
+    auto destroy_events = [&]() {
+        for (auto& ev : landed)
+            if (ev) cudaEventDestroy(ev);
+        for (auto& ev : done)
+            if (ev) cudaEventDestroy(ev);
+    };
     size_t off = 0;
     for (int g = 0; g < ngroups; ++g) {
         for (int w = gbeg[g]; w < gbeg[g + 1]; ++w) {
             double* d = ws->series.as<double>() + off;
-            ACF_CUDA_OK(cudaMemcpyAsync(d, series[w], (size_t)n[w] * 8, cudaMemcpyHostToDevice, ws->copy_stream));
+            cudaError_t e = cudaMemcpyAsync(d, series[w], (size_t)n[w] * 8, cudaMemcpyHostToDevice, ws->copy_stream);
+            if (e != cudaSuccess) {
+                set_error("window upload failed: %s", cudaGetErrorString(e));
+                cudaStreamSynchronize(ws->copy_stream);
+                destroy_events();
+                return ACFB200_ERR_CUDA;
+            }
             d_ptr[w] = d;
             off += even_up(n[w]);
         }
-        ACF_CUDA_OK(cudaEventCreateWithFlags(&landed[g], cudaEventDisableTiming));
-        ACF_CUDA_OK(cudaEventRecord(landed[g], ws->copy_stream));
+        cudaEventCreateWithFlags(&landed[g], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming);
+        cudaEventRecord(landed[g], ws->copy_stream);
     }
-    int rc = 0;
+    // size the device workspaces for the largest group before anything is enqueued: growing one later would mean a
+    // cudaFree, i.e. a device-wide synchronisation in the middle of the pipeline
+    {
+        int big = 0;
+        for (int g = 1; g < ngroups; ++g)
+            if (gbeg[g + 1] - gbeg[g] > gbeg[big + 1] - gbeg[big]) big = g;
+        const int cnt = gbeg[big + 1] - gbeg[big];
+        size_t tot = 0;
+        long long longest = 3;
+        for (int w = gbeg[big]; w < gbeg[big + 1]; ++w) {
+            tot += even_up(n[w]);
+            if (n[w] > longest) longest = n[w];
+        }
+        rc = ws->y.ensure(tot * 8);
+        if (rc == 0) rc = ws->vel.ensure(tot * 8);
+        if (rc == 0) rc = ws->scratch.ensure(sizeof(ReduceScratch) * (size_t)cnt, true);
+        if (rc == 0) rc = ws->out.ensure((size_t)2 * cnt * ncorr * 8);
+        if (rc == 0) rc = ws->small.ensure((size_t)16 * cnt);
+        if (rc == 0) rc = ws->wins.ensure(sizeof(WindowDesc) * (size_t)cnt);
+        DirectPlan plan;
+        if (rc == 0 && g_method == 0 && plan_direct(longest - 2, ncorr, 2 * cnt, ws->sm_count, g_force_variant, &plan) == 0) {
+            rc = ws->desc.ensure(sizeof(SeriesDesc) * (size_t)2 * cnt);
+            if (rc == 0) rc = ws->partials.ensure(direct_partial_elems(plan, 2 * cnt) * sizeof(double));
+        }
+        if (rc != 0) {
+            cudaStreamSynchronize(ws->copy_stream);
+            destroy_events();
+            return rc;
+        }
+    }
+    std::vector<PipelineStage> stages(ngroups);
     for (int g = 0; g < ngroups && rc == 0; ++g) {
         const int w0 = gbeg[g], cnt = gbeg[g + 1] - gbeg[g];
         if (cnt == 0) continue;
         cudaStreamWaitEvent(st, landed[g], 0);
-        rc = pipeline_batch_device(ws, d_ptr.data() + w0, n + w0, cnt, ncorr, dt, cutoff, nullptr, nullptr,
-                                   result ? result + w0 : nullptr, st);
+        stages[g].carve(h_scal + PipelineStage::doubles(w0), cnt);
+        rc = pipeline_batch_enqueue(ws, d_ptr.data() + w0, n + w0, cnt, ncorr, dt, cutoff, nullptr, nullptr,
+                                    result ? &stages[g] : nullptr, st);
         if (rc != 0) break;
-        // this group's results sit in ws->out as [window][acf|vacf][ncorr]; copy them out before the next group runs
+        // this group's results sit in ws->out as [window][acf|vacf][ncorr]; they leave before the next group runs
         const double* d_o = ws->out.as<double>();
         cudaError_t e = cudaSuccess;
-        if (acf)
-            e = cudaMemcpy2DAsync(acf + (size_t)w0 * ncorr, ncorr * 8, d_o, 2 * ncorr * 8, ncorr * 8, cnt,
-                                  cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess && vacf)
-            e = cudaMemcpy2DAsync(vacf + (size_t)w0 * ncorr, ncorr * 8, d_o + ncorr, 2 * ncorr * 8, ncorr * 8, cnt,
-                                  cudaMemcpyDeviceToHost, st);
+        if (want_lags && staged) {
+            e = cudaMemcpyAsync(h_lags + (size_t)2 * w0 * ncorr, d_o, (size_t)2 * cnt * ncorr * 8, cudaMemcpyDeviceToHost, st);
+        } else if (want_lags) {
+            if (acf)
+                e = cudaMemcpy2DAsync(acf + (size_t)w0 * ncorr, ncorr * 8, d_o, 2 * ncorr * 8, ncorr * 8, cnt,
+                                      cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && vacf)
+                e = cudaMemcpy2DAsync(vacf + (size_t)w0 * ncorr, ncorr * 8, d_o + ncorr, 2 * ncorr * 8, ncorr * 8, cnt,
+                                      cudaMemcpyDeviceToHost, st);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(done[g], st);
         if (e != cudaSuccess) {
             set_error("result copy failed: %s", cudaGetErrorString(e));
             rc = ACFB200_ERR_CUDA;
         }
     }
+    // the host follows the device group by group
+    for (int g = 0; g < ngroups && rc == 0; ++g) {
+        const int w0 = gbeg[g], cnt = gbeg[g + 1] - gbeg[g];
+        if (cnt == 0) continue;
+        const cudaError_t e = cudaEventSynchronize(done[g]);
+        if (e != cudaSuccess) {
+            set_error("acf_pipeline_batch: group %d failed: %s", g, cudaGetErrorString(e));
+            rc = ACFB200_ERR_CUDA;
+            break;
+        }
+        if (want_lags && staged)
+            for (int w = w0; w < w0 + cnt; ++w) {
+                const double* src = h_lags + (size_t)2 * w * ncorr;
+                if (acf) memcpy(acf + (size_t)w * ncorr, src, (size_t)ncorr * 8);
+                if (vacf) memcpy(vacf + (size_t)w * ncorr, src + ncorr, (size_t)ncorr * 8);
+            }
+        if (result) pipeline_batch_collect(stages[g], n + w0, cnt, result + w0);
+    }
     cudaError_t es = cudaStreamSynchronize(st);
     cudaStreamSynchronize(ws->copy_stream);
-    for (auto& ev : landed) cudaEventDestroy(ev);
+    destroy_events();
     if (rc == 0 && es != cudaSuccess) {
         set_error("stream synchronize failed: %s", cudaGetErrorString(es));
         rc = ACFB200_ERR_CUDA;

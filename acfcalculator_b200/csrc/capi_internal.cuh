@@ -71,14 +71,53 @@ struct Buf {
     }
 };
 
+// Grow-only page-locked host buffer (results are staged here so that device-to-host copies are truly asynchronous).
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) {
+            set_error("cudaMallocHost(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            cudaGetLastError();
+            p = nullptr;
+            return ACFB200_ERR_NOMEM;
+        }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const
+    {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
 struct Workspace {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;      // second compute stream: independent time pieces of one series overlap their tails
     cudaStream_t copy_stream = nullptr;  // H2D of the next window group while the current one computes
     Buf series, y, vel, desc, partials, out, scratch, small, fftwork, queue, wins;
+    HostBuf pinned;                      // staging of results on their way to pageable caller memory
     void release()
     {
+        pinned.release();
+        if (stream2) cudaStreamDestroy(stream2);
+        stream2 = nullptr;
         series.release();
         y.release();
         vel.release();
