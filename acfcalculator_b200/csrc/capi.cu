@@ -437,10 +437,12 @@ int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int
 // Long host series, direct summation: the upload of a series is cut into pieces on the copy stream and the lag kernel
 // of piece p (a time block whose halo of ncorr samples belongs to piece p+1, SeriesDesc.i_end < n) starts as soon as
 // the samples it can touch have landed.  Copy p therefore carries piece p plus the halo after it, and the pieces grow
-// geometrically (1 : 4 : 16 of n/21 units): at maxcorr = 1e4 the host link is ~4x faster than the kernel consumes
-// samples, so only the first, small piece's transfer is exposed, and every extra piece costs about one CTA wave of
-// fixed cost (~80 us), which is why there are three pieces and not five (1 : 2 : 4 : 8 : 17 measured 6.77 ms end to
-// end at N = 1e7 against 6.29 ms on the device).  Every piece has its own plan (same variant and row pitch, its own chunk count); the per-chunk partial
+// geometrically, 1 : 2 : 4 : 8 : 16 of n/31 units: alone on the box the host link is ~4x faster than the kernel consumes
+// samples at maxcorr = 1e4, with eight processes pulling from one NUMA node it drops towards 2x, and a ratio of two
+// keeps every upload hidden under the previous piece's kernel in both cases, so only the first, small piece's
+// transfer is exposed.  (Round 1 ran the pieces in one stream, where every piece boundary cost a partly empty CTA wave,
+// ~80 us, and therefore used three pieces 1 : 4 : 16; that split lost 1.6 ms per step at eight GPUs.  The pieces now
+// alternate between two compute streams.)  Every piece has its own plan (same variant and row pitch, its own chunk count); the per-chunk partial
 // sums of all pieces lie back to back and are folded by one reduce launch in fixed order, as for a single launch.
 // Several series go one after the other: the upload of series s+1 runs under the kernels of series s.
 // Everything is only ENQUEUED here (compute stream + copy stream); the caller synchronises and then destroys `events`.

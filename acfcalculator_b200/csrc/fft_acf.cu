@@ -33,21 +33,10 @@ struct FftGeom {
     int three;        // L = 3 * 2^a: the first axis carries the factor 3 (radix 8 x 8 x 6), the others are powers of two
     int n1;           // N1 (1 when absent)
     int q;            // log2(Nc) (power-of-two transforms only)
-    int zero;         // always 0, but only the host knows: lets a kernel make one instruction depend on another (see order_after)
     long long Nc, L;
     long long n, ncorr;
     long long x_stride, out_stride;  // batch: series b starts at x + b*x_stride, its lags go to out + b*out_stride
 };
-
-// Returns 0, in a way that makes whatever is computed from the result data-dependent on `x`: used to keep the prefetch loads
-// of the next tile BEHIND the first consumer of the previous prefetch.  Loads that are still in flight share a handful of
-// scoreboards with everything else a warp is waiting for; when the new loads are issued first, the wait for the OLD data
-// also waits for the NEW loads (r2c ncu: `long_scoreboard` on the first DADD of radix pass 1 although its operands had
-// been requested a whole tile earlier).
-__device__ __forceinline__ unsigned int order_after(double x, int opaque_zero)
-{
-    return (unsigned int)(__double2hiint(x) & opaque_zero);
-}
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -380,17 +369,6 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     //   tw2[(u-1)*(NB8/8) + p]       = W_NB^{8*p*u}   middle pass (stride 8, p = g >> 3)
     // the last pass of a Stockham transform has p = 0: no twiddles
     double2* tw2 = tw + 7 * NB8;
-    // Inter-step twiddles of a tile (MODE 0-2, NB >= 128).  Output row gg + 64u of column cc gets W_Nc^{e(gg,cc) + u*de(cc)}
-    // with e linear in gg: e = off(cc) + gg * slope(cc), de = 64 * slope(cc).  Writing gg = 8*a8 + b, the 512 (gg, cc)
-    // values of a tile are products of 17*TC table entries  TA[a8][c] = W^{off + 8*a8*slope},  TB[b][c] = W^{b*slope},
-    // D[c] = W^{64*slope}, which a few threads look up at the start of the tile (one W_L look-up each = two gathers) while
-    // everybody else is in radix pass 1.  Before (round 1 / r2b ncu): every thread fetched its own W^{e} and W^{de}, four
-    // fully divergent 16-byte gathers per thread and tile -- about a quarter of the LSU wavefronts of a column pass, and
-    // the `long_scoreboard` stalls of its last radix pass.  Two table sets alternate with the tile parity.
-    constexpr bool TILE_TW = HAS_MID && MODE != 3;
-    constexpr int TT_ENTRIES = 17 * TC;
-    constexpr int TT_PER = (TT_ENTRIES + kColThreads - 1) / kColThreads;   // 1, or 2 for 32-column tiles
-    double2* ttab = tw + 512;
     {
         const unsigned int wstep = (unsigned int)(G.L / NB);   // W_NB = W_L^wstep
         for (int m = tid; m < 7 * NB8 + 7 * (NB8 / 8); m += kColThreads) {
@@ -433,8 +411,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     // Their inter-step twiddles W_Nc^{e_u} have exponents in arithmetic progression (e_u = e_0 + u*de), so two
     // table look-ups (W^{e_0}, W^{de}) and R-1 complex multiplies replace R look-ups: the look-ups are L2-latency
     // loads and were the top stall of the first version (profiles/r1_fft_ncu.md).
-    auto store_group = [&](unsigned int a, unsigned int cc, unsigned int base, unsigned int stride, int R, double2* r,
-                           const double2* tt) {
+    auto store_group = [&](unsigned int a, unsigned int cc, unsigned int base, unsigned int stride, int R, double2* r) {
         if (MODE == 3) {
             double* o = out + batch * G.out_stride;
             const double inv_nc = 1.0 / (double)G.Nc;
@@ -458,29 +435,22 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
             }
             return;
         }
-        double2 t, d;
-        if (TILE_TW) {
-            const unsigned int cl = cc & (TC - 1);
-            t = cmul(tt[((base >> 3) << LTC) + cl], tt[((8 + (base & 7)) << LTC) + cl]);
-            d = tt[(16 << LTC) + cl];
+        unsigned int e0, de;  // exponents of W_Nc; every product stays below 2^28
+        if (MODE == 0) {
+            e0 = base * cc;
+            de = stride * cc;
+        } else if (MODE == 1) {
+            e0 = (base * n1) * cc;
+            de = (stride * n1) * cc;
         } else {
-            unsigned int e0, de;  // exponents of W_Nc; every product stays below 2^28
-            if (MODE == 0) {
-                e0 = base * cc;
-                de = stride * cc;
-            } else if (MODE == 1) {
-                e0 = (base * n1) * cc;
-                de = (stride * n1) * cc;
-            } else {
-                e0 = ((base << logC) + cc) * a;
-                de = (stride << logC) * a;
-            }
-            t = tw_L(lo, hi, 2ull * (e0 & nc_mask));  // W_Nc = W_L^2
-            d = tw_L(lo, hi, 2ull * (de & nc_mask));
-            if (DIR > 0) {
-                t = cconj(t);
-                d = cconj(d);
-            }
+            e0 = ((base << logC) + cc) * a;
+            de = (stride << logC) * a;
+        }
+        double2 t = tw_L(lo, hi, 2ull * (e0 & nc_mask));  // W_Nc = W_L^2
+        double2 d = tw_L(lo, hi, 2ull * (de & nc_mask));
+        if (DIR > 0) {
+            t = cconj(t);
+            d = cconj(d);
         }
         double2* dst = bdata + (((size_t)a * NB) << logC) + cc;
         for (int u = 0; u < R; ++u) {
@@ -489,54 +459,34 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
         }
     };
 
-    // One tile: `v` holds this thread's eight pass-1 inputs (loaded one tile ago), `nx` receives those of the CTA's next
-    // tile.  The tile loop below is unrolled by two with the register sets swapping roles.  (ncu, round 2: with a single
-    // loop-carried set the compiler loads into scratch registers and copies them into the carried set right after radix
-    // pass 1 -- 32 moves that wait for the loads, so the prefetch covered one radix pass instead of a whole tile: 18 % of
-    // all stall samples of the 384-row forward pass sat on the first of those moves.)
-    auto do_tile = [&](unsigned int tile, double2 (&v)[8], double2 (&nx)[8], const unsigned int parity) {
+    // One tile.  `cur` holds this thread's eight pass-1 inputs (loaded one tile ago), `nx` receives those of the CTA's next
+    // tile.  Two calling patterns (round-2 ncu, profiles/r2_fft_notes.md):
+    //   cur == nx  one loop-carried register set: the inputs are copied out first, then the set is reloaded.  The copy
+    //              matters: a warp waits for the OLD loads on a scoreboard before the NEW ones are issued.  This is what
+    //              the 512-row passes run at 0.82-0.84 of the measured HBM peak with.
+    //   cur != nx  the tile loop unrolled by two, two sets swapping roles (AB).  Only where the compiler otherwise loads
+    //              into scratch registers and copies them into the carried set right after radix pass 1 -- 32 moves that
+    //              wait for the loads, so the prefetch covered one radix pass instead of a tile: the 384-row forward
+    //              pass (0.99 -> 0.80 ms at config 5).  Everywhere else the unrolled form was slower (0.58 -> 0.72 ms):
+    //              with the new loads issued first, the first butterfly's wait for the old data also waits for them.
+    constexpr bool AB = THREE && MODE == 0;
+    auto do_tile = [&](unsigned int tile, double2 (&cur)[8], double2 (&nx)[8], const unsigned int parity) {
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & ((1u << tiles_c_log) - 1)) << LTC;
         double2* sa = HAS_MID ? s0 : (parity ? s1 : s0);
-        double2* tt = ttab + parity * TT_ENTRIES;
-        double2 pend[TT_PER];
-        unsigned int after = 0;   // 0, known only after radix pass 1 has consumed this tile's registers
         if (p1) {
+            double2 v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = cur[t];
+            if (tile + gridDim.x < tiles) load_tile(tile + gridDim.x, nx);   // in flight during the math below
+
             // ---- radix pass 1 (Stockham stride 1, p = g) on registers
             dft8<DIR>(v);
-            after = order_after(v[0].x, G.zero);
-            if (tile + gridDim.x < tiles) load_tile(tile + gridDim.x + after, nx);   // in flight for the rest of the tile
-        }
-        if (TILE_TW) {
-            // the highest thread ids first: in the 384-row kernels those warps have no radix-8 work
-#pragma unroll
-            for (int i = 0; i < TT_PER; ++i) {
-                const int idx = (kColThreads - 1 - tid) + i * kColThreads + after;
-                if (idx < TT_ENTRIES) {
-                    const unsigned int row = idx >> LTC, cc = c0 + (idx & (TC - 1));
-                    unsigned int slope, off;
-                    if (MODE == 0) {
-                        slope = cc;
-                        off = 0;
-                    } else if (MODE == 1) {
-                        slope = n1 * cc;
-                        off = 0;
-                    } else {
-                        slope = a << logC;
-                        off = cc * a;
-                    }
-                    const unsigned int e = row < 8 ? off + 8u * row * slope : (row < 16 ? (row - 8) * slope : 64u * slope);
-                    const double2 w = tw_L(lo, hi, 2ull * (e & nc_mask));  // W_Nc = W_L^2
-                    pend[i] = DIR > 0 ? cconj(w) : w;
-                }
-            }
-        }
-        if (p1) {
             if (g != 0) {
 #pragma unroll
                 for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], tw[(u - 1) * NB8 + g]);
             }
             if (NB == 8) {
-                store_group(a, c0 + c, 0, 1, 8, v, nullptr);
+                store_group(a, c0 + c, 0, 1, 8, v);
                 return;
             }
             // with a middle pass: pass 1 -> s0, middle s0 -> s1, last reads s1.  Without: the buffers alternate per tile.
@@ -560,13 +510,6 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
                 const int base = qq + ps * 8;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) s1[((base + 8 * u) << LTC) + c] = r[u];
-            }
-            if (TILE_TW) {
-#pragma unroll
-                for (int i = 0; i < TT_PER; ++i) {
-                    const int idx = (kColThreads - 1 - tid) + i * kColThreads;
-                    if (idx < TT_ENTRIES) tt[idx] = pend[i];   // read after the barrier below, in the last pass
-                }
             }
             __syncthreads();
             sa = s1;
@@ -595,23 +538,26 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
                     dft4<DIR>(r);
                 else
                     dft2(r);
-                store_group(a, c0 + cc, gg, STRIDE, R, r, tt);
+                store_group(a, c0 + cc, gg, STRIDE, R, r);
             }
         }
-        // no barrier here: the next tile's pass 1 writes the buffer that was last READ two barriers ago, and the next
-        // tile's twiddle table is the other of the two sets
+        // no barrier here: the next tile's pass 1 writes the buffer that was last READ two barriers ago
     };
 
     double2 ra[8], rb[8];
     unsigned int tile = blockIdx.x;
     if (tile < tiles && p1) load_tile(tile, ra);
     __syncthreads();  // twiddle table ready
-    while (tile < tiles) {
-        do_tile(tile, ra, rb, 0);
-        tile += gridDim.x;
-        if (tile >= tiles) break;
-        do_tile(tile, rb, ra, 1);
-        tile += gridDim.x;
+    if (AB) {
+        while (tile < tiles) {
+            do_tile(tile, ra, rb, 0);
+            tile += gridDim.x;
+            if (tile >= tiles) break;
+            do_tile(tile, rb, ra, 1);
+            tile += gridDim.x;
+        }
+    } else {
+        for (unsigned int parity = 0; tile < tiles; tile += gridDim.x, parity ^= 1) do_tile(tile, ra, ra, parity);
     }
 }
 
@@ -754,9 +700,6 @@ row_pass_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict
 // on registers.  Each row thread evaluates the pair formula for its own 8 spectrum points (the mirror thread
 // evaluates it again from its side) so that the inverse transform starts from registers without another exchange.
 // Work list: one entry per unordered row pair {(k1,k2), mirror}; self-mirrored rows fill both slots of their pair.
-// two tile buffers, butterfly twiddles (<= 512 entries), wg (<= 64), two sets of 18 per-row factors for <= 32 rows
-constexpr size_t kRowSmemBytes = (size_t)(2 * 4096 + 512 + 64 + 2 * 18 * 32) * 16;
-
 template <int B3>
 __global__ void __launch_bounds__(kColThreads, 1)
 row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict__ lo, const double2* __restrict__ hi)
@@ -778,18 +721,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     double2* bdata = data + (long long)blockIdx.y * G.Nc;
     // butterfly twiddles in warp-contiguous layout: twf[(u-1)*G8 + g] = W_N3^{g*u}, twm[(u-1)*(G8/8) + p] = W_N3^{8pu}
     double2* twm = twf + 7 * G8;
-    // Per-row factors looked up once per tile by a few threads of the row instead of per thread (r2b ncu: the LSU data pipe
-    // of this kernel sat at 87 % of its wavefront peak, a quarter of it fully divergent 16-byte table gathers):
-    //   wg[g]              = W_L^{g*N1*N2}                      (built once; the thread-dependent factor of the pair-op W)
-    //   rt[e*ROWS + slot]  e < 8: conj W_Nc^{8e*f};  e < 16: conj W_Nc^{(e-8)*f};  e = 16: conj W_Nc^{64f};  e = 17: W_L^{kbase}
-    // with f and kbase the row's post-twiddle factor and spectrum offset.  The post twiddle of output j0 + 64u is then
-    // rt[j0>>3] * rt[8 + (j0&7)] * rt[16]^u, and the pair-op twiddle rt[17] * wg[g].  Two sets alternate with the parity.
-    constexpr int RT_ROWS = 18;
-    double2* wg = twf + 512;
-    double2* rtab = wg + 64;
-    constexpr int RT_PER = (RT_ROWS + G8 - 1) / G8;   // table entries per thread of a row: 1 (2 for 128-point rows)
-    const unsigned int n12 = ((unsigned int)G.n1) << G.b2;   // N1 * N2: spectrum index k = k1 + N1*k2 + N1*N2*k3
-    if (tid < G8) wg[tid] = tw_L(lo, hi, (unsigned long long)tid * n12);
     {
         const unsigned int wstep = (unsigned int)(G.L >> B3);
         for (int m = tid; m < 7 * G8 + 7 * (G8 / 8); m += kColThreads) {
@@ -802,6 +733,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         }
     }
     const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);  // exponents stay below Nc anyway
+    const unsigned int n12 = N1 << G.b2;              // N1 * N2: spectrum index k = k1 + N1*k2 + N1*N2*k3
 
     // digits (k1, k2) of the row held by slot `rs` of tile `tile`; false past the end of the list
     auto slot_row = [&](unsigned int tile, unsigned int& r1, unsigned int& r2, bool& origin) -> bool {
@@ -871,23 +803,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         unsigned int r1 = 0, r2 = 0;
         bool origin = false;
         const bool valid = slot_row(tile, r1, r2, origin);
-        double2* rt = rtab + parity * (RT_ROWS * ROWS);
-        // this row's table entries: look-ups issued now, stored after radix pass 1 (first read after two pair barriers)
-        const unsigned int kbase = r1 + r2 * N1;
-        const unsigned int f = (G.b2 > 0) ? (r2 * N1) : r1;   // post twiddle conj(W_Nc^{j3 * f})
-        double2 pend[RT_PER];
-#pragma unroll
-        for (int i = 0; i < RT_PER; ++i) {
-            const int e = g + i * G8;
-            if (e < RT_ROWS) {
-                if (e == 17) {
-                    pend[i] = tw_L(lo, hi, (unsigned long long)kbase);
-                } else {
-                    const unsigned int ex = (e < 8 ? 8u * e : (e < 16 ? (unsigned int)(e - 8) : 64u)) * f;
-                    pend[i] = cconj(tw_L(lo, hi, 2ull * (ex & nc_mask)));
-                }
-            }
-        }
         double2 v[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[t] = nxt[t];
@@ -900,11 +815,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) bx[sw(8 * g + u)] = v[u];
-#pragma unroll
-        for (int i = 0; i < RT_PER; ++i) {
-            const int e = g + i * G8;
-            if (e < RT_ROWS) rt[e * ROWS + rs] = pend[i];
-        }
 #pragma unroll
         for (int t = 0; t < 8; ++t) nxt[t] = make_double2(0.0, 0.0);
         if (tile + gridDim.x < ntiles) load_row(tile + gridDim.x, nxt);
@@ -923,7 +833,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             for (int u = 0; u < 8; ++u) by[sw(qq + ps * 8 + 8 * u)] = r[u];
             pair_sync();
         }
-        double2 za[8];   // this thread's spectrum points k3 = g + t*G8 after the last forward pass (also written to X for the mirror row)
         {   // last forward pass: radix 2^(B3-6), stride 64, Y -> X in natural order
             constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
             double2 r[8];
@@ -942,22 +851,19 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
 #pragma unroll
                 for (int u = 0; u < R; ++u) bx[sw(gg + 64 * u)] = r[it * R + u];
             }
-            // output (it, u) sits at k3 = g + it*G8 + 64u = g + (it + GPT*u)*G8: pair-op slot t = it + GPT*u
-            static_assert(64 / G8 == GPT, "the last-pass outputs of a thread are its own pair-op points");
-#pragma unroll
-            for (int t = 0; t < 8; ++t) za[t] = r[(t % GPT) * R + t / GPT];
             pair_sync();
         }
 
-        // ================= |X|^2 pair operation for this thread's 8 spectrum points (mirror values from X) =================
+        // ================= |X|^2 pair operation for this thread's 8 spectrum points (reads X) =================
         // W_L^k for k = kbase + N1*N2*(g + t*N3/8): successive t differ by W_L^{Nc/8} = exp(-i pi/8), a constant
-        double2 W = cmul(rt[17 * ROWS + rs], wg[g]);
+        const unsigned int kbase = r1 + r2 * N1;
+        double2 W = tw_L(lo, hi, (unsigned long long)(kbase + (unsigned int)g * n12));
         const double2 rot = make_double2(0.92387953251128675613, -0.38268343236508977173);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             const int k3 = g + t * G8;
             const int p3 = origin ? ((N3 - k3) & (N3 - 1)) : (N3 - 1 - k3);
-            const double2 Za = za[t];
+            const double2 Za = bx[sw(k3)];
             const double2 Zb = mx[sw(p3)];
             const double2 S = make_double2(Za.x + Zb.x, Za.y - Zb.y);   // Za + conj Zb
             const double2 D = make_double2(Za.x - Zb.x, Za.y + Zb.y);   // Za - conj Zb
@@ -996,8 +902,8 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         }
         {   // last inverse pass (reads X) -> post twiddle conj(W_Nc^{j3 * f}) -> HBM
             constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
+            const unsigned int f = (G.b2 > 0) ? (r2 * N1) : r1;
             double2* dst = bdata + ((size_t)((r1 << G.b2) + r2) << B3);
-            const double2 dq = rt[16 * ROWS + rs];
 #pragma unroll
             for (int it = 0; it < GPT; ++it) {
                 const int gg = g + it * G8;
@@ -1012,7 +918,8 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                     dft2(r);
                 // post twiddle conj(W_Nc^{j3*f}), j3 = j0 + 64u: exponents in arithmetic progression
                 const unsigned int j0 = gg;
-                double2 tq = cmul(rt[(j0 >> 3) * ROWS + rs], rt[(8 + (j0 & 7)) * ROWS + rs]);
+                double2 tq = cconj(tw_L(lo, hi, 2ull * ((j0 * f) & nc_mask)));
+                const double2 dq = cconj(tw_L(lo, hi, 2ull * ((64u * f) & nc_mask)));
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
                     if (valid) dst[j0 + 64 * u] = cmul(r[u], tq);
@@ -1020,7 +927,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                 }
             }
         }
-        // no barrier: the next tile starts by writing buffer Y, last read before the barrier above, and the other table set
+        // no barrier: the next tile starts by writing buffer Y, last read before the barrier above
     }
 }
 
@@ -1091,7 +998,6 @@ static int make_geom(long long n, long long ncorr, FftGeom* g)
     g->x_stride = n;
     g->out_stride = ncorr;
     g->three = 0;
-    g->zero = 0;
     // 3 * 2^(lq-2) lies between 2^(lq-1) (< need) and 2^lq
     const int a3 = lq - 2, rest = a3 - 8;  // rest = log2(N2 * N3)
     if (a3 >= 8 && 3ll << a3 >= need && three_allowed() && ((rest >= 7 && rest <= 9) || (rest >= 12 && rest <= 18))) {
@@ -1203,17 +1109,15 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         cudaFuncSetAttribute(col_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
-        cudaFuncSetAttribute(row_pass2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemBytes);
-        cudaFuncSetAttribute(row_pass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemBytes);
-        cudaFuncSetAttribute(row_pass2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemBytes);
+        cudaFuncSetAttribute(row_pass2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
         for (int mode = 0; mode < 4; ++mode)
             for (int bb = 3; bb <= 9; ++bb)
                 cudaFuncSetAttribute(col2_select(mode, bb), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (2 * kTileElems + 512 + 2 * 17 * 32) * 16);
-        cudaFuncSetAttribute(col2_three(0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (2 * kTileElems + 512 + 2 * 17 * 32) * 16);
-        cudaFuncSetAttribute(col2_three(3), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (2 * kTileElems + 512 + 2 * 17 * 32) * 16);
+                                     (2 * kTileElems + 512) * 16);
+        cudaFuncSetAttribute(col2_three(0), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
+        cudaFuncSetAttribute(col2_three(3), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
         if (dev < 64) attr_done[dev] = true;
     }
     const long long N1 = g.n1, N2 = 1ll << g.b2, N3 = 1ll << g.b3;
@@ -1227,7 +1131,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         return -1;
     }
     auto pgrid = [sms](long long tiles) { return (unsigned)(tiles < sms ? tiles : sms); };
-    const size_t smem2 = (size_t)(2 * kTileElems + 512 + 2 * 17 * 32) * 16;  // two tile buffers + butterfly twiddles + tile twiddle tables
+    const size_t smem2 = (size_t)(2 * kTileElems + 512) * 16;  // two tile buffers + butterfly twiddles
     auto tc_for = [](int b, long long C) {
         long long tc = kTileElems >> b;
         if (tc > C) tc = C;
@@ -1261,7 +1165,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         ++launches;
     }
     if (pipelined && g.b1 > 0 && g.b3 >= 7) {
-        const size_t smem = kRowSmemBytes;
+        const size_t smem = (size_t)(2 * 4096 + N3) * 16;
         if (g.b3 == 9)
             row_pass2_kernel<9><<<dim3(sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         else if (g.b3 == 8)
