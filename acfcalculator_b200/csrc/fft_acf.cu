@@ -17,6 +17,7 @@
 //             -- fused, so the spectrum never goes to HBM in natural order and no transpose/bit-reversal pass exists
 //   col_pass  inverse step 2' and step 1' (fused: 1/Nc, /(n-k), only the first ncorr lags are written)
 // Algorithmic bytes: 8n + 8M + 8L*(2*passes - 2) with passes = number of factors > 1, counted per series.
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -559,6 +560,296 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
     } else {
         for (unsigned int parity = 0; tile < tiles; tile += gridDim.x, parity ^= 1) do_tile(tile, ra, ra, parity);
     }
+}
+
+// ---- column pass, tensor-map TMA form (NB = 512 or 384, 8-column tiles) -------------------------------------------------
+// Same transform, modes and arithmetic as col_pass2_kernel<MODE, 9> / <MODE, 7, true>; what changes is how a tile gets on
+// chip and who waits for whom (round-2 ncu, profiles/r2_fft_notes.md: the 16 warps of col_pass2 march through load /
+// butterfly / exchange phases together, so the LSU pipe idles while the FP64 pipe works and vice versa; the 384-row
+// forward and inverse passes, whose tiles carry less HBM traffic, ran at 0.4 of the DRAM rate):
+//   * tiles arrive by TMA: one 3-D tensor map (columns x rows x series) over the work array -- or, for MODE 0, over the
+//     caller's REAL series viewed as rows of 2C doubles, where rows beyond the data come back as zeros without touching
+//     HBM -- and a producer warp that issues one 128-row box per 16 KB (SASS UTMALDG) into one of two landing buffers,
+//     gated by full/empty mbarriers.  No registers, no LSU instructions and no scoreboards are tied up by the prefetch, and
+//     the next tile is requested as soon as the tile before the current one has been consumed;
+//   * the 8 columns of a tile are independent transforms: the 512 compute threads form two groups of 256, one per half of
+//     the columns, each with a named barrier of its own, so the groups drift apart and one computes while the other
+//     exchanges.  Both still consume whole 128-byte rows of HBM (a group of its own tile would need twice the memory);
+//   * three 64 KB buffers: landing L[0], L[1] (alternating per tile) and scratch S.  Radix pass 1 reads L and writes S, the
+//     middle pass writes back into L over the consumed input, the last pass reads L and stores to HBM.
+// Bank conflicts: a warp now touches 8 rows x 4 columns (64 bytes per row).  L carries the TMA 128-byte swizzle (16-byte
+// chunk c of row r at chunk c ^ (r & 7)), S the software swizzle c ^ ((r ^ (r >> 3)) & 7); with either, the eight rows of
+// every access pattern below fall into both 64-byte halves four times: four wavefronts per 512 bytes, the minimum.
+constexpr int kC4Threads = 512 + 32;   // 16 compute warps + the producer warp
+constexpr int kC4BoxRows = 128;
+constexpr size_t kC4SmemBytes = 1024 /* alignment slack */ + (size_t)3 * 4096 * 16 + 512 * 16 + 64;
+
+__device__ __forceinline__ int c4_unit_l(int row, int c) { return (row << 3) | ((c ^ row) & 7); }
+__device__ __forceinline__ int c4_unit_s(int row, int c) { return (row << 3) | ((c ^ row ^ (row >> 3)) & 7); }
+
+template <int MODE, bool THREE>
+__global__ void __launch_bounds__(kC4Threads, 1)
+col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ data, const double* __restrict__ x,
+                 double* __restrict__ out, FftGeom G, int logC, int A, const double2* __restrict__ lo,
+                 const double2* __restrict__ hi)
+{
+    constexpr int DIR = (MODE <= 1) ? -1 : +1;
+    constexpr int NB = THREE ? 384 : 512;
+    constexpr int NB8 = NB >> 3;                   // 64 or 48 radix-8 groups per column
+    constexpr int TILE = NB * 8;                   // elements per tile
+    constexpr int P1_PER_GROUP = NB8 * 4;          // threads of a group with a radix-8 item: 256 or 192
+    constexpr int R = NB / 64;                     // last radix: 8 or 6
+    extern __shared__ unsigned char smem_c4[];
+    // SWIZZLE_128B wants the landing buffers 1024-byte aligned
+    unsigned char* base1k = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_c4) + 1023) & ~(uintptr_t)1023);
+    double2* L0 = reinterpret_cast<double2*>(base1k);
+    double2* S = L0 + 2 * 4096;
+    double2* tw = S + 4096;                        // tw[(u-1)*NB8 + g] = W_NB^{g*u} (conjugated for the inverse)
+    double2* tw2 = tw + 7 * NB8;                   // tw2[(u-1)*(NB8/8) + p] = W_NB^{8*p*u}
+    uint64_t* full = reinterpret_cast<uint64_t*>(tw + 512);
+    uint64_t* empty = full + 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned int tiles_c_log = logC - 3;
+    unsigned int tiles = (unsigned int)A << tiles_c_log;
+    if (MODE == 3) {
+        const long long need = (G.ncorr + 1) / 2;  // complex outputs j < need
+        if (need < (1ll << logC)) tiles = (unsigned int)((need + 7) >> 3);
+    }
+    const unsigned int c_mask = (1u << tiles_c_log) - 1;
+    const int batch = blockIdx.y;
+    if (tid == 0) {
+        prefetch_tensormap(&tmap);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&full[b], 1);      // the producer's expect_tx arrival; the TMA boxes complete the bytes
+            mbar_init(&empty[b], 16);    // one arrival per compute warp
+        }
+    }
+    if (tid < 512) {
+        const unsigned int wstep = (unsigned int)(G.L / NB);   // W_NB = W_L^wstep
+        for (int m = tid; m < 7 * NB8 + 7 * (NB8 / 8); m += 512) {
+            unsigned int e;
+            if (m < 7 * NB8)
+                e = (unsigned int)(m % NB8) * (unsigned int)(m / NB8 + 1);
+            else
+                e = 8u * (unsigned int)((m - 7 * NB8) % (NB8 / 8)) * (unsigned int)((m - 7 * NB8) / (NB8 / 8) + 1);
+            const double2 w = tw_L(lo, hi, (unsigned long long)e * wstep);
+            tw[m] = DIR > 0 ? cconj(w) : w;
+        }
+    }
+    __syncthreads();
+
+    if (warp == 16) {
+        // ===== producer: one lane walks this CTA's tiles, two in flight at most =====
+        if (lane == 0) {
+            unsigned int j = 0;
+            for (unsigned int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
+                const unsigned int b = j & 1;
+                if (j >= 2) mbar_wait(&empty[b], ((j - 2) >> 1) & 1);   // tile j-2 has left this buffer
+                const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
+                mbar_expect_tx(&full[b], (uint32_t)(TILE * 16));
+                double2* dst = L0 + b * 4096;
+#pragma unroll
+                for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
+                    tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[b]);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: group = half of the columns =====
+    const int grp = tid >> 8, tl = tid & 255;
+    const int g = tl >> 2, c = (grp << 2) | (tl & 3);     // pass-1 / middle-pass role: radix group g of column c
+    const bool p1 = !THREE || tl < P1_PER_GROUP;
+    double2* bdata = data + (long long)batch * G.Nc;
+    const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);
+    const unsigned int n1 = (unsigned int)G.n1;
+    // MODE 0: the series ends inside row `edge_row` (unless n is a multiple of 2C); the tensor map covers the full rows only
+    // and the samples of that last, partial row are fetched by the threads that own it, one tile ahead
+    const long long two_c = 2ll << logC;
+    const int edge_row = (MODE == 0) ? (int)(G.n / two_c) : 0;
+    const bool edge_any = (MODE == 0) && (G.n % two_c != 0) && edge_row < NB;
+    int edge_t = -1;
+    if (edge_any && p1 && edge_row >= g && (edge_row - g) % NB8 == 0) edge_t = (edge_row - g) / NB8;
+    const double* xs = (MODE == 0) ? x + (long long)batch * G.x_stride : nullptr;
+    auto load_edge = [&](unsigned int tile) -> double2 {
+        double2 z = make_double2(0.0, 0.0);
+        if (edge_t >= 0 && tile < tiles) {
+            const unsigned int c0 = (tile & c_mask) << 3;
+            const long long jj = ((long long)edge_row << logC) + c0 + c;   // complex index: samples 2jj, 2jj+1
+            if (2 * jj + 1 < G.n)
+                z = *reinterpret_cast<const double2*>(xs + 2 * jj);
+            else if (2 * jj < G.n)
+                z.x = xs[2 * jj];
+        }
+        return z;
+    };
+
+    auto store_group = [&](unsigned int a, unsigned int cc, unsigned int base, double2* r) {
+        if (MODE == 3) {
+            double* o = out + (long long)batch * G.out_stride;
+            const double inv_nc = 1.0 / (double)G.Nc;
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const long long j = ((long long)(base + 64 * u) << logC) + cc;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const long long k = 2 * j + h;
+                    if (k < G.ncorr) {
+                        const long long m = G.n - k;
+                        double val = (h ? r[u].y : r[u].x) * inv_nc;
+                        if (m > 0)
+                            val = val / (double)m;
+                        else if (m == 0)
+                            val = __longlong_as_double(0xFFF8000000000000ull);  // reference: 0/0
+                        else
+                            val = -0.0;                                          // reference: 0/negative
+                        o[k] = val;
+                    }
+                }
+            }
+            return;
+        }
+        unsigned int e0, de;  // exponents of W_Nc (see col_pass2_kernel); every product stays below Nc
+        if (MODE == 0) {
+            e0 = base * cc;
+            de = 64u * cc;
+        } else if (MODE == 1) {
+            e0 = (base * n1) * cc;
+            de = (64u * n1) * cc;
+        } else {
+            e0 = ((base << logC) + cc) * a;
+            de = (64u << logC) * a;
+        }
+        double2 t = tw_L(lo, hi, 2ull * (e0 & nc_mask));  // W_Nc = W_L^2
+        double2 d = tw_L(lo, hi, 2ull * (de & nc_mask));
+        if (DIR > 0) {
+            t = cconj(t);
+            d = cconj(d);
+        }
+        double2* dst = bdata + (((size_t)a * NB) << logC) + cc;
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            dst[(size_t)(base + 64 * u) << logC] = cmul(r[u], t);
+            t = cmul(t, d);
+        }
+    };
+
+    double2 edge = load_edge(blockIdx.x);
+    unsigned int j = 0;
+    for (unsigned int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
+        const unsigned int b = j & 1;
+        const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
+        double2* Lb = L0 + b * 4096;
+        const double2 edge_now = edge;
+        if (MODE == 0) edge = load_edge(tile + gridDim.x);
+        mbar_wait(&full[b], (j >> 1) & 1);
+
+        // ---- radix pass 1 (Stockham stride 1, p = g): L -> registers -> S
+        if (p1) {
+            double2 v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = Lb[c4_unit_l(g + t * NB8, c)];
+            if (MODE == 0) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (t == edge_t) v[t] = edge_now;
+            }
+            dft8<DIR>(v);
+            if (g != 0) {
+#pragma unroll
+                for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], tw[(u - 1) * NB8 + g]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) S[c4_unit_s(8 * g + u, c)] = v[u];
+        }
+        named_bar_sync(1 + grp, 256);
+
+        // ---- middle radix-8 pass (stride 8): S -> registers -> L (over the consumed input)
+        if (p1) {
+            double2 r[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) r[t] = S[c4_unit_s(g + t * NB8, c)];
+            dft8<DIR>(r);
+            const int qq = g & 7, ps = g - qq;
+            if (ps != 0) {
+#pragma unroll
+                for (int u = 1; u < 8; ++u) r[u] = cmul(r[u], tw2[(u - 1) * (NB8 / 8) + (g >> 3)]);
+            }
+            const int base = qq + ps * 8;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) Lb[c4_unit_l(base + 8 * u, c)] = r[u];
+        }
+        named_bar_sync(1 + grp, 256);
+
+        // ---- last pass (radix 8 or 6, stride 64, no butterfly twiddles): L -> registers -> HBM
+        {
+            const int gg = tl >> 2;                 // 64 groups x 4 columns = every thread of the group
+            double2 r[8];
+#pragma unroll
+            for (int t = 0; t < R; ++t) r[t] = Lb[c4_unit_l(gg + t * 64, c)];
+            if (R == 8)
+                dft8<DIR>(r);
+            else
+                dft6<DIR>(r);
+            // the values are in registers: this warp is done with the landing buffer
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[b]);
+            store_group(a, c0 + c, gg, r);
+        }
+        // no barrier: the next tile's pass 1 writes S, last read by this group before its second barrier above
+    }
+}
+
+typedef void (*col4_fn)(const CUtensorMap, double2*, const double*, double*, FftGeom, int, int, const double2*, const double2*);
+static col4_fn col4_select(int mode, bool three)
+{
+    if (three) return mode == 0 ? col_pass4_kernel<0, true> : col_pass4_kernel<3, true>;
+    return mode == 0 ? col_pass4_kernel<0, false>
+                     : mode == 1 ? col_pass4_kernel<1, false> : mode == 2 ? col_pass4_kernel<2, false> : col_pass4_kernel<3, false>;
+}
+
+// cuTensorMapEncodeTiled through the runtime (libcuda is not linked)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn tensor_map_encoder()
+{
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// Tensor map over `rows` rows of `row_doubles` FP64 values each, `nbatch` such arrays `batch_stride_doubles` apart; boxes of
+// 16 doubles (one 128-byte row segment = 8 complex values) x 128 rows, 128-byte swizzle, zeros out of bounds.
+static bool make_col_tensor_map(CUtensorMap* m, const void* base, unsigned long long row_doubles, unsigned long long rows,
+                                unsigned long long nbatch, unsigned long long batch_stride_doubles)
+{
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc || rows == 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+    if (nbatch <= 1) {
+        nbatch = 1;
+        batch_stride_doubles = row_doubles * rows;   // unused by a single series, but must be a valid stride
+    }
+    if ((batch_stride_doubles & 1) != 0) return false;
+    const cuuint64_t dims[3] = {row_doubles, rows, nbatch};
+    const cuuint64_t strides[2] = {row_doubles * 8, batch_stride_doubles * 8};   // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {16, (cuuint32_t)kC4BoxRows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (strides[0] >= (1ull << 40) || strides[1] >= (1ull << 40)) return false;
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
 }
 
 typedef void (*col2_fn)(double2*, const double*, double*, FftGeom, int, int, const double2*, const double2*);
@@ -1116,6 +1407,10 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
             for (int bb = 3; bb <= 9; ++bb)
                 cudaFuncSetAttribute(col2_select(mode, bb), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (2 * kTileElems + 512) * 16);
+        for (int mode = 0; mode < 4; ++mode)
+            cudaFuncSetAttribute(col4_select(mode, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC4SmemBytes);
+        cudaFuncSetAttribute(col4_select(0, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC4SmemBytes);
+        cudaFuncSetAttribute(col4_select(3, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC4SmemBytes);
         cudaFuncSetAttribute(col2_three(0), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
         cudaFuncSetAttribute(col2_three(3), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
         if (dev < 64) attr_done[dev] = true;
@@ -1131,6 +1426,12 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         return -1;
     }
     auto pgrid = [sms](long long tiles) { return (unsigned)(tiles < sms ? tiles : sms); };
+    // 512- and 384-row column passes: the tensor-map TMA kernels (col_pass4_kernel); ACFB200_FFT_COL4=0 keeps col_pass2
+    const char* env4 = getenv("ACFB200_FFT_COL4");
+    const bool col4 = pipelined && !(env4 && env4[0] == '0');
+    const bool axis1_c4 = col4 && g.b1 > 0 && (g.three || g.b1 == 9) && g.b2 + g.b3 >= 3;
+    const bool axis2_c4 = col4 && g.b2 == 9;
+    CUtensorMap tm;
     const size_t smem2 = (size_t)(2 * kTileElems + 512) * 16;  // two tile buffers + butterfly twiddles
     auto tc_for = [](int b, long long C) {
         long long tc = kTileElems >> b;
@@ -1140,7 +1441,11 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     if (g.b1 > 0) {
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
-        if (g.three)
+        // MODE 0 reads the caller's real series: rows of 2C doubles, only the full rows are in the tensor map
+        if (axis1_c4 && make_col_tensor_map(&tm, d_x, 2ull * C, (unsigned long long)(n / (2 * C)), nb, x_stride))
+            col4_select(0, g.three)<<<dim3(pgrid(C >> 3), nb, 1), kC4Threads, kC4SmemBytes, st>>>(
+                tm, data, d_x, nullptr, g, g.b2 + g.b3, 1, lo, hi);
+        else if (g.three)
             col2_three(0)<<<dim3(pgrid(C >> 3), nb, 1), kColThreads, smem2, st>>>(data, d_x, nullptr, g, g.b2 + g.b3, 1, lo,
                                                                                    hi);
         else if (pipelined)
@@ -1156,7 +1461,10 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     }
     if (g.b2 > 0) {
         const int TC = tc_for(g.b2, N3);
-        if (pipelined)
+        if (axis2_c4 && make_col_tensor_map(&tm, data, 2ull * N3, (unsigned long long)(N1 * N2), nb, 2ull * g.Nc))
+            col4_select(1, false)<<<dim3(pgrid((N3 >> 3) * N1), nb, 1), kC4Threads, kC4SmemBytes, st>>>(
+                tm, data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
+        else if (pipelined)
             col2_select(1, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), nb, 1), kColThreads, smem2, st>>>(
                 data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
         else
@@ -1182,7 +1490,10 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     }
     if (g.b2 > 0) {
         const int TC = tc_for(g.b2, N3);
-        if (pipelined)
+        if (axis2_c4 && make_col_tensor_map(&tm, data, 2ull * N3, (unsigned long long)(N1 * N2), nb, 2ull * g.Nc))
+            col4_select(2, false)<<<dim3(pgrid((N3 >> 3) * N1), nb, 1), kC4Threads, kC4SmemBytes, st>>>(
+                tm, data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
+        else if (pipelined)
             col2_select(2, g.b2)<<<dim3(pgrid((N3 >> (12 - g.b2)) * N1), nb, 1), kColThreads, smem2, st>>>(
                 data, nullptr, nullptr, g, g.b3, (int)N1, lo, hi);
         else
@@ -1193,7 +1504,10 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     if (g.b1 > 0) {
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
-        if (g.three)
+        if (axis1_c4 && make_col_tensor_map(&tm, data, 2ull * C, (unsigned long long)N1, nb, 2ull * g.Nc))
+            col4_select(3, g.three)<<<dim3(pgrid(C >> 3), nb, 1), kC4Threads, kC4SmemBytes, st>>>(
+                tm, data, nullptr, d_out, g, g.b2 + g.b3, 1, lo, hi);
+        else if (g.three)
             col2_three(3)<<<dim3(pgrid(C >> 3), nb, 1), kColThreads, smem2, st>>>(data, nullptr, d_out, g, g.b2 + g.b3, 1,
                                                                                    lo, hi);
         else if (pipelined)
