@@ -657,9 +657,14 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     }
 
     // ===== consumers: group = half of the columns =====
+    // Thread roles inside a group: a warp owns 8 consecutive radix groups x 4 columns.  A 128-bit shared-memory access is
+    // served eight lanes at a time, so the two rows a quarter-warp touches must land in different 64-byte halves: under
+    // both swizzles the half follows bit 2 of the row, hence lanes 4..7 of each octet take the group 4 further on.
     const int grp = tid >> 8, tl = tid & 255;
-    const int g = tl >> 2, c = (grp << 2) | (tl & 3);     // pass-1 / middle-pass role: radix group g of column c
-    const bool p1 = !THREE || tl < P1_PER_GROUP;
+    const int gl = (tl >> 2) & 7;
+    const int g = ((tl >> 5) << 3) | ((gl & 1) << 2) | (gl >> 1);
+    const int c = (grp << 2) | (tl & 3);                  // pass-1 / middle-pass role: radix group g of column c
+    const bool p1 = !THREE || g < NB8;            // the 384-row passes have 48 radix-8 groups per column
     double2* bdata = data + (long long)batch * G.Nc;
     const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);
     const unsigned int n1 = (unsigned int)G.n1;
@@ -783,7 +788,7 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
 
         // ---- last pass (radix 8 or 6, stride 64, no butterfly twiddles): L -> registers -> HBM
         {
-            const int gg = tl >> 2;                 // 64 groups x 4 columns = every thread of the group
+            const int gg = g;                       // 64 groups x 4 columns = every thread of the group
             double2 r[8];
 #pragma unroll
             for (int t = 0; t < R; ++t) r[t] = Lb[c4_unit_l(gg + t * 64, c)];
