@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libacf_b200.so")
+# ACFB200_LIB selects another build of the same ABI (tests use it for the debug-bounds twin libacf_b200_bounds.so)
+LIB_PATH = os.environ.get("ACFB200_LIB") or os.path.join(HERE, "libacf_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM = 0, 1, 2, 3
 

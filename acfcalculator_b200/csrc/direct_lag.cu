@@ -30,6 +30,24 @@ namespace acfb200 {
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxWarps = 16;
 
+// Debug-bounds build (-DACFB200_BOUNDS, libacf_b200_bounds.so; compute-sanitizer is closed on the GPU pool): every
+// 16-byte shared-memory load of the lag kernel is checked against the staged regions and the kernel traps on a violation.
+//   window operand   [b_s, b_s + bsz)
+//   a operand        [a_s, a_s + ti + 2): the software pipeline fetches a_next one pair ahead, so the last time lane reads
+//                    the first two doubles of b_s after its final step (value never used)
+#ifdef ACFB200_BOUNDS
+__device__ __forceinline__ double2 lds2_chk(const double* p, const double* lo, const double* hi)
+{
+    if (p < lo || p + 2 > hi || (reinterpret_cast<uintptr_t>(p) & 15) != 0) __trap();
+    return lds2(p);
+}
+#define LDS2_B(p, lo, hi) lds2_chk((p), (lo), (hi))
+#define BOUNDS_ASSERT(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define LDS2_B(p, lo, hi) lds2(p)
+#define BOUNDS_ASSERT(cond) do { } while (0)
+#endif
+
 // MSD = false: S[k] += x[i]*x[i+k].   MSD = true: S[k] += (x[i+k]-x[i])^2 -- the displacement sums of
 // traj2diffusion.cpp:530-541 for unit origin stride; same staging, ring and partial-sum layout, one extra
 // DADD per term (so the FP64 pipe runs two instructions per displacement instead of one per product).
@@ -77,6 +95,8 @@ direct_lag_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int ts, 
 
     const double* ap = a_s + li * ts;
     const double* bp = b_s + li * ts + warp * LKRK + lk * RK;
+    BOUNDS_ASSERT(ts % R == 0 && ti + bsz <= (int)((reinterpret_cast<unsigned char*>(bar) - smem_raw) / 8));
+    BOUNDS_ASSERT(!warp_active || (LI - 1) * ts + (nwarps - 1) * LKRK + (LK - 1) * RK + ts + RK + 2 * PF <= bsz);
 
     for (long long t = t0; t < t1; ++t) {
         const long long it = t * ti;
@@ -130,17 +150,17 @@ direct_lag_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int ts, 
         double win[R];
 #pragma unroll
         for (int e = 0; e < RK + 2 * PF; e += 2) {
-            const double2 v = lds2(bp + e);
+            const double2 v = LDS2_B(bp + e, b_s, b_s + bsz);
             win[e % R] = v.x;
             win[(e + 1) % R] = v.y;
         }
-        double2 a_next = lds2(ap);
+        double2 a_next = LDS2_B(ap, a_s, a_s + ti + 2);
         for (int s = 0; s < ts; s += R) {
 #pragma unroll
             for (int u = 0; u < R; u += 2) {
                 const double2 a = a_next;
-                a_next = lds2(ap + s + u + 2);
-                const double2 nw = lds2(bp + s + u + RK + 2 * PF);
+                a_next = LDS2_B(ap + s + u + 2, a_s, a_s + ti + 2);
+                const double2 nw = LDS2_B(bp + s + u + RK + 2 * PF, b_s, b_s + bsz);
                 win[(u + RK + 2 * PF) % R] = nw.x;
                 win[(u + RK + 2 * PF + 1) % R] = nw.y;
                 if constexpr (MSD) {
@@ -174,6 +194,7 @@ direct_lag_kernel(const SeriesDesc* __restrict__ desc, long long ncorr, int ts, 
     }
     if (li == 0) {
         double* dst = partials + ((size_t)blockIdx.z * chunks + blockIdx.y) * (size_t)mpad + kb + lk * RK;
+        BOUNDS_ASSERT(kb + lk * RK + RK <= mpad);
 #pragma unroll
         for (int j = 0; j < RK; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(acc[j], acc[j + 1]);
     }

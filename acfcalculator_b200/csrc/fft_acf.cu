@@ -582,7 +582,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
 // every access pattern below fall into both 64-byte halves four times: four wavefronts per 512 bytes, the minimum.
 constexpr int kC4Threads = 512 + 32;   // 16 compute warps + the producer warp
 constexpr int kC4BoxRows = 128;
-constexpr size_t kC4SmemBytes = 1024 /* alignment slack */ + (size_t)3 * 4096 * 16 + 512 * 16 + 64;
+constexpr size_t kC4SmemBytes = (size_t)3 * 4096 * 16 + 512 * 16 + 64;
 
 __device__ __forceinline__ int c4_unit_l(int row, int c) { return (row << 3) | ((c ^ row) & 7); }
 __device__ __forceinline__ int c4_unit_s(int row, int c) { return (row << 3) | ((c ^ row ^ (row >> 3)) & 7); }
@@ -597,12 +597,13 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     constexpr int NB = THREE ? 384 : 512;
     constexpr int NB8 = NB >> 3;                   // 64 or 48 radix-8 groups per column
     constexpr int TILE = NB * 8;                   // elements per tile
-    constexpr int P1_PER_GROUP = NB8 * 4;          // threads of a group with a radix-8 item: 256 or 192
     constexpr int R = NB / 64;                     // last radix: 8 or 6
-    extern __shared__ unsigned char smem_c4[];
-    // SWIZZLE_128B wants the landing buffers 1024-byte aligned
-    unsigned char* base1k = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_c4) + 1023) & ~(uintptr_t)1023);
-    double2* L0 = reinterpret_cast<double2*>(base1k);
+    // SWIZZLE_128B wants the landing buffers 1024-byte aligned; the declaration asks for it and the kernel checks.  (No
+    // pointer arithmetic through integers here: it would lose the shared address space and turn every LDS/STS into a
+    // generic LD/ST -- the first version did, r2h ncu.)
+    extern __shared__ __align__(1024) unsigned char smem_c4[];
+    if ((smem_u32(smem_c4) & 1023u) != 0) __trap();
+    double2* L0 = reinterpret_cast<double2*>(smem_c4);
     double2* S = L0 + 2 * 4096;
     double2* tw = S + 4096;                        // tw[(u-1)*NB8 + g] = W_NB^{g*u} (conjugated for the inverse)
     double2* tw2 = tw + 7 * NB8;                   // tw2[(u-1)*(NB8/8) + p] = W_NB^{8*p*u}
@@ -796,8 +797,10 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
                 dft8<DIR>(r);
             else
                 dft6<DIR>(r);
-            // the values are in registers: this warp is done with the landing buffer
-            fence_proxy_async();
+            // The values are in registers: this warp is done with the landing buffer.  Its own writes to the buffer (middle
+            // pass) were read back by the whole group after a barrier, so they are performed; the release/acquire pair on
+            // `empty` orders the producer's next TMA box behind them.  (A fence.proxy.async here compiles to MEMBAR.ALL.CTA
+            // + FENCE.VIEW.ASYNC per thread and tile and showed up as a drain in r2h.)
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[b]);
             store_group(a, c0 + c, gg, r);
