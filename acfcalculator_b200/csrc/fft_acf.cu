@@ -582,7 +582,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
 // every access pattern below fall into both 64-byte halves four times: four wavefronts per 512 bytes, the minimum.
 constexpr int kC4Threads = 512 + 32;   // 16 compute warps + the producer warp
 constexpr int kC4BoxRows = 128;
-constexpr size_t kC4SmemBytes = (size_t)3 * 4096 * 16 + 512 * 16 + 64;
+constexpr size_t kC4SmemBytes = (size_t)3 * 4096 * 16 + (512 + 80) * 16 + 64;
 
 __device__ __forceinline__ int c4_unit_l(int row, int c) { return (row << 3) | ((c ^ row) & 7); }
 __device__ __forceinline__ int c4_unit_s(int row, int c) { return (row << 3) | ((c ^ row ^ (row >> 3)) & 7); }
@@ -607,7 +607,10 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     double2* S = L0 + 2 * 4096;
     double2* tw = S + 4096;                        // tw[(u-1)*NB8 + g] = W_NB^{g*u} (conjugated for the inverse)
     double2* tw2 = tw + 7 * NB8;                   // tw2[(u-1)*(NB8/8) + p] = W_NB^{8*p*u}
-    uint64_t* full = reinterpret_cast<uint64_t*>(tw + 512);
+    // MODE 0 only: rho[gg] = W_Nc^{gg * 8 * gridDim.x} (gg < 64) and rho[64] = W_Nc^{64 * 8 * gridDim.x}: the factors by which a
+    // thread's inter-step twiddles advance from one of its CTA's tiles to the next (see the tile loop)
+    double2* rho = tw + 512;
+    uint64_t* full = reinterpret_cast<uint64_t*>(rho + 80);
     uint64_t* empty = full + 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned int tiles_c_log = logC - 3;
@@ -636,6 +639,7 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
             const double2 w = tw_L(lo, hi, (unsigned long long)e * wstep);
             tw[m] = DIR > 0 ? cconj(w) : w;
         }
+        if (MODE == 0 && tid <= 64) rho[tid] = tw_L(lo, hi, 2ull * ((unsigned long long)tid * 8ull * gridDim.x));
     }
     __syncthreads();
 
@@ -690,16 +694,37 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
         return z;
     };
 
-    auto store_group = [&](unsigned int a, unsigned int cc, unsigned int base, double2* r) {
+    // MODE 3 epilogue: lag k = 2j + h gets r / (Nc * (n - k)).  Where both lags of a complex value are wanted, have a positive
+    // count and the output is 16-byte aligned: one 128-bit store, and the quotient through a reciprocal refined by two
+    // Newton steps from MUFU.RCP64H (<= 1.5 ulp from the correctly rounded divide; this path never was bit-exact with the
+    // direct sum).  IEEE division costs ~25 instructions per lag and was 45 % of this pass's instruction count (r2i ncu).
+    double* o3 = (MODE == 3) ? out + (long long)batch * G.out_stride : nullptr;
+    const bool o3_aligned = (reinterpret_cast<uintptr_t>(o3) & 15) == 0;
+    const double inv_nc = 1.0 / (double)G.Nc;
+    auto fast_rcp = [](double md) {
+        double r0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(md));
+        double e = fma(-md, r0, 1.0);
+        r0 = fma(r0, e, r0);
+        e = fma(-md, r0, 1.0);
+        return fma(r0, e, r0);
+    };
+    auto store_group = [&](unsigned int a, unsigned int cc, unsigned int base, double2* r, double2 t, double2 d) {
         if (MODE == 3) {
-            double* o = out + (long long)batch * G.out_stride;
-            const double inv_nc = 1.0 / (double)G.Nc;
 #pragma unroll
             for (int u = 0; u < R; ++u) {
                 const long long j = ((long long)(base + 64 * u) << logC) + cc;
+                const long long k0 = 2 * j;
+                if (k0 >= G.ncorr) continue;
+                const long long m0 = G.n - k0;
+                if (o3_aligned && k0 + 1 < G.ncorr && m0 > 1 && m0 < (1ll << 31)) {
+                    const double s0 = inv_nc * fast_rcp((double)(int)m0), s1 = inv_nc * fast_rcp((double)(int)(m0 - 1));
+                    *reinterpret_cast<double2*>(o3 + k0) = make_double2(r[u].x * s0, r[u].y * s1);
+                    continue;
+                }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const long long k = 2 * j + h;
+                    const long long k = k0 + h;
                     if (k < G.ncorr) {
                         const long long m = G.n - k;
                         double val = (h ? r[u].y : r[u].x) * inv_nc;
@@ -709,28 +734,27 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
                             val = __longlong_as_double(0xFFF8000000000000ull);  // reference: 0/0
                         else
                             val = -0.0;                                          // reference: 0/negative
-                        o[k] = val;
+                        o3[k] = val;
                     }
                 }
             }
             return;
         }
-        unsigned int e0, de;  // exponents of W_Nc (see col_pass2_kernel); every product stays below Nc
-        if (MODE == 0) {
-            e0 = base * cc;
-            de = 64u * cc;
-        } else if (MODE == 1) {
-            e0 = (base * n1) * cc;
-            de = (64u * n1) * cc;
-        } else {
-            e0 = ((base << logC) + cc) * a;
-            de = (64u << logC) * a;
-        }
-        double2 t = tw_L(lo, hi, 2ull * (e0 & nc_mask));  // W_Nc = W_L^2
-        double2 d = tw_L(lo, hi, 2ull * (de & nc_mask));
-        if (DIR > 0) {
-            t = cconj(t);
-            d = cconj(d);
+        if (MODE != 0) {
+            unsigned int e0, de;  // exponents of W_Nc (see col_pass2_kernel); every product stays below Nc
+            if (MODE == 1) {
+                e0 = (base * n1) * cc;
+                de = (64u * n1) * cc;
+            } else {
+                e0 = ((base << logC) + cc) * a;
+                de = (64u << logC) * a;
+            }
+            t = tw_L(lo, hi, 2ull * (e0 & nc_mask));  // W_Nc = W_L^2
+            d = tw_L(lo, hi, 2ull * (de & nc_mask));
+            if (DIR > 0) {
+                t = cconj(t);
+                d = cconj(d);
+            }
         }
         double2* dst = bdata + (((size_t)a * NB) << logC) + cc;
 #pragma unroll
@@ -741,10 +765,27 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     };
 
     double2 edge = load_edge(blockIdx.x);
+    // MODE 0 (one slab, c0 = 8 * tile): the inter-step twiddles of this thread's last-pass outputs, W_Nc^{gg*cc} and
+    // W_Nc^{64*cc} with cc = c0 + c, advance by the thread-constant factors rho[gg] and rho[64] from one tile of the CTA to
+    // the next, so they are carried in registers and re-read from the W_L table only every kReseed tiles (which bounds the
+    // rounding drift to a few ulp).  The four divergent 16-byte gathers per thread and tile they replace were a quarter of
+    // this pass's LSU wavefronts and its top stall (r2i ncu: long_scoreboard on the first multiply by the twiddle).
+    constexpr unsigned int kReseed = 8;
+    double2 t0 = make_double2(1.0, 0.0), d0 = make_double2(1.0, 0.0);
     unsigned int j = 0;
     for (unsigned int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
         const unsigned int b = j & 1;
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
+        if (MODE == 0) {
+            if (j % kReseed == 0) {
+                const unsigned int cc = c0 + c;
+                t0 = tw_L(lo, hi, 2ull * ((unsigned int)g * cc));
+                d0 = tw_L(lo, hi, 2ull * (64u * cc));
+            } else {
+                t0 = cmul(t0, rho[g]);
+                d0 = cmul(d0, rho[64]);
+            }
+        }
         double2* Lb = L0 + b * 4096;
         const double2 edge_now = edge;
         if (MODE == 0) edge = load_edge(tile + gridDim.x);
@@ -803,7 +844,7 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
             // + FENCE.VIEW.ASYNC per thread and tile and showed up as a drain in r2h.)
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[b]);
-            store_group(a, c0 + c, gg, r);
+            store_group(a, c0 + c, gg, r, t0, d0);
         }
         // no barrier: the next tile's pass 1 writes S, last read by this group before its second barrier above
     }
