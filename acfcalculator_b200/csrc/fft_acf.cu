@@ -569,7 +569,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
 // forward and inverse passes, whose tiles carry less HBM traffic, ran at 0.4 of the DRAM rate):
 //   * tiles arrive by TMA: one 3-D tensor map (columns x rows x series) over the work array -- or, for MODE 0, over the
 //     caller's REAL series viewed as rows of 2C doubles, where rows beyond the data come back as zeros without touching
-//     HBM -- and a producer warp that issues one 128-row box per 16 KB (SASS UTMALDG) into one of two landing buffers,
+//     HBM -- and one elected thread that issues one 128-row box per 16 KB (SASS UTMALDG) into one of two landing buffers,
 //     gated by full/empty mbarriers.  No registers, no LSU instructions and no scoreboards are tied up by the prefetch, and
 //     the next tile is requested as soon as the tile before the current one has been consumed;
 //   * the 8 columns of a tile are independent transforms: the 512 compute threads form two groups of 256, one per half of
@@ -580,7 +580,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
 // Bank conflicts: a warp now touches 8 rows x 4 columns (64 bytes per row).  L carries the TMA 128-byte swizzle (16-byte
 // chunk c of row r at chunk c ^ (r & 7)), S the software swizzle c ^ ((r ^ (r >> 3)) & 7); with either, the eight rows of
 // every access pattern below fall into both 64-byte halves four times: four wavefronts per 512 bytes, the minimum.
-constexpr int kC4Threads = 512 + 32;   // 16 compute warps + the producer warp
+constexpr int kC4Threads = 512;        // 16 compute warps; thread 0 doubles as the TMA producer
 constexpr int kC4BoxRows = 128;
 constexpr size_t kC4SmemBytes = (size_t)3 * 4096 * 16 + (512 + 80) * 16 + 64;
 
@@ -612,7 +612,7 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     double2* rho = tw + 512;
     uint64_t* full = reinterpret_cast<uint64_t*>(rho + 80);
     uint64_t* empty = full + 2;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     const unsigned int tiles_c_log = logC - 3;
     unsigned int tiles = (unsigned int)A << tiles_c_log;
     if (MODE == 3) {
@@ -643,23 +643,21 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     }
     __syncthreads();
 
-    if (warp == 16) {
-        // ===== producer: one lane walks this CTA's tiles, two in flight at most =====
-        if (lane == 0) {
-            unsigned int j = 0;
-            for (unsigned int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
-                const unsigned int b = j & 1;
-                if (j >= 2) mbar_wait(&empty[b], ((j - 2) >> 1) & 1);   // tile j-2 has left this buffer
-                const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
-                mbar_expect_tx(&full[b], (uint32_t)(TILE * 16));
-                double2* dst = L0 + b * 4096;
+    // ===== producer duty (thread 0): tile j+1 is requested at the top of tile j, as soon as BOTH groups have taken tile j-1
+    // out of its landing buffer.  Thread 0 belongs to group 0, so group 0 can lead group 1 by one radix pass at most --
+    // which is the stagger wanted: one group computes while the other exchanges or stores.  (A 17th warp as a dedicated
+    // producer caps the kernel at 96 registers per thread -- warps are allocated four at a time -- and spilled.)
+    auto request_tile = [&](unsigned int tile, unsigned int jj) {
+        const unsigned int bb = jj & 1;
+        if (jj >= 2) mbar_wait(&empty[bb], ((jj - 2) >> 1) & 1);   // tile jj-2 has left this buffer
+        const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
+        mbar_expect_tx(&full[bb], (uint32_t)(TILE * 16));
+        double2* dst = L0 + bb * 4096;
 #pragma unroll
-                for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
-                    tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[b]);
-            }
-        }
-        return;
-    }
+        for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
+            tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[bb]);
+    };
+    if (tid == 0 && blockIdx.x < tiles) request_tile(blockIdx.x, 0);
 
     // ===== consumers: group = half of the columns =====
     // Thread roles inside a group: a warp owns 8 consecutive radix groups x 4 columns.  A 128-bit shared-memory access is
@@ -776,6 +774,7 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     for (unsigned int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
         const unsigned int b = j & 1;
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
+        if (tid == 0 && tile + gridDim.x < tiles) request_tile(tile + gridDim.x, j + 1);
         if (MODE == 0) {
             if (j % kReseed == 0) {
                 const unsigned int cc = c0 + c;
@@ -1040,9 +1039,6 @@ row_pass_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict
 // on registers.  Each row thread evaluates the pair formula for its own 8 spectrum points (the mirror thread
 // evaluates it again from its side) so that the inverse transform starts from registers without another exchange.
 // Work list: one entry per unordered row pair {(k1,k2), mirror}; self-mirrored rows fill both slots of their pair.
-// two tile buffers, butterfly twiddles (<= 512 entries), wg (<= 64), two sets of 18 per-row factors for <= 32 rows
-constexpr size_t kRowSmemBytes = (size_t)(2 * 4096 + 512 + 64 + 2 * 18 * 32) * 16;
-
 template <int B3>
 __global__ void __launch_bounds__(kColThreads, 1)
 row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict__ lo, const double2* __restrict__ hi)
@@ -1064,18 +1060,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     double2* bdata = data + (long long)blockIdx.y * G.Nc;
     // butterfly twiddles in warp-contiguous layout: twf[(u-1)*G8 + g] = W_N3^{g*u}, twm[(u-1)*(G8/8) + p] = W_N3^{8pu}
     double2* twm = twf + 7 * G8;
-    // Per-row factors looked up once per tile by a few threads of the row instead of per thread (r2b ncu: the LSU data pipe
-    // of this kernel sat at 87 % of its wavefront peak, a quarter of it fully divergent 16-byte table gathers):
-    //   wg[g]              = W_L^{g*N1*N2}                      (built once; the thread-dependent factor of the pair-op W)
-    //   rt[e*ROWS + slot]  e < 8: conj W_Nc^{8e*f};  e < 16: conj W_Nc^{(e-8)*f};  e = 16: conj W_Nc^{64f};  e = 17: W_L^{kbase}
-    // with f and kbase the row's post-twiddle factor and spectrum offset.  The post twiddle of output j0 + 64u is then
-    // rt[j0>>3] * rt[8 + (j0&7)] * rt[16]^u, and the pair-op twiddle rt[17] * wg[g].  Two sets alternate with the parity.
-    constexpr int RT_ROWS = 18;
-    double2* wg = twf + 512;
-    double2* rtab = wg + 64;
-    constexpr int RT_PER = (RT_ROWS + G8 - 1) / G8;   // table entries per thread of a row: 1 (2 for 128-point rows)
-    const unsigned int n12 = ((unsigned int)G.n1) << G.b2;   // N1 * N2: spectrum index k = k1 + N1*k2 + N1*N2*k3
-    if (tid < G8) wg[tid] = tw_L(lo, hi, (unsigned long long)tid * n12);
     {
         const unsigned int wstep = (unsigned int)(G.L >> B3);
         for (int m = tid; m < 7 * G8 + 7 * (G8 / 8); m += kColThreads) {
@@ -1088,6 +1072,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         }
     }
     const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);  // exponents stay below Nc anyway
+    const unsigned int n12 = N1 << G.b2;              // N1 * N2: spectrum index k = k1 + N1*k2 + N1*N2*k3
 
     // digits (k1, k2) of the row held by slot `rs` of tile `tile`; false past the end of the list
     auto slot_row = [&](unsigned int tile, unsigned int& r1, unsigned int& r2, bool& origin) -> bool {
@@ -1144,35 +1129,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     // One 512-thread CTA per SM (128 registers, no spills).  The tile lives in two shared-memory buffers: every radix
     // pass reads one and writes the other, and the roles swap from tile to tile, so each of the five hand-offs of a
     // tile needs exactly one pair barrier (the in-place version needed ten).
-    // this thread's share of the 18 factors of the row with digits (r1, r2)
-    auto row_factors = [&](unsigned int r1, unsigned int r2, double2 (&pend)[RT_PER]) {
-        const unsigned int kbase = r1 + r2 * N1;
-        const unsigned int f = (G.b2 > 0) ? (r2 * N1) : r1;   // post twiddle conj(W_Nc^{j3 * f})
-#pragma unroll
-        for (int i = 0; i < RT_PER; ++i) {
-            const int e = g + i * G8;
-            if (e < RT_ROWS) {
-                if (e == 17) {
-                    pend[i] = tw_L(lo, hi, (unsigned long long)kbase);
-                } else {
-                    const unsigned int ex = (e < 8 ? 8u * e : (e < 16 ? (unsigned int)(e - 8) : 64u)) * f;
-                    pend[i] = cconj(tw_L(lo, hi, 2ull * (ex & nc_mask)));
-                }
-            }
-        }
-    };
-    {   // first tile: its factors are needed right away
-        unsigned int q1 = 0, q2 = 0;
-        bool qo = false;
-        double2 pend[RT_PER];
-        slot_row(blockIdx.x, q1, q2, qo);
-        row_factors(q1, q2, pend);
-#pragma unroll
-        for (int i = 0; i < RT_PER; ++i) {
-            const int e = g + i * G8;
-            if (e < RT_ROWS) rtab[e * ROWS + rs] = pend[i];
-        }
-    }
     __syncthreads();
     double2 nxt[8];  // the next tile's row, in flight while this one is transformed
 #pragma unroll
@@ -1186,7 +1142,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         unsigned int r1 = 0, r2 = 0;
         bool origin = false;
         const bool valid = slot_row(tile, r1, r2, origin);
-        double2* rt = rtab + parity * (RT_ROWS * ROWS);
         double2 v[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[t] = nxt[t];
@@ -1202,16 +1157,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
 #pragma unroll
         for (int t = 0; t < 8; ++t) nxt[t] = make_double2(0.0, 0.0);
         if (tile + gridDim.x < ntiles) load_row(tile + gridDim.x, nxt);
-        // The NEXT tile's table entries for this row slot: look-ups issued here (after radix pass 1 has consumed the previous
-        // prefetch -- a wait for old data on a shared scoreboard would otherwise also wait for these), stored at the end of
-        // this tile into the other table set, first read a tile later: their latency never sits between two pair barriers.
-        double2 pend[RT_PER];
-        {
-            unsigned int q1 = 0, q2 = 0;
-            bool qo = false;
-            slot_row(tile + gridDim.x, q1, q2, qo);
-            row_factors(q1, q2, pend);
-        }
         pair_sync();
         {   // middle pass: radix 8, stride 8, X -> Y
             double2 r[8];
@@ -1227,7 +1172,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             for (int u = 0; u < 8; ++u) by[sw(qq + ps * 8 + 8 * u)] = r[u];
             pair_sync();
         }
-        double2 za[8];   // this thread's spectrum points k3 = g + t*G8 after the last forward pass (also written to X for the mirror row)
         {   // last forward pass: radix 2^(B3-6), stride 64, Y -> X in natural order
             constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
             double2 r[8];
@@ -1246,22 +1190,19 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
 #pragma unroll
                 for (int u = 0; u < R; ++u) bx[sw(gg + 64 * u)] = r[it * R + u];
             }
-            // output (it, u) sits at k3 = g + it*G8 + 64u = g + (it + GPT*u)*G8: pair-op slot t = it + GPT*u
-            static_assert(64 / G8 == GPT, "the last-pass outputs of a thread are its own pair-op points");
-#pragma unroll
-            for (int t = 0; t < 8; ++t) za[t] = r[(t % GPT) * R + t / GPT];
             pair_sync();
         }
 
-        // ================= |X|^2 pair operation for this thread's 8 spectrum points (mirror values from X) =================
+        // ================= |X|^2 pair operation for this thread's 8 spectrum points (reads X) =================
         // W_L^k for k = kbase + N1*N2*(g + t*N3/8): successive t differ by W_L^{Nc/8} = exp(-i pi/8), a constant
-        double2 W = cmul(rt[17 * ROWS + rs], wg[g]);
+        const unsigned int kbase = r1 + r2 * N1;
+        double2 W = tw_L(lo, hi, (unsigned long long)(kbase + (unsigned int)g * n12));
         const double2 rot = make_double2(0.92387953251128675613, -0.38268343236508977173);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             const int k3 = g + t * G8;
             const int p3 = origin ? ((N3 - k3) & (N3 - 1)) : (N3 - 1 - k3);
-            const double2 Za = za[t];
+            const double2 Za = bx[sw(k3)];
             const double2 Zb = mx[sw(p3)];
             const double2 S = make_double2(Za.x + Zb.x, Za.y - Zb.y);   // Za + conj Zb
             const double2 D = make_double2(Za.x - Zb.x, Za.y + Zb.y);   // Za - conj Zb
@@ -1300,8 +1241,8 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         }
         {   // last inverse pass (reads X) -> post twiddle conj(W_Nc^{j3 * f}) -> HBM
             constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
+            const unsigned int f = (G.b2 > 0) ? (r2 * N1) : r1;
             double2* dst = bdata + ((size_t)((r1 << G.b2) + r2) << B3);
-            const double2 dq = rt[16 * ROWS + rs];
 #pragma unroll
             for (int it = 0; it < GPT; ++it) {
                 const int gg = g + it * G8;
@@ -1316,21 +1257,13 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                     dft2(r);
                 // post twiddle conj(W_Nc^{j3*f}), j3 = j0 + 64u: exponents in arithmetic progression
                 const unsigned int j0 = gg;
-                double2 tq = cmul(rt[(j0 >> 3) * ROWS + rs], rt[(8 + (j0 & 7)) * ROWS + rs]);
+                double2 tq = cconj(tw_L(lo, hi, 2ull * ((j0 * f) & nc_mask)));
+                const double2 dq = cconj(tw_L(lo, hi, 2ull * ((64u * f) & nc_mask)));
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
                     if (valid) dst[j0 + 64 * u] = cmul(r[u], tq);
                     tq = cmul(tq, dq);
                 }
-            }
-        }
-        // the next tile's row factors go into the other table set (last read a tile ago, before this tile's first barrier)
-        {
-            double2* rn = rtab + (parity ^ 1) * (RT_ROWS * ROWS);
-#pragma unroll
-            for (int i = 0; i < RT_PER; ++i) {
-                const int e = g + i * G8;
-                if (e < RT_ROWS) rn[e * ROWS + rs] = pend[i];
             }
         }
         // no barrier: the next tile starts by writing buffer Y, last read before the barrier above
@@ -1515,9 +1448,9 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         cudaFuncSetAttribute(col_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
-        cudaFuncSetAttribute(row_pass2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemBytes);
-        cudaFuncSetAttribute(row_pass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemBytes);
-        cudaFuncSetAttribute(row_pass2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowSmemBytes);
+        cudaFuncSetAttribute(row_pass2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
         for (int mode = 0; mode < 4; ++mode)
             for (int bb = 3; bb <= 9; ++bb)
                 cudaFuncSetAttribute(col2_select(mode, bb), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1588,7 +1521,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         ++launches;
     }
     if (pipelined && g.b1 > 0 && g.b3 >= 7) {
-        const size_t smem = kRowSmemBytes;
+        const size_t smem = (size_t)(2 * 4096 + N3) * 16;
         if (g.b3 == 9)
             row_pass2_kernel<9><<<dim3(sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         else if (g.b3 == 8)
