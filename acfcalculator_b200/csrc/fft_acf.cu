@@ -569,7 +569,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
 // forward and inverse passes, whose tiles carry less HBM traffic, ran at 0.4 of the DRAM rate):
 //   * tiles arrive by TMA: one 3-D tensor map (columns x rows x series) over the work array -- or, for MODE 0, over the
 //     caller's REAL series viewed as rows of 2C doubles, where rows beyond the data come back as zeros without touching
-//     HBM -- and one elected thread that issues one 128-row box per 16 KB (SASS UTMALDG) into one of two landing buffers,
+//     HBM -- and a producer warp that issues one 128-row box per 16 KB (SASS UTMALDG) into one of two landing buffers,
 //     gated by full/empty mbarriers.  No registers, no LSU instructions and no scoreboards are tied up by the prefetch, and
 //     the next tile is requested as soon as the tile before the current one has been consumed;
 //   * the 8 columns of a tile are independent transforms: the 512 compute threads form two groups of 256, one per half of
@@ -580,7 +580,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
 // Bank conflicts: a warp now touches 8 rows x 4 columns (64 bytes per row).  L carries the TMA 128-byte swizzle (16-byte
 // chunk c of row r at chunk c ^ (r & 7)), S the software swizzle c ^ ((r ^ (r >> 3)) & 7); with either, the eight rows of
 // every access pattern below fall into both 64-byte halves four times: four wavefronts per 512 bytes, the minimum.
-constexpr int kC4Threads = 512;        // 16 compute warps; thread 0 doubles as the TMA producer
+constexpr int kC4Threads = 512 + 32;   // 16 compute warps + the producer warp
 constexpr int kC4BoxRows = 128;
 constexpr size_t kC4SmemBytes = (size_t)3 * 4096 * 16 + (512 + 80) * 16 + 64;
 
@@ -612,7 +612,7 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     double2* rho = tw + 512;
     uint64_t* full = reinterpret_cast<uint64_t*>(rho + 80);
     uint64_t* empty = full + 2;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned int tiles_c_log = logC - 3;
     unsigned int tiles = (unsigned int)A << tiles_c_log;
     if (MODE == 3) {
@@ -643,21 +643,23 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     }
     __syncthreads();
 
-    // ===== producer duty (thread 0): tile j+1 is requested at the top of tile j, as soon as BOTH groups have taken tile j-1
-    // out of its landing buffer.  Thread 0 belongs to group 0, so group 0 can lead group 1 by one radix pass at most --
-    // which is the stagger wanted: one group computes while the other exchanges or stores.  (A 17th warp as a dedicated
-    // producer caps the kernel at 96 registers per thread -- warps are allocated four at a time -- and spilled.)
-    auto request_tile = [&](unsigned int tile, unsigned int jj) {
-        const unsigned int bb = jj & 1;
-        if (jj >= 2) mbar_wait(&empty[bb], ((jj - 2) >> 1) & 1);   // tile jj-2 has left this buffer
-        const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
-        mbar_expect_tx(&full[bb], (uint32_t)(TILE * 16));
-        double2* dst = L0 + bb * 4096;
+    if (warp == 16) {
+        // ===== producer: one lane walks this CTA's tiles, two in flight at most =====
+        if (lane == 0) {
+            unsigned int j = 0;
+            for (unsigned int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
+                const unsigned int b = j & 1;
+                if (j >= 2) mbar_wait(&empty[b], ((j - 2) >> 1) & 1);   // tile j-2 has left this buffer
+                const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
+                mbar_expect_tx(&full[b], (uint32_t)(TILE * 16));
+                double2* dst = L0 + b * 4096;
 #pragma unroll
-        for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
-            tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[bb]);
-    };
-    if (tid == 0 && blockIdx.x < tiles) request_tile(blockIdx.x, 0);
+                for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
+                    tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[b]);
+            }
+        }
+        return;
+    }
 
     // ===== consumers: group = half of the columns =====
     // Thread roles inside a group: a warp owns 8 consecutive radix groups x 4 columns.  A 128-bit shared-memory access is
@@ -774,7 +776,6 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     for (unsigned int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
         const unsigned int b = j & 1;
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
-        if (tid == 0 && tile + gridDim.x < tiles) request_tile(tile + gridDim.x, j + 1);
         if (MODE == 0) {
             if (j % kReseed == 0) {
                 const unsigned int cc = c0 + c;
