@@ -696,20 +696,20 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
     // Window groups: all uploads are queued on the copy stream up front, one event per group; the compute stream
     // starts group g as soon as its windows have landed, so the H2D of group g+1 overlaps the kernels of group g
     // (with pageable host memory the copies degrade to synchronous staging and nothing is lost).
-    // The groups grow 1 : 2 : 4 : 8 : 16 -- every upload hides under the previous group's kernels as long as the host
+    // The groups grow 1 : 1 : 2 : 4 : 8 : ... -- every upload hides under the previous group's kernels as long as the host
     // link delivers windows at least twice as fast as the kernels consume them (alone on the box it is ~4x; with eight
     // processes pulling from one NUMA node it drops towards 2x, which is what the round-1 1 : 4 : 16 split stalled on).
     // Nothing below waits for the device until everything is enqueued: results (lags and scalars) are copied to
     // page-locked staging memory asynchronously, then the host walks the groups' completion events and moves each
     // group's results to the caller's arrays while the later groups are still computing.
-    const int ngroups = nwindows >= 8 ? 5 : 1;
+    // group boundaries 0, 1, 2, 4, 8, 16, ... windows: the only exposed transfer is the first window's
+    // (small batches -- setup.sh's 80 windows of 5001 samples -- go as one group: there is no transfer worth hiding)
+    std::vector<int> gbeg(1, 0);
+    if (nwindows >= 4 && total * 8 >= ((size_t)32 << 20))
+        for (int e = 1; e < nwindows; e *= 2) gbeg.push_back(e);
+    gbeg.push_back(nwindows);
+    const int ngroups = (int)gbeg.size() - 1;
     std::vector<cudaEvent_t> landed(ngroups, nullptr), done(ngroups, nullptr);
-    std::vector<int> gbeg(ngroups + 1, 0);
-    if (ngroups == 5) {
-        const int cum[6] = {0, 1, 3, 7, 15, 31};
-        for (int g = 1; g <= 5; ++g) gbeg[g] = (int)(((long long)nwindows * cum[g] + 30) / 31);
-    }
-    gbeg[ngroups] = nwindows;
     const bool want_lags = acf || vacf;
     const size_t lag_doubles = want_lags ? (size_t)2 * nwindows * ncorr : 0;
     const bool staged = lag_doubles * 8 <= ((size_t)1 << 30);   // beyond 1 GiB: copy straight to the caller (blocking)

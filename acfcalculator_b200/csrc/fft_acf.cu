@@ -62,6 +62,21 @@ __device__ __forceinline__ double2 tw_L(const double2* __restrict__ lo, const do
     return cmul(a, b);
 }
 
+// Debug-bounds build (-DACFB200_BOUNDS, see direct_lag.cu): every W_L table exponent is checked against L, every landing /
+// scratch tile index against the tile, every work-array index against Nc; the kernels trap on a violation.
+#ifdef ACFB200_BOUNDS
+__device__ __forceinline__ double2 tw_L_chk(const double2* __restrict__ lo, const double2* __restrict__ hi,
+                                            unsigned long long e, long long L)
+{
+    if (e >= (unsigned long long)L) __trap();
+    return tw_L(lo, hi, e);
+}
+#define tw_L(lo, hi, e) tw_L_chk((lo), (hi), (e), G.L)
+#define FFT_ASSERT(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define FFT_ASSERT(cond) do { } while (0)
+#endif
+
 __global__ void fft_table_kernel(double2* lo, double2* hi, long long L)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,6 +179,9 @@ __device__ __forceinline__ void stockham_pass(double2* s, int NB, int ncols, int
 {
     constexpr int R = 1 << LR;
     constexpr int GPT = 8 / R;
+#ifdef ACFB200_BOUNDS
+    const struct { long long L; } G = {L};  // the bounds-checking tw_L macro reads G.L
+#endif
     const int groups = NB / R;  // per column
     const int total = groups * ncols;
     double2 v[8];
@@ -455,6 +473,7 @@ col_pass2_kernel(double2* __restrict__ data, const double* __restrict__ x, doubl
         }
         double2* dst = bdata + (((size_t)a * NB) << logC) + cc;
         for (int u = 0; u < R; ++u) {
+            FFT_ASSERT((((size_t)a * NB) << logC) + cc + ((size_t)(base + stride * u) << logC) < (size_t)G.Nc);
             dst[(size_t)(base + stride * u) << logC] = cmul(r[u], t);
             t = cmul(t, d);
         }
@@ -584,8 +603,16 @@ constexpr int kC4Threads = 512 + 32;   // 16 compute warps + the producer warp
 constexpr int kC4BoxRows = 128;
 constexpr size_t kC4SmemBytes = (size_t)3 * 4096 * 16 + (512 + 80) * 16 + 64;
 
-__device__ __forceinline__ int c4_unit_l(int row, int c) { return (row << 3) | ((c ^ row) & 7); }
-__device__ __forceinline__ int c4_unit_s(int row, int c) { return (row << 3) | ((c ^ row ^ (row >> 3)) & 7); }
+__device__ __forceinline__ int c4_unit_l(int row, int c)
+{
+    FFT_ASSERT(row >= 0 && row < 512 && c >= 0 && c < 8);
+    return (row << 3) | ((c ^ row) & 7);
+}
+__device__ __forceinline__ int c4_unit_s(int row, int c)
+{
+    FFT_ASSERT(row >= 0 && row < 512 && c >= 0 && c < 8);
+    return (row << 3) | ((c ^ row ^ (row >> 3)) & 7);
+}
 
 template <int MODE, bool THREE>
 __global__ void __launch_bounds__(kC4Threads, 1)
@@ -759,6 +786,7 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
         double2* dst = bdata + (((size_t)a * NB) << logC) + cc;
 #pragma unroll
         for (int u = 0; u < R; ++u) {
+            FFT_ASSERT((((size_t)a * NB) << logC) + cc + ((size_t)(base + 64 * u) << logC) < (size_t)G.Nc);
             dst[(size_t)(base + 64 * u) << logC] = cmul(r[u], t);
             t = cmul(t, d);
         }
@@ -1262,6 +1290,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                 const double2 dq = cconj(tw_L(lo, hi, 2ull * ((64u * f) & nc_mask)));
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
+                    FFT_ASSERT(!valid || ((size_t)((r1 << G.b2) + r2) << B3) + j0 + 64 * u < (size_t)G.Nc);
                     if (valid) dst[j0 + 64 * u] = cmul(r[u], tq);
                     tq = cmul(tq, dq);
                 }

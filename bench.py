@@ -763,12 +763,14 @@ def run_native(args):
                     env.barrier()
             if line is not None:
                 line["multi_gpu"] = multi
-    if rank == 0:
-        if world == 1 and not args.no_cpu and args.allcores:
-            line["cpu_baseline_allcores"] = cpu_allcores_rate(args.workload)
-        print(json.dumps(line), flush=True)
+    if rank == 0 and world == 1 and not args.no_cpu and args.allcores:
+        line["cpu_baseline_allcores"] = cpu_allcores_rate(args.workload)
     if world > 1:
-        env.dist.destroy_process_group()
+        env.barrier()
+        env.dist.destroy_process_group()   # NCCL's teardown log (NCCL_DEBUG=INFO goes to stdout) ends before the line
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 def main():
