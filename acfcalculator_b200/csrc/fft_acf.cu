@@ -34,6 +34,7 @@ struct FftGeom {
     int three;        // L = 3 * 2^a: the first axis carries the factor 3 (radix 8 x 8 x 6), the others are powers of two
     int n1;           // N1 (1 when absent)
     int q;            // log2(Nc) (power-of-two transforms only)
+    int dbg;          // ACFB200_FFT_DBG bits (experiments on the TMA column pass; 0 in production)
     long long Nc, L;
     long long n, ncorr;
     long long x_stride, out_stride;  // batch: series b starts at x + b*x_stride, its lags go to out + b*out_stride
@@ -680,9 +681,15 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
                 const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
                 mbar_expect_tx(&full[b], (uint32_t)(TILE * 16));
                 double2* dst = L0 + b * 4096;
+                if (G.dbg & 8) {
 #pragma unroll
-                for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
-                    tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[b]);
+                    for (int r0 = NB - kC4BoxRows; r0 >= 0; r0 -= kC4BoxRows)
+                        tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[b]);
+                } else {
+#pragma unroll
+                    for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
+                        tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[b]);
+                }
             }
         }
         return;
@@ -805,7 +812,7 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
         const unsigned int b = j & 1;
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
         if (MODE == 0) {
-            if (j % kReseed == 0) {
+            if (j % kReseed == 0 || (G.dbg & 1)) {
                 const unsigned int cc = c0 + c;
                 t0 = tw_L(lo, hi, 2ull * ((unsigned int)g * cc));
                 d0 = tw_L(lo, hi, 2ull * (64u * cc));
@@ -824,6 +831,11 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
             double2 v[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) v[t] = Lb[c4_unit_l(g + t * NB8, c)];
+            if (MODE == 0 && (G.dbg & 2)) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (g + t * NB8 >= edge_row) v[t] = make_double2(0.0, 0.0);
+            }
             if (MODE == 0) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t)
@@ -866,12 +878,14 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
                 dft8<DIR>(r);
             else
                 dft6<DIR>(r);
-            // The values are in registers: this warp is done with the landing buffer.  Its own writes to the buffer (middle
-            // pass) were read back by the whole group after a barrier, so they are performed; the release/acquire pair on
-            // `empty` orders the producer's next TMA box behind them.  (A fence.proxy.async here compiles to MEMBAR.ALL.CTA
-            // + FENCE.VIEW.ASYNC per thread and tile and showed up as a drain in r2h.)
+            // This warp is done with the landing buffer once its loads have RETURNED: the arrival takes a butterfly output
+            // (a function of every loaded value) as an operand, so it cannot be issued while a load of the warp is still
+            // queued in the load/store unit.  The warp's own writes to the buffer (middle pass) were read back by the whole
+            // group after a barrier, so they are performed; the release/acquire pair on `empty` orders the producer's next
+            // TMA box behind them.  (fence.proxy.async here = MEMBAR.ALL.CTA per thread and tile: a drain in r2h.)
+            if (G.dbg & 4) fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[b]);
+            if (lane == 0) mbar_arrive_after(&empty[b], r[0].x + r[R - 1].y);
             store_group(a, c0 + c, gg, r, t0, d0);
         }
         // no barrier: the next tile's pass 1 writes S, last read by this group before its second barrier above
@@ -1367,6 +1381,10 @@ static int make_geom(long long n, long long ncorr, FftGeom* g)
     g->x_stride = n;
     g->out_stride = ncorr;
     g->three = 0;
+    {
+        const char* ed = getenv("ACFB200_FFT_DBG");
+        g->dbg = ed ? atoi(ed) : 0;
+    }
     // 3 * 2^(lq-2) lies between 2^(lq-1) (< need) and 2^lq
     const int a3 = lq - 2, rest = a3 - 8;  // rest = log2(N2 * N3)
     if (a3 >= 8 && 3ll << a3 >= need && three_allowed() && ((rest >= 7 && rest <= 9) || (rest >= 12 && rest <= 18))) {
@@ -1505,10 +1523,12 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     }
     auto pgrid = [sms](long long tiles) { return (unsigned)(tiles < sms ? tiles : sms); };
     // 512- and 384-row column passes: the tensor-map TMA kernels (col_pass4_kernel); ACFB200_FFT_COL4=0 keeps col_pass2
+    // (a digit 1..7 selects passes: bit 0 forward axis 1, bit 1 the middle passes, bit 2 inverse axis 1)
     const char* env4 = getenv("ACFB200_FFT_COL4");
-    const bool col4 = pipelined && !(env4 && env4[0] == '0');
-    const bool axis1_c4 = col4 && g.b1 > 0 && (g.three || g.b1 == 9) && g.b2 + g.b3 >= 3;
-    const bool axis2_c4 = col4 && g.b2 == 9;
+    const int c4mask = !pipelined ? 0 : (env4 && env4[0] >= '0' && env4[0] <= '7') ? env4[0] - '0' : 7;
+    const bool axis1_ok = g.b1 > 0 && (g.three || g.b1 == 9) && g.b2 + g.b3 >= 3;
+    const bool fwd1_c4 = (c4mask & 1) && axis1_ok, inv1_c4 = (c4mask & 4) && axis1_ok;
+    const bool axis2_c4 = (c4mask & 2) && g.b2 == 9;
     CUtensorMap tm;
     const size_t smem2 = (size_t)(2 * kTileElems + 512) * 16;  // two tile buffers + butterfly twiddles
     auto tc_for = [](int b, long long C) {
@@ -1520,7 +1540,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
         // MODE 0 reads the caller's real series: rows of 2C doubles, only the full rows are in the tensor map
-        if (axis1_c4 && make_col_tensor_map(&tm, d_x, 2ull * C, (unsigned long long)(n / (2 * C)), nb, x_stride))
+        if (fwd1_c4 && make_col_tensor_map(&tm, d_x, 2ull * C, (unsigned long long)(n / (2 * C)), nb, x_stride))
             col4_select(0, g.three)<<<dim3(pgrid(C >> 3), nb, 1), kC4Threads, kC4SmemBytes, st>>>(
                 tm, data, d_x, nullptr, g, g.b2 + g.b3, 1, lo, hi);
         else if (g.three)
@@ -1582,7 +1602,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     if (g.b1 > 0) {
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
-        if (axis1_c4 && make_col_tensor_map(&tm, data, 2ull * C, (unsigned long long)N1, nb, 2ull * g.Nc))
+        if (inv1_c4 && make_col_tensor_map(&tm, data, 2ull * C, (unsigned long long)N1, nb, 2ull * g.Nc))
             col4_select(3, g.three)<<<dim3(pgrid(C >> 3), nb, 1), kC4Threads, kC4SmemBytes, st>>>(
                 tm, data, nullptr, d_out, g, g.b2 + g.b3, 1, lo, hi);
         else if (g.three)
