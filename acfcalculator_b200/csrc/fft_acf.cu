@@ -34,7 +34,7 @@ struct FftGeom {
     int three;        // L = 3 * 2^a: the first axis carries the factor 3 (radix 8 x 8 x 6), the others are powers of two
     int n1;           // N1 (1 when absent)
     int q;            // log2(Nc) (power-of-two transforms only)
-    int dbg;          // ACFB200_FFT_DBG bits (experiments on the TMA column pass; 0 in production)
+    int zero;         // always 0, but only the host knows it: lets a kernel tie one instruction to another (mbar_arrive_after)
     long long Nc, L;
     long long n, ncorr;
     long long x_stride, out_stride;  // batch: series b starts at x + b*x_stride, its lags go to out + b*out_stride
@@ -681,15 +681,9 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
                 const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
                 mbar_expect_tx(&full[b], (uint32_t)(TILE * 16));
                 double2* dst = L0 + b * 4096;
-                if (G.dbg & 8) {
 #pragma unroll
-                    for (int r0 = NB - kC4BoxRows; r0 >= 0; r0 -= kC4BoxRows)
-                        tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[b]);
-                } else {
-#pragma unroll
-                    for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
-                        tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[b]);
-                }
+                for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
+                    tma_load_3d(dst + r0 * 8, &tmap, (int)(2 * c0), (int)(a * NB + r0), batch, &full[b]);
             }
         }
         return;
@@ -812,7 +806,7 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
         const unsigned int b = j & 1;
         const unsigned int a = tile >> tiles_c_log, c0 = (tile & c_mask) << 3;
         if (MODE == 0) {
-            if (j % kReseed == 0 || (G.dbg & 1)) {
+            if (j % kReseed == 0) {
                 const unsigned int cc = c0 + c;
                 t0 = tw_L(lo, hi, 2ull * ((unsigned int)g * cc));
                 d0 = tw_L(lo, hi, 2ull * (64u * cc));
@@ -831,11 +825,6 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
             double2 v[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) v[t] = Lb[c4_unit_l(g + t * NB8, c)];
-            if (MODE == 0 && (G.dbg & 2)) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (g + t * NB8 >= edge_row) v[t] = make_double2(0.0, 0.0);
-            }
             if (MODE == 0) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t)
@@ -883,9 +872,8 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
             // queued in the load/store unit.  The warp's own writes to the buffer (middle pass) were read back by the whole
             // group after a barrier, so they are performed; the release/acquire pair on `empty` orders the producer's next
             // TMA box behind them.  (fence.proxy.async here = MEMBAR.ALL.CTA per thread and tile: a drain in r2h.)
-            if (G.dbg & 4) fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive_after(&empty[b], r[0].x + r[R - 1].y);
+            if (lane == 0) mbar_arrive_after(&empty[b], r[0].x + r[R - 1].y, G.zero);
             store_group(a, c0 + c, gg, r, t0, d0);
         }
         // no barrier: the next tile's pass 1 writes S, last read by this group before its second barrier above
@@ -1381,10 +1369,7 @@ static int make_geom(long long n, long long ncorr, FftGeom* g)
     g->x_stride = n;
     g->out_stride = ncorr;
     g->three = 0;
-    {
-        const char* ed = getenv("ACFB200_FFT_DBG");
-        g->dbg = ed ? atoi(ed) : 0;
-    }
+    g->zero = 0;
     // 3 * 2^(lq-2) lies between 2^(lq-1) (< need) and 2^lq
     const int a3 = lq - 2, rest = a3 - 8;  // rest = log2(N2 * N3)
     if (a3 >= 8 && 3ll << a3 >= need && three_allowed() && ((rest >= 7 && rest <= 9) || (rest >= 12 && rest <= 18))) {
