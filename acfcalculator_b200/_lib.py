@@ -65,6 +65,7 @@ SIGNATURES = {
     "acfb200_green_kubo": (C.c_int, [_PP, C.c_int, _I64, _I64, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "acfb200_lag_sums_device": (C.c_int, [C.c_void_p, _I64, _I64, _I64, C.c_void_p, C.c_void_p]),
+    "acfb200_lag_sums_blocks": (C.c_int, [_PP, _PI64, _PI64, C.c_int, _I64, C.c_void_p]),
     "acfb200_normalise_device": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p, C.c_void_p]),
     "acfb200_calc_correlation_device": (C.c_int, [C.c_void_p, _I64, _I64, C.c_void_p, C.c_void_p]),
     "acfb200_calc_correlation_batch_device": (C.c_int, [_PP, _PI64, _PI64, C.c_int, _I64, C.c_void_p, C.c_int,

@@ -318,6 +318,21 @@ def lag_sums_device(x, ncorr, i_end=None, out=None, stream=None):
     return out
 
 
+def lag_sums_blocks(blocks, i_end, ncorr, out=None):
+    """Raw lag sums of host-resident time blocks (numpy arrays, block + halo each) -> device tensor [len(blocks), ncorr];
+    uploads pipelined with the lag kernels inside the library.  The sums are complete when this returns."""
+    import torch
+    arrs = [_f64(b) for b in blocks]
+    ns = len(arrs)
+    ptrs = (C.c_void_p * ns)(*[a.ctypes.data for a in arrs])
+    lens = (C.c_int64 * ns)(*[a.size for a in arrs])
+    ie = (C.c_int64 * ns)(*[int(v) for v in i_end])
+    if out is None:
+        out = torch.empty((ns, int(ncorr)), dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+    check(_lib.load().acfb200_lag_sums_blocks(ptrs, lens, ie, ns, int(ncorr), C.c_void_p(out.data_ptr())))
+    return out
+
+
 def normalise_device(sums, n_total, out=None, stream=None):
     import torch
     _check_dev(sums)

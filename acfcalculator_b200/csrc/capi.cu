@@ -399,7 +399,7 @@ int acfb200_describe_plan(int64_t n, int64_t ncorr, int nseries, char* buf, int 
 // -------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // -------------------------------------------------------------------------------------------------
-static bool pipelined_eligible(const int64_t* n, int nseries, long long ncorr);
+bool pipelined_eligible(const int64_t* n, int nseries, long long ncorr);
 static int calc_correlation_pipelined(Workspace* ws, const double* const* y, const int64_t* n, int nseries,
                                       long long ncorr, double* corr);
 
@@ -446,7 +446,7 @@ int acfb200_calc_correlation_batch(const double* const* y, const int64_t* n, int
 // sums of all pieces lie back to back and are folded by one reduce launch in fixed order, as for a single launch.
 // Several series go one after the other: the upload of series s+1 runs under the kernels of series s.
 // Everything is only ENQUEUED here (compute stream + copy stream); the caller synchronises and then destroys `events`.
-static bool pipelined_eligible(const int64_t* n, int nseries, long long ncorr)
+bool pipelined_eligible(const int64_t* n, int nseries, long long ncorr)
 {
     if (g_method != 0 || nseries < 1 || nseries > 16 || ncorr < 1) return false;
     for (int s = 0; s < nseries; ++s)
@@ -454,8 +454,10 @@ static bool pipelined_eligible(const int64_t* n, int nseries, long long ncorr)
     return true;
 }
 
-static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_t* n, int nseries, long long ncorr,
-                             double* d_out, std::vector<cudaEvent_t>& events)
+// i_end (nullable: whole series): series s is a time block that owns the first elements [0, i_end[s]) and carries a halo
+// up to n[s]; normalise = 0 leaves the raw lag sums (they are combined across blocks before the divide).
+int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_t* n, const int64_t* i_end, int nseries,
+                      long long ncorr, double* d_out, int normalise, std::vector<cudaEvent_t>& events)
 {
     const int kMaxPieces = 6;
     cudaStream_t st = ws->stream;
@@ -471,14 +473,15 @@ static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_
     };
     size_t series_off = 0;
     for (int s = 0; s < nseries; ++s) {
-        const long long ns = n[s];
-        long long unit = (ns / 31 + 1) & ~1ll;
+        const long long ns = n[s];                      // samples present (block + halo)
+        const long long ie = i_end ? i_end[s] : ns;     // first elements owned
+        long long unit = (ie / 31 + 1) & ~1ll;
         if (unit < 4 * ncorr) unit = (4 * ncorr + 1) & ~1ll;  // a piece much shorter than its halo is all overhead
         long long bounds[kMaxPieces + 1] = {0};
         int np = 0;
-        for (long long w = 1; np < kMaxPieces && bounds[np] < ns; w *= 2) {
+        for (long long w = 1; np < kMaxPieces && bounds[np] < ie; w *= 2) {
             long long e = bounds[np] + w * unit;
-            if (np == kMaxPieces - 1 || e + unit / 2 >= ns) e = ns;
+            if (np == kMaxPieces - 1 || e + unit / 2 >= ie) e = ie;
             bounds[++np] = e;
         }
         double* d = ws->series.as<double>() + series_off;
@@ -508,7 +511,7 @@ static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_
             const long long reach = e + ncorr < ns ? e + ncorr : ns;  // last sample a pair starting in this piece can touch
             descs[p] = {d + b, reach - b, e - b};
         }
-        descs[np] = {d, ns, ns};  // the whole series, for the divide by (n - k)
+        descs[np] = {d, ns, ie};  // the whole series / block, for the divide by (n - k)
         // stream-ordered after the previous series' reduce, which was the last reader of this descriptor block
         ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * descs.size(), cudaMemcpyHostToDevice, st));
         // The pieces are independent launches (disjoint partial sums): they alternate between two compute streams so
@@ -549,7 +552,7 @@ static int enqueue_pipelined(Workspace* ws, const double* const* y, const int64_
         DirectPlan all = plans[0];
         all.chunks = (int)chunks_total;
         ACF_TRY(launch_reduce_partials(all, ws->desc.as<SeriesDesc>() + np, 1, ncorr, ws->partials.as<double>(),
-                                       d_out + (size_t)s * ncorr, 1, st));
+                                       d_out + (size_t)s * ncorr, normalise, st));
         g_launches += 1;
     }
     return 0;
@@ -561,7 +564,7 @@ static int calc_correlation_pipelined(Workspace* ws, const double* const* y, con
 {
     ACF_TRY(ws->out.ensure((size_t)nseries * ncorr * 8));
     std::vector<cudaEvent_t> events;
-    int rc = enqueue_pipelined(ws, y, n, nseries, ncorr, ws->out.as<double>(), events);
+    int rc = enqueue_pipelined(ws, y, n, nullptr, nseries, ncorr, ws->out.as<double>(), 1, events);
     cudaError_t e = cudaSuccess;
     if (rc == 0)
         e = cudaMemcpyAsync(corr, ws->out.p, (size_t)nseries * ncorr * 8, cudaMemcpyDeviceToHost, ws->stream);
@@ -571,6 +574,62 @@ static int calc_correlation_pipelined(Workspace* ws, const double* const* y, con
     if (rc == 0 && (e != cudaSuccess || es != cudaSuccess)) {
         set_error("pipelined calc_correlation failed: %s", cudaGetErrorString(e != cudaSuccess ? e : es));
         rc = ACFB200_ERR_CUDA;
+    }
+    return rc;
+}
+
+}  // extern "C"
+
+namespace acfb200 {
+// Raw lag sums of host-resident time blocks into device memory, everything only enqueued on the workspace streams:
+// long blocks are uploaded in pieces under their own lag kernels, short ones in one go.  `events` must outlive the work.
+int lag_sums_blocks_enqueue(Workspace* ws, const double* const* y, const int64_t* n, const int64_t* i_end,
+                                     int nseries, long long ncorr, double* d_sums, std::vector<cudaEvent_t>& events)
+{
+    if (pipelined_eligible(i_end, nseries, ncorr)) return enqueue_pipelined(ws, y, n, i_end, nseries, ncorr, d_sums, 0, events);
+    cudaStream_t st = ws->stream;
+    size_t total = 0;
+    for (int s = 0; s < nseries; ++s) total += even_up(n[s] > 0 ? n[s] : 1);
+    ACF_TRY(ws->series.ensure(total * 8));
+    std::vector<SeriesDesc> descs(nseries);
+    size_t off = 0;
+    for (int s = 0; s < nseries; ++s) {
+        double* d = ws->series.as<double>() + off;
+        if (n[s] > 0) ACF_CUDA_OK(cudaMemcpyAsync(d, y[s], (size_t)n[s] * 8, cudaMemcpyHostToDevice, st));
+        descs[s] = {d, n[s] > 0 ? (long long)n[s] : 0, (long long)i_end[s]};
+        off += even_up(n[s] > 0 ? n[s] : 1);
+    }
+    return run_direct(ws, descs, ncorr, d_sums, 0, st);
+}
+
+}  // namespace acfb200
+
+extern "C" {
+
+int acfb200_lag_sums_blocks(const double* const* y, const int64_t* n, const int64_t* i_end, int nseries, int64_t ncorr,
+                            double* d_sums)
+{
+    Lock lk(g_mu);
+    if (!y || !n || !i_end || !d_sums || nseries < 1 || ncorr < 1) {
+        set_error("lag_sums_blocks: null argument, nseries < 1 or ncorr < 1");
+        return ACFB200_ERR_ARG;
+    }
+    for (int s = 0; s < nseries; ++s)
+        if (!y[s] || n[s] < 0 || i_end[s] < 0 || i_end[s] > n[s]) {
+            set_error("lag_sums_blocks: block %d needs a pointer and 0 <= i_end <= n (n=%lld i_end=%lld)", s, (long long)n[s],
+                      (long long)i_end[s]);
+            return ACFB200_ERR_ARG;
+        }
+    Workspace* ws;
+    ACF_TRY(get_ws(&ws));
+    std::vector<cudaEvent_t> events;
+    const int rc = lag_sums_blocks_enqueue(ws, y, n, i_end, nseries, ncorr, d_sums, events);
+    const cudaError_t e1 = cudaStreamSynchronize(ws->stream), e2 = cudaStreamSynchronize(ws->stream2),
+                      e3 = cudaStreamSynchronize(ws->copy_stream);
+    for (auto& ev : events) cudaEventDestroy(ev);
+    if (rc == 0 && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+        set_error("lag_sums_blocks failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+        return ACFB200_ERR_CUDA;
     }
     return rc;
 }
@@ -887,7 +946,7 @@ int acfb200_green_kubo(const double* const* comps, int ncomp, int64_t n, int64_t
     std::vector<int64_t> lens(ncomp, n);
     if (pipelined_eligible(lens.data(), ncomp, ncorr)) {
         // long components: component c+1 uploads under the kernels of component c
-        const int rc = enqueue_pipelined(ws, comps, lens.data(), ncomp, ncorr, d_o, events);
+        const int rc = enqueue_pipelined(ws, comps, lens.data(), nullptr, ncomp, ncorr, d_o, 1, events);
         if (rc != 0) {
             cudaStreamSynchronize(st);
             cudaStreamSynchronize(ws->copy_stream);

@@ -144,6 +144,10 @@ inline size_t even_up(long long n) { return (size_t)((n + 1) & ~1ll); }
 int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long long ncorr, double* d_out, int normalise,
                cudaStream_t st);
 int check_common(const void* p, long long n, long long ncorr, const char* what);
+// Raw lag sums of host-resident time blocks (block + halo each) into device memory, enqueued on ws->stream (plus the
+// copy stream / second compute stream when the blocks are long enough to pipeline); capi.cu
+int lag_sums_blocks_enqueue(Workspace* ws, const double* const* y, const int64_t* n, const int64_t* i_end, int nseries,
+                            long long ncorr, double* d_sums, std::vector<cudaEvent_t>& events);
 int pipeline_batch_device(Workspace* ws, const double* const* d_series, const int64_t* n, int nw, long long ncorr,
                           double dt, double cutoff, double* d_acf, double* d_vacf, acfb200_result* res, cudaStream_t st);
 

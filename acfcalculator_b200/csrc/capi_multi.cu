@@ -39,6 +39,9 @@ std::mutex g_nccl_mu;
 int nccl_clique(int ndev, NcclApi** out)
 {
     if (!g_nccl.lib) {
+        // NCCL writes its version banner / debug log to stdout unless told otherwise; stdout is the front-ends' result
+        // stream (viscosity prints its table there), so an unset NCCL_DEBUG_FILE is pointed at stderr
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
             g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (g_nccl.lib) break;
@@ -270,37 +273,28 @@ int acfb200_multi_gpu_calc_correlation(const double* const* y, const int64_t* n,
         NcclApi* nccl = nullptr;
         ACF_TRY(nccl_clique(ndev, &nccl));
         std::vector<double*> sums(ndev, nullptr);
+        std::vector<std::vector<cudaEvent_t>> pending(ndev);   // events of the pipelined uploads, destroyed after the sync
         rc = for_each_device_exchange(
             ndev,
             // prepare: block + halo of every series, back to back, and the raw lag sums of the block
             [&](int d) -> int {
                 Workspace* ws;
                 ACF_TRY(get_ws(&ws));
-                cudaStream_t st = ws->stream;
-                std::vector<SeriesDesc> descs(nseries);
-                size_t total = 0;
-                std::vector<long long> lo(nseries), len(nseries);
+                // block d of every series: first elements [b, e), samples up to e + ncorr - 1 (the halo)
+                std::vector<const double*> py(nseries);
+                std::vector<int64_t> pn(nseries), pi(nseries);
                 for (int s = 0; s < nseries; ++s) {
                     const long long b = n[s] * d / ndev, e = n[s] * (d + 1) / ndev;
                     long long reach = e + ncorr - 1;
                     if (reach > n[s]) reach = n[s];
-                    lo[s] = b;
-                    len[s] = reach - b;
-                    total += even_up(len[s] > 0 ? len[s] : 1);
+                    py[s] = y[s] + b;
+                    pn[s] = reach - b > 0 ? reach - b : 0;
+                    pi[s] = e - b;
                 }
-                ACF_TRY(ws->series.ensure(total * 8));
                 ACF_TRY(ws->out.ensure((size_t)nseries * ncorr * 8));
-                size_t off = 0;
-                for (int s = 0; s < nseries; ++s) {
-                    double* dst = ws->series.as<double>() + off;
-                    const long long e = n[s] * (d + 1) / ndev;
-                    if (len[s] > 0)
-                        ACF_CUDA_OK(cudaMemcpyAsync(dst, y[s] + lo[s], (size_t)len[s] * 8, cudaMemcpyHostToDevice, st));
-                    descs[s] = {dst, len[s] > 0 ? len[s] : 0, e - lo[s]};
-                    off += even_up(len[s] > 0 ? len[s] : 1);
-                }
                 sums[d] = ws->out.as<double>();
-                ACF_TRY(run_direct(ws, descs, ncorr, sums[d], 0, st));
+                // uploads in pieces under the lag kernels when the blocks are long (config 4: 150 MB per device at 8 GPUs)
+                ACF_TRY(lag_sums_blocks_enqueue(ws, py.data(), pn.data(), pi.data(), nseries, ncorr, sums[d], pending[d]));
                 return 0;
             },
             // exchange: ONE all-reduce of the lag sums, the divide after the sum on device 0
@@ -328,6 +322,11 @@ int acfb200_multi_gpu_calc_correlation(const double* const* y, const int64_t* n,
                 return 0;
             });
         nccl_forget_if_broken();
+        for (int d = 0; d < ndev; ++d) {
+            if (pending[d].empty()) continue;
+            cudaSetDevice(d);
+            for (auto& ev : pending[d]) cudaEventDestroy(ev);
+        }
     }
     cudaSetDevice(home);
     return rc;

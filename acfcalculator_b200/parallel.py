@@ -77,42 +77,20 @@ def time_block_correlation_batch(blocks, i_count, n_total, m, batch_fn, normalis
     return torch.stack([normalise_fn(sums[c], n_total) for c in range(sums.shape[0])])
 
 
-_copy_streams = {}
-
-
 def time_block_correlation_batch_host(h_blocks, i_count, n_total, m, stream=None, group=None):
     """Host-buffer form of time_block_correlation_batch for one process per GPU: `h_blocks` are this rank's time blocks
-    (block + halo) of several series in host memory (numpy arrays or CPU tensors; pinned memory makes the copies
-    asynchronous).  Series c+1 is uploaded on a copy stream while the lag kernel of series c runs; then ONE all-reduce
-    of [len(h_blocks), m] doubles and the divide by (n_total - k).  Returns corr [C, m] on the device (same on every
-    rank); the caller's .cpu() is the device-to-host read."""
-    import numpy as np
+    (block + halo) of several series in host memory (numpy arrays; pinned memory makes the copies asynchronous).  The
+    library uploads every block in pieces under its own lag kernels (acfb200_lag_sums_blocks), then ONE all-reduce of
+    [len(h_blocks), m] doubles and the divide by (n_total - k).  Returns corr [C, m] on the device (same on every rank);
+    the caller's .cpu() is the device-to-host read."""
     from . import api
-    dev = torch.device("cuda", torch.cuda.current_device())
     st = torch.cuda.current_stream() if stream is None else stream
-    copy = _copy_streams.get(dev.index)
-    if copy is None:
-        copy = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
-    nser = len(h_blocks)
-    sums = torch.empty((nser, int(m)), dtype=torch.float64, device=dev)
-    copy.wait_stream(st)
-    staged = []
-    for h in h_blocks:
-        t = torch.from_numpy(h) if isinstance(h, np.ndarray) else h
-        with torch.cuda.stream(copy):
-            d = t.to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy)
-        d.record_stream(st)
-        staged.append((d, ev))
-    for c, (d, ev) in enumerate(staged):
-        st.wait_event(ev)
-        api.lag_sums_device(d, int(m), i_end=int(i_count), out=sums[c], stream=st)
+    sums = api.lag_sums_blocks(h_blocks, [int(i_count)] * len(h_blocks), int(m))   # complete on return
     _, world = world_info(group)
     if world > 1:
         with torch.cuda.stream(st):
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    return torch.stack([api.normalise_device(sums[c], n_total, stream=st) for c in range(nser)])
+    return torch.stack([api.normalise_device(sums[c], n_total, stream=st) for c in range(len(h_blocks))])
 
 
 def gather_results(local, nitems, group=None):

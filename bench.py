@@ -387,7 +387,7 @@ def build_workload(env, name, n, m, world=None, rank=None, windows=0):
                                                np.max(np.abs(hv[0] - o["vacf"])) / o["var_vel"],
                                                abs(hr[0]["diffusivity"] - d_ref) / abs(d_ref)))
             return out
-        w.update(step=step, e2e_step=e2e_step if mine else None, parity=parity if mine else None)
+        w.update(step=step, e2e_step=e2e_step if mine else None, parity=parity if mine else None, pinned=h_w)
     elif name == "viscosity":
         from acfcalculator_b200 import parallel as P
         comps = int(wl["comps"])
@@ -455,7 +455,7 @@ def build_workload(env, name, n, m, world=None, rank=None, windows=0):
                     worst_e2e = max(worst_e2e or 0.0, float(np.max(np.abs(res["e2e_corr"][c][lags] - ref)) / abs(ref[0])))
             return {"components": comps, "lags_checked": int(lags.size) * comps, "max_rel_to_c0": worst,
                     "e2e_max_rel_to_c0": worst_e2e, "oracle": "calc_correlation_lags on the full series (rank 0)"}
-        w.update(step=step, e2e_step=e2e_step, parity=parity if keep_full else None)
+        w.update(step=step, e2e_step=e2e_step, parity=parity if keep_full else None, pinned=h_b)
     elif name == "msd":
         axes = walk_xyz(n, 20260401 + rank)
         h_a = [env.pin(a) for a in axes]
@@ -649,6 +649,27 @@ def sub_record(env, name, n, m, steps, peak_tf, peaks, with_auto=False):
     return rec, w
 
 
+def concurrent_h2d(env, pinned, reps=5):
+    """All ranks copy their step's pinned inputs to their GPU at the same time (plain cudaMemcpyAsync, nothing else
+    running): the host link as the end-to-end path sees it when every process of the box pulls at once."""
+    torch = env.torch
+    if not pinned:
+        return None
+    dst = [torch.empty_like(h, device=env.dev) for h in pinned]
+    nbytes = sum(h.numel() * 8 for h in pinned)
+    for d, h in zip(dst, pinned):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for d, h in zip(dst, pinned):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+    dt = env.max_over_ranks((time.perf_counter() - t0) / reps)
+    return {"bytes_per_rank": int(nbytes), "ms": dt * 1e3, "gb_per_s_per_rank": nbytes / dt / 1e9, "ranks": env.world}
+
+
 def multi_gpu_record(env, name, n, m, steps, peak_tf, peaks):
     """A strong-scaling workload on all ranks, next to the SAME job on rank 0 alone in the same run."""
     torch = env.torch
@@ -656,6 +677,7 @@ def multi_gpu_record(env, name, n, m, steps, peak_tf, peaks):
     t = time_device(env, w, steps, 3)
     e2e = time_e2e(env, w, steps)
     parity = w["parity"]() if (w["parity"] and env.rank == 0) else None
+    h2d = concurrent_h2d(env, w.get("pinned"))
     rec = {"workload": w["desc"], "n": n, "maxcorr": m, "steps": steps, "n_gpus": env.world, "scaling": w["scaling"],
            "ms_per_step": t["ms_per_step"], "value": w["total_products"] / (t["ms_per_step"] * 1e-3),
            "unit": metric_of(name)[1], "gpu_launches_rank0": t["launches"], "plan_rank0": w["plan"], "e2e": e2e,
@@ -664,6 +686,12 @@ def multi_gpu_record(env, name, n, m, steps, peak_tf, peaks):
            if name == "viscosity" else "none (independent windows)"}
     if name == "viscosity":
         rec["allreduce_bytes"] = w["allreduce_bytes"]
+    if h2d and e2e:
+        # what bounds the end-to-end step: the larger of the device time and the time the host link needs for this step's
+        # inputs when every rank pulls at once, plus whatever of the first transfer cannot hide behind a kernel
+        rec["h2d_all_ranks_concurrent"] = h2d
+        rec["e2e_limit"] = ("host link (%.1f GB/s per rank with %d ranks pulling)" % (h2d["gb_per_s_per_rank"], env.world)
+                            if h2d["ms"] > 0.8 * rec["ms_per_step"] else "device time + first exposed transfer")
     del w
     torch.cuda.empty_cache()
     env.barrier()

@@ -151,6 +151,14 @@ ACFB200_API int acfb200_acf_pipeline_batch_device(const double* const* d_series,
                                       double dt, double cutoff, double* d_acf, double* d_vacf, acfb200_result* result,
                                       void* stream);
 
+/* Raw lag sums of HOST-resident time blocks into DEVICE memory (the per-process building block of time-block sharding,
+ * SURVEY.md section 8e): block s is y[s][0, n[s]) = the first elements [0, i_end[s]) it owns plus its halo;
+ * d_sums[s][k] = sum_{i < i_end[s], i + k < n[s]} y[s][i] * y[s][i+k] for k < ncorr, on the current device.  Long blocks are
+ * uploaded in pieces under their own lag kernels.  Returns when the sums are complete; the caller combines them across
+ * processes (one all-reduce) and divides with acfb200_normalise_device (ACFcalculator.cpp:139-143 after the sum). */
+ACFB200_API int acfb200_lag_sums_blocks(const double* const* y, const int64_t* n, const int64_t* i_end, int nseries,
+                                        int64_t ncorr, double* d_sums);
+
 /* ---- several GPUs of one box, one process (one host thread per device) ----------------------------------------
  * nseries >= devices: series s on device s mod G, no communication.  Fewer series: every series is cut into G time
  * blocks (block g plus its (ncorr-1)-sample halo on device g), raw lag sums per block, ONE ncclAllReduce(sum) of

@@ -103,6 +103,7 @@ def test_green_kubo_and_viscosity_cli(acf, oracle, ngpus, tmp_path):
     one = subprocess.run([exe, log], capture_output=True, text=True)
     many = subprocess.run([exe, log, "--gpus", str(ngpus)], capture_output=True, text=True)
     assert one.returncode == 0 and many.returncode == 0, many.stderr
+    assert "NCCL" not in many.stdout          # the collective library's log must not leak into the result stream
     assert len(one.stdout.splitlines()) == len(many.stdout.splitlines())
     assert one.stdout.splitlines()[-1].split()[:2] == many.stdout.splitlines()[-1].split()[:2]
     # component selection on several GPUs: three components on >= 2 devices (time blocks when G > 3)
