@@ -161,14 +161,22 @@ def acf_pipeline(series, nCorr, timestep, cutoff=0.0):
     return d
 
 
-def acf_pipeline_batch(windows, nCorr, timestep, cutoff=0.0):
-    """setup.sh-style windows in one call -> (acf [W,nCorr], vacf [W,nCorr], [dict per window])."""
+def acf_pipeline_batch(windows, nCorr, timestep, cutoff=0.0, out=None):
+    """setup.sh-style windows in one call -> (acf [W,nCorr], vacf [W,nCorr], [dict per window]).
+    out: optional (acf, vacf) float64 arrays of shape [W, nCorr] to receive the lags (page-locked ones -- numpy views of
+    pinned torch tensors -- are filled by the device directly, without staging)."""
     arrs = [_f64(s) for s in windows]
     nw = len(arrs)
     ptrs = (C.c_void_p * nw)(*[a.ctypes.data for a in arrs])
     lens = (C.c_int64 * nw)(*[a.size for a in arrs])
-    acf = np.empty((nw, int(nCorr)), dtype=np.float64)
-    vacf = np.empty((nw, int(nCorr)), dtype=np.float64)
+    if out is None:
+        acf = np.empty((nw, int(nCorr)), dtype=np.float64)
+        vacf = np.empty((nw, int(nCorr)), dtype=np.float64)
+    else:
+        acf, vacf = out
+        for a in (acf, vacf):
+            if a.dtype != np.float64 or a.shape != (nw, int(nCorr)) or not a.flags.c_contiguous:
+                raise ValueError("out arrays must be C-contiguous float64 of shape [windows, nCorr]")
     res = (Result * nw)()
     check(_lib.load().acfb200_acf_pipeline_batch(ptrs, lens, nw, int(nCorr), float(timestep), float(cutoff),
                                                  _vp(acf), _vp(vacf), res))

@@ -763,15 +763,31 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
     // group's results to the caller's arrays while the later groups are still computing.
     // group boundaries 0, 1, 2, 4, 8, 16, ... windows: the only exposed transfer is the first window's
     // (small batches -- setup.sh's 80 windows of 5001 samples -- go as one group: there is no transfer worth hiding)
+    // ... and no group beyond 16 windows: what follows the LAST group's kernels (its results' way to the caller) is exposed
     std::vector<int> gbeg(1, 0);
     if (nwindows >= 4 && total * 8 >= ((size_t)32 << 20))
-        for (int e = 1; e < nwindows; e *= 2) gbeg.push_back(e);
+        for (int e = 1, step = 1; e < nwindows; e += step) {
+            gbeg.push_back(e);
+            if (e >= 2 * step && step < 16) step *= 2;
+        }
     gbeg.push_back(nwindows);
     const int ngroups = (int)gbeg.size() - 1;
     std::vector<cudaEvent_t> landed(ngroups, nullptr), done(ngroups, nullptr);
     const bool want_lags = acf || vacf;
-    const size_t lag_doubles = want_lags ? (size_t)2 * nwindows * ncorr : 0;
-    const bool staged = lag_doubles * 8 <= ((size_t)1 << 30);   // beyond 1 GiB: copy straight to the caller (blocking)
+    // page-locked caller arrays take the lags straight from the device (asynchronous, nothing to unpack); pageable ones
+    // go through page-locked staging -- beyond 1 GiB of it, straight to the caller with blocking copies
+    auto page_locked = [](const void* p) {
+        if (!p) return true;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool direct_out = want_lags && page_locked(acf) && page_locked(vacf);
+    const size_t lag_doubles = (want_lags && !direct_out) ? (size_t)2 * nwindows * ncorr : 0;
+    const bool staged = want_lags && !direct_out && lag_doubles * 8 <= ((size_t)1 << 30);
     int rc = ws->pinned.ensure((PipelineStage::doubles(nwindows) + (staged ? lag_doubles : 0)) * 8);
     if (rc != 0) return rc;
     double* h_scal = ws->pinned.as<double>();
