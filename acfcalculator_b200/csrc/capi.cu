@@ -2,6 +2,8 @@
 // No CPU fallback lives here: every compute entry point needs a CUDA device and says so when it fails.
 // (traj2diffusion entry points: capi_msd.cu; multi-GPU entry points: capi_multi.cu; shared internals: capi_internal.cuh)
 
+#include <chrono>
+
 #include "capi_internal.cuh"
 
 namespace acfb200 {
@@ -846,6 +848,11 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
             return rc;
         }
     }
+    // ACFB200_TRACE=1: host-side timeline of this call on stderr (when each group was enqueued / seen complete)
+    static const bool trace = getenv("ACFB200_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    std::vector<double> t_enq(ngroups, 0.0), t_done(ngroups, 0.0);
     std::vector<PipelineStage> stages(ngroups);
     for (int g = 0; g < ngroups && rc == 0; ++g) {
         const int w0 = gbeg[g], cnt = gbeg[g + 1] - gbeg[g];
@@ -873,6 +880,7 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
             set_error("result copy failed: %s", cudaGetErrorString(e));
             rc = ACFB200_ERR_CUDA;
         }
+        t_enq[g] = since();
     }
     // the host follows the device group by group
     for (int g = 0; g < ngroups && rc == 0; ++g) {
@@ -891,6 +899,13 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
                 if (vacf) memcpy(vacf + (size_t)w * ncorr, src + ncorr, (size_t)ncorr * 8);
             }
         if (result) pipeline_batch_collect(stages[g], n + w0, cnt, result + w0);
+        t_done[g] = since();
+    }
+    if (trace) {
+        fprintf(stderr, "acfb200 trace: pipeline_batch %d windows, %d groups:", nwindows, ngroups);
+        for (int g = 0; g < ngroups; ++g)
+            fprintf(stderr, " [%d win: enq %.3f done %.3f]", gbeg[g + 1] - gbeg[g], t_enq[g], t_done[g]);
+        fprintf(stderr, " ms\n");
     }
     cudaError_t es = cudaStreamSynchronize(st);
     cudaStreamSynchronize(ws->copy_stream);

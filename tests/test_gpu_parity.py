@@ -288,6 +288,41 @@ def test_batch_device_pipeline_equals_host_batch(acf):
     assert dres == res
 
 
+def test_pipeline_batch_page_locked_outputs(acf):
+    """acfb200_acf_pipeline_batch fills page-locked result arrays straight from the device and stages pageable ones; both
+    ways, with enough windows for several upload groups, give identical bits."""
+    import torch
+    wins = [ou_series(700_000 + 11 * w, 30.0 + w, sigma=0.25, mu=-3.0 + w, seed=900 + w) for w in range(11)]
+    a, v, res = acf.acf_pipeline_batch(wins, 600, 2.0, 0.05)
+    pa = torch.empty((11, 600), dtype=torch.float64).pin_memory()
+    pv = torch.empty((11, 600), dtype=torch.float64).pin_memory()
+    a2, v2, res2 = acf.acf_pipeline_batch(wins, 600, 2.0, 0.05, out=(pa.numpy(), pv.numpy()))
+    assert np.array_equal(a, pa.numpy()) and np.array_equal(v, pv.numpy()) and res == res2
+    one = [acf.acf_pipeline(w, 600, 2.0, 0.05) for w in wins[:3]]
+    for w in range(3):   # and the same numbers as window-by-window calls, to rounding (different launch grouping)
+        assert rel_to_c0(a[w], one[w]["acf"], one[w]["var"]) <= 1e-13 and res[w]["cutoff_index"] == one[w]["cutoff_index"]
+
+
+def test_lag_sums_blocks_host_entry(acf, oracle):
+    """acfb200_lag_sums_blocks: host time blocks (block + halo) -> raw lag sums on the device, long blocks uploaded in
+    pieces under their kernels; the blocks' sums add up to the whole series' sums (oracle.lag_sums_block)."""
+    x = ou_series(9_000_001, 120.0, sigma=3.0, seed=5)
+    m = 3000
+    cuts = [0, 4_500_000, 9_000_001]
+    blocks = [x[cuts[i]:min(x.size, cuts[i + 1] + m - 1)] for i in range(2)]
+    sums = acf.lag_sums_blocks(blocks, [cuts[1] - cuts[0], cuts[2] - cuts[1]], m).cpu().numpy()
+    total = sums[0] + sums[1]
+    lags = np.array([0, 1, 2, 17, 999, 2999])
+    ref = oracle.calc_correlation_lags(x, lags) * (x.size - lags)
+    assert np.max(np.abs(total[lags] - ref)) <= 1e-10 * ref[0]
+    for b in range(2):
+        want = oracle.lag_sums_block(x, cuts[b], cuts[b + 1], 8)
+        assert np.max(np.abs(sums[b][:8] - want)) <= 1e-12 * abs(want[0])
+    short = acf.lag_sums_blocks([x[:5000]], [4000], 700).cpu().numpy()[0]     # the un-pipelined path
+    want = oracle.lag_sums_block(x[:5000], 0, 4000, 700)
+    assert np.max(np.abs(short - want)) <= 1e-12 * abs(want[0])
+
+
 def test_method_selection_fft_and_auto(acf, oracle):
     """acfb200_set_method: the pipelines and calcCorrelation through the FFT path agree with direct summation."""
     x = ou_series(200000, 300.0, mu=2.0, seed=77)
