@@ -211,10 +211,17 @@ struct PipelineStage {
     }
 };
 
+// slot / slot_windows: the result buffers (lags, integrals, reduction scratch) hold two slots of slot_windows windows so
+// that consecutive groups of the host batch call can alternate -- group g+1 computes while group g's results are copied
+// out on `copy_st` (after the event `computed`, recorded on `st` behind the last kernel).  Single calls use slot 0 and
+// copy on `st` itself.  *d_out_slot receives the slot's [window][acf|vacf][ncorr] block.
 static int pipeline_batch_enqueue(Workspace* ws, const double* const* d_series, const int64_t* n, int nw, long long ncorr,
                                   double dt, double cutoff, double* d_acf, double* d_vacf, const PipelineStage* stage,
-                                  cudaStream_t st)
+                                  cudaStream_t st, int slot = 0, int slot_windows = 0, cudaStream_t copy_st = nullptr,
+                                  cudaEvent_t computed = nullptr, double** d_out_slot = nullptr)
 {
+    if (slot_windows < nw) slot_windows = nw;
+    if (!copy_st) copy_st = st;
     size_t total = 0;
     for (int w = 0; w < nw; ++w) {
         if (n[w] < 3) {
@@ -226,10 +233,11 @@ static int pipeline_batch_enqueue(Workspace* ws, const double* const* d_series, 
     }
     ACF_TRY(ws->y.ensure(total * 8));
     ACF_TRY(ws->vel.ensure(total * 8));
-    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch) * (size_t)nw, true));
-    ACF_TRY(ws->out.ensure((size_t)2 * nw * ncorr * 8));
-    ACF_TRY(ws->small.ensure((size_t)16 * nw));
-    ReduceScratch* sc = ws->scratch.as<ReduceScratch>();
+    const size_t slots = (size_t)slot + 1;
+    ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch) * slots * slot_windows, true));
+    ACF_TRY(ws->out.ensure(slots * 2 * slot_windows * ncorr * 8));
+    ACF_TRY(ws->small.ensure(slots * 16 * slot_windows));
+    ReduceScratch* sc = ws->scratch.as<ReduceScratch>() + (size_t)slot * slot_windows;
     std::vector<SeriesDesc> descs(2 * (size_t)nw);
     std::vector<WindowDesc> wins(nw);
     size_t off = 0;
@@ -247,20 +255,25 @@ static int pipeline_batch_enqueue(Workspace* ws, const double* const* d_series, 
     ACF_CUDA_OK(cudaMemcpyAsync(ws->wins.p, wins.data(), sizeof(WindowDesc) * (size_t)nw, cudaMemcpyHostToDevice, st));
     ACF_TRY(launch_window_prep(ws->wins.as<WindowDesc>(), nw, sc, dt, st));
     g_launches += 3;
-    double* d_o = ws->out.as<double>();  // [window][acf|vacf][ncorr]
+    double* d_o = ws->out.as<double>() + (size_t)slot * 2 * slot_windows * ncorr;  // [window][acf|vacf][ncorr]
+    if (d_out_slot) *d_out_slot = d_o;
     ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
-    double* d_small = ws->small.as<double>();
+    double* d_small = ws->small.as<double>() + (size_t)slot * 2 * slot_windows;
     ACF_TRY(launch_integrate_cutoff_batch(d_o, 2 * ncorr, nw, ncorr, dt, cutoff, d_small, st));
     g_launches += 1;
+    if (copy_st != st) {
+        ACF_CUDA_OK(cudaEventRecord(computed, st));
+        ACF_CUDA_OK(cudaStreamWaitEvent(copy_st, computed, 0));
+    }
     if (d_acf)
         ACF_CUDA_OK(cudaMemcpy2DAsync(d_acf, ncorr * 8, d_o, 2 * ncorr * 8, ncorr * 8, nw, cudaMemcpyDeviceToDevice, st));
     if (d_vacf)
         ACF_CUDA_OK(cudaMemcpy2DAsync(d_vacf, ncorr * 8, d_o + ncorr, 2 * ncorr * 8, ncorr * 8, nw,
                                       cudaMemcpyDeviceToDevice, st));
     if (stage) {
-        ACF_CUDA_OK(cudaMemcpyAsync(stage->small, d_small, (size_t)2 * nw * 8, cudaMemcpyDeviceToHost, st));
-        ACF_CUDA_OK(cudaMemcpy2DAsync(stage->means, 32, sc, sizeof(ReduceScratch), 32, nw, cudaMemcpyDeviceToHost, st));
-        ACF_CUDA_OK(cudaMemcpy2DAsync(stage->c0, 8, d_o, ncorr * 8, 8, 2 * (size_t)nw, cudaMemcpyDeviceToHost, st));
+        ACF_CUDA_OK(cudaMemcpyAsync(stage->small, d_small, (size_t)2 * nw * 8, cudaMemcpyDeviceToHost, copy_st));
+        ACF_CUDA_OK(cudaMemcpy2DAsync(stage->means, 32, sc, sizeof(ReduceScratch), 32, nw, cudaMemcpyDeviceToHost, copy_st));
+        ACF_CUDA_OK(cudaMemcpy2DAsync(stage->c0, 8, d_o, ncorr * 8, 8, 2 * (size_t)nw, cudaMemcpyDeviceToHost, copy_st));
     }
     return 0;
 }
@@ -774,7 +787,8 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
         }
     gbeg.push_back(nwindows);
     const int ngroups = (int)gbeg.size() - 1;
-    std::vector<cudaEvent_t> landed(ngroups, nullptr), done(ngroups, nullptr);
+    std::vector<cudaEvent_t> landed(ngroups, nullptr), done(ngroups, nullptr), computed(ngroups, nullptr);
+    cudaStream_t out_st = ws->stream2;
     const bool want_lags = acf || vacf;
     // page-locked caller arrays take the lags straight from the device (asynchronous, nothing to unpack); pageable ones
     // go through page-locked staging -- beyond 1 GiB of it, straight to the caller with blocking copies
@@ -799,6 +813,8 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
             if (ev) cudaEventDestroy(ev);
         for (auto& ev : done)
             if (ev) cudaEventDestroy(ev);
+        for (auto& ev : computed)
+            if (ev) cudaEventDestroy(ev);
     };
     size_t off = 0;
     for (int g = 0; g < ngroups; ++g) {
@@ -816,10 +832,12 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
         }
         cudaEventCreateWithFlags(&landed[g], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&computed[g], cudaEventDisableTiming);
         cudaEventRecord(landed[g], ws->copy_stream);
     }
     // size the device workspaces for the largest group before anything is enqueued: growing one later would mean a
     // cudaFree, i.e. a device-wide synchronisation in the middle of the pipeline
+    int slot_windows = nwindows;
     {
         int big = 0;
         for (int g = 1; g < ngroups; ++g)
@@ -833,9 +851,10 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
         }
         rc = ws->y.ensure(tot * 8);
         if (rc == 0) rc = ws->vel.ensure(tot * 8);
-        if (rc == 0) rc = ws->scratch.ensure(sizeof(ReduceScratch) * (size_t)cnt, true);
-        if (rc == 0) rc = ws->out.ensure((size_t)2 * cnt * ncorr * 8);
-        if (rc == 0) rc = ws->small.ensure((size_t)16 * cnt);
+        slot_windows = cnt;   // two result slots of the largest group's size
+        if (rc == 0) rc = ws->scratch.ensure(sizeof(ReduceScratch) * (size_t)2 * cnt, true);
+        if (rc == 0) rc = ws->out.ensure((size_t)2 * 2 * cnt * ncorr * 8);
+        if (rc == 0) rc = ws->small.ensure((size_t)2 * 16 * cnt);
         if (rc == 0) rc = ws->wins.ensure(sizeof(WindowDesc) * (size_t)cnt);
         DirectPlan plan;
         if (rc == 0 && g_method == 0 && plan_direct(longest - 2, ncorr, 2 * cnt, ws->sm_count, g_force_variant, &plan) == 0) {
@@ -858,24 +877,28 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
         const int w0 = gbeg[g], cnt = gbeg[g + 1] - gbeg[g];
         if (cnt == 0) continue;
         cudaStreamWaitEvent(st, landed[g], 0);
+        // Results leave on a stream of their own (ws->stream2) from one of two slots, so the next group's kernels do not
+        // wait for this group's device-to-host copies (a dozen small dependent operations, ~0.1 ms per group when they sat
+        // on the compute stream); a slot is reused two groups later, once its copies are done.
+        const int slot = g & 1;
+        if (g >= 2 && done[g - 2]) cudaStreamWaitEvent(st, done[g - 2], 0);
         stages[g].carve(h_scal + PipelineStage::doubles(w0), cnt);
+        double* d_o = nullptr;
         rc = pipeline_batch_enqueue(ws, d_ptr.data() + w0, n + w0, cnt, ncorr, dt, cutoff, nullptr, nullptr,
-                                    result ? &stages[g] : nullptr, st);
+                                    result ? &stages[g] : nullptr, st, slot, slot_windows, out_st, computed[g], &d_o);
         if (rc != 0) break;
-        // this group's results sit in ws->out as [window][acf|vacf][ncorr]; they leave before the next group runs
-        const double* d_o = ws->out.as<double>();
         cudaError_t e = cudaSuccess;
         if (want_lags && staged) {
-            e = cudaMemcpyAsync(h_lags + (size_t)2 * w0 * ncorr, d_o, (size_t)2 * cnt * ncorr * 8, cudaMemcpyDeviceToHost, st);
+            e = cudaMemcpyAsync(h_lags + (size_t)2 * w0 * ncorr, d_o, (size_t)2 * cnt * ncorr * 8, cudaMemcpyDeviceToHost, out_st);
         } else if (want_lags) {
             if (acf)
                 e = cudaMemcpy2DAsync(acf + (size_t)w0 * ncorr, ncorr * 8, d_o, 2 * ncorr * 8, ncorr * 8, cnt,
-                                      cudaMemcpyDeviceToHost, st);
+                                      cudaMemcpyDeviceToHost, out_st);
             if (e == cudaSuccess && vacf)
                 e = cudaMemcpy2DAsync(vacf + (size_t)w0 * ncorr, ncorr * 8, d_o + ncorr, 2 * ncorr * 8, ncorr * 8, cnt,
-                                      cudaMemcpyDeviceToHost, st);
+                                      cudaMemcpyDeviceToHost, out_st);
         }
-        if (e == cudaSuccess) e = cudaEventRecord(done[g], st);
+        if (e == cudaSuccess) e = cudaEventRecord(done[g], out_st);
         if (e != cudaSuccess) {
             set_error("result copy failed: %s", cudaGetErrorString(e));
             rc = ACFB200_ERR_CUDA;
@@ -908,6 +931,7 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
         fprintf(stderr, " ms\n");
     }
     cudaError_t es = cudaStreamSynchronize(st);
+    cudaStreamSynchronize(out_st);
     cudaStreamSynchronize(ws->copy_stream);
     destroy_events();
     if (rc == 0 && es != cudaSuccess) {

@@ -2,6 +2,7 @@
 // windows / trajectories shard with no communication, long series are cut into time blocks whose lag sums are
 // combined with one ncclAllReduce (NCCL resolved with dlopen so single-GPU users do not need it).
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <condition_variable>
@@ -39,8 +40,9 @@ std::mutex g_nccl_mu;
 int nccl_clique(int ndev, NcclApi** out)
 {
     if (!g_nccl.lib) {
-        // NCCL writes its version banner / debug log to stdout unless told otherwise; stdout is the front-ends' result
-        // stream (viscosity prints its table there), so an unset NCCL_DEBUG_FILE is pointed at stderr
+        // NCCL writes its debug log to stdout unless told otherwise; stdout is the front-ends' result stream (viscosity
+        // prints its table there), so an unset NCCL_DEBUG_FILE is pointed at stderr.  (The version banner of
+        // NCCL_DEBUG=VERSION ignores that variable: see the descriptor swap around ncclCommInitAll below.)
         setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
             g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
@@ -66,7 +68,16 @@ int nccl_clique(int ndev, NcclApi** out)
         g_nccl.comms.assign(ndev, nullptr);
         std::vector<int> devs(ndev);
         for (int d = 0; d < ndev; ++d) devs[d] = d;
+        // the first communicator prints "NCCL version ..." on stdout when NCCL_DEBUG is set: send it to stderr
+        fflush(stdout);
+        const int saved_stdout = dup(STDOUT_FILENO);
+        if (saved_stdout >= 0) dup2(STDERR_FILENO, STDOUT_FILENO);
         const ncclResult_t r = g_nccl.CommInitAll(g_nccl.comms.data(), ndev, devs.data());
+        if (saved_stdout >= 0) {
+            fflush(stdout);
+            dup2(saved_stdout, STDOUT_FILENO);
+            close(saved_stdout);
+        }
         if (r != ncclSuccess) {
             set_error("ncclCommInitAll(%d devices) failed: %s", ndev, g_nccl.GetErrorString(r));
             g_nccl.comms.clear();
