@@ -606,7 +606,9 @@ def roofline_of(env, w, ms_per_step, peak_tf, peaks):
             "algorithmic_bytes_per_step": w["hbm_alg_bytes"]}
 
 
-TRAFFIC_FFT3 = {}  # (n, m) -> (bytes, source) for L = 3*2^a plans, filled from the round-2 ncu capture
+TRAFFIC_FFT3 = {  # (n, m) -> (bytes, source) for L = 3*2^a plans
+    (2**27, 2**26): (14.27e9, "profiles/r2z_fft_kernels_ncu_raw.csv (sum over the five passes of one step, L = 3*2^26)"),
+}
 
 
 def auto_method_timing(env, w, steps=5):
