@@ -68,6 +68,7 @@ int get_ws(Workspace** out)
         w->sm_count = prop.multiProcessorCount;
         e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream3, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
             set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
@@ -83,7 +84,7 @@ int get_ws(Workspace** out)
 
 // Direct lag sums of `nseries` device-resident series described by host-side descs.
 int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long long ncorr, double* d_out,
-                      int normalise, cudaStream_t st)
+                      int normalise, cudaStream_t st, const DirectLane* lane)
 {
     const int ns = (int)descs.size();
     long long max_i_end = 1;
@@ -163,15 +164,27 @@ int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long long nc
     }
     DirectPlan plan;
     ACF_TRY(plan_direct(max_i_end, ncorr, ns, ws->sm_count, g_force_variant, &plan));
-    ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)ns));
-    ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, ns) * sizeof(double)));
+    SeriesDesc* d_desc;
+    double* d_partials;
+    if (lane) {
+        if (direct_partial_elems(plan, ns) > lane->partial_elems) {
+            set_error("run_direct: lane too small for this launch (%zu > %zu partial sums)", direct_partial_elems(plan, ns),
+                      lane->partial_elems);
+            return ACFB200_ERR_ARG;
+        }
+        d_desc = lane->desc;
+        d_partials = lane->partials;
+    } else {
+        ACF_TRY(ws->desc.ensure(sizeof(SeriesDesc) * (size_t)ns));
+        ACF_TRY(ws->partials.ensure(direct_partial_elems(plan, ns) * sizeof(double)));
+        d_desc = ws->desc.as<SeriesDesc>();
+        d_partials = ws->partials.as<double>();
+    }
     // pageable source: the runtime stages it before returning, so `descs` may die right after
-    ACF_CUDA_OK(cudaMemcpyAsync(ws->desc.p, descs.data(), sizeof(SeriesDesc) * (size_t)ns, cudaMemcpyHostToDevice, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(d_desc, descs.data(), sizeof(SeriesDesc) * (size_t)ns, cudaMemcpyHostToDevice, st));
     ACF_TRY(ws->queue.ensure(64, true));
-    ACF_TRY(launch_direct(plan, ws->desc.as<SeriesDesc>(), ns, ncorr, ws->partials.as<double>(),
-                          ws->queue.as<unsigned int>(), ws->sm_count, st));
-    ACF_TRY(launch_reduce_partials(plan, ws->desc.as<SeriesDesc>(), ns, ncorr, ws->partials.as<double>(), d_out,
-                                   normalise, st));
+    ACF_TRY(launch_direct(plan, d_desc, ns, ncorr, d_partials, ws->queue.as<unsigned int>(), ws->sm_count, st));
+    ACF_TRY(launch_reduce_partials(plan, d_desc, ns, ncorr, d_partials, d_out, normalise, st));
     g_launches += 2;
     return 0;
 }
@@ -211,6 +224,15 @@ struct PipelineStage {
     }
 };
 
+// Per-lane working memory of the host batch call (centred series, velocities, descriptors, partial sums): two lanes let
+// two window groups be in flight on two compute streams; null = the workspace's single set.
+struct WindowLane {
+    double* y;
+    double* vel;
+    WindowDesc* wins;
+    DirectLane direct;
+};
+
 // slot / slot_windows: the result buffers (lags, integrals, reduction scratch) hold two slots of slot_windows windows so
 // that consecutive groups of the host batch call can alternate -- group g+1 computes while group g's results are copied
 // out on `copy_st` (after the event `computed`, recorded on `st` behind the last kernel).  Single calls use slot 0 and
@@ -218,7 +240,8 @@ struct PipelineStage {
 static int pipeline_batch_enqueue(Workspace* ws, const double* const* d_series, const int64_t* n, int nw, long long ncorr,
                                   double dt, double cutoff, double* d_acf, double* d_vacf, const PipelineStage* stage,
                                   cudaStream_t st, int slot = 0, int slot_windows = 0, cudaStream_t copy_st = nullptr,
-                                  cudaEvent_t computed = nullptr, double** d_out_slot = nullptr)
+                                  cudaEvent_t computed = nullptr, double** d_out_slot = nullptr,
+                                  const struct WindowLane* lane = nullptr)
 {
     if (slot_windows < nw) slot_windows = nw;
     if (!copy_st) copy_st = st;
@@ -231,8 +254,14 @@ static int pipeline_batch_enqueue(Workspace* ws, const double* const* d_series, 
         }
         total += even_up(n[w]);
     }
-    ACF_TRY(ws->y.ensure(total * 8));
-    ACF_TRY(ws->vel.ensure(total * 8));
+    if (!lane) {
+        ACF_TRY(ws->y.ensure(total * 8));
+        ACF_TRY(ws->vel.ensure(total * 8));
+        ACF_TRY(ws->wins.ensure(sizeof(WindowDesc) * (size_t)nw));
+    }
+    double* lane_y = lane ? lane->y : ws->y.as<double>();
+    double* lane_v = lane ? lane->vel : ws->vel.as<double>();
+    WindowDesc* lane_w = lane ? lane->wins : ws->wins.as<WindowDesc>();
     const size_t slots = (size_t)slot + 1;
     ACF_TRY(ws->scratch.ensure(sizeof(ReduceScratch) * slots * slot_windows, true));
     ACF_TRY(ws->out.ensure(slots * 2 * slot_windows * ncorr * 8));
@@ -242,8 +271,8 @@ static int pipeline_batch_enqueue(Workspace* ws, const double* const* d_series, 
     std::vector<WindowDesc> wins(nw);
     size_t off = 0;
     for (int w = 0; w < nw; ++w) {
-        double* d_y = ws->y.as<double>() + off;
-        double* d_v = ws->vel.as<double>() + off;
+        double* d_y = lane_y + off;
+        double* d_v = lane_v + off;
         wins[w] = {d_series[w], d_y, d_v, (long long)n[w]};
         const long long m = n[w] - 2;  // ACFcalculator.cpp:718
         descs[2 * w] = {d_y, m, m};
@@ -251,13 +280,12 @@ static int pipeline_batch_enqueue(Workspace* ws, const double* const* d_series, 
         off += even_up(n[w]);
     }
     // mean -> centre + velocity -> velocity mean, all windows per launch
-    ACF_TRY(ws->wins.ensure(sizeof(WindowDesc) * (size_t)nw));
-    ACF_CUDA_OK(cudaMemcpyAsync(ws->wins.p, wins.data(), sizeof(WindowDesc) * (size_t)nw, cudaMemcpyHostToDevice, st));
-    ACF_TRY(launch_window_prep(ws->wins.as<WindowDesc>(), nw, sc, dt, st));
+    ACF_CUDA_OK(cudaMemcpyAsync(lane_w, wins.data(), sizeof(WindowDesc) * (size_t)nw, cudaMemcpyHostToDevice, st));
+    ACF_TRY(launch_window_prep(lane_w, nw, sc, dt, st));
     g_launches += 3;
     double* d_o = ws->out.as<double>() + (size_t)slot * 2 * slot_windows * ncorr;  // [window][acf|vacf][ncorr]
     if (d_out_slot) *d_out_slot = d_o;
-    ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st));
+    ACF_TRY(run_direct(ws, descs, ncorr, d_o, 1, st, lane ? &lane->direct : nullptr));
     double* d_small = ws->small.as<double>() + (size_t)slot * 2 * slot_windows;
     ACF_TRY(launch_integrate_cutoff_batch(d_o, 2 * ncorr, nw, ncorr, dt, cutoff, d_small, st));
     g_launches += 1;
@@ -788,7 +816,7 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
     gbeg.push_back(nwindows);
     const int ngroups = (int)gbeg.size() - 1;
     std::vector<cudaEvent_t> landed(ngroups, nullptr), done(ngroups, nullptr), computed(ngroups, nullptr);
-    cudaStream_t out_st = ws->stream2;
+    cudaStream_t out_st = ws->stream3;
     const bool want_lags = acf || vacf;
     // page-locked caller arrays take the lags straight from the device (asynchronous, nothing to unpack); pageable ones
     // go through page-locked staging -- beyond 1 GiB of it, straight to the caller with blocking copies
@@ -835,38 +863,60 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
         cudaEventCreateWithFlags(&computed[g], cudaEventDisableTiming);
         cudaEventRecord(landed[g], ws->copy_stream);
     }
-    // size the device workspaces for the largest group before anything is enqueued: growing one later would mean a
-    // cudaFree, i.e. a device-wide synchronisation in the middle of the pipeline
+    // Size the device workspaces before anything is enqueued (growing one later would mean a cudaFree, i.e. a device-wide
+    // synchronisation in the middle of the pipeline) -- for TWO lanes: consecutive groups alternate between two compute
+    // streams with working memory of their own, so that group g+1's kernels fill the SMs as group g's last CTAs drain.
+    // A lag launch over a few windows runs 3-13 % below the rate of a 64-window launch (short time chunks, a partly
+    // empty last wave: tools/sweep_small_batches.py); back to back in ONE stream every group boundary paid that in full.
     int slot_windows = nwindows;
+    const bool two_lanes = ngroups > 1 && g_method == 0;
+    size_t lane_samples = 0, lane_partials = 0;
     {
-        int big = 0;
-        for (int g = 1; g < ngroups; ++g)
-            if (gbeg[g + 1] - gbeg[g] > gbeg[big + 1] - gbeg[big]) big = g;
-        const int cnt = gbeg[big + 1] - gbeg[big];
-        size_t tot = 0;
+        int cnt = 1;
         long long longest = 3;
-        for (int w = gbeg[big]; w < gbeg[big + 1]; ++w) {
-            tot += even_up(n[w]);
-            if (n[w] > longest) longest = n[w];
+        for (int g = 0; g < ngroups; ++g) {
+            const int c = gbeg[g + 1] - gbeg[g];
+            if (c > cnt) cnt = c;
+            size_t tot = 0;
+            long long lg = 3;
+            for (int w = gbeg[g]; w < gbeg[g + 1]; ++w) {
+                tot += even_up(n[w]);
+                if (n[w] > lg) lg = n[w];
+            }
+            if (tot > lane_samples) lane_samples = tot;
+            if (lg > longest) longest = lg;
+            DirectPlan plan;
+            if (c > 0 && g_method == 0 && plan_direct(lg - 2, ncorr, 2 * c, ws->sm_count, g_force_variant, &plan) == 0) {
+                const size_t pe = direct_partial_elems(plan, 2 * c);
+                if (pe > lane_partials) lane_partials = pe;
+            }
         }
-        rc = ws->y.ensure(tot * 8);
-        if (rc == 0) rc = ws->vel.ensure(tot * 8);
+        lane_partials = (lane_partials + 1) & ~(size_t)1;
+        const size_t lanes = two_lanes ? 2 : 1;
+        rc = ws->y.ensure(lanes * lane_samples * 8);
+        if (rc == 0) rc = ws->vel.ensure(lanes * lane_samples * 8);
         slot_windows = cnt;   // two result slots of the largest group's size
         if (rc == 0) rc = ws->scratch.ensure(sizeof(ReduceScratch) * (size_t)2 * cnt, true);
         if (rc == 0) rc = ws->out.ensure((size_t)2 * 2 * cnt * ncorr * 8);
         if (rc == 0) rc = ws->small.ensure((size_t)2 * 16 * cnt);
-        if (rc == 0) rc = ws->wins.ensure(sizeof(WindowDesc) * (size_t)cnt);
-        DirectPlan plan;
-        if (rc == 0 && g_method == 0 && plan_direct(longest - 2, ncorr, 2 * cnt, ws->sm_count, g_force_variant, &plan) == 0) {
-            rc = ws->desc.ensure(sizeof(SeriesDesc) * (size_t)2 * cnt);
-            if (rc == 0) rc = ws->partials.ensure(direct_partial_elems(plan, 2 * cnt) * sizeof(double));
-        }
+        if (rc == 0) rc = ws->wins.ensure(sizeof(WindowDesc) * lanes * cnt);
+        if (rc == 0) rc = ws->desc.ensure(sizeof(SeriesDesc) * lanes * 2 * cnt);
+        if (rc == 0 && lane_partials) rc = ws->partials.ensure(lanes * lane_partials * sizeof(double));
         if (rc != 0) {
             cudaStreamSynchronize(ws->copy_stream);
             destroy_events();
             return rc;
         }
     }
+    WindowLane lanes_mem[2];
+    for (int l = 0; l < 2; ++l) {
+        lanes_mem[l].y = ws->y.as<double>() + (size_t)l * lane_samples;
+        lanes_mem[l].vel = ws->vel.as<double>() + (size_t)l * lane_samples;
+        lanes_mem[l].wins = ws->wins.as<WindowDesc>() + (size_t)l * slot_windows;
+        lanes_mem[l].direct = {ws->desc.as<SeriesDesc>() + (size_t)l * 2 * slot_windows,
+                               ws->partials.as<double>() + (size_t)l * lane_partials, lane_partials};
+    }
+    cudaStream_t lane_stream[2] = {ws->stream, ws->stream2};
     // ACFB200_TRACE=1: host-side timeline of this call on stderr (when each group was enqueued / seen complete)
     static const bool trace = getenv("ACFB200_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -876,16 +926,21 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
     for (int g = 0; g < ngroups && rc == 0; ++g) {
         const int w0 = gbeg[g], cnt = gbeg[g + 1] - gbeg[g];
         if (cnt == 0) continue;
-        cudaStreamWaitEvent(st, landed[g], 0);
-        // Results leave on a stream of their own (ws->stream2) from one of two slots, so the next group's kernels do not
-        // wait for this group's device-to-host copies (a dozen small dependent operations, ~0.1 ms per group when they sat
-        // on the compute stream); a slot is reused two groups later, once its copies are done.
-        const int slot = g & 1;
-        if (g >= 2 && done[g - 2]) cudaStreamWaitEvent(st, done[g - 2], 0);
+        // Lane = group parity: compute stream, working memory and result slot.  Results leave on a stream of their own
+        // (ws->stream3), so the next group's kernels do not wait for this group's device-to-host copies (a dozen small
+        // dependent operations); a lane's memory is reused two groups later, once its copies are done.
+        const int slot = two_lanes ? (g & 1) : 0;
+        cudaStream_t gs = lane_stream[slot];
+        cudaStreamWaitEvent(gs, landed[g], 0);
+        if (two_lanes ? g >= 2 : g >= 1) {
+            const int prev = two_lanes ? g - 2 : g - 1;
+            if (done[prev]) cudaStreamWaitEvent(gs, done[prev], 0);
+        }
         stages[g].carve(h_scal + PipelineStage::doubles(w0), cnt);
         double* d_o = nullptr;
         rc = pipeline_batch_enqueue(ws, d_ptr.data() + w0, n + w0, cnt, ncorr, dt, cutoff, nullptr, nullptr,
-                                    result ? &stages[g] : nullptr, st, slot, slot_windows, out_st, computed[g], &d_o);
+                                    result ? &stages[g] : nullptr, gs, slot, slot_windows, out_st, computed[g], &d_o,
+                                    g_method == 0 ? &lanes_mem[slot] : nullptr);
         if (rc != 0) break;
         cudaError_t e = cudaSuccess;
         if (want_lags && staged) {
@@ -931,6 +986,7 @@ int acfb200_acf_pipeline_batch(const double* const* series, const int64_t* n, in
         fprintf(stderr, " ms\n");
     }
     cudaError_t es = cudaStreamSynchronize(st);
+    cudaStreamSynchronize(ws->stream2);
     cudaStreamSynchronize(out_st);
     cudaStreamSynchronize(ws->copy_stream);
     destroy_events();

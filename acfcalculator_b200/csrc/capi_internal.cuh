@@ -110,6 +110,7 @@ struct Workspace {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;      // second compute stream: independent time pieces of one series overlap their tails
+    cudaStream_t stream3 = nullptr;      // results of the window batch on their way out
     cudaStream_t copy_stream = nullptr;  // H2D of the next window group while the current one computes
     Buf series, y, vel, desc, partials, out, scratch, small, fftwork, queue, wins;
     HostBuf pinned;                      // staging of results on their way to pageable caller memory
@@ -118,6 +119,8 @@ struct Workspace {
         pinned.release();
         if (stream2) cudaStreamDestroy(stream2);
         stream2 = nullptr;
+        if (stream3) cudaStreamDestroy(stream3);
+        stream3 = nullptr;
         series.release();
         y.release();
         vel.release();
@@ -141,8 +144,15 @@ struct Workspace {
 int get_ws(Workspace** out);
 inline size_t even_up(long long n) { return (size_t)((n + 1) & ~1ll); }
 // Direct lag sums (or, by acfb200_set_method, the FFT path) of device-resident series described by host-side descs.
+// lane (nullable): descriptor / partial-sum memory of the caller's choosing instead of the workspace's single set, so
+// that two launches can be in flight on two streams (the window batch).  Direct summation only.
+struct DirectLane {
+    SeriesDesc* desc;
+    double* partials;
+    size_t partial_elems;
+};
 int run_direct(Workspace* ws, const std::vector<SeriesDesc>& descs, long long ncorr, double* d_out, int normalise,
-               cudaStream_t st);
+               cudaStream_t st, const DirectLane* lane = nullptr);
 int check_common(const void* p, long long n, long long ncorr, const char* what);
 // Raw lag sums of host-resident time blocks (block + halo each) into device memory, enqueued on ws->stream (plus the
 // copy stream / second compute stream when the blocks are long enough to pipeline); capi.cu
