@@ -46,6 +46,11 @@ int main()
         run<32>(a, b, total16, 512, stride16);
         run<64>(a, b, total16, 512, stride16);
     }
+    // power-of-two row pitch against a padded one (axis-1 passes of the FFT path: 384 rows 4 MB apart)
+    for (size_t pad : {(size_t)0, (size_t)8, (size_t)16, (size_t)24, (size_t)136}) {
+        run<8>(a, b, total16, 384, ((size_t)1 << 18) + pad);
+        run<16>(a, b, total16, 384, ((size_t)1 << 18) + pad);
+    }
     run<32>(a, b, total16, 128, (size_t)1 << 20);
     run<16>(a, b, total16, 256, (size_t)1 << 12);
     return 0;
