@@ -491,16 +491,10 @@ int plan_direct(long long max_i_end, long long ncorr, int nseries, int sm_count,
     if (fch > 0) chunks = fch;
     if (chunks < 1) chunks = 1;
     p.chunks = (int)chunks;
-    // Small batches (a window group of the host pipeline: 2-8 series): when the whole launch is only a few waves, tiles of
-    // half the length finish it 2-3 % sooner at the same chunk count (finer granularity in the last wave, an earlier first
-    // product): 2 series 0.708 -> 0.689 ms, 4 series 1.362 -> 1.327, 8 series 2.611 -> 2.581; no gain from 16 series on
-    // (tools/sweep_small_batches.py, profiles/r2_sweep_small_batches.txt).  Single-series launches keep their tuned tiles.
-    if (fts <= 0 && nseries >= 2 && groups * chunks <= 4 * slots && p.ts >= 4 * R) {
-        p.ts = p.ts / 2 / R * R;
-        p.ti = LI * p.ts;
-        p.bsz = p.ti + best_w * lkrk + 2 * V.pf;
-        p.smem_bytes = (size_t)(p.ti + p.bsz) * 8 + 16;
-    }
+    // (Tried in round 2: half-length tiles for multi-series launches of at most four waves.  Alone, such launches finish
+    // 2-3 % sooner -- tools/sweep_small_batches.py, profiles/r2_sweep_small_batches.txt -- but the window pipeline runs
+    // consecutive groups on two streams, where the tails overlap anyway and the extra tiles cost: 5.58 -> 5.83 ms for 8
+    // windows end to end.  Not kept.)
     *plan = p;
     return 0;
 }

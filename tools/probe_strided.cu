@@ -14,9 +14,11 @@ __global__ void __launch_bounds__(512) strided_copy(const double2* __restrict__ 
         double2 v[8];
         for (int rr = r0; rr < rows; rr += RPI * 8) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = src[base + (size_t)(rr + t * RPI) * stride16];
+            for (int t = 0; t < 8; ++t)
+                if (rr + t * RPI < rows) v[t] = src[base + (size_t)(rr + t * RPI) * stride16];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) dst[base + (size_t)(rr + t * RPI) * stride16] = v[t];
+            for (int t = 0; t < 8; ++t)
+                if (rr + t * RPI < rows) dst[base + (size_t)(rr + t * RPI) * stride16] = v[t];
         }
     }
 }
