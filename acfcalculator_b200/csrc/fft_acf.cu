@@ -880,6 +880,269 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     }
 }
 
+// ---- column pass for the 384-row axis, 16-column tiles (MODE 0 and MODE 3 of the L = 3*2^a plans) -------------------
+// The two axis-1 passes walk rows that are C complex values = megabytes apart; with 8-column tiles (128-byte row
+// segments) that access pattern delivers 4.4-4.5 TB/s, with 16-column tiles (256 bytes) 5.6-5.7 (tools/probe_strided.cu),
+// and col_pass4's 384-row forward pass sat at 3.2.  Same arithmetic as col_pass4_kernel<MODE, true>, tiles twice as wide:
+//   * 384 x 16 tiles (96 KB): ONE landing buffer L filled by three TMA boxes of 128 rows x 256 bytes (3-D tensor map, no
+//     swizzle: an 8-lane octet reads one 128-byte row half, conflict free) and one scratch buffer S of the same shape;
+//   * two groups of 256 threads, one per half of the columns, each with a named barrier of its own; a thread carries up
+//     to two radix items per pass (independent butterflies back to back: the 384-row passes are latency bound);
+//   * radix pass 1: L -> S, after which the warp hands L back (arrival tied to its loaded values, mbar_arrive_after) and
+//     thread 0 requests the next tile as soon as all sixteen warps have; the middle pass runs in place in S (read, barrier,
+//     write), the last pass reads S and stores to HBM (MODE 0: twiddles carried across tiles; MODE 3: lags).
+constexpr int kC5Threads = 512;
+constexpr size_t kC5SmemBytes = (size_t)2 * 384 * 16 * 16 + (512 + 80) * 16 + 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(kC5Threads, 1)
+col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ data, const double* __restrict__ x,
+                 double* __restrict__ out, FftGeom G, int logC, const double2* __restrict__ lo, const double2* __restrict__ hi)
+{
+    static_assert(MODE == 0 || MODE == 3, "axis-1 passes only");
+    constexpr int DIR = (MODE == 0) ? -1 : +1;
+    constexpr int NB = 384, NB8 = 48, R = 6;
+    constexpr int TILE = NB * 16;
+    extern __shared__ __align__(1024) unsigned char smem_c5[];
+    double2* L = reinterpret_cast<double2*>(smem_c5);
+    double2* S = L + TILE;
+    double2* tw = S + TILE;                        // tw[(u-1)*NB8 + g] = W_NB^{g*u} (conjugated for the inverse)
+    double2* tw2 = tw + 7 * NB8;                   // tw2[(u-1)*6 + p] = W_NB^{8*p*u}
+    double2* rho = tw + 512;                       // MODE 0: rho[gg] = W_Nc^{gg*16*gridDim.x}, rho[64] = W_Nc^{64*16*gridDim.x}
+    uint64_t* full = reinterpret_cast<uint64_t*>(rho + 80);
+    uint64_t* empty = full + 1;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned int tiles_c_log = logC - 4;
+    unsigned int tiles = 1u << tiles_c_log;
+    if (MODE == 3) {
+        const long long need = (G.ncorr + 1) / 2;  // complex outputs j < need
+        if (need < (1ll << logC)) tiles = (unsigned int)((need + 15) >> 4);
+    }
+    const int batch = blockIdx.y;
+    if (tid == 0) {
+        prefetch_tensormap(&tmap);
+        mbar_init(full, 1);      // thread 0's expect_tx arrival; the TMA boxes complete the bytes
+        mbar_init(empty, 16);    // one arrival per warp, after its pass-1 loads have returned
+    }
+    {
+        const unsigned int wstep = (unsigned int)(G.L / NB);   // W_NB = W_L^wstep
+        for (int m = tid; m < 7 * NB8 + 7 * (NB8 / 8); m += kC5Threads) {
+            unsigned int e;
+            if (m < 7 * NB8)
+                e = (unsigned int)(m % NB8) * (unsigned int)(m / NB8 + 1);
+            else
+                e = 8u * (unsigned int)((m - 7 * NB8) % (NB8 / 8)) * (unsigned int)((m - 7 * NB8) / (NB8 / 8) + 1);
+            const double2 w = tw_L(lo, hi, (unsigned long long)e * wstep);
+            tw[m] = DIR > 0 ? cconj(w) : w;
+        }
+        if (MODE == 0 && tid <= 64) rho[tid] = tw_L(lo, hi, 2ull * ((unsigned long long)tid * 16ull * gridDim.x));
+    }
+    __syncthreads();
+
+    auto request_tile = [&](unsigned int tile, unsigned int jj) {
+        if (jj >= 1) mbar_wait(empty, (jj - 1) & 1);   // every warp has taken tile jj-1 out of L
+        mbar_expect_tx(full, (uint32_t)(TILE * 16));
+#pragma unroll
+        for (int r0 = 0; r0 < NB; r0 += kC4BoxRows)
+            tma_load_3d(L + r0 * 16, &tmap, (int)(32 * tile), r0, batch, full);
+    };
+    if (tid == 0 && blockIdx.x < tiles) request_tile(blockIdx.x, 0);
+
+    // roles: group = half of the columns; items i = tl and tl + 256: radix group (i >> 3), column (i & 7) of the half
+    const int grp = tid >> 8, tl = tid & 255;
+    const int c = (grp << 3) | (tl & 7);           // column inside the tile, 0..15
+    const int g0 = tl >> 3;                        // 0..31; second item: g0 + 32 (radix-8 passes: only while < 48)
+    const bool two8 = g0 + 32 < NB8;               // this thread has a second radix-8 item
+    double2* bdata = data + (long long)batch * G.Nc;
+    const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);
+    // MODE 0: the series ends inside row `edge_row` (unless n is a multiple of 2C); the tensor map covers the full rows only
+    const long long two_c = 2ll << logC;
+    const int edge_row = (MODE == 0) ? (int)(G.n / two_c) : 0;
+    const bool edge_any = (MODE == 0) && (G.n % two_c != 0) && edge_row < NB;
+    int edge_t0 = -1, edge_t1 = -1;   // which of the eight pass-1 inputs of item 0 / item 1 lies in that row
+    if (edge_any) {
+        if (edge_row >= g0 && (edge_row - g0) % NB8 == 0) edge_t0 = (edge_row - g0) / NB8;
+        if (g0 + 32 < NB8 && edge_row >= g0 + 32 && (edge_row - g0 - 32) % NB8 == 0) edge_t1 = (edge_row - g0 - 32) / NB8;
+    }
+    const double* xs = (MODE == 0) ? x + (long long)batch * G.x_stride : nullptr;
+    auto load_edge = [&](unsigned int tile) -> double2 {
+        double2 z = make_double2(0.0, 0.0);
+        if ((edge_t0 >= 0 || edge_t1 >= 0) && tile < tiles) {
+            const long long jj = ((long long)edge_row << logC) + 16ll * tile + c;   // complex index: samples 2jj, 2jj+1
+            if (2 * jj + 1 < G.n)
+                z = *reinterpret_cast<const double2*>(xs + 2 * jj);
+            else if (2 * jj < G.n)
+                z.x = xs[2 * jj];
+        }
+        return z;
+    };
+    double* o3 = (MODE == 3) ? out + (long long)batch * G.out_stride : nullptr;
+    const bool o3_aligned = (reinterpret_cast<uintptr_t>(o3) & 15) == 0;
+    const double inv_nc = 1.0 / (double)G.Nc;
+    auto fast_rcp = [](double md) {
+        double r0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(md));
+        double e = fma(-md, r0, 1.0);
+        r0 = fma(r0, e, r0);
+        e = fma(-md, r0, 1.0);
+        return fma(r0, e, r0);
+    };
+    // the six outputs of one last-pass item: rows base + 64u of column cc
+    auto store_group = [&](unsigned int cc, unsigned int base, double2* r, double2 t, double2 d) {
+        if (MODE == 3) {
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const long long j = ((long long)(base + 64 * u) << logC) + cc;
+                const long long k0 = 2 * j;
+                if (k0 >= G.ncorr) continue;
+                const long long m0 = G.n - k0;
+                if (o3_aligned && k0 + 1 < G.ncorr && m0 > 1 && m0 < (1ll << 31)) {
+                    const double s0 = inv_nc * fast_rcp((double)(int)m0), s1 = inv_nc * fast_rcp((double)(int)(m0 - 1));
+                    *reinterpret_cast<double2*>(o3 + k0) = make_double2(r[u].x * s0, r[u].y * s1);
+                    continue;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const long long k = k0 + h;
+                    if (k < G.ncorr) {
+                        const long long m = G.n - k;
+                        double val = (h ? r[u].y : r[u].x) * inv_nc;
+                        if (m > 0)
+                            val = val / (double)m;
+                        else if (m == 0)
+                            val = __longlong_as_double(0xFFF8000000000000ull);  // reference: 0/0
+                        else
+                            val = -0.0;                                          // reference: 0/negative
+                        o3[k] = val;
+                    }
+                }
+            }
+            return;
+        }
+        double2* dst = bdata + cc;
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            FFT_ASSERT(cc + ((size_t)(base + 64 * u) << logC) < (size_t)G.Nc);
+            dst[(size_t)(base + 64 * u) << logC] = cmul(r[u], t);
+            t = cmul(t, d);
+        }
+    };
+
+    double2 edge = load_edge(blockIdx.x);
+    // MODE 0: inter-step twiddles of this thread's two last-pass items (rows gg and gg + 32), carried across tiles
+    constexpr unsigned int kReseed = 8;
+    double2 ta = make_double2(1.0, 0.0), tb = ta, d0 = ta;
+    unsigned int j = 0;
+    for (unsigned int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
+        const unsigned int cc = 16u * tile + c;
+        if (MODE == 0) {
+            if (j % kReseed == 0) {
+                ta = tw_L(lo, hi, 2ull * ((unsigned int)g0 * cc));
+                tb = tw_L(lo, hi, 2ull * ((unsigned int)(g0 + 32) * cc));
+                d0 = tw_L(lo, hi, 2ull * (64u * cc));
+            } else {
+                ta = cmul(ta, rho[g0]);
+                tb = cmul(tb, rho[g0 + 32]);
+                d0 = cmul(d0, rho[64]);
+            }
+        }
+        const double2 edge_now = edge;
+        if (MODE == 0) edge = load_edge(tile + gridDim.x);
+        mbar_wait(full, j & 1);
+
+        // ---- radix pass 1 (Stockham stride 1, p = g): L -> registers -> S
+        {
+            double2 v[2][8];
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int g = g0 + 32 * it;
+                if (it == 0 || two8) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) v[it][t] = L[(g + t * NB8) * 16 + c];
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int g = g0 + 32 * it;
+                if (it == 0 || two8) {
+                    if (MODE == 0) {
+                        const int et = it == 0 ? edge_t0 : edge_t1;
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            v[it][t].x = (t == et) ? edge_now.x : v[it][t].x;
+                            v[it][t].y = (t == et) ? edge_now.y : v[it][t].y;
+                        }
+                    }
+                    dft8<DIR>(v[it]);
+                }
+            }
+            // the loads have returned (the butterflies consumed them): hand L back
+            __syncwarp();
+            if (lane == 0) mbar_arrive_after(empty, v[0][0].x + v[0][7].y, G.zero);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int g = g0 + 32 * it;
+                if (it == 0 || two8) {
+                    if (g != 0) {
+#pragma unroll
+                        for (int u = 1; u < 8; ++u) v[it][u] = cmul(v[it][u], tw[(u - 1) * NB8 + g]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) S[(8 * g + u) * 16 + c] = v[it][u];
+                }
+            }
+        }
+        named_bar_sync(1 + grp, 256);
+        if (tid == 0 && tile + gridDim.x < tiles) request_tile(tile + gridDim.x, j + 1);
+
+        // ---- middle radix-8 pass (stride 8), in place in S: read, barrier, write
+        {
+            double2 r[2][8];
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int g = g0 + 32 * it;
+                if (it == 0 || two8) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) r[it][t] = S[(g + t * NB8) * 16 + c];
+                }
+            }
+            named_bar_sync(1 + grp, 256);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int g = g0 + 32 * it;
+                if (it == 0 || two8) {
+                    dft8<DIR>(r[it]);
+                    const int qq = g & 7, ps = g - qq;
+                    if (ps != 0) {
+#pragma unroll
+                        for (int u = 1; u < 8; ++u) r[it][u] = cmul(r[it][u], tw2[(u - 1) * (NB8 / 8) + (g >> 3)]);
+                    }
+                    const int base = qq + ps * 8;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) S[(base + 8 * u) * 16 + c] = r[it][u];
+                }
+            }
+        }
+        named_bar_sync(1 + grp, 256);
+
+        // ---- last pass (radix 6, stride 64, no butterfly twiddles): S -> registers -> HBM; two items per thread
+        {
+            double2 r[2][6];
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int gg = g0 + 32 * it;
+#pragma unroll
+                for (int t = 0; t < R; ++t) r[it][t] = S[(gg + t * 64) * 16 + c];
+            }
+#pragma unroll
+            for (int it = 0; it < 2; ++it) dft6<DIR>(r[it]);
+            named_bar_sync(1 + grp, 256);   // S may be overwritten by the next tile's pass 1 from here on
+            store_group(cc, g0, r[0], ta, d0);
+            store_group(cc, g0 + 32, r[1], tb, d0);
+        }
+    }
+}
+
 typedef void (*col4_fn)(const CUtensorMap, double2*, const double*, double*, FftGeom, int, int, const double2*, const double2*);
 static col4_fn col4_select(int mode, bool three)
 {
@@ -910,8 +1173,10 @@ static encode_tiled_fn tensor_map_encoder()
 
 // Tensor map over `rows` rows of `row_doubles` FP64 values each, `nbatch` such arrays `batch_stride_doubles` apart; boxes of
 // 16 doubles (one 128-byte row segment = 8 complex values) x 128 rows, 128-byte swizzle, zeros out of bounds.
+// wide = false: boxes of 16 doubles (one 128-byte row segment = 8 complex values), 128-byte swizzle (col_pass4_kernel);
+// wide = true:  boxes of 32 doubles (256-byte segments = 16 complex values), no swizzle (col_pass5_kernel).
 static bool make_col_tensor_map(CUtensorMap* m, const void* base, unsigned long long row_doubles, unsigned long long rows,
-                                unsigned long long nbatch, unsigned long long batch_stride_doubles)
+                                unsigned long long nbatch, unsigned long long batch_stride_doubles, bool wide = false)
 {
     encode_tiled_fn enc = tensor_map_encoder();
     if (!enc || rows == 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
@@ -922,11 +1187,12 @@ static bool make_col_tensor_map(CUtensorMap* m, const void* base, unsigned long 
     if ((batch_stride_doubles & 1) != 0) return false;
     const cuuint64_t dims[3] = {row_doubles, rows, nbatch};
     const cuuint64_t strides[2] = {row_doubles * 8, batch_stride_doubles * 8};   // bytes, dimensions 1 and 2
-    const cuuint32_t box[3] = {16, (cuuint32_t)kC4BoxRows, 1};
+    const cuuint32_t box[3] = {wide ? 32u : 16u, (cuuint32_t)kC4BoxRows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     if (strides[0] >= (1ull << 40) || strides[1] >= (1ull << 40)) return false;
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, wide ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                           wide ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -1491,6 +1757,8 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         for (int mode = 0; mode < 4; ++mode)
             cudaFuncSetAttribute(col4_select(mode, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC4SmemBytes);
         cudaFuncSetAttribute(col4_select(0, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC4SmemBytes);
+        cudaFuncSetAttribute(col_pass5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5SmemBytes);
+        cudaFuncSetAttribute(col_pass5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5SmemBytes);
         cudaFuncSetAttribute(col4_select(3, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC4SmemBytes);
         cudaFuncSetAttribute(col2_three(0), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
         cudaFuncSetAttribute(col2_three(3), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
@@ -1513,6 +1781,11 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     const int c4mask = !pipelined ? 0 : (env4 && env4[0] >= '0' && env4[0] <= '7') ? env4[0] - '0' : 7;
     const bool axis1_ok = g.b1 > 0 && (g.three || g.b1 == 9) && g.b2 + g.b3 >= 3;
     const bool fwd1_c4 = (c4mask & 1) && axis1_ok, inv1_c4 = (c4mask & 4) && axis1_ok;
+    // the 384-row axis-1 passes with 16-column tiles (col_pass5_kernel); ACFB200_FFT_COL5=0 keeps col_pass4 for them
+    const char* env5 = getenv("ACFB200_FFT_COL5");
+    const int c5mask = (env5 && env5[0] >= '0' && env5[0] <= '7') ? env5[0] - '0' : 5;
+    const bool c5_ok = g.three && g.b2 + g.b3 >= 4;
+    const bool fwd1_c5 = fwd1_c4 && c5_ok && (c5mask & 1), inv1_c5 = inv1_c4 && c5_ok && (c5mask & 4);
     const bool axis2_c4 = (c4mask & 2) && g.b2 == 9;
     CUtensorMap tm;
     const size_t smem2 = (size_t)(2 * kTileElems + 512) * 16;  // two tile buffers + butterfly twiddles
@@ -1525,7 +1798,10 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
         // MODE 0 reads the caller's real series: rows of 2C doubles, only the full rows are in the tensor map
-        if (fwd1_c4 && make_col_tensor_map(&tm, d_x, 2ull * C, (unsigned long long)(n / (2 * C)), nb, x_stride))
+        if (fwd1_c5 && make_col_tensor_map(&tm, d_x, 2ull * C, (unsigned long long)(n / (2 * C)), nb, x_stride, true))
+            col_pass5_kernel<0><<<dim3(pgrid(C >> 4), nb, 1), kC5Threads, kC5SmemBytes, st>>>(tm, data, d_x, nullptr, g,
+                                                                                             g.b2 + g.b3, lo, hi);
+        else if (fwd1_c4 && make_col_tensor_map(&tm, d_x, 2ull * C, (unsigned long long)(n / (2 * C)), nb, x_stride))
             col4_select(0, g.three)<<<dim3(pgrid(C >> 3), nb, 1), kC4Threads, kC4SmemBytes, st>>>(
                 tm, data, d_x, nullptr, g, g.b2 + g.b3, 1, lo, hi);
         else if (g.three)
@@ -1587,7 +1863,10 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
     if (g.b1 > 0) {
         const long long C = N2 * N3;
         const int TC = tc_for(g.b1, C);
-        if (inv1_c4 && make_col_tensor_map(&tm, data, 2ull * C, (unsigned long long)N1, nb, 2ull * g.Nc))
+        if (inv1_c5 && make_col_tensor_map(&tm, data, 2ull * C, (unsigned long long)N1, nb, 2ull * g.Nc, true))
+            col_pass5_kernel<3><<<dim3(pgrid(C >> 4), nb, 1), kC5Threads, kC5SmemBytes, st>>>(tm, data, nullptr, d_out, g,
+                                                                                             g.b2 + g.b3, lo, hi);
+        else if (inv1_c4 && make_col_tensor_map(&tm, data, 2ull * C, (unsigned long long)N1, nb, 2ull * g.Nc))
             col4_select(3, g.three)<<<dim3(pgrid(C >> 3), nb, 1), kC4Threads, kC4SmemBytes, st>>>(
                 tm, data, nullptr, d_out, g, g.b2 + g.b3, 1, lo, hi);
         else if (g.three)
