@@ -892,9 +892,11 @@ col_pass4_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
 //     thread 0 requests the next tile as soon as all sixteen warps have; the middle pass runs in place in S (read, barrier,
 //     write), the last pass reads S and stores to HBM (MODE 0: twiddles carried across tiles; MODE 3: lags).
 constexpr int kC5Threads = 512;
-constexpr size_t kC5SmemBytes = (size_t)2 * 384 * 16 * 16 + (512 + 80) * 16 + 64;
+constexpr size_t kC5SmemBytes = (size_t)2 * 384 * 16 * 16 + (512 + 80 + 3 * 512) * 16 + 64;
 
-template <int MODE>
+// EDGE: the series ends inside a tile row (n is not a multiple of 2C), MODE 0 only; the common case without it carries no
+// registers for that row.
+template <int MODE, bool EDGE = false>
 __global__ void __launch_bounds__(kC5Threads, 1)
 col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ data, const double* __restrict__ x,
                  double* __restrict__ out, FftGeom G, int logC, const double2* __restrict__ lo, const double2* __restrict__ hi)
@@ -909,7 +911,11 @@ col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     double2* tw = S + TILE;                        // tw[(u-1)*NB8 + g] = W_NB^{g*u} (conjugated for the inverse)
     double2* tw2 = tw + 7 * NB8;                   // tw2[(u-1)*6 + p] = W_NB^{8*p*u}
     double2* rho = tw + 512;                       // MODE 0: rho[gg] = W_Nc^{gg*16*gridDim.x}, rho[64] = W_Nc^{64*16*gridDim.x}
-    uint64_t* full = reinterpret_cast<uint64_t*>(rho + 80);
+    // MODE 0: the three inter-step twiddles a thread carries from tile to tile (W^{g0*cc}, W^{(g0+32)*cc}, W^{64*cc}) live
+    // here, component-major, and are in registers only inside the last pass: held across the passes they pushed the kernel
+    // over 128 registers (r3i ncu: 37 M sectors of local-memory traffic per launch)
+    double2* tstate = rho + 80;
+    uint64_t* full = reinterpret_cast<uint64_t*>(tstate + (MODE == 0 ? 3 * kC5Threads : 0));
     uint64_t* empty = full + 1;
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned int tiles_c_log = logC - 4;
@@ -954,11 +960,10 @@ col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     const int g0 = tl >> 3;                        // 0..31; second item: g0 + 32 (radix-8 passes: only while < 48)
     const bool two8 = g0 + 32 < NB8;               // this thread has a second radix-8 item
     double2* bdata = data + (long long)batch * G.Nc;
-    const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);
     // MODE 0: the series ends inside row `edge_row` (unless n is a multiple of 2C); the tensor map covers the full rows only
     const long long two_c = 2ll << logC;
     const int edge_row = (MODE == 0) ? (int)(G.n / two_c) : 0;
-    const bool edge_any = (MODE == 0) && (G.n % two_c != 0) && edge_row < NB;
+    const bool edge_any = EDGE && (MODE == 0) && (G.n % two_c != 0) && edge_row < NB;
     int edge_t0 = -1, edge_t1 = -1;   // which of the eight pass-1 inputs of item 0 / item 1 lies in that row
     if (edge_any) {
         if (edge_row >= g0 && (edge_row - g0) % NB8 == 0) edge_t0 = (edge_row - g0) / NB8;
@@ -967,7 +972,7 @@ col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     const double* xs = (MODE == 0) ? x + (long long)batch * G.x_stride : nullptr;
     auto load_edge = [&](unsigned int tile) -> double2 {
         double2 z = make_double2(0.0, 0.0);
-        if ((edge_t0 >= 0 || edge_t1 >= 0) && tile < tiles) {
+        if (EDGE && (edge_t0 >= 0 || edge_t1 >= 0) && tile < tiles) {
             const long long jj = ((long long)edge_row << logC) + 16ll * tile + c;   // complex index: samples 2jj, 2jj+1
             if (2 * jj + 1 < G.n)
                 z = *reinterpret_cast<const double2*>(xs + 2 * jj);
@@ -1031,23 +1036,18 @@ col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
     double2 edge = load_edge(blockIdx.x);
     // MODE 0: inter-step twiddles of this thread's two last-pass items (rows gg and gg + 32), carried across tiles
     constexpr unsigned int kReseed = 8;
-    double2 ta = make_double2(1.0, 0.0), tb = ta, d0 = ta;
     unsigned int j = 0;
     for (unsigned int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
         const unsigned int cc = 16u * tile + c;
-        if (MODE == 0) {
-            if (j % kReseed == 0) {
-                ta = tw_L(lo, hi, 2ull * ((unsigned int)g0 * cc));
-                tb = tw_L(lo, hi, 2ull * ((unsigned int)(g0 + 32) * cc));
-                d0 = tw_L(lo, hi, 2ull * (64u * cc));
-            } else {
-                ta = cmul(ta, rho[g0]);
-                tb = cmul(tb, rho[g0 + 32]);
-                d0 = cmul(d0, rho[64]);
-            }
+        const bool reseed = (j % kReseed == 0);
+        if (MODE == 0 && reseed) {
+            // every kReseed tiles from the W_L table (bounds the rounding drift of the rotation); read back in the last pass
+            tstate[tid] = tw_L(lo, hi, 2ull * ((unsigned int)g0 * cc));
+            tstate[kC5Threads + tid] = tw_L(lo, hi, 2ull * ((unsigned int)(g0 + 32) * cc));
+            tstate[2 * kC5Threads + tid] = tw_L(lo, hi, 2ull * (64u * cc));
         }
         const double2 edge_now = edge;
-        if (MODE == 0) edge = load_edge(tile + gridDim.x);
+        if (MODE == 0 && EDGE) edge = load_edge(tile + gridDim.x);
         mbar_wait(full, j & 1);
 
         // ---- radix pass 1 (Stockham stride 1, p = g): L -> registers -> S
@@ -1063,9 +1063,8 @@ col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
             }
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
-                const int g = g0 + 32 * it;
                 if (it == 0 || two8) {
-                    if (MODE == 0) {
+                    if (MODE == 0 && EDGE) {
                         const int et = it == 0 ? edge_t0 : edge_t1;
 #pragma unroll
                         for (int t = 0; t < 8; ++t) {
@@ -1137,6 +1136,20 @@ col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
 #pragma unroll
             for (int it = 0; it < 2; ++it) dft6<DIR>(r[it]);
             named_bar_sync(1 + grp, 256);   // S may be overwritten by the next tile's pass 1 from here on
+            double2 ta = make_double2(1.0, 0.0), tb = ta, d0 = ta;
+            if (MODE == 0) {
+                ta = tstate[tid];
+                tb = tstate[kC5Threads + tid];
+                d0 = tstate[2 * kC5Threads + tid];
+                if (!reseed) {   // advance from this CTA's previous tile: cc grew by 16 * gridDim.x
+                    ta = cmul(ta, rho[g0]);
+                    tb = cmul(tb, rho[g0 + 32]);
+                    d0 = cmul(d0, rho[64]);
+                    tstate[tid] = ta;
+                    tstate[kC5Threads + tid] = tb;
+                    tstate[2 * kC5Threads + tid] = d0;
+                }
+            }
             store_group(cc, g0, r[0], ta, d0);
             store_group(cc, g0 + 32, r[1], tb, d0);
         }
@@ -1757,7 +1770,8 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         for (int mode = 0; mode < 4; ++mode)
             cudaFuncSetAttribute(col4_select(mode, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC4SmemBytes);
         cudaFuncSetAttribute(col4_select(0, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC4SmemBytes);
-        cudaFuncSetAttribute(col_pass5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5SmemBytes);
+        cudaFuncSetAttribute(col_pass5_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5SmemBytes);
+        cudaFuncSetAttribute(col_pass5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5SmemBytes);
         cudaFuncSetAttribute(col_pass5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5SmemBytes);
         cudaFuncSetAttribute(col4_select(3, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC4SmemBytes);
         cudaFuncSetAttribute(col2_three(0), cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kTileElems + 512) * 16);
@@ -1799,8 +1813,9 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         const int TC = tc_for(g.b1, C);
         // MODE 0 reads the caller's real series: rows of 2C doubles, only the full rows are in the tensor map
         if (fwd1_c5 && make_col_tensor_map(&tm, d_x, 2ull * C, (unsigned long long)(n / (2 * C)), nb, x_stride, true))
-            col_pass5_kernel<0><<<dim3(pgrid(C >> 4), nb, 1), kC5Threads, kC5SmemBytes, st>>>(tm, data, d_x, nullptr, g,
-                                                                                             g.b2 + g.b3, lo, hi);
+            (n % (2 * C) != 0 ? col_pass5_kernel<0, true> : col_pass5_kernel<0, false>)<<<dim3(pgrid(C >> 4), nb, 1), kC5Threads,
+                                                                                           kC5SmemBytes, st>>>(
+                tm, data, d_x, nullptr, g, g.b2 + g.b3, lo, hi);
         else if (fwd1_c4 && make_col_tensor_map(&tm, d_x, 2ull * C, (unsigned long long)(n / (2 * C)), nb, x_stride))
             col4_select(0, g.three)<<<dim3(pgrid(C >> 3), nb, 1), kC4Threads, kC4SmemBytes, st>>>(
                 tm, data, d_x, nullptr, g, g.b2 + g.b3, 1, lo, hi);
