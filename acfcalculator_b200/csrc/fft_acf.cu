@@ -1048,6 +1048,9 @@ col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
         }
         const double2 edge_now = edge;
         if (MODE == 0 && EDGE) edge = load_edge(tile + gridDim.x);
+        // the group's last-pass reads of S (previous tile) are done before anyone writes S in pass 1 below; the barrier sits
+        // here, where no butterfly is live (between the last pass's butterflies and its stores it cost eight 64-bit spills)
+        if (j != 0) named_bar_sync(1 + grp, 256);
         mbar_wait(full, j & 1);
 
         // ---- radix pass 1 (Stockham stride 1, p = g): L -> registers -> S
@@ -1124,34 +1127,34 @@ col_pass5_kernel(const __grid_constant__ CUtensorMap tmap, double2* __restrict__
         }
         named_bar_sync(1 + grp, 256);
 
-        // ---- last pass (radix 6, stride 64, no butterfly twiddles): S -> registers -> HBM; two items per thread
+        // ---- last pass (radix 6, stride 64, no butterfly twiddles): S -> registers -> HBM; two items per thread, one after
+        //      the other (both in registers at once, with their twiddles, spilled)
         {
-            double2 r[2][6];
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const int gg = g0 + 32 * it;
-#pragma unroll
-                for (int t = 0; t < R; ++t) r[it][t] = S[(gg + t * 64) * 16 + c];
-            }
-#pragma unroll
-            for (int it = 0; it < 2; ++it) dft6<DIR>(r[it]);
-            named_bar_sync(1 + grp, 256);   // S may be overwritten by the next tile's pass 1 from here on
-            double2 ta = make_double2(1.0, 0.0), tb = ta, d0 = ta;
+            double2 d0 = make_double2(1.0, 0.0);
             if (MODE == 0) {
-                ta = tstate[tid];
-                tb = tstate[kC5Threads + tid];
                 d0 = tstate[2 * kC5Threads + tid];
                 if (!reseed) {   // advance from this CTA's previous tile: cc grew by 16 * gridDim.x
-                    ta = cmul(ta, rho[g0]);
-                    tb = cmul(tb, rho[g0 + 32]);
                     d0 = cmul(d0, rho[64]);
-                    tstate[tid] = ta;
-                    tstate[kC5Threads + tid] = tb;
                     tstate[2 * kC5Threads + tid] = d0;
                 }
             }
-            store_group(cc, g0, r[0], ta, d0);
-            store_group(cc, g0 + 32, r[1], tb, d0);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int gg = g0 + 32 * it;
+                double2 r[6];
+#pragma unroll
+                for (int t = 0; t < R; ++t) r[t] = S[(gg + t * 64) * 16 + c];
+                dft6<DIR>(r);
+                double2 tt = make_double2(1.0, 0.0);
+                if (MODE == 0) {
+                    tt = tstate[it * kC5Threads + tid];
+                    if (!reseed) {
+                        tt = cmul(tt, rho[gg]);
+                        tstate[it * kC5Threads + tid] = tt;
+                    }
+                }
+                store_group(cc, gg, r, tt, d0);
+            }
         }
     }
 }
