@@ -1485,6 +1485,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             for (int u = 0; u < 8; ++u) by[sw(qq + ps * 8 + 8 * u)] = r[u];
             pair_sync();
         }
+        double2 za[8];   // this thread's spectrum points k3 = g + t*G8 (also written to X for the mirror row's thread)
         {   // last forward pass: radix 2^(B3-6), stride 64, Y -> X in natural order
             constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
             double2 r[8];
@@ -1503,6 +1504,10 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
 #pragma unroll
                 for (int u = 0; u < R; ++u) bx[sw(gg + 64 * u)] = r[it * R + u];
             }
+            // output (it, u) sits at k3 = g + it*G8 + 64u = g + (it + GPT*u)*G8: it IS this thread's pair-op point t = it + GPT*u
+            static_assert(64 / G8 == GPT, "the last-pass outputs of a thread are its own pair-op points");
+#pragma unroll
+            for (int t = 0; t < 8; ++t) za[t] = r[(t % GPT) * R + t / GPT];
             pair_sync();
         }
 
@@ -1515,7 +1520,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
         for (int t = 0; t < 8; ++t) {
             const int k3 = g + t * G8;
             const int p3 = origin ? ((N3 - k3) & (N3 - 1)) : (N3 - 1 - k3);
-            const double2 Za = bx[sw(k3)];
+            const double2 Za = za[t];   // (round 1 re-read it from shared memory)
             const double2 Zb = mx[sw(p3)];
             const double2 S = make_double2(Za.x + Zb.x, Za.y - Zb.y);   // Za + conj Zb
             const double2 D = make_double2(Za.x - Zb.x, Za.y + Zb.y);   // Za - conj Zb
