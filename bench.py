@@ -607,7 +607,7 @@ def roofline_of(env, w, ms_per_step, peak_tf, peaks):
 
 
 TRAFFIC_FFT3 = {  # (n, m) -> (bytes, source) for L = 3*2^a plans
-    (2**27, 2**26): (14.27e9, "profiles/r2z_fft_kernels_ncu_raw.csv (sum over the five passes of one step, L = 3*2^26)"),
+    (2**27, 2**26): (14.26e9, "profiles/r2z_fft_kernels_ncu_raw.csv (sum over the five passes of one step, L = 3*2^26)"),
 }
 
 
