@@ -1352,6 +1352,9 @@ row_pass_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict
 // on registers.  Each row thread evaluates the pair formula for its own 8 spectrum points (the mirror thread
 // evaluates it again from its side) so that the inverse transform starts from registers without another exchange.
 // Work list: one entry per unordered row pair {(k1,k2), mirror}; self-mirrored rows fill both slots of their pair.
+// dynamic shared memory: two tile buffers, butterfly tables (N3 slots), twp (N3/8), tqb (N3) and tqa (N2)
+static inline size_t row_smem_bytes(int n3, int n2) { return (size_t)(2 * 4096 + 2 * n3 + n3 / 8 + n2) * 16; }
+constexpr int kRowSmemMax = (2 * 4096 + 2 * 512 + 64 + 512) * 16;
 template <int B3>
 __global__ void __launch_bounds__(kColThreads, 1)
 row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restrict__ lo, const double2* __restrict__ hi)
@@ -1373,6 +1376,28 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     double2* bdata = data + (long long)blockIdx.y * G.Nc;
     // butterfly twiddles in warp-contiguous layout: twf[(u-1)*G8 + g] = W_N3^{g*u}, twm[(u-1)*(G8/8) + p] = W_N3^{8pu}
     double2* twm = twf + 7 * G8;
+    // Twiddles that used to be gathered from the global W_L tables once per thread and tile (scattered 16-byte loads: 32
+    // L1 wavefronts per warp and load, 18 % of the kernel's LSU traffic in round 2) come from three more shared tables:
+    //   twp[g]  = W_L^{g*N1*N2} = W_{2*N3}^g            pair-op twiddle W_L^k = W_L^{k1 + N1*k2} * twp[g] * rot^t
+    //   tqb[j]  = W_{N2*N3}^j,  tqa[i] = W_{N2}^i       post twiddle W_Nc^{j3*N1*k2} = W_{N2*N3}^{j3*k2} = tqa[p >> B3] * tqb[p % N3]
+    // (the post-twiddle tables exist when N2 > 1; the two-factor plans keep the gathers)
+    double2* twp = twf + N3;
+    double2* tqb = twp + G8;
+    double2* tqa = tqb + N3;
+    const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);  // exponents stay below Nc anyway
+    const unsigned int n12 = N1 << G.b2;              // N1 * N2: spectrum index k = k1 + N1*k2 + N1*N2*k3
+    {
+        for (int m = tid; m < G8; m += kColThreads) twp[m] = tw_L(lo, hi, (unsigned long long)m * n12);
+        if (G.b2 > 0) {
+            const unsigned long long ustep = (unsigned long long)(G.L >> (G.b2 + B3));   // W_{N2*N3} = W_L^ustep
+            for (int m = tid; m < N3 + (int)N2; m += kColThreads) {
+                if (m < N3)
+                    tqb[m] = tw_L(lo, hi, (unsigned long long)m * ustep);
+                else
+                    tqa[m - N3] = tw_L(lo, hi, ((unsigned long long)(m - N3) << B3) * ustep);
+            }
+        }
+    }
     {
         const unsigned int wstep = (unsigned int)(G.L >> B3);
         for (int m = tid; m < 7 * G8 + 7 * (G8 / 8); m += kColThreads) {
@@ -1384,8 +1409,6 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             twf[m] = tw_L(lo, hi, (unsigned long long)e * wstep);
         }
     }
-    const unsigned int nc_mask = G.three ? 0xFFFFFFFFu : (unsigned int)(G.Nc - 1);  // exponents stay below Nc anyway
-    const unsigned int n12 = N1 << G.b2;              // N1 * N2: spectrum index k = k1 + N1*k2 + N1*N2*k3
 
     // digits (k1, k2) of the row held by slot `rs` of tile `tile`; false past the end of the list
     auto slot_row = [&](unsigned int tile, unsigned int& r1, unsigned int& r2, bool& origin) -> bool {
@@ -1443,6 +1466,24 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
     // pass reads one and writes the other, and the roles swap from tile to tile, so each of the five hand-offs of a
     // tile needs exactly one pair barrier (the in-place version needed ten).
     __syncthreads();
+    // First-pass twiddles W_N3^{g*u}, u = 1..7, of this thread's radix group: u = 1, 2, 4 from the table, the other four as
+    // products (three shared loads and 16 FP64 instructions instead of seven loads; the kernel is bound by the shared
+    // memory pipe, not by FP64.  Keeping the three in registers across tiles was not faster and a fourth spilled).
+    auto apply_twf = [&](double2 (&v)[8], const bool inverse) {
+        if (g == 0) return;
+        const double2 t1 = twf[g], t2 = twf[G8 + g], t4 = twf[3 * G8 + g];
+        const double sg = inverse ? -1.0 : 1.0;
+        const double2 w1 = make_double2(t1.x, sg * t1.y), w2 = make_double2(t2.x, sg * t2.y),
+                      w4 = make_double2(t4.x, sg * t4.y);
+        const double2 w3 = cmul(w1, w2);
+        v[1] = cmul(v[1], w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], cmul(w4, w1));
+        v[6] = cmul(v[6], cmul(w4, w2));
+        v[7] = cmul(v[7], cmul(w4, w3));
+    };
     double2 nxt[8];  // the next tile's row, in flight while this one is transformed
 #pragma unroll
     for (int t = 0; t < 8; ++t) nxt[t] = make_double2(0.0, 0.0);
@@ -1461,10 +1502,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
 
         // ================= forward transform along the row (DIR = -1) =================
         dft8<-1>(v);
-        if (g != 0) {
-#pragma unroll
-            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], twf[(u - 1) * G8 + g]);
-        }
+        apply_twf(v, false);
 #pragma unroll
         for (int u = 0; u < 8; ++u) bx[sw(8 * g + u)] = v[u];
 #pragma unroll
@@ -1485,6 +1523,9 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
             for (int u = 0; u < 8; ++u) by[sw(qq + ps * 8 + 8 * u)] = r[u];
             pair_sync();
         }
+        // W_L^{k1 + N1*k2} of this row (one address per row: a broadcast load), asked for a pass ahead of its use
+        const unsigned int kbase = r1 + r2 * N1;
+        const double2 wrow = tw_L(lo, hi, (unsigned long long)kbase);
         double2 za[8];   // this thread's spectrum points k3 = g + t*G8 (also written to X for the mirror row's thread)
         {   // last forward pass: radix 2^(B3-6), stride 64, Y -> X in natural order
             constexpr int LEFT = B3 - 6, R = 1 << LEFT, GPT = 8 / R, GROUPS = N3 / R;
@@ -1513,8 +1554,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
 
         // ================= |X|^2 pair operation for this thread's 8 spectrum points (reads X) =================
         // W_L^k for k = kbase + N1*N2*(g + t*N3/8): successive t differ by W_L^{Nc/8} = exp(-i pi/8), a constant
-        const unsigned int kbase = r1 + r2 * N1;
-        double2 W = tw_L(lo, hi, (unsigned long long)(kbase + (unsigned int)g * n12));
+        double2 W = cmul(wrow, twp[g]);
         const double2 rot = make_double2(0.92387953251128675613, -0.38268343236508977173);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -1536,10 +1576,7 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
 
         // ================= inverse transform along the row (DIR = +1, conjugated table) =================
         dft8<+1>(v);
-        if (g != 0) {
-#pragma unroll
-            for (int u = 1; u < 8; ++u) v[u] = cmul(v[u], cconj(twf[(u - 1) * G8 + g]));
-        }
+        apply_twf(v, true);
 #pragma unroll
         for (int u = 0; u < 8; ++u) by[sw(8 * g + u)] = v[u];
         pair_sync();
@@ -1575,8 +1612,16 @@ row_pass2_kernel(double2* __restrict__ data, FftGeom G, const double2* __restric
                     dft2(r);
                 // post twiddle conj(W_Nc^{j3*f}), j3 = j0 + 64u: exponents in arithmetic progression
                 const unsigned int j0 = gg;
-                double2 tq = cconj(tw_L(lo, hi, 2ull * ((j0 * f) & nc_mask)));
-                const double2 dq = cconj(tw_L(lo, hi, 2ull * ((64u * f) & nc_mask)));
+                double2 tq, dq;
+                if (G.b2 > 0) {   // f = N1*k2: W_Nc^{j*f} = W_{N2*N3}^{j*k2}, j*k2 < N2*N3
+                    const unsigned int p = j0 * r2, pd = 64u * r2;
+                    FFT_ASSERT((p >> B3) < N2 && (pd >> B3) < N2);
+                    tq = cconj(cmul(tqa[p >> B3], tqb[p & (N3 - 1)]));
+                    dq = cconj(cmul(tqa[pd >> B3], tqb[pd & (N3 - 1)]));
+                } else {
+                    tq = cconj(tw_L(lo, hi, 2ull * ((j0 * f) & nc_mask)));
+                    dq = cconj(tw_L(lo, hi, 2ull * ((64u * f) & nc_mask)));
+                }
 #pragma unroll
                 for (int u = 0; u < R; ++u) {
                     FFT_ASSERT(!valid || ((size_t)((r1 << G.b2) + r2) << B3) + j0 + 64 * u < (size_t)G.Nc);
@@ -1768,9 +1813,9 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         cudaFuncSetAttribute(col_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
         cudaFuncSetAttribute(col_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 16);
-        cudaFuncSetAttribute(row_pass2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
-        cudaFuncSetAttribute(row_pass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
-        cudaFuncSetAttribute(row_pass2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4096 + 512) * 16);
+        cudaFuncSetAttribute(row_pass2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemMax);
+        cudaFuncSetAttribute(row_pass2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemMax);
+        cudaFuncSetAttribute(row_pass2_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemMax);
         for (int mode = 0; mode < 4; ++mode)
             for (int bb = 3; bb <= 9; ++bb)
                 cudaFuncSetAttribute(col2_select(mode, bb), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1855,7 +1900,7 @@ int launch_fft_acf_batch(const double* d_x, long long n, long long x_stride, int
         ++launches;
     }
     if (pipelined && g.b1 > 0 && g.b3 >= 7) {
-        const size_t smem = (size_t)(2 * 4096 + N3) * 16;
+        const size_t smem = row_smem_bytes((int)N3, (int)N2);
         if (g.b3 == 9)
             row_pass2_kernel<9><<<dim3(sms, nb, 1), kColThreads, smem, st>>>(data, g, lo, hi);
         else if (g.b3 == 8)
