@@ -98,6 +98,7 @@ SIGNATURES = {
                                      C.c_void_p]),
     "acfb200_image_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _I64, C.c_double, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
+    "acfb200_msd_last_path": (C.c_int, [C.POINTER(C.c_int), _P, _PI64]),
     "acfb200_describe_plan": (C.c_int, [_I64, _I64, C.c_int, C.c_char_p, C.c_int]),
     "acfb200_set_variant": (C.c_int, [C.c_int]),
     "acfb200_set_method": (C.c_int, [C.c_int]),

@@ -232,6 +232,14 @@ def msd(x, y=None, z=None, stride=1, max_s=1000):
     return out, cnt
 
 
+def msd_last_path():
+    """How this thread's last single-device MSD call computed its sums: dict(path='direct' | 'hybrid' | 'hybrid-refused',
+    cond, j0) -- see acfb200_msd_last_path in include/acf_b200.h."""
+    path, cond, j0 = C.c_int(), C.c_double(), C.c_int64()
+    check(_lib.load().acfb200_msd_last_path(C.byref(path), C.byref(cond), C.byref(j0)))
+    return {"path": ("direct", "hybrid", "hybrid-refused")[path.value], "cond": cond.value, "j0": j0.value}
+
+
 def image(x, y, z, L):
     """Unwrapped copies of the coordinate arrays (image(), traj2diffusion.cpp:275-340)."""
     x, y, z = (_f64(a).copy() for a in (x, y, z))

@@ -113,6 +113,7 @@ struct Workspace {
     cudaStream_t stream3 = nullptr;      // results of the window batch on their way out
     cudaStream_t copy_stream = nullptr;  // H2D of the next window group while the current one computes
     Buf series, y, vel, desc, partials, out, scratch, small, fftwork, queue, wins;
+    Buf msd_c, msd_w, msd_sc;            // hybrid FFT form of the MSD: centred axes, lags / edge sums / combined sums, reductions
     HostBuf pinned;                      // staging of results on their way to pageable caller memory
     void release()
     {
@@ -132,6 +133,9 @@ struct Workspace {
         fftwork.release();
         queue.release();
         wins.release();
+        msd_c.release();
+        msd_w.release();
+        msd_sc.release();
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         stream = nullptr;

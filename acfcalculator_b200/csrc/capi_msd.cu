@@ -85,6 +85,97 @@ int msd_finalize_sums(Workspace* ws, int axes, const long long* n_total, int ntr
     return 0;
 }
 
+// ---- hybrid Wiener-Khinchin form of the unit-stride MSD (acfb200_set_method fft / auto; kernels in msd.cu) -----------
+// Which way the calling thread's last single-device MSD call went (acfb200_msd_last_path).
+struct MsdPathInfo {
+    int path = 0;        // 0 direct displacement kernel; 1 hybrid; 2 hybrid refused by its conditioning guard, recomputed directly
+    double cond = 0.0;   // the guard's figure of the last hybrid attempt: max_{j >= j0} 2 sum(y^2) / displacement sum
+    long long j0 = 0;    // first lag taken from the Wiener-Khinchin form
+};
+static thread_local MsdPathInfo g_msd_info;
+
+// The form computes a displacement sum as a difference of terms of size T = sum(y^2): it loses log10(2T / sum) digits
+// on top of the FFT's own ~1e-15 * T.  2T / sum <= kMsdCondMax keeps the result within ~2e-12 relative, a factor 50
+// inside north_star's 1e-10.  For a diffusing particle 2T / sum ~ n / (3 j): lags below j0 = max(2048, n / 4096) stay
+// with the direct kernel; anything worse than the bound at a later lag (drift, a trajectory pinned far from its mean)
+// sends the whole call back to the direct kernel.
+constexpr double kMsdCondMax = 2000.0;
+constexpr long long kMsdHybridMinLags = 4096;
+
+static long long msd_hybrid_j0(long long n)
+{
+    long long j0 = (n / 4096 + 255) / 256 * 256;
+    return j0 < 2048 ? 2048 : j0;
+}
+
+// One trajectory, unit stride, max_s in [4096, n], a transform the FFT kernels have a plan for; under `auto` also cheaper
+// by the cost model (rates measured on B200: displacement kernel 2.9e12 frame-lag pairs/s, FFT passes 4.2e12 B/s).
+static bool msd_hybrid_wanted(long long n, long long stride, long long max_s, int per, size_t* fft_bytes)
+{
+    if (g_method == 0 || stride != 1 || max_s < kMsdHybridMinLags || max_s > n) return false;
+    const long long j0 = msd_hybrid_j0(n);
+    if (2 * j0 > max_s) return false;
+    long long L = 0;
+    if ((long long)n + max_s - 1 > (1ll << 28) || fft_acf_workspace_bytes_batch(n, max_s, per, fft_bytes, &L) != 0)
+        return false;
+    if (g_method == 1) return true;
+    const double t_direct = (double)per * (double)n * (double)max_s / 2.9e12;
+    const double t_hybrid = (double)per * (double)n * (double)j0 / 2.9e12 +
+                            (double)per * (40.0 * (double)n + 64.0 * (double)L) / 4.2e12 + 2.0e-4;
+    return t_hybrid < t_direct;
+}
+
+// Returns 0 (d_msd / d_counter hold the result), an error code > 0, or -1: the conditioning guard refused the form and
+// the caller runs the direct kernel.  Synchronises `st` once (the guard's figure is read on the host).
+static int msd_hybrid_device(Workspace* ws, const double* const* axes, int per, long long n, long long max_s,
+                             size_t fft_bytes, double* d_msd, int* d_counter, cudaStream_t st)
+{
+    const long long j0 = msd_hybrid_j0(n);
+    const size_t pitch = even_up(n), m = (size_t)max_s;
+    ACF_TRY(ws->msd_c.ensure((size_t)per * pitch * 8));
+    ACF_TRY(ws->msd_w.ensure(((size_t)4 * per * m + (size_t)per * j0 + 2) * 8));
+    ACF_TRY(ws->msd_sc.ensure(sizeof(ReduceScratch) * 3, true));
+    ACF_TRY(ws->fftwork.ensure(fft_bytes));
+    double* yc = ws->msd_c.as<double>();
+    double* d_c = ws->msd_w.as<double>();                 // [per][max_s] lags of the centred axes
+    double* d_edge = d_c + (size_t)per * m;               // [per][2][max_s]
+    double* d_sums = d_edge + (size_t)2 * per * m;        // [per][max_s]
+    double* d_head = d_sums + (size_t)per * m;            // [per][j0] direct sums of the small lags
+    unsigned long long* d_cond = reinterpret_cast<unsigned long long*>(d_head + (size_t)per * j0);
+    ReduceScratch* sc = ws->msd_sc.as<ReduceScratch>();
+    // lags below j0: the displacement kernel on the caller's (uncentred) axes, bit for bit the direct path's sums
+    std::vector<SeriesDesc> descs(per);
+    for (int a = 0; a < per; ++a) descs[a] = {axes[a], n, n};
+    ACF_TRY(msd_block_sums(ws, descs, 1, j0, st));        // -> ws->out [per][j0]; ws->desc keeps {x, n, n} per axis
+    ACF_CUDA_OK(cudaMemcpyAsync(d_head, ws->out.p, (size_t)per * j0 * 8, cudaMemcpyDeviceToDevice, st));
+    // centred copies and their sums of squares
+    for (int a = 0; a < per; ++a) {
+        ACF_TRY(launch_sum(axes[a], n, sc + a, st));
+        ACF_TRY(launch_center_velocity(axes[a], n, sc + a, yc + (size_t)a * pitch, nullptr, 1.0, st));
+        ACF_TRY(launch_sumsq(yc + (size_t)a * pitch, n, sc + a, st));
+    }
+    g_launches += 3 * per;
+    const int fl = launch_fft_acf_batch(yc, n, (long long)pitch, per, max_s, d_c, max_s, 1, ws->fftwork.p, ws->fftwork.cap, st);
+    if (fl < 0) return ACFB200_ERR_CUDA;
+    g_launches += fl;
+    ACF_TRY(launch_msd_edge_sums(yc, (long long)pitch, per, n, max_s, d_edge, st));
+    ACF_CUDA_OK(cudaMemsetAsync(d_cond, 0, 8, st));
+    ACF_TRY(launch_msd_fft_combine(d_c, d_edge, sc, d_head, n, max_s, j0, per, d_sums, d_cond, st));
+    ACF_TRY(launch_msd_finalize(d_sums, ws->desc.as<SeriesDesc>(), per, 1, 1, max_s, d_msd, d_counter, st));
+    g_launches += 3;
+    double cond = 0.0;
+    ACF_CUDA_OK(cudaMemcpyAsync(&cond, d_cond, 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaStreamSynchronize(st));
+    g_msd_info.cond = cond;
+    g_msd_info.j0 = j0;
+    if (!(cond <= kMsdCondMax)) {
+        g_msd_info.path = 2;
+        return -1;
+    }
+    g_msd_info.path = 1;
+    return 0;
+}
+
 // Displacement sums of ntraj device-resident trajectories -> msd[ntraj][max_s], counter[ntraj][max_s] (device), one
 // launch over all axes of all trajectories.  axes[3*t + a] is coordinate a of trajectory t; when every trajectory
 // passes one array three times (the general reader's y = z = x) each is computed once.  Unit stride runs the tiled
@@ -99,6 +190,12 @@ static int msd_batch_device(Workspace* ws, const double* const* axes, const long
         if (n[t] > n_max) n_max = n[t];
     }
     const int per = one_axis ? 1 : 3, ns = per * ntraj;
+    g_msd_info = MsdPathInfo();
+    size_t fft_bytes = 0;
+    if (ntraj == 1 && msd_hybrid_wanted(n[0], stride, max_s, per, &fft_bytes)) {
+        const int rc = msd_hybrid_device(ws, axes, per, n[0], max_s, fft_bytes, d_msd, d_counter, st);
+        if (rc >= 0) return rc;  // -1: refused by the conditioning guard, the direct kernel below recomputes everything
+    }
     std::vector<SeriesDesc> descs(ns);
     for (int t = 0; t < ntraj; ++t)
         for (int a = 0; a < per; ++a) descs[per * t + a] = {axes[3 * t + a], n[t], n[t]};
@@ -185,6 +282,14 @@ int acfb200_msd_device(const double* d_x, const double* d_y, const double* d_z, 
     Workspace* ws;
     ACF_TRY(get_ws(&ws));
     return msd_device(ws, d_x, d_y, d_z, n, stride, max_s, d_msd, d_counter, (cudaStream_t)stream);
+}
+
+int acfb200_msd_last_path(int* path, double* cond, int64_t* j0)
+{
+    if (path) *path = g_msd_info.path;
+    if (cond) *cond = g_msd_info.cond;
+    if (j0) *j0 = g_msd_info.j0;
+    return 0;
 }
 
 int acfb200_image_device(const double* d_x, const double* d_y, const double* d_z, int64_t n, double cell, double* d_xo,

@@ -148,6 +148,128 @@ int launch_msd_slope(const double* d_msd, long long n, int ncurves, double* d_ou
 }
 
 // ------------------------------------------------------------------------------------------------
+// Hybrid Wiener-Khinchin form of the unit-stride displacement sums for large max_s (traj2diffusion.cpp:530-541 at
+// `max` >~ 1e4, where the direct kernel's n*max_s terms dominate).  Per axis, with y = x - mean(x):
+//     sum_{i < n-j} (y[i+j] - y[i])^2 = (T - pre[j]) + (T - suf[j]) - 2 S[j]
+//     T = sum y^2,  pre[j] = sum_{i<j} y[i]^2,  suf[j] = sum_{i<j} y[n-1-i]^2,  S[j] = sum_{i<n-j} y[i] y[i+j]
+// S comes from the FFT kernels (fft_acf.cu), T from sum_kernel<SQUARE>, pre/suf from the scan below.  The four terms
+// are each of size T while the result is the displacement sum, so the form loses log10(2T / result) digits: lags below
+// j0 keep the direct kernel's sums, and the combine kernel reports the worst 2T / result it met so that the host can
+// refuse the form (capi_msd.cu) when a trajectory is too ill-conditioned for the 1e-10 bar.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEdgeThreads = 1024;
+
+// grid (2 sides, axes): edge[axis][0][j] = pre[j], edge[axis][1][j] = suf[j] for j < m (m <= n).  One CTA per curve:
+// contiguous slice per thread, exclusive scan across the threads (the scheme of integrate_cutoff_kernel).
+__global__ void __launch_bounds__(kEdgeThreads)
+msd_edge_sums_kernel(const double* __restrict__ y, long long pitch, long long n, long long m, double* __restrict__ edge)
+{
+    __shared__ double sh_sum[32];
+    const int side = blockIdx.x, axis = blockIdx.y;
+    const double* __restrict__ ya = y + (long long)axis * pitch;
+    double* __restrict__ out = edge + ((long long)axis * 2 + side) * m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long per = (m + kEdgeThreads - 1) / kEdgeThreads;
+    long long lo = (long long)tid * per;
+    if (lo > m) lo = m;
+    const long long hi = lo + per < m ? lo + per : m;
+    double local = 0.0;
+    for (long long i = lo; i < hi; ++i) {
+        const double v = side ? ya[n - 1 - i] : ya[i];
+        local += v * v;
+    }
+    double incl = local;  // inclusive scan across the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+    }
+    if (lane == 31) sh_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        double w = sh_sum[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += o;
+        }
+        sh_sum[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    double run = (incl - local) + (warp > 0 ? sh_sum[warp - 1] : 0.0);  // squares of [0, lo)
+    for (long long i = lo; i < hi; ++i) {
+        out[i] = run;
+        const double v = side ? ya[n - 1 - i] : ya[i];
+        run += v * v;
+    }
+}
+
+// sums[a][j] for j < m: the direct kernel's head[a][j] below j0, the Wiener-Khinchin form from j0 on (c = the FFT path's
+// lags of the centred axes, i.e. S[j] / (n - j)).  *cond_bits (zeroed by the caller) receives the bit pattern of
+// max_{j >= j0} 2 sum_a T_a / sum_a sums[a][j]  (+inf when a combined sum is not positive or not a number).
+__global__ void __launch_bounds__(256)
+msd_fft_combine_kernel(const double* __restrict__ c, const double* __restrict__ edge, const ReduceScratch* __restrict__ sc,
+                       const double* __restrict__ head, long long n, long long m, long long j0, int axes,
+                       double* __restrict__ sums, unsigned long long* __restrict__ cond_bits)
+{
+    __shared__ double sh[8];
+    const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
+    double cond = 0.0;
+    if (j < m) {
+        if (j < j0) {
+            for (int a = 0; a < axes; ++a) sums[(long long)a * m + j] = head[(long long)a * j0 + j];
+        } else {
+            const double cnt = (double)(n - j);
+            double t_all = 0.0, s_all = 0.0;
+            for (int a = 0; a < axes; ++a) {
+                const double T = sc[a].meansq * (double)n;
+                const double pre = edge[((long long)a * 2) * m + j], suf = edge[((long long)a * 2 + 1) * m + j];
+                const double v = ((T - pre) + (T - suf)) - 2.0 * (c[(long long)a * m + j] * cnt);
+                sums[(long long)a * m + j] = v;
+                t_all += T;
+                s_all += v;
+            }
+            cond = s_all > 0.0 ? 2.0 * t_all / s_all : __longlong_as_double(0x7FF0000000000000ull);
+            if (!(cond == cond)) cond = __longlong_as_double(0x7FF0000000000000ull);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, cond, off);
+        cond = o > cond ? o : cond;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cond;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double w = sh[0];
+        for (int k = 1; k < 8; ++k) w = sh[k] > w ? sh[k] : w;
+        if (w > 0.0) atomicMax(cond_bits, (unsigned long long)__double_as_longlong(w));  // non-negative doubles order like their bits
+    }
+}
+
+int launch_msd_edge_sums(const double* d_y, long long pitch, int axes, long long n, long long m, double* d_edge,
+                         cudaStream_t st)
+{
+    if (m < 1 || m > n || axes < 1) {
+        set_error("launch_msd_edge_sums: need 1 <= m <= n (got m=%lld, n=%lld)", m, n);
+        return 1;
+    }
+    msd_edge_sums_kernel<<<dim3(2, axes), kEdgeThreads, 0, st>>>(d_y, pitch, n, m, d_edge);
+    ACF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_msd_fft_combine(const double* d_c, const double* d_edge, const ReduceScratch* d_sc, const double* d_head,
+                           long long n, long long m, long long j0, int axes, double* d_sums,
+                           unsigned long long* d_cond_bits, cudaStream_t st)
+{
+    msd_fft_combine_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_c, d_edge, d_sc, d_head, n, m, j0, axes, d_sums,
+                                                                        d_cond_bits);
+    ACF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Imaging
 // ------------------------------------------------------------------------------------------------
 constexpr int kImgThreads = 256;

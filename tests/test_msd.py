@@ -287,3 +287,178 @@ def test_gpu_msd_argument_errors(acf):
     for kw in (dict(stride=0), dict(max_s=0)):
         with pytest.raises(acf._lib.AcfError):
             acf.msd(x, x, x, **{**dict(stride=1, max_s=4), **kw})
+
+
+# ---- hybrid Wiener-Khinchin form for large max_s (acfb200_set_method fft / auto) --------------------------------
+# CPU: a numpy model of the two kernels (msd.cu: msd_edge_sums_kernel, msd_fft_combine_kernel) and of the host rule
+# (capi_msd.cu: j0, the conditioning guard) against the oracle -- pins the algorithm and its constants.
+# GPU: the library itself against the oracle, and the guard's fallback.
+COND_MAX, MIN_LAGS = 2000.0, 4096
+
+
+def hybrid_j0(n):
+    return max(2048, (n // 4096 + 255) // 256 * 256)
+
+
+def edge_sums_model(y, m, threads=1024):
+    """pre[j] = sum_{i<j} y[i]^2 and suf[j] = sum_{i<j} y[n-1-i]^2, j < m, with the kernel's slicing: a contiguous
+    slice per thread, exclusive scan across the threads."""
+    out = []
+    for side in (0, 1):
+        sq = (y[::-1][:m] if side else y[:m]) ** 2
+        per = (m + threads - 1) // threads
+        local = np.array([sq[min(t * per, m):min(t * per + per, m)].sum() for t in range(threads)])
+        base = np.concatenate(([0.0], np.cumsum(local)[:-1]))
+        e = np.empty(m)
+        for t in range(threads):
+            lo, hi = min(t * per, m), min(t * per + per, m)
+            if hi > lo:
+                e[lo:hi] = base[t] + np.concatenate(([0.0], np.cumsum(sq[lo:hi])[:-1]))
+        out.append(e)
+    return out
+
+
+def hybrid_model(axes, max_s, head):
+    """(sums[axis][max_s], cond): the combine kernel.  head[axis][j0] = the direct sums of the small lags."""
+    from scipy.fft import irfft, next_fast_len, rfft
+    n = axes[0].size
+    j0 = hybrid_j0(n)
+    sums, t_all = [], 0.0
+    for a, x in enumerate(axes):
+        y = x - x.sum() / n
+        T = (y * y).sum() / n * n
+        L = next_fast_len(n + max_s - 1, real=True)
+        X = rfft(y, L)
+        c = irfft(X * np.conj(X), L)[:max_s] / (n - np.arange(max_s))     # what the FFT kernels return
+        pre, suf = edge_sums_model(y, max_s)
+        s = ((T - pre) + (T - suf)) - 2.0 * (c * (n - np.arange(max_s)))
+        s[:j0] = head[a]
+        sums.append(s)
+        t_all += T
+    tot = np.sum(sums, axis=0)[j0:]
+    cond = np.max(np.where(tot > 0, 2.0 * t_all / np.where(tot > 0, tot, 1.0), np.inf))
+    return np.array(sums), float(cond)
+
+
+def test_edge_sums_model_is_a_prefix_sum():
+    y = np.random.default_rng(4).standard_normal(5000)
+    for m in (1, 2, 1023, 1024, 1025, 4999, 5000):
+        pre, suf = edge_sums_model(y, m)
+        assert np.allclose(pre, np.concatenate(([0.0], np.cumsum(y[:m - 1] ** 2))), rtol=1e-13, atol=0)
+        assert np.allclose(suf, np.concatenate(([0.0], np.cumsum(y[::-1][:m - 1] ** 2))), rtol=1e-13, atol=0)
+
+
+def test_hybrid_model_matches_oracle_and_guard_rejects_drift(oracle):
+    n, max_s = 60000, 9000
+    j0 = hybrid_j0(n)
+    assert j0 == 2048 and 2 * j0 <= max_s and max_s >= MIN_LAGS
+    r = walk(n, 91)
+    axes = [np.ascontiguousarray(r[:, a]) for a in range(3)]
+    want, cnt = oracle.msd(axes[0], axes[1], axes[2], 1, max_s, threads=0)
+    head = []
+    for a in range(3):   # per-axis direct sums of the small lags (msd of one axis three times = 3 * its sums / cnt)
+        m1, c1 = oracle.msd(axes[a], axes[a], axes[a], 1, j0, threads=0)
+        head.append(m1 * c1 / 3.0)
+    sums, cond = hybrid_model(axes, max_s, head)
+    got = sums.sum(axis=0) / cnt
+    assert cond <= COND_MAX                      # a diffusing particle: 2T/sum ~ n/(3 j0) ~ 10
+    assert rel_err(got[1:], want[1:]) <= 1e-11   # a factor 10 inside the bar at cond ~ 10
+    # drift: the spread about the mean grows like n^2 while the displacements grow like j^2 -> refused
+    # (2T/sum ~ n^2 / (6 j^2) at lag j: 2480 at j0 for 250 000 frames)
+    n = 250000
+    t = np.arange(n, dtype=np.float64)
+    drift = [0.01 * t + 0.001 * np.random.default_rng(5 + a).standard_normal(n) for a in range(3)]
+    head = []
+    for a in range(3):
+        m1, c1 = oracle.msd(drift[a], drift[a], drift[a], 1, j0, threads=0)
+        head.append(m1 * c1 / 3.0)
+    sums, cond = hybrid_model(drift, max_s, head)
+    assert COND_MAX < cond < 3000
+    # ... and what the guard protects against: the form is still good to ~cond * 1e-15 there, not to 1e-15
+    want, cnt = oracle.msd(drift[0], drift[1], drift[2], 1, max_s, threads=0)
+    err = rel_err((sums.sum(axis=0) / cnt)[1:], want[1:])
+    assert 1e-14 < err < 1e-10
+
+
+def _default_method():
+    import os
+    return os.environ.get("ACFB200_TEST_METHOD") or "direct"
+
+
+@pytest.mark.gpu
+def test_gpu_msd_hybrid_against_oracle(acf, oracle):
+    n, max_s = 300_000, 60_000
+    r = walk(n, 91)
+    x, y, z = (np.ascontiguousarray(r[:, a]) for a in range(3))
+    want, wcnt = oracle.msd(x, y, z, 1, max_s, threads=0)
+    try:
+        acf.set_method("direct")
+        head, _ = acf.msd(x, y, z, max_s=2048)
+        assert acf.msd_last_path()["path"] == "direct"
+        acf.set_method("fft")
+        got, cnt = acf.msd(x, y, z, max_s=max_s)
+        info = acf.msd_last_path()
+        acf.set_method("auto")                    # 18 ms of displacement kernel against < 1 ms: the cost model agrees
+        got2, _ = acf.msd(x, y, z, max_s=max_s)
+        info2 = acf.msd_last_path()
+        small, _ = acf.msd(x, y, z, max_s=1000)   # ... and leaves the program's default max alone
+        info3 = acf.msd_last_path()
+    finally:
+        acf.set_method(_default_method())
+    assert info["path"] == "hybrid" and info["j0"] == 2048 and 0 < info["cond"] <= COND_MAX, info
+    assert rel_err(got, want) <= REL
+    assert np.array_equal(cnt, wcnt)
+    assert np.array_equal(got[:2048], head)      # small lags: the displacement kernel's own sums, bit for bit
+    assert info2["path"] == "hybrid" and np.array_equal(got2, got)
+    assert info3["path"] == "direct" and rel_err(small, want[:1000]) <= REL
+
+
+@pytest.mark.gpu
+def test_gpu_msd_hybrid_guard_falls_back_to_direct(acf, oracle):
+    n, max_s = 300_000, 20_000
+    t = np.arange(n, dtype=np.float64)
+    axes = [0.01 * t + 0.001 * np.random.default_rng(5 + a).standard_normal(n) for a in range(3)]
+    try:
+        acf.set_method("direct")
+        direct, dcnt = acf.msd(*axes, max_s=max_s)
+        acf.set_method("fft")
+        got, cnt = acf.msd(*axes, max_s=max_s)
+        info = acf.msd_last_path()
+    finally:
+        acf.set_method(_default_method())
+    assert info["path"] == "hybrid-refused" and info["cond"] > COND_MAX, info
+    assert np.array_equal(got, direct) and np.array_equal(cnt, dcnt)
+    lags = [0, 1, 2047, 2048, 5000, max_s - 1]
+    for j in lags:
+        want = sum(float(np.dot(a[j:] - a[:n - j], a[j:] - a[:n - j])) for a in axes) / (n - j)
+        assert got[j] == 0.0 if j == 0 else abs(got[j] - want) <= REL * want, j
+
+
+@pytest.mark.gpu
+def test_gpu_traj2diffusion_hybrid_with_imaging_and_one_axis(acf, oracle):
+    """main() of traj2diffusion with a large max: imaging on the device, hybrid sums, slope and D; then the general
+    reader's y = z = x shape (one array three times) and the device-resident entry point."""
+    import torch
+    n, max_s, box = 120_000, 30_000, 9.5
+    r = walk(n, 17, step=0.9)
+    w = [np.ascontiguousarray((r - box * np.floor(r / box))[:, a]) for a in range(3)]
+    un = oracle.image(w[0], w[1], w[2], box)
+    want, wcnt = oracle.msd(un[0], un[1], un[2], 1, max_s, threads=0)
+    want1, _ = oracle.msd(un[0], un[0], un[0], 1, max_s, threads=0)
+    try:
+        acf.set_method("fft")
+        d = acf.traj2diffusion(w[0], w[1], w[2], stride=1, max_s=max_s, timestep=2.0, cell=box)
+        info = acf.msd_last_path()
+        one, _ = acf.msd(un[0], max_s=max_s)
+        info1 = acf.msd_last_path()
+        xs = [torch.from_numpy(a).cuda() for a in un]
+        dev, dcnt = acf.msd_device(*xs, stride=1, max_s=max_s)
+        torch.cuda.synchronize()
+        info2 = acf.msd_last_path()
+    finally:
+        acf.set_method(_default_method())
+    assert info["path"] == info1["path"] == info2["path"] == "hybrid", (info, info1, info2)
+    assert rel_err(d["msd"], want) <= REL and np.array_equal(d["counter"], wcnt)
+    assert abs(d["diffusivity"] - oracle.msd_diffusivity(want, 2.0, 1)) <= REL * abs(d["diffusivity"])
+    assert rel_err(one, want1) <= REL
+    assert rel_err(dev.cpu().numpy(), want) <= REL and np.array_equal(dcnt.cpu().numpy(), wcnt)
