@@ -14,6 +14,12 @@
 // its OUTFILE, or to this program's stdout after a "#batch run i: <arguments>" line; a run that fails is reported with
 // the status the single run would have had ("#batch run i ended with status s") and the others go on; the exit status
 // is the first failure's.
+//
+// Extension: --method direct|fft|auto (anywhere on the command line, also with --batch) -- acfb200_set_method.  `direct`
+// (the default) sums the displacements like the reference; `auto` lets a unit-stride run with a large --max take the
+// hybrid Wiener-Khinchin form (include/acf_b200.h, acfb200_msd_last_path: 33x at 1e7 frames, --max 100000) when the
+// cost model expects it to be faster, `fft` whenever it applies; both keep MSD within ~1e-12 relative of the direct sums
+// or fall back to them.  ACFB200_TRACE=1 reports on stderr which form a single run took.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -275,8 +281,26 @@ int run_batch(const std::string& list_fname, int gpus)
 }
 }  // namespace
 
-int main(int argc, char* argv[])
+int main(int argc0, char* argv0[])
 {
+    // --method M is taken out of the command line first; what is left is handled exactly as before
+    std::vector<char*> kept;
+    for (int i = 0; i < argc0; ++i) {
+        if (i > 0 && strcmp(argv0[i], "--method") == 0) {
+            const char* m = i + 1 < argc0 ? argv0[i + 1] : "";
+            const int method = strcmp(m, "direct") == 0 ? 0 : strcmp(m, "fft") == 0 ? 1 : strcmp(m, "auto") == 0 ? 2 : -1;
+            if (method < 0) {
+                std::cerr << "traj2diffusion: --method takes direct, fft or auto" << std::endl;
+                return 1;
+            }
+            acfb200_set_method(method);
+            ++i;
+            continue;
+        }
+        kept.push_back(argv0[i]);
+    }
+    const int argc = (int)kept.size();
+    char** argv = kept.data();
     // the batch extension is recognised before the reference's option handling, which stays exactly as it was
     for (int i = 1; i < argc; ++i) {
         if (strcmp(argv[i], "--batch") == 0) {
@@ -315,6 +339,14 @@ int main(int argc, char* argv[])
         if (acfb200_traj2diffusion(x, y, z, r.nframes, r.stride, r.max_s, r.dt, r.L, r.imaging ? 1 : 0, r.msd.data(), nullptr,
                                    &r.res) != ACFB200_OK)
             return gpu_failure(std::cerr);
+        if (getenv("ACFB200_TRACE")) {
+            int path = 0;
+            double cond = 0.0;
+            int64_t j0 = 0;
+            acfb200_msd_last_path(&path, &cond, &j0);
+            std::cerr << "#msd path: " << (path == 1 ? "hybrid" : path == 2 ? "hybrid-refused" : "direct") << " j0 " << j0
+                      << " cond " << cond << std::endl;
+        }
     } else {
         no_frames(r);
     }

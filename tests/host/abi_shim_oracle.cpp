@@ -121,6 +121,13 @@ int acfb200_calc_correlation(const double* y, int64_t n, int64_t ncorr, double* 
     return 0;
 }
 int acfb200_set_method(int) { return 0; }
+int acfb200_msd_last_path(int* path, double* cond, int64_t* j0)
+{
+    if (path) *path = 0;
+    if (cond) *cond = 0.0;
+    if (j0) *j0 = 0;
+    return 0;
+}
 int acfb200_warmup(void) { return 0; }
 
 int acfb200_acf_pipeline(const double* series, int64_t n, int64_t ncorr, double dt, double cutoff, double* acf,

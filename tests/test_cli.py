@@ -520,6 +520,22 @@ def test_traj2diffusion_refuses_nonpositive_stride(oracle_frontends, tmp_path):
     assert p.returncode == 1 and "stride" in p.stderr
 
 
+def test_traj2diffusion_method_extension(oracle_frontends, tmp_path):
+    """--method direct|fft|auto is taken out of the command line before the reference's option handling: the run is
+    otherwise unchanged (with the oracle backend the method is a no-op), anything else is refused."""
+    exe = oracle_frontends["traj2diffusion"]
+    name = "general_default"
+    p0, inp = run_t2d(exe, name, tmp_path)
+    for extra in (["--method", "auto"], ["--method", "direct"]):
+        p = subprocess.run([exe, "--method", extra[1], "-t", inp] + T2D[name]["args"], capture_output=True, text=True)
+        assert p.returncode == p0.returncode and p.stdout == p0.stdout
+        p = subprocess.run([exe, "-t", inp] + T2D[name]["args"] + extra, capture_output=True, text=True)
+        assert p.returncode == p0.returncode and p.stdout == p0.stdout
+    for bad in (["--method", "bogus"], ["--method"]):
+        p = subprocess.run([exe, "-t", inp] + bad, capture_output=True, text=True)
+        assert p.returncode == 1 and "--method takes direct, fft or auto" in p.stderr and p.stdout == ""
+
+
 # ---- GPU: the shipped binaries end to end -----------------------------------------------------------------
 GPU_BIN = os.path.join(ROOT, "acfcalculator_b200", "bin")
 # gle_exp_rounding sits, by construction, where one ulp in one exp() moves the fitting window of the host-side D(s)
@@ -574,3 +590,23 @@ def test_gpu_viscosity_on_irregular_logs(variant, tmp_path):
 def test_gpu_traj2diffusion_matches_reference_program(name, tmp_path):
     p, inp = run_t2d(os.path.join(GPU_BIN, "traj2diffusion"), name, tmp_path)
     check_t2d(p, inp, name, rel=2e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_traj2diffusion_method_auto_takes_the_hybrid_form(tmp_path):
+    """A colvars trajectory of 60000 frames with --max 20000 (1.2 ms of displacement kernel against ~0.35 ms): `--method
+    auto` takes the hybrid Wiener-Khinchin form (reported under ACFB200_TRACE) and prints the table the direct run prints."""
+    rng = np.random.default_rng(33)
+    xyz = 5.0 + np.cumsum(rng.standard_normal((60000, 3)) * 0.4, axis=0)
+    inp = str(tmp_path / "walk.traj")
+    write_traj(inp, xyz, "namd")
+    exe = os.path.join(GPU_BIN, "traj2diffusion")
+    env = dict(os.environ, ACFB200_TRACE="1")
+    args = ["-t", inp, "-f", "namd", "-d", "2", "-m", "20000"]
+    direct = subprocess.run([exe] + args, capture_output=True, text=True, env=env)
+    auto = subprocess.run([exe] + args + ["--method", "auto"], capture_output=True, text=True, env=env)
+    assert direct.returncode == 0 and auto.returncode == 0, (direct.stderr[-300:], auto.stderr[-300:])
+    assert "#msd path: direct" in direct.stderr and "#msd path: hybrid j0 2048" in auto.stderr, auto.stderr[-300:]
+    assert len(auto.stdout.splitlines()) == len(direct.stdout.splitlines()) >= 20005
+    assert same_text(auto.stdout, direct.stdout, 2e-6)
+    assert sum(a != b for a, b in zip(auto.stdout.splitlines(), direct.stdout.splitlines())) <= 5  # last printed digit at most

@@ -49,9 +49,23 @@ def main():
                            "j0": info["j0"], "frame_lag_pairs_per_s": 3.0 * n * max_s / (e0.elapsed_time(e1) / args.reps * 1e-3)}
         finally:
             A.set_method("direct")
+    # end to end: host arrays in, MSD table and D out (acfb200_traj2diffusion: upload, sums, slope)
+    import time
+    host = [t.cpu().numpy() for t in axes]
+    for method in ("direct", "fft"):
+        A.set_method(method)
+        try:
+            A.traj2diffusion(*host, stride=1, max_s=max_s, timestep=1.0)
+            t0 = time.perf_counter()
+            for _ in range(args.reps):
+                A.traj2diffusion(*host, stride=1, max_s=max_s, timestep=1.0)
+            out[method]["e2e_ms"] = (time.perf_counter() - t0) / args.reps * 1e3
+        finally:
+            A.set_method("direct")
     a, b = res["direct"].cpu().numpy(), res["fft"].cpu().numpy()
     out["max_rel_diff"] = float(np.max(np.abs(a[1:] - b[1:]) / a[1:]))
     out["speedup"] = out["direct"]["ms"] / out["fft"]["ms"]
+    out["e2e_speedup"] = out["direct"]["e2e_ms"] / out["fft"]["e2e_ms"]
     print(json.dumps(out))
 
 
