@@ -3,7 +3,7 @@
 # leg, and the same at --max 1e6.
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 60 python -m pytest tests/test_cli.py -m gpu -q -x -k "method_auto or traj2diffusion_matches" > $OUT/r2_msd_hybrid_cli_pytest.log 2>&1
+timeout 60 python -m pytest tests/test_cli.py -m gpu -q -x -k "method_auto" > $OUT/r2_msd_hybrid_cli_pytest.log 2>&1
 echo "pytest cli rc=$?" | tee -a $OUT/r2_msd_hybrid_cli_pytest.log; tail -n 25 $OUT/r2_msd_hybrid_cli_pytest.log
 timeout 40 python tools/msd_hybrid_bench.py > $OUT/r2_msd_hybrid_bench_1e5.json 2> $OUT/r2_msd_hybrid_bench.err
 echo "bench rc=$?"; cat $OUT/r2_msd_hybrid_bench_1e5.json; tail -n 5 $OUT/r2_msd_hybrid_bench.err
