@@ -109,7 +109,9 @@ static long long msd_hybrid_j0(long long n)
 }
 
 // One trajectory, unit stride, max_s in [4096, n], a transform the FFT kernels have a plan for; under `auto` also cheaper
-// by the cost model (rates measured on B200: displacement kernel 2.9e12 frame-lag pairs/s, FFT passes 4.2e12 B/s).
+// by the cost model (rates measured on B200: displacement kernel 8.7e12 axis terms/s = 2.9e12 frame-lag pairs/s on three
+// axes, FFT passes and the streaming helpers 4.2e12 B/s, ~0.2 ms of launches and the synchronisation; at 1e7 frames and
+// max 1e5 the model says 9.9 ms and the hardware 9.9 ms, profiles/r2_msd_hybrid_bench.json).
 static bool msd_hybrid_wanted(long long n, long long stride, long long max_s, int per, size_t* fft_bytes)
 {
     if (g_method == 0 || stride != 1 || max_s < kMsdHybridMinLags || max_s > n) return false;
@@ -119,8 +121,8 @@ static bool msd_hybrid_wanted(long long n, long long stride, long long max_s, in
     if ((long long)n + max_s - 1 > (1ll << 28) || fft_acf_workspace_bytes_batch(n, max_s, per, fft_bytes, &L) != 0)
         return false;
     if (g_method == 1) return true;
-    const double t_direct = (double)per * (double)n * (double)max_s / 2.9e12;
-    const double t_hybrid = (double)per * (double)n * (double)j0 / 2.9e12 +
+    const double t_direct = (double)per * (double)n * (double)max_s / 8.7e12;
+    const double t_hybrid = (double)per * (double)n * (double)j0 / 8.7e12 +
                             (double)per * (40.0 * (double)n + 64.0 * (double)L) / 4.2e12 + 2.0e-4;
     return t_hybrid < t_direct;
 }
