@@ -469,12 +469,60 @@ def build_workload(env, name, n, m, world=None, rank=None, windows=0):
                  total_products=float(n) * m * world,
                  plan="displacement kernel (direct_lag_kernel<MSD>), geometry from the 16-warp-capable variants, 3 axes per launch")
 
+        # max >= 4096: the opt-in hybrid Wiener-Khinchin form (acfb200_set_method auto) -- the
+        # displacement kernel below j0, FFT lags from j0 on; its work is not the displacement kernel's, so no FP64 roofline
+        large = m >= 4096
+
+        def scoped(fn):
+            if not large:
+                return fn
+
+            def run():
+                A.set_method("auto")
+                try:
+                    fn()
+                finally:
+                    A.set_method("direct")
+            return run
+
         def step():
             res["msd"] = A.msd_device(d_a[0], d_a[1], d_a[2], stride=1, max_s=m, stream=stream)
+            res["path"] = A.msd_last_path()
 
         def e2e_step():
-            A.traj2diffusion(h_a[0].numpy(), h_a[1].numpy(), h_a[2].numpy(), stride=1, max_s=m, timestep=1.0)
-        w.update(step=step, e2e_step=e2e_step)
+            res["e2e"] = A.traj2diffusion(h_a[0].numpy(), h_a[1].numpy(), h_a[2].numpy(), stride=1, max_s=m, timestep=1.0)
+
+        def parity():
+            # per-lag displacement sums on the host (numpy, the oracle's formula traj2diffusion.cpp:530-545) for a lag subset
+            torch.cuda.synchronize()
+            got, got_e2e = res["msd"][0].cpu().numpy(), res.get("e2e", {}).get("msd")
+            j0 = int(res["path"]["j0"])
+            lags = sorted(set(j for j in (1, 2, 3, 10, 100, 999, j0 - 1, j0, j0 + 1, m // 2, m - 1) if 0 < j < m))
+            worst, worst_e2e = 0.0, None
+            for j in lags:
+                want = sum(float(np.dot(a[j:] - a[:n - j], a[j:] - a[:n - j])) for a in axes) / (n - j)
+                worst = max(worst, abs(got[j] - want) / want)
+                if got_e2e is not None:
+                    worst_e2e = max(worst_e2e or 0.0, abs(got_e2e[j] - want) / want)
+            return {"lags_checked": len(lags), "max_rel": worst, "e2e_max_rel": worst_e2e, "msd0_is_zero": bool(got[0] == 0.0),
+                    "oracle": "per-lag displacement sums (numpy) of the same trajectory"}
+
+        def extra():
+            out = {"msd_path": res.get("path")}
+            if large:
+                # the same call through the displacement kernel alone, once, for the ratio
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                A.msd_device(d_a[0], d_a[1], d_a[2], stride=1, max_s=min(m, 2048), stream=stream)  # warm
+                e0.record(stream)
+                A.msd_device(d_a[0], d_a[1], d_a[2], stride=1, max_s=m, stream=stream)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                out["direct_method_ms"] = e0.elapsed_time(e1)
+            return out
+        w.update(step=scoped(step), e2e_step=scoped(e2e_step), parity=parity, extra=extra)
+        if large:
+            w.update(fp64_instr_rank=None, no_roofline=True,
+                     plan="hybrid: displacement kernel below j0 + Wiener-Khinchin lags from j0 on (method auto)")
     else:  # fft
         x = ou_series(n, 1.0e4, seed=20260301 + rank)
         h_x = env.pin(x)
@@ -646,9 +694,14 @@ def sub_record(env, name, n, m, steps, peak_tf, peaks, with_auto=False):
     rec = {"workload": w["desc"], "n": n, "maxcorr": m, "steps": steps, "ms_per_step": t["ms_per_step"],
            "value": w["total_products"] / (t["ms_per_step"] * 1e-3), "unit": metric_of(name)[1], "scaling": w["scaling"],
            "gpu_launches": t["launches"], "plan": w["plan"], "e2e": e2e,
-           "roofline": roofline_of(env, w, t["ms_per_step"], peak_tf, peaks) if env.rank == 0 else None}
+           "roofline": roofline_of(env, w, t["ms_per_step"], peak_tf, peaks)
+           if env.rank == 0 and not w.get("no_roofline") else None}
     if w["parity"] and env.rank == 0:
         rec["parity"] = w["parity"]()
+    if w.get("extra") and env.rank == 0:
+        rec.update(w["extra"]())
+        if rec.get("direct_method_ms"):
+            rec["speedup_vs_direct_method"] = rec["direct_method_ms"] / rec["ms_per_step"]
     if with_auto and env.world == 1:
         rec["alt_method"] = auto_method_timing(env, w)
     return rec, w
@@ -740,7 +793,7 @@ def run_native(args):
     peak_tf, eff_mhz = A.measure_dfma_peak()
     line = None
     if rank == 0:
-        roofline = roofline_of(env, w, ms_per_step, peak_tf, peaks)
+        roofline = None if w.get("no_roofline") else roofline_of(env, w, ms_per_step, peak_tf, peaks)
         parity = w["parity"]() if w["parity"] else None
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -776,7 +829,11 @@ def run_native(args):
             for key, name, nn, mm, k, auto in (("n1e8", "ou", 10**8, 10**4, 5, False),
                                                ("windows", "windows", 10**6, 5000, 10, True),
                                                ("viscosity", "viscosity", 10**8, 2 * 10**4, 3, False),
-                                               ("fft", "fft", 2**27, 2**26, 10, False)):
+                                               ("fft", "fft", 2**27, 2**26, 10, False),
+                                               ("msd", "msd", 10**7, 1000, 10, False),
+                                               ("msd_max1e5", "msd", 10**7, 10**5, 3, False)):
+                if args.extras and key not in args.extras.split(","):
+                    continue
                 try:
                     rec, wx = sub_record(env, name, nn, mm, k, peak_tf, peaks, with_auto=auto)
                     del wx
@@ -819,6 +876,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true",
                     help="headline only: skip the sub-records of the other BASELINE configs (configs / multi_gpu)")
+    ap.add_argument("--extras", default="", help="comma-separated subset of the one-GPU sub-records to run "
+                                                  "(n1e8,windows,viscosity,fft,msd,msd_max1e5; default: all)")
     ap.add_argument("--allcores", action="store_true", help="also time the other CPU builds of SURVEY 8d (lag-parallel port, -O0, racy OpenMP)")
     args = ap.parse_args()
     if args.impl == "reference":
