@@ -521,6 +521,7 @@ def build_workload(env, name, n, m, world=None, rank=None, windows=0):
             return out
         w.update(step=scoped(step), e2e_step=scoped(e2e_step), parity=parity, extra=extra)
         if large:
+            w["desc"] = "traj2diffusion: 3-D random walk, 1e7 frames, stride 1, max %d, hybrid Wiener-Khinchin form" % m
             w.update(fp64_instr_rank=None, no_roofline=True,
                      plan="hybrid: displacement kernel below j0 + Wiener-Khinchin lags from j0 on (method auto)")
     else:  # fft
