@@ -88,69 +88,63 @@ int msd_finalize_sums(Workspace* ws, int axes, const long long* n_total, int ntr
 // ---- hybrid Wiener-Khinchin form of the unit-stride MSD (acfb200_set_method fft / auto; kernels in msd.cu) -----------
 // Which way the calling thread's last single-device MSD call went (acfb200_msd_last_path).
 struct MsdPathInfo {
-    int path = 0;        // 0 direct displacement kernel; 1 hybrid; 2 hybrid refused by its conditioning guard, recomputed directly
-    double cond = 0.0;   // the guard's figure of the last hybrid attempt: max_{j >= j0} 2 sum(y^2) / displacement sum
+    int path = 0;        // 0 direct displacement kernel; 1 hybrid; 2 hybrid refused by its conditioning bound, computed directly
+    double cond = 0.0;   // largest 2 sum(y^2) / displacement sum among the lags the form was allowed to serve
     long long j0 = 0;    // first lag taken from the Wiener-Khinchin form
 };
 static thread_local MsdPathInfo g_msd_info;
 
 // The form computes a displacement sum as a difference of terms of size T = sum(y^2): it loses log10(2T / sum) digits
-// on top of the FFT's own ~1e-15 * T.  2T / sum <= kMsdCondMax keeps the result within ~2e-12 relative, a factor 50
-// inside north_star's 1e-10.  For a diffusing particle 2T / sum ~ n / (3 j): lags below j0 = max(2048, n / 4096) stay
-// with the direct kernel; anything worse than the bound at a later lag (drift, a trajectory pinned far from its mean)
-// sends the whole call back to the direct kernel.
+// on top of the FFT's own ~1e-15 * T.  cond(j) = 2T / sum_j <= kMsdCondMax keeps a lag within ~2e-12 relative, a factor
+// 50 inside north_star's 1e-10 (measured on B200: 3.5e-13 between the two forms at cond 583).  cond is measured per lag
+// on the device; j0 = the first multiple of 256 (at least kMsdFirstLag) beyond the LAST lag that exceeds the bound, so
+// every lag >= j0 is admissible whatever the shape of the curve.  For a diffusing particle cond ~ n / (7 j): j0 ~ 768 at
+// 1e7 frames.  Lags below j0 come from the displacement kernel; when that would be more than half of them (drift, a
+// trajectory far from its mean) the whole call goes to the displacement kernel.
 constexpr double kMsdCondMax = 2000.0;
 constexpr long long kMsdHybridMinLags = 4096;
+constexpr long long kMsdFirstLag = 256;
 
-static long long msd_hybrid_j0(long long n)
-{
-    long long j0 = (n / 4096 + 255) / 256 * 256;
-    return j0 < 2048 ? 2048 : j0;
-}
+static long long round_up_256(long long v) { return (v + 255) / 256 * 256; }
 
 // One trajectory, unit stride, max_s in [4096, n], a transform the FFT kernels have a plan for; under `auto` also cheaper
 // by the cost model (rates measured on B200: displacement kernel 8.7e12 axis terms/s = 2.9e12 frame-lag pairs/s on three
-// axes, FFT passes and the streaming helpers 4.2e12 B/s, ~0.2 ms of launches and the synchronisation; at 1e7 frames and
-// max 1e5 the model says 9.9 ms and the hardware 9.9 ms, profiles/r2_msd_hybrid_bench.json).
+// axes, FFT passes and the streaming helpers 4.2e12 B/s, ~0.2 ms of launches and the synchronisation), with j0 guessed
+// for a diffusing particle.
 static bool msd_hybrid_wanted(long long n, long long stride, long long max_s, int per, size_t* fft_bytes)
 {
     if (g_method == 0 || stride != 1 || max_s < kMsdHybridMinLags || max_s > n) return false;
-    const long long j0 = msd_hybrid_j0(n);
-    if (2 * j0 > max_s) return false;
     long long L = 0;
     if ((long long)n + max_s - 1 > (1ll << 28) || fft_acf_workspace_bytes_batch(n, max_s, per, fft_bytes, &L) != 0)
         return false;
     if (g_method == 1) return true;
+    long long j0 = round_up_256(n / 6000);
+    if (j0 < kMsdFirstLag) j0 = kMsdFirstLag;
+    if (2 * j0 > max_s) return false;
     const double t_direct = (double)per * (double)n * (double)max_s / 8.7e12;
     const double t_hybrid = (double)per * (double)n * (double)j0 / 8.7e12 +
                             (double)per * (40.0 * (double)n + 64.0 * (double)L) / 4.2e12 + 2.0e-4;
     return t_hybrid < t_direct;
 }
 
-// Returns 0 (d_msd / d_counter hold the result), an error code > 0, or -1: the conditioning guard refused the form and
-// the caller runs the direct kernel.  Synchronises `st` once (the guard's figure is read on the host).
+// Returns 0 (the result is enqueued into d_msd / d_counter), an error code > 0, or -1: the conditioning bound leaves the
+// form less than half of the lags and the caller runs the displacement kernel for all of them.  Synchronises `st` once
+// (j0 is decided on the host).
 static int msd_hybrid_device(Workspace* ws, const double* const* axes, int per, long long n, long long max_s,
                              size_t fft_bytes, double* d_msd, int* d_counter, cudaStream_t st)
 {
-    const long long j0 = msd_hybrid_j0(n);
     const size_t pitch = even_up(n), m = (size_t)max_s;
     ACF_TRY(ws->msd_c.ensure((size_t)per * pitch * 8));
-    ACF_TRY(ws->msd_w.ensure(((size_t)4 * per * m + (size_t)per * j0 + 2) * 8));
+    ACF_TRY(ws->msd_w.ensure(((size_t)4 * per * m + 2) * 8));
     ACF_TRY(ws->msd_sc.ensure(sizeof(ReduceScratch) * 3, true));
     ACF_TRY(ws->fftwork.ensure(fft_bytes));
     double* yc = ws->msd_c.as<double>();
     double* d_c = ws->msd_w.as<double>();                 // [per][max_s] lags of the centred axes
     double* d_edge = d_c + (size_t)per * m;               // [per][2][max_s]
     double* d_sums = d_edge + (size_t)2 * per * m;        // [per][max_s]
-    double* d_head = d_sums + (size_t)per * m;            // [per][j0] direct sums of the small lags
-    unsigned long long* d_cond = reinterpret_cast<unsigned long long*>(d_head + (size_t)per * j0);
+    unsigned long long* d_flags = reinterpret_cast<unsigned long long*>(d_sums + (size_t)per * m);  // [2]
     ReduceScratch* sc = ws->msd_sc.as<ReduceScratch>();
-    // lags below j0: the displacement kernel on the caller's (uncentred) axes, bit for bit the direct path's sums
-    std::vector<SeriesDesc> descs(per);
-    for (int a = 0; a < per; ++a) descs[a] = {axes[a], n, n};
-    ACF_TRY(msd_block_sums(ws, descs, 1, j0, st));        // -> ws->out [per][j0]; ws->desc keeps {x, n, n} per axis
-    ACF_CUDA_OK(cudaMemcpyAsync(d_head, ws->out.p, (size_t)per * j0 * 8, cudaMemcpyDeviceToDevice, st));
-    // centred copies and their sums of squares
+    // centred copies, their sums of squares, their lags, the edge sums; then the form for every lag from kMsdFirstLag on
     for (int a = 0; a < per; ++a) {
         ACF_TRY(launch_sum(axes[a], n, sc + a, st));
         ACF_TRY(launch_center_velocity(axes[a], n, sc + a, yc + (size_t)a * pitch, nullptr, 1.0, st));
@@ -161,19 +155,27 @@ static int msd_hybrid_device(Workspace* ws, const double* const* axes, int per, 
     if (fl < 0) return ACFB200_ERR_CUDA;
     g_launches += fl;
     ACF_TRY(launch_msd_edge_sums(yc, (long long)pitch, per, n, max_s, d_edge, st));
-    ACF_CUDA_OK(cudaMemsetAsync(d_cond, 0, 8, st));
-    ACF_TRY(launch_msd_fft_combine(d_c, d_edge, sc, d_head, n, max_s, j0, per, d_sums, d_cond, st));
-    ACF_TRY(launch_msd_finalize(d_sums, ws->desc.as<SeriesDesc>(), per, 1, 1, max_s, d_msd, d_counter, st));
-    g_launches += 3;
-    double cond = 0.0;
-    ACF_CUDA_OK(cudaMemcpyAsync(&cond, d_cond, 8, cudaMemcpyDeviceToHost, st));
+    ACF_CUDA_OK(cudaMemsetAsync(d_flags, 0, 16, st));
+    ACF_TRY(launch_msd_fft_combine(d_c, d_edge, sc, n, max_s, kMsdFirstLag, kMsdCondMax, per, d_sums, d_flags, st));
+    g_launches += 2;
+    unsigned long long flags[2] = {0, 0};
+    ACF_CUDA_OK(cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, st));
     ACF_CUDA_OK(cudaStreamSynchronize(st));
-    g_msd_info.cond = cond;
+    long long j0 = round_up_256((long long)flags[0]);     // flags[0] = 1 + the last inadmissible lag
+    if (j0 < kMsdFirstLag) j0 = kMsdFirstLag;
+    memcpy(&g_msd_info.cond, &flags[1], 8);
     g_msd_info.j0 = j0;
-    if (!(cond <= kMsdCondMax)) {
+    if (2 * j0 > max_s) {
         g_msd_info.path = 2;
         return -1;
     }
+    // lags below j0: the displacement kernel on the caller's (uncentred) axes -- bit for bit a direct call with max_s = j0
+    std::vector<SeriesDesc> descs(per);
+    for (int a = 0; a < per; ++a) descs[a] = {axes[a], n, n};
+    ACF_TRY(msd_block_sums(ws, descs, 1, j0, st));        // -> ws->out [per][j0]; ws->desc keeps {x, n, n} per axis
+    ACF_CUDA_OK(cudaMemcpy2DAsync(d_sums, m * 8, ws->out.p, (size_t)j0 * 8, (size_t)j0 * 8, per, cudaMemcpyDeviceToDevice, st));
+    ACF_TRY(launch_msd_finalize(d_sums, ws->desc.as<SeriesDesc>(), per, 1, 1, max_s, d_msd, d_counter, st));
+    g_launches += 1;
     g_msd_info.path = 1;
     return 0;
 }
@@ -196,7 +198,7 @@ static int msd_batch_device(Workspace* ws, const double* const* axes, const long
     size_t fft_bytes = 0;
     if (ntraj == 1 && msd_hybrid_wanted(n[0], stride, max_s, per, &fft_bytes)) {
         const int rc = msd_hybrid_device(ws, axes, per, n[0], max_s, fft_bytes, d_msd, d_counter, st);
-        if (rc >= 0) return rc;  // -1: refused by the conditioning guard, the direct kernel below recomputes everything
+        if (rc >= 0) return rc;  // -1: refused by the conditioning bound, the displacement kernel below computes every lag
     }
     std::vector<SeriesDesc> descs(ns);
     for (int t = 0; t < ntraj; ++t)

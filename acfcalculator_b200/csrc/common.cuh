@@ -113,12 +113,12 @@ int launch_msd_slope(const double* d_msd, long long n, int ncurves, double* d_ou
 //   d_edge[a][0][j] = sum_{i<j} y_a[i]^2, d_edge[a][1][j] = sum_{i<j} y_a[n-1-i]^2, j < m <= n; axis a at d_y + a*pitch
 int launch_msd_edge_sums(const double* d_y, long long pitch, int axes, long long n, long long m, double* d_edge,
                          cudaStream_t st);
-//   d_sums[a][j] = d_head[a][j] (j < j0, the direct kernel's sums, row pitch j0) or the FFT form built from the
-//   normalised lags d_c[a][j] of the centred axes, d_edge and d_sc[a].meansq; *d_cond_bits (zeroed by the caller) = bits
-//   of the largest 2 T / sum met for j >= j0
-int launch_msd_fft_combine(const double* d_c, const double* d_edge, const ReduceScratch* d_sc, const double* d_head,
-                           long long n, long long m, long long j0, int axes, double* d_sums,
-                           unsigned long long* d_cond_bits, cudaStream_t st);
+//   d_sums[a][j], jmin <= j < m, in the FFT form built from the normalised lags d_c[a][j] of the centred axes, d_edge and
+//   d_sc[a].meansq; d_flags (two words, zeroed by the caller): 1 + the last lag whose 2 T / sum exceeds cond_max, and the
+//   bits of the largest 2 T / sum that does not
+int launch_msd_fft_combine(const double* d_c, const double* d_edge, const ReduceScratch* d_sc, long long n, long long m,
+                           long long jmin, double cond_max, int axes, double* d_sums, unsigned long long* d_flags,
+                           cudaStream_t st);
 size_t image_workspace_bytes(long long n);
 int launch_image(const double* const d_in[3], double* const d_out[3], long long n, double L, void* d_work,
                  cudaStream_t st);

@@ -153,9 +153,9 @@ int launch_msd_slope(const double* d_msd, long long n, int ncurves, double* d_ou
 //     sum_{i < n-j} (y[i+j] - y[i])^2 = (T - pre[j]) + (T - suf[j]) - 2 S[j]
 //     T = sum y^2,  pre[j] = sum_{i<j} y[i]^2,  suf[j] = sum_{i<j} y[n-1-i]^2,  S[j] = sum_{i<n-j} y[i] y[i+j]
 // S comes from the FFT kernels (fft_acf.cu), T from sum_kernel<SQUARE>, pre/suf from the scan below.  The four terms
-// are each of size T while the result is the displacement sum, so the form loses log10(2T / result) digits: lags below
-// j0 keep the direct kernel's sums, and the combine kernel reports the worst 2T / result it met so that the host can
-// refuse the form (capi_msd.cu) when a trajectory is too ill-conditioned for the 1e-10 bar.
+// are each of size T while the result is the displacement sum, so the form loses log10(2T / result) digits: the combine
+// kernel measures cond(j) = 2T / result per lag and reports the last lag that exceeds the bound; the host (capi_msd.cu)
+// takes the lags beyond it from this form and the ones up to it from the displacement kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int kEdgeThreads = 1024;
 
@@ -204,46 +204,59 @@ msd_edge_sums_kernel(const double* __restrict__ y, long long pitch, long long n,
     }
 }
 
-// sums[a][j] for j < m: the direct kernel's head[a][j] below j0, the Wiener-Khinchin form from j0 on (c = the FFT path's
-// lags of the centred axes, i.e. S[j] / (n - j)).  *cond_bits (zeroed by the caller) receives the bit pattern of
-// max_{j >= j0} 2 sum_a T_a / sum_a sums[a][j]  (+inf when a combined sum is not positive or not a number).
+// sums[a][j] for jmin <= j < m in the Wiener-Khinchin form (c = the FFT path's lags of the centred axes, i.e.
+// S[j] / (n - j)); lags below jmin are left alone.  With cond(j) = 2 sum_a T_a / sum_a sums[a][j] (+inf when the combined
+// sum is not positive or not a number), flags (zeroed by the caller) receive
+//   flags[0] = 1 + the largest lag whose cond exceeds cond_max (0: none)  -- the form may serve the lags from there on
+//   flags[1] = the bit pattern of the largest cond that does not.
 __global__ void __launch_bounds__(256)
 msd_fft_combine_kernel(const double* __restrict__ c, const double* __restrict__ edge, const ReduceScratch* __restrict__ sc,
-                       const double* __restrict__ head, long long n, long long m, long long j0, int axes,
-                       double* __restrict__ sums, unsigned long long* __restrict__ cond_bits)
+                       long long n, long long m, long long jmin, double cond_max, int axes, double* __restrict__ sums,
+                       unsigned long long* __restrict__ flags)
 {
-    __shared__ double sh[8];
+    __shared__ double sh_cond[8];
+    __shared__ unsigned long long sh_bad[8];
     const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
-    double cond = 0.0;
-    if (j < m) {
-        if (j < j0) {
-            for (int a = 0; a < axes; ++a) sums[(long long)a * m + j] = head[(long long)a * j0 + j];
-        } else {
-            const double cnt = (double)(n - j);
-            double t_all = 0.0, s_all = 0.0;
-            for (int a = 0; a < axes; ++a) {
-                const double T = sc[a].meansq * (double)n;
-                const double pre = edge[((long long)a * 2) * m + j], suf = edge[((long long)a * 2 + 1) * m + j];
-                const double v = ((T - pre) + (T - suf)) - 2.0 * (c[(long long)a * m + j] * cnt);
-                sums[(long long)a * m + j] = v;
-                t_all += T;
-                s_all += v;
-            }
-            cond = s_all > 0.0 ? 2.0 * t_all / s_all : __longlong_as_double(0x7FF0000000000000ull);
-            if (!(cond == cond)) cond = __longlong_as_double(0x7FF0000000000000ull);
+    double cond = 0.0;              // largest admissible figure seen by this thread
+    unsigned long long bad = 0;     // 1 + lag, if this thread's lag is not admissible
+    if (j >= jmin && j < m) {
+        const double cnt = (double)(n - j);
+        double t_all = 0.0, s_all = 0.0;
+        for (int a = 0; a < axes; ++a) {
+            const double T = sc[a].meansq * (double)n;
+            const double pre = edge[((long long)a * 2) * m + j], suf = edge[((long long)a * 2 + 1) * m + j];
+            const double v = ((T - pre) + (T - suf)) - 2.0 * (c[(long long)a * m + j] * cnt);
+            sums[(long long)a * m + j] = v;
+            t_all += T;
+            s_all += v;
         }
+        const double cj = 2.0 * t_all / s_all;
+        if (s_all > 0.0 && cj <= cond_max)   // false for NaN as well
+            cond = cj;
+        else
+            bad = (unsigned long long)j + 1ull;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        const double o = __shfl_xor_sync(0xffffffffu, cond, off);
-        cond = o > cond ? o : cond;
+        const double oc = __shfl_xor_sync(0xffffffffu, cond, off);
+        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bad, off);
+        cond = oc > cond ? oc : cond;
+        bad = ob > bad ? ob : bad;
     }
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cond;
+    if ((threadIdx.x & 31) == 0) {
+        sh_cond[threadIdx.x >> 5] = cond;
+        sh_bad[threadIdx.x >> 5] = bad;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double w = sh[0];
-        for (int k = 1; k < 8; ++k) w = sh[k] > w ? sh[k] : w;
-        if (w > 0.0) atomicMax(cond_bits, (unsigned long long)__double_as_longlong(w));  // non-negative doubles order like their bits
+        double wc = sh_cond[0];
+        unsigned long long wb = sh_bad[0];
+        for (int k = 1; k < 8; ++k) {
+            wc = sh_cond[k] > wc ? sh_cond[k] : wc;
+            wb = sh_bad[k] > wb ? sh_bad[k] : wb;
+        }
+        if (wb > 0) atomicMax(&flags[0], wb);
+        if (wc > 0.0) atomicMax(&flags[1], (unsigned long long)__double_as_longlong(wc));  // non-negative doubles order like their bits
     }
 }
 
@@ -259,12 +272,12 @@ int launch_msd_edge_sums(const double* d_y, long long pitch, int axes, long long
     return 0;
 }
 
-int launch_msd_fft_combine(const double* d_c, const double* d_edge, const ReduceScratch* d_sc, const double* d_head,
-                           long long n, long long m, long long j0, int axes, double* d_sums,
-                           unsigned long long* d_cond_bits, cudaStream_t st)
+int launch_msd_fft_combine(const double* d_c, const double* d_edge, const ReduceScratch* d_sc, long long n, long long m,
+                           long long jmin, double cond_max, int axes, double* d_sums, unsigned long long* d_flags,
+                           cudaStream_t st)
 {
-    msd_fft_combine_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_c, d_edge, d_sc, d_head, n, m, j0, axes, d_sums,
-                                                                        d_cond_bits);
+    msd_fft_combine_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_c, d_edge, d_sc, n, m, jmin, cond_max, axes, d_sums,
+                                                                        d_flags);
     ACF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -234,15 +234,17 @@ ACFB200_API int acfb200_msd_device(const double* d_x, const double* d_y, const d
 ACFB200_API int acfb200_image_device(const double* d_x, const double* d_y, const double* d_z, int64_t n, double cell,
                                      double* d_xo, double* d_yo, double* d_zo, void* stream);
 /* Large max_s (traj2diffusion.cpp:530-541 with `max` >~ 1e4): under acfb200_set_method(1 fft | 2 auto) a unit-stride MSD
- * of ONE trajectory with 4096 <= max_s <= n may run in a hybrid form -- lags below j0 = max(2048, n/4096) from the
- * displacement kernel as always, lags from j0 on as (T - pre[j]) + (T - suf[j]) - 2 S[j] per centred axis with S from the
- * Wiener-Khinchin kernels (O(n log n) instead of O(n * max_s)).  That form cancels digits when the trajectory's spread
- * about its mean is large against the displacements, so the call measures cond = max_j 2 sum(y^2) / sum_j and, above
- * 2000 (results no longer safely within 1e-10), recomputes everything with the displacement kernel.  The hybrid form
- * synchronises the stream once, also in acfb200_msd_device.  Method 0 (default) never takes it.
+ * of ONE trajectory with 4096 <= max_s <= n may run in a hybrid form -- per centred axis the displacement sum of lag j is
+ * (T - pre[j]) + (T - suf[j]) - 2 S[j] with S from the Wiener-Khinchin kernels (O(n log n) instead of O(n * max_s)).  That
+ * form cancels digits when the trajectory's spread about its mean is large against the displacements, so the call
+ * measures cond(j) = 2 sum(y^2) / sum_j for every lag and serves from it only the lags from j0 on, j0 = the first multiple
+ * of 256 (at least 256) beyond the last lag with cond > 2000 (~2e-12 relative); the lags below j0 come from the
+ * displacement kernel as always.  If that leaves the form less than half of the lags (drift, a trajectory far from its
+ * mean) the displacement kernel computes all of them.  The hybrid form synchronises the stream once, also in
+ * acfb200_msd_device.  Method 0 (default) never takes it.
  * acfb200_msd_last_path: how the calling thread's last single-device MSD call went -- *path = 0 direct, 1 hybrid,
- * 2 hybrid refused by the guard and recomputed directly; *cond, *j0 as above (0 when no hybrid attempt was made).
- * Outputs may be NULL. */
+ * 2 hybrid refused by the bound and computed directly; *j0 as above, *cond = the largest cond among the lags the form
+ * was allowed to serve (both 0 when no hybrid attempt was made).  Outputs may be NULL. */
 ACFB200_API int acfb200_msd_last_path(int* path, double* cond, int64_t* j0);
 
 /* ---- tuning / introspection / measurement ---------------------------------------------------- */

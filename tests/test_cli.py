@@ -606,7 +606,7 @@ def test_gpu_traj2diffusion_method_auto_takes_the_hybrid_form(tmp_path):
     direct = subprocess.run([exe] + args, capture_output=True, text=True, env=env)
     auto = subprocess.run([exe] + args + ["--method", "auto"], capture_output=True, text=True, env=env)
     assert direct.returncode == 0 and auto.returncode == 0, (direct.stderr[-300:], auto.stderr[-300:])
-    assert "#msd path: direct" in direct.stderr and "#msd path: hybrid j0 2048" in auto.stderr, auto.stderr[-300:]
+    assert "#msd path: direct" in direct.stderr and "#msd path: hybrid j0 " in auto.stderr, auto.stderr[-300:]
     assert len(auto.stdout.splitlines()) == len(direct.stdout.splitlines()) >= 20005
     assert same_text(auto.stdout, direct.stdout, 2e-6)
     assert sum(a != b for a, b in zip(auto.stdout.splitlines(), direct.stdout.splitlines())) <= 5  # last printed digit at most

@@ -291,13 +291,9 @@ def test_gpu_msd_argument_errors(acf):
 
 # ---- hybrid Wiener-Khinchin form for large max_s (acfb200_set_method fft / auto) --------------------------------
 # CPU: a numpy model of the two kernels (msd.cu: msd_edge_sums_kernel, msd_fft_combine_kernel) and of the host rule
-# (capi_msd.cu: j0, the conditioning guard) against the oracle -- pins the algorithm and its constants.
-# GPU: the library itself against the oracle, and the guard's fallback.
-COND_MAX, MIN_LAGS = 2000.0, 4096
-
-
-def hybrid_j0(n):
-    return max(2048, (n // 4096 + 255) // 256 * 256)
+# (capi_msd.cu: the per-lag conditioning bound and the j0 it implies) against the oracle -- pins the algorithm and its
+# constants.  GPU: the library itself against the oracle, and the refusal.
+COND_MAX, MIN_LAGS, FIRST_LAG = 2000.0, 4096, 256
 
 
 def edge_sums_model(y, m, threads=1024):
@@ -318,26 +314,39 @@ def edge_sums_model(y, m, threads=1024):
     return out
 
 
-def hybrid_model(axes, max_s, head):
-    """(sums[axis][max_s], cond): the combine kernel.  head[axis][j0] = the direct sums of the small lags."""
+def hybrid_model(axes, max_s):
+    """(sums[axis][max_s] in the Wiener-Khinchin form, j0, cond): the combine kernel and the host's choice of j0 =
+    the first multiple of 256 (at least 256) beyond the last lag whose 2T/sum exceeds COND_MAX."""
     from scipy.fft import irfft, next_fast_len, rfft
     n = axes[0].size
-    j0 = hybrid_j0(n)
     sums, t_all = [], 0.0
-    for a, x in enumerate(axes):
+    for x in axes:
         y = x - x.sum() / n
         T = (y * y).sum() / n * n
         L = next_fast_len(n + max_s - 1, real=True)
         X = rfft(y, L)
         c = irfft(X * np.conj(X), L)[:max_s] / (n - np.arange(max_s))     # what the FFT kernels return
         pre, suf = edge_sums_model(y, max_s)
-        s = ((T - pre) + (T - suf)) - 2.0 * (c * (n - np.arange(max_s)))
-        s[:j0] = head[a]
-        sums.append(s)
+        sums.append(((T - pre) + (T - suf)) - 2.0 * (c * (n - np.arange(max_s))))
         t_all += T
-    tot = np.sum(sums, axis=0)[j0:]
-    cond = np.max(np.where(tot > 0, 2.0 * t_all / np.where(tot > 0, tot, 1.0), np.inf))
-    return np.array(sums), float(cond)
+    tot = np.sum(sums, axis=0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cond = np.where(tot > 0, 2.0 * t_all / tot, np.inf)
+    ok = cond <= COND_MAX
+    bad = np.nonzero(~ok[FIRST_LAG:])[0]
+    worst = FIRST_LAG + int(bad[-1]) + 1 if bad.size else 0
+    j0 = max(FIRST_LAG, (worst + 255) // 256 * 256)
+    good = cond[FIRST_LAG:][ok[FIRST_LAG:]]
+    return np.array(sums), j0, float(good.max()) if good.size else 0.0
+
+
+def head_sums(oracle, axes, j0):
+    """Per-axis direct sums of the lags below j0 (the MSD of one axis three times = 3 * its sums / counter)."""
+    out = []
+    for a in axes:
+        m1, c1 = oracle.msd(a, a, a, 1, j0, threads=0)
+        out.append(m1 * c1 / 3.0)
+    return out
 
 
 def test_edge_sums_model_is_a_prefix_sum():
@@ -348,36 +357,34 @@ def test_edge_sums_model_is_a_prefix_sum():
         assert np.allclose(suf, np.concatenate(([0.0], np.cumsum(y[::-1][:m - 1] ** 2))), rtol=1e-13, atol=0)
 
 
-def test_hybrid_model_matches_oracle_and_guard_rejects_drift(oracle):
+def test_hybrid_model_matches_oracle_and_the_bound_moves_j0(oracle):
     n, max_s = 60000, 9000
-    j0 = hybrid_j0(n)
-    assert j0 == 2048 and 2 * j0 <= max_s and max_s >= MIN_LAGS
     r = walk(n, 91)
     axes = [np.ascontiguousarray(r[:, a]) for a in range(3)]
     want, cnt = oracle.msd(axes[0], axes[1], axes[2], 1, max_s, threads=0)
-    head = []
-    for a in range(3):   # per-axis direct sums of the small lags (msd of one axis three times = 3 * its sums / cnt)
-        m1, c1 = oracle.msd(axes[a], axes[a], axes[a], 1, j0, threads=0)
-        head.append(m1 * c1 / 3.0)
-    sums, cond = hybrid_model(axes, max_s, head)
-    got = sums.sum(axis=0) / cnt
-    assert cond <= COND_MAX                      # a diffusing particle: 2T/sum ~ n/(3 j0) ~ 10
-    assert rel_err(got[1:], want[1:]) <= 1e-11   # a factor 10 inside the bar at cond ~ 10
-    # drift: the spread about the mean grows like n^2 while the displacements grow like j^2 -> refused
-    # (2T/sum ~ n^2 / (6 j^2) at lag j: 2480 at j0 for 250 000 frames)
+    sums, j0, cond = hybrid_model(axes, max_s)
+    assert j0 == FIRST_LAG and cond <= COND_MAX     # a diffusing particle: 2T/sum ~ n/(7 j) ~ 35 at lag 256
+    for a, h in enumerate(head_sums(oracle, axes, j0)):
+        sums[a][:j0] = h
+    assert rel_err((sums.sum(axis=0) / cnt)[1:], want[1:]) <= 1e-11
+    # drift: the spread about the mean grows like n^2 while the displacements grow like j^2, 2T/sum ~ n^2 / (6 j^2):
+    # the bound is met from lag ~2280 on for 250 000 frames
     n = 250000
     t = np.arange(n, dtype=np.float64)
     drift = [0.01 * t + 0.001 * np.random.default_rng(5 + a).standard_normal(n) for a in range(3)]
-    head = []
-    for a in range(3):
-        m1, c1 = oracle.msd(drift[a], drift[a], drift[a], 1, j0, threads=0)
-        head.append(m1 * c1 / 3.0)
-    sums, cond = hybrid_model(drift, max_s, head)
-    assert COND_MAX < cond < 3000
-    # ... and what the guard protects against: the form is still good to ~cond * 1e-15 there, not to 1e-15
+    sums, j0, cond = hybrid_model(drift, max_s)
+    assert j0 == 2304 and 1900 < cond <= COND_MAX
+    assert 2 * j0 <= max_s                            # the form serves 9000 - 2304 lags ...
+    assert 2 * j0 > 4500                              # ... and would be refused for max_s = 4500
     want, cnt = oracle.msd(drift[0], drift[1], drift[2], 1, max_s, threads=0)
+    for a, h in enumerate(head_sums(oracle, drift, j0)):
+        sums[a][:j0] = h
     err = rel_err((sums.sum(axis=0) / cnt)[1:], want[1:])
-    assert 1e-14 < err < 1e-10
+    assert err < 1e-11                                # at the bound the form is good to ~cond * 1e-15
+    # what the bound protects against: the lags just below it are already an order of magnitude worse
+    raw, _, _ = hybrid_model(drift, max_s)
+    worse = np.abs(raw.sum(axis=0)[64:512] / cnt[64:512] - want[64:512]) / want[64:512]
+    assert worse.max() > 10 * err
 
 
 def _default_method():
@@ -392,46 +399,54 @@ def test_gpu_msd_hybrid_against_oracle(acf, oracle):
     x, y, z = (np.ascontiguousarray(r[:, a]) for a in range(3))
     want, wcnt = oracle.msd(x, y, z, 1, max_s, threads=0)
     try:
-        acf.set_method("direct")
-        head, _ = acf.msd(x, y, z, max_s=2048)
-        assert acf.msd_last_path()["path"] == "direct"
         acf.set_method("fft")
         got, cnt = acf.msd(x, y, z, max_s=max_s)
         info = acf.msd_last_path()
-        acf.set_method("auto")                    # 18 ms of displacement kernel against < 1 ms: the cost model agrees
+        acf.set_method("auto")                    # 6 ms of displacement kernel against < 1 ms: the cost model agrees
         got2, _ = acf.msd(x, y, z, max_s=max_s)
         info2 = acf.msd_last_path()
         small, _ = acf.msd(x, y, z, max_s=1000)   # ... and leaves the program's default max alone
         info3 = acf.msd_last_path()
+        acf.set_method("direct")
+        head, _ = acf.msd(x, y, z, max_s=int(info["j0"]))
+        info4 = acf.msd_last_path()
     finally:
         acf.set_method(_default_method())
-    assert info["path"] == "hybrid" and info["j0"] == 2048 and 0 < info["cond"] <= COND_MAX, info
+    assert info["path"] == "hybrid" and 0 < info["cond"] <= COND_MAX, info
+    assert FIRST_LAG <= info["j0"] <= 2048 and info["j0"] % 256 == 0, info
     assert rel_err(got, want) <= REL
     assert np.array_equal(cnt, wcnt)
-    assert np.array_equal(got[:2048], head)      # small lags: the displacement kernel's own sums, bit for bit
-    assert info2["path"] == "hybrid" and np.array_equal(got2, got)
+    assert info4["path"] == "direct"
+    assert np.array_equal(got[:info["j0"]], head)   # small lags: the displacement kernel's own sums, bit for bit
+    assert info2 == info and np.array_equal(got2, got)
     assert info3["path"] == "direct" and rel_err(small, want[:1000]) <= REL
 
 
 @pytest.mark.gpu
-def test_gpu_msd_hybrid_guard_falls_back_to_direct(acf, oracle):
-    n, max_s = 300_000, 20_000
+def test_gpu_msd_hybrid_bound_under_drift(acf, oracle):
+    """A drifting trajectory: 2T/sum ~ n^2 / (6 j^2) meets the bound from lag ~2750 on.  With max_s = 20000 the form serves
+    the lags from j0 = 2816 on; with max_s = 5000 that is less than half of them and the displacement kernel does it all."""
+    n = 300_000
     t = np.arange(n, dtype=np.float64)
     axes = [0.01 * t + 0.001 * np.random.default_rng(5 + a).standard_normal(n) for a in range(3)]
     try:
         acf.set_method("direct")
-        direct, dcnt = acf.msd(*axes, max_s=max_s)
+        direct, dcnt = acf.msd(*axes, max_s=5000)
         acf.set_method("fft")
-        got, cnt = acf.msd(*axes, max_s=max_s)
+        got, cnt = acf.msd(*axes, max_s=5000)
         info = acf.msd_last_path()
+        wide, _ = acf.msd(*axes, max_s=20000)
+        info2 = acf.msd_last_path()
     finally:
         acf.set_method(_default_method())
-    assert info["path"] == "hybrid-refused" and info["cond"] > COND_MAX, info
+    assert info["path"] == "hybrid-refused" and info["j0"] == 2816, info
     assert np.array_equal(got, direct) and np.array_equal(cnt, dcnt)
-    lags = [0, 1, 2047, 2048, 5000, max_s - 1]
-    for j in lags:
+    assert info2["path"] == "hybrid" and info2["j0"] == 2816 and 1900 < info2["cond"] <= COND_MAX, info2
+    for j in (0, 1, 2815, 2816, 2817, 5000, 19999):
         want = sum(float(np.dot(a[j:] - a[:n - j], a[j:] - a[:n - j])) for a in axes) / (n - j)
-        assert got[j] == 0.0 if j == 0 else abs(got[j] - want) <= REL * want, j
+        assert wide[j] == 0.0 if j == 0 else abs(wide[j] - want) <= REL * want, j
+        if j < 5000:
+            assert got[j] == 0.0 if j == 0 else abs(got[j] - want) <= REL * want, j
 
 
 @pytest.mark.gpu
