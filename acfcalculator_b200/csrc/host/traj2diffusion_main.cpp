@@ -17,7 +17,7 @@
 //
 // Extension: --method direct|fft|auto (anywhere on the command line, also with --batch) -- acfb200_set_method.  `direct`
 // (the default) sums the displacements like the reference; `auto` lets a unit-stride run with a large --max take the
-// hybrid Wiener-Khinchin form (include/acf_b200.h, acfb200_msd_last_path: 33x at 1e7 frames, --max 100000) when the
+// hybrid Wiener-Khinchin form (include/acf_b200.h, acfb200_msd_last_path: 78x at 1e7 frames, --max 100000) when the
 // cost model expects it to be faster, `fft` whenever it applies; both keep MSD within ~1e-12 relative of the direct sums
 // or fall back to them.  ACFB200_TRACE=1 reports on stderr which form a single run took.
 #include <cmath>
