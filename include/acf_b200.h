@@ -17,6 +17,10 @@
  *     usable GPU every compute entry point returns ACFB200_ERR_CUDA.
  *   - Calls are serialised by an internal lock (the reference is not re-entrant either, it keeps its
  *     state in file-scope globals, ACFcalculator.cpp:70-74).
+ *   - The "_device" entry points only ENQUEUE work, and all of them use the same per-device working memory
+ *     (descriptors, partial sums, reduction scratch, result staging).  Consecutive calls must therefore be
+ *     issued on ONE stream, or be separated by a synchronisation of the earlier call's stream; two calls in
+ *     flight on different streams of one device would overwrite each other's working memory.
  */
 #ifndef ACF_B200_H
 #define ACF_B200_H
